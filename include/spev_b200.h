@@ -1,0 +1,203 @@
+/* spev_b200.h -- C ABI of the B200-native spectral hot path for SPEV-TTS.
+ *
+ * The reference (DhrG23/spev-tts) has no FFI/plugin interface: its boundary for this path is
+ * a handful of Python call sites (file:line are in /root/reference/).  Each entry point below
+ * names the reference call it replaces; the Python shims in spev_tts_b200/ keep the
+ * reference's own signatures on top of this ABI (INTEGRATION.md shows the ctypes binding).
+ *
+ * Conventions
+ *   - every pointer marked "dev" is device memory on the ctx's GPU; "host" is host memory.
+ *   - the caller owns every buffer (inputs, outputs, workspace).  The library allocates only
+ *     ctx-owned constants in spev_create and frees them in spev_destroy.
+ *   - all work is enqueued asynchronously on `stream` (a cudaStream_t passed as void*); no
+ *     entry point synchronises.
+ *   - return value 0 = ok, negative = error (SPEV_E_*); text via spev_last_error()
+ *     (thread-local).  No C++ exception crosses the ABI.  There is NO CPU fallback: without
+ *     an sm_100 device spev_create fails with SPEV_E_DEVICE.
+ *   - batches are "flat": items (utterances / spectrograms) are concatenated and described by
+ *     prefix-offset arrays plus tile tables built on the host by spev_plan_tiles().
+ */
+#ifndef SPEV_B200_H
+#define SPEV_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPEV_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define SPEV_API __attribute__((visibility("default")))
+#else
+#define SPEV_API
+#endif
+
+#define SPEV_OK 0
+#define SPEV_E_INVALID (-1)     /* bad argument */
+#define SPEV_E_UNSUPPORTED (-2) /* configuration outside what the kernels implement */
+#define SPEV_E_DEVICE (-3)      /* no sm_100 device / wrong device */
+#define SPEV_E_CUDA (-4)        /* CUDA runtime error (message has the cudaError string) */
+#define SPEV_E_WORKSPACE (-5)   /* workspace too small */
+
+#define SPEV_TILE_FRAMES 32 /* frames per CTA tile (STFT-type kernels); == spev_tile_frames() */
+#define SPEV_TILE_CHUNKS 29 /* 256-sample output chunks per CTA tile (ISTFT); == spev_tile_chunks() */
+#define SPEV_SPEC_LD 520    /* row pitch (elements) of internal [F,513] spectra */
+
+typedef struct spev_ctx spev_ctx;
+
+/* Flat batch descriptor.  Item i owns frames [frame_off[i], frame_off[i+1]) and, for waveform
+ * inputs, samples [sample_off[i], sample_off[i+1]).  T_i frames <-> N_i samples with
+ * T_i = 1 + N_i / hop (librosa center=True framing).  Tile tables come from spev_plan_tiles. */
+typedef struct spev_batch {
+    int32_t n_items;
+    int32_t n_ftiles;          /* tiles of SPEV_TILE_FRAMES frames */
+    int32_t n_ctiles;          /* tiles of SPEV_TILE_CHUNKS output chunks (ISTFT); may be 0 */
+    int32_t reserved;
+    int64_t n_frames;          /* == frame_off[n_items] */
+    const int64_t* sample_off; /* dev [n_items+1]; may be NULL for spectrogram-only calls */
+    const int64_t* frame_off;  /* dev [n_items+1] */
+    const int32_t* ftile_item; /* dev [n_ftiles] */
+    const int32_t* ftile_t0;   /* dev [n_ftiles] first frame (item-local) of the tile */
+    const int32_t* ctile_item; /* dev [n_ctiles] */
+    const int32_t* ctile_c0;   /* dev [n_ctiles] first output chunk (item-local) of the tile */
+} spev_batch;
+
+SPEV_API int spev_abi_version(void);
+SPEV_API const char* spev_last_error(void);
+SPEV_API int spev_tile_frames(void); /* tile sizes the loaded library was built with */
+SPEV_API int spev_tile_chunks(void);
+
+/* ctx: immutable after creation, one per device, shareable between host threads.
+ * Owns the periodic Hann window, FFT twiddles, the Slaney mel basis keyed on
+ * (sr, n_fft, n_mels, fmin, fmax) in dense + banded form, and its pseudo-inverse.
+ * fmax <= 0 means sr/2 (librosa's fmax=None).  This round supports n_fft = win = 1024,
+ * hop = 256 (the reference CONFIG, spev_real_metrics.py:60-67); anything else returns
+ * SPEV_E_UNSUPPORTED.   Replaces: librosa.filters.mel / get_window under :363 and :730-733. */
+SPEV_API int spev_create(spev_ctx** out, int device, int sr, int n_fft, int hop, int win, int n_mels,
+                float fmin, float fmax);
+SPEV_API void spev_destroy(spev_ctx* ctx);
+
+/* Host copies of ctx constants (tests, INTEGRATION).  basis: [n_mels*513], pinv: [513*n_mels]
+ * (row-major), window: [n_fft]. */
+SPEV_API int spev_get_mel_basis(const spev_ctx* ctx, float* basis_host);
+SPEV_API int spev_get_mel_pinv(const spev_ctx* ctx, float* pinv_host);
+SPEV_API int spev_get_window(const spev_ctx* ctx, float* window_host);
+
+/* Host-only (no GPU needed): the float32 Slaney basis [n_mels, 1+n_fft/2] exactly as the ctx
+ * builds it, and the float64-Jacobi pseudo-inverse [n, m] of a row-major [m, n] matrix. */
+SPEV_API int spev_host_mel_basis(int sr, int n_fft, int n_mels, float fmin, float fmax, float* basis);
+SPEV_API int spev_host_pinv(const float* a, int m, int n, float* pinv);
+
+/* Host helper: split `n` items with `counts[i]` units into tiles of `per_tile` units.
+ * Returns the number of tiles; fills tile_item/tile_start when non-NULL (size >= return). */
+SPEV_API int64_t spev_plan_tiles(const int64_t* counts_host, int n, int per_tile, int32_t* tile_item,
+                        int32_t* tile_start);
+
+/* STFT -> |.|^2 -> mel -> (optional) log compression, fused, one launch.
+ *   samples : dev float32, flat; item i at sample_off[i]
+ *   out     : dev float32 [n_frames, n_mels] row-major  (== the reference's cache layout
+ *             `mel.T`, spev_real_metrics.py:421)
+ *   mode 0  : mel power            (librosa.feature.melspectrogram, :363)
+ *   mode 1  : clamp(log(max(mel, floor)), lo, hi)   (:364-366; reference: 1e-5, -10, 2)
+ * Replaces spev_real_metrics.py:363-367. */
+SPEV_API int spev_logmel(spev_ctx* ctx, const spev_batch* batch, const float* samples, float* out,
+                int mode, float floor, float lo, float hi, void* stream);
+
+/* Same front end, but writes the power spectrum |STFT|^2 as [n_frames, SPEV_SPEC_LD] (pad
+ * columns zero) -- the A operand of spev_mel_project. */
+SPEV_API int spev_stft_power(spev_ctx* ctx, const spev_batch* batch, const float* samples, float* power,
+                    void* stream);
+
+/* Tensor-core (tcgen05, 3xTF32, TMA-staged) mel projection  power[F,513] . basis^T -> [F,n_mels]
+ * with the same epilogue modes as spev_logmel.  Replaces the einsum inside
+ * librosa.feature.melspectrogram (:363) + :364-366. */
+SPEV_API int spev_mel_project(spev_ctx* ctx, const float* power, int64_t n_frames, float* out, int mode,
+                     float floor, float lo, float hi, void* stream);
+
+/* mel -> linear magnitude: S = sqrt(max(pinv(basis) . M, 0)), the warm start that librosa's
+ * NNLS (util.nnls, L-BFGS-B) returns unchanged for reference-range inputs.
+ *   mel     : dev float32.  layout 0: [n_frames, n_mels] frame-major flat;
+ *             layout 1: per item [n_mels, T_i] at element offset frame_off[i]*n_mels
+ *             (the reference's Vocoder.infer input, :725-733)
+ *   is_log  : 1 -> apply exp() first (:729)
+ *   S       : dev float32 [n_frames, ld_s]
+ * Replaces librosa.feature.inverse.mel_to_stft under :730. */
+SPEV_API int spev_mel_to_mag(spev_ctx* ctx, const spev_batch* batch, const float* mel, int layout,
+                    int is_log, float* S, int64_t ld_s, void* stream);
+
+/* ISTFT (irFFT-1024, Hann, gather overlap-add, window-sum-square normalisation).
+ *   spec : dev float2 [n_frames, ld] ; y : dev float32, item i at 256*(frame_off[i]-i),
+ *   length (T_i-1)*256.   Replaces librosa.istft inside griffinlim (:730-733). */
+SPEV_API int spev_istft(spev_ctx* ctx, const spev_batch* batch, const void* spec, int64_t ld, float* y,
+               void* stream);
+
+/* STFT of y (same item layout as spev_istft's output) -> spec [n_frames, ld] float2. */
+SPEV_API int spev_stft(spev_ctx* ctx, const spev_batch* batch, const float* y, void* spec, int64_t ld,
+              void* stream);
+
+/* One Griffin-Lim phase update (the body of librosa.griffinlim's loop after the istft):
+ *   reb = STFT(y); a = reb - alpha*tprev (skipped when has_prev == 0);
+ *   ang = S * a / (|a| + tiny);  tprev <- reb (in place).
+ * ang, tprev: dev float2 [n_frames, ld]; S: dev float32 [n_frames, ld_s]. */
+SPEV_API int spev_gl_phase_update(spev_ctx* ctx, const spev_batch* batch, const float* y, const float* S,
+                         int64_t ld_s, void* ang, void* tprev, int64_t ld, float alpha,
+                         int has_prev, void* stream);
+
+/* Full Griffin-Lim: ang0 = S*exp(i*phase); n_iter x (istft, stft + phase update); final istft.
+ *   init_phase : dev float32 [n_frames, 513] radians, or NULL -> 2*pi*U[0,1) from `seed`
+ *   y          : dev float32 [256*(n_frames - n_items)]
+ *   workspace  : dev, >= spev_griffinlim_workspace_bytes(n_frames)
+ * Replaces librosa.griffinlim under spev_real_metrics.py:730-733 (n_iter default 32 there,
+ * momentum 0.99). */
+SPEV_API size_t spev_griffinlim_workspace_bytes(int64_t n_frames);
+SPEV_API int spev_griffinlim(spev_ctx* ctx, const spev_batch* batch, const float* S, int64_t ld_s,
+                    const float* init_phase, uint64_t seed, int n_iter, float momentum, float* y,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* LengthRegulator, phase 1: sanitise durations (non-finite / <0 / >1000 -> 0, truncate),
+ * inclusive row cumsum, mel_lens = max(total, 1), max_len = max(mel_lens).
+ *   dur       : dev [B,T], dur_dtype 0=int64 1=int32 2=float32 3=float64 4=float16 5=bfloat16
+ *   cumsum    : dev int32 [B,T]
+ *   mel_lens  : dev int64 [B]
+ *   max_len_dev  : dev int64 [1];  max_len_host : pinned host int64 [1] or NULL (async copy;
+ *                  the caller synchronises the stream once before reading it)
+ * Replaces the validation loop of LengthRegulator.forward, spev_real_metrics.py:126-142. */
+SPEV_API int spev_lr_plan(const void* dur, int dur_dtype, int B, int T, int32_t* cumsum, int64_t* mel_lens,
+                 int64_t* max_len_dev, int64_t* max_len_host, void* stream);
+
+/* LengthRegulator, phase 2: out[b,f,:] = x[b, idx(b,f), :] for f < total_b else 0, where
+ * idx = searchsorted(cumsum[b], f, right).  Rows are copied verbatim (row_bytes = H*itemsize),
+ * so any dtype is bit-exact.  Replaces repeat/cat/pad/stack, :135-146 (and expand_feat,
+ * :228-236, with row_bytes = itemsize). */
+SPEV_API int spev_lr_expand(const void* x, int64_t row_bytes, const int32_t* cumsum, int B, int T,
+                   void* out, int64_t max_len, void* stream);
+
+/* Fused expand of the hidden states plus n_feat scalar curves in one launch (the six
+ * LengthRegulator calls of RealMetricsFastSpeech2.forward, :226-236, with the post-clamps of
+ * :239-243 applied when clamp_lo/hi are non-NULL).
+ *   feats : dev float32 [n_feat, B, T];  feats_out : dev float32 [n_feat, B, max_len] */
+SPEV_API int spev_lr_expand_fused(const void* x, int64_t row_bytes, const float* feats, int n_feat,
+                         const float* clamp_lo_host, const float* clamp_hi_host,
+                         const int32_t* cumsum, int B, int T, void* out, float* feats_out,
+                         int64_t max_len, void* stream);
+
+/* Inference duration rule, spev_real_metrics.py:215:
+ *   dur = (int64) rint(clamp((exp(log_dur) - 1) * d_control, 0, 500))   (round-half-even) */
+SPEV_API int spev_duration_rule(const float* log_dur, int64_t n, float d_control, int64_t* dur,
+                       void* stream);
+
+/* Bucketize + embedding lookup (canonical FastSpeech 2 variance embedding; no reference site,
+ * semantics = torch.bucketize(right) + F.embedding, SURVEY a-13).
+ *   idx_out : dev int64 [n] or NULL;  out : dev float32 [n,H] or NULL;
+ *   accumulate != 0 -> out += table[idx] */
+SPEV_API int spev_bucketize_embed(const float* v, int64_t n, const float* boundaries, int n_boundaries,
+                         int right, const float* table, int H, int64_t* idx_out, float* out,
+                         int accumulate, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPEV_B200_H */

@@ -1,0 +1,120 @@
+"""Generate ``tests/golden/*.npz``  --  TEST INFRASTRUCTURE ONLY.
+
+Run in the build container (where ``/root/reference`` is mounted):
+
+    PYTHONDONTWRITEBYTECODE=1 python -m oracle.make_golden
+
+* ``lr_*.npz``      -- produced by the REFERENCE'S OWN ``LengthRegulator``
+                       (``/root/reference/spev_real_metrics.py:122-146``) and the reference's
+                       duration rule (``:215``, evaluated with torch exactly as written there).
+                       These pin the LengthRegulator restatement and the CUDA kernels.
+* ``bucketize.npz`` -- ``torch.bucketize`` + ``F.embedding`` known answers (no reference
+                       implementation exists in-tree, SURVEY a-13).
+* ``logmel_*.npz``, ``gl_*.npz`` -- produced by ``oracle.librosa_restated`` (the reference's
+                       librosa is not installable: parity for these is unpinned by the
+                       reference; the fixtures freeze the restatement so that it cannot
+                       drift silently, and ``tests/test_oracle_pins.py`` checks it against
+                       torch / torchaudio / scipy independently).
+
+Inputs are regenerated from seeds by ``tests/synth.py``; large outputs are stored as
+SHA-256 digests plus a decimated slice so that the fixtures stay small.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import librosa_restated as lr  # noqa: E402
+from oracle import reference_import  # noqa: E402
+from tests import synth  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def sha(a: np.ndarray) -> str:
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def main() -> None:
+    os.makedirs(OUT, exist_ok=True)
+    ref = reference_import.load()
+    LR = ref.LengthRegulator()
+
+    # ---- cfg2: B=32, T<=200, H=256, int64 durations (reference class, CPU) -------------
+    x, dur, lens = synth.cfg2_batch(seed=2)
+    out, mel_lens = LR(torch.from_numpy(x), torch.from_numpy(dur))
+    out = out.numpy()
+    np.savez_compressed(os.path.join(OUT, "lr_cfg2.npz"), mel_lens=mel_lens.numpy(),
+                        shape=np.array(out.shape), sha256=np.array(sha(out)),
+                        row3=out[3, ::7, :16].copy(), lens=lens)
+    # the five scalar curves go through the same class with H=1 (``:228-236``)
+    feats = synth.cfg2_features(seed=2)
+    fo = [LR(torch.from_numpy(f).unsqueeze(-1), torch.from_numpy(dur))[0].numpy()[..., 0]
+          for f in feats]
+    np.savez_compressed(os.path.join(OUT, "lr_cfg2_feats.npz"), feats=np.stack(fo))
+
+    # ---- small dense case, stored in full ---------------------------------------------
+    rng = np.random.default_rng(22)
+    xs = rng.standard_normal((5, 17, 12)).astype(np.float32)
+    ds = rng.integers(0, 6, (5, 17)).astype(np.int64)
+    ds[2] = 0
+    o, l = LR(torch.from_numpy(xs), torch.from_numpy(ds))
+    np.savez_compressed(os.path.join(OUT, "lr_small.npz"), x=xs, dur=ds, out=o.numpy(),
+                        mel_lens=l.numpy())
+
+    # ---- edge cases (SURVEY App. B last row) -------------------------------------------
+    cases = {}
+    for name, (xe, de) in synth.lr_edge_cases().items():
+        o, l = LR(torch.from_numpy(xe), torch.from_numpy(de))
+        cases[name + "_x"] = xe
+        cases[name + "_dur"] = de
+        cases[name + "_out"] = o.numpy()
+        cases[name + "_lens"] = l.numpy()
+    np.savez_compressed(os.path.join(OUT, "lr_edge.npz"), **cases)
+
+    # ---- inference duration rule, exactly ``spev_real_metrics.py:215`` -----------------
+    ld = synth.log_durations(seed=7)
+    rule = {}
+    for dc in (1.0, 0.5, 1.7):
+        t = torch.clamp((torch.exp(torch.from_numpy(ld)) - 1) * dc, min=0, max=500).round().long()
+        rule[f"d_{dc}"] = t.numpy()
+    half = np.array([0.5, 1.5, 2.5, 3.5, 499.5, 500.5, 1e9, -3.0], dtype=np.float32)
+    rule["half_in"] = half
+    rule["half_out"] = torch.clamp(torch.from_numpy(half), min=0, max=500).round().long().numpy()
+    np.savez_compressed(os.path.join(OUT, "duration_rule.npz"), log_dur=ld, **rule)
+
+    # ---- bucketize + embedding (torch CPU ops are the oracle) --------------------------
+    v, bins, table = synth.bucketize_case(seed=2)
+    idx = torch.bucketize(torch.from_numpy(v), torch.from_numpy(bins))
+    idx_r = torch.bucketize(torch.from_numpy(v), torch.from_numpy(bins), right=True)
+    emb = torch.nn.functional.embedding(idx, torch.from_numpy(table)).numpy()
+    np.savez_compressed(os.path.join(OUT, "bucketize.npz"), idx=idx.numpy(),
+                        idx_right=idx_r.numpy(), emb_sha256=np.array(sha(emb)),
+                        emb_head=emb[:4, :8].copy())
+
+    # ---- restated librosa path (unpinned by the reference; frozen here) ----------------
+    for name, y in (("white", synth.white(seed=0)), ("speechy", synth.speechy(seed=1))):
+        lm = lr.reference_logmel(y)
+        np.savez_compressed(os.path.join(OUT, f"logmel_{name}.npz"), logmel=lm)
+    lm = lr.reference_logmel(synth.speechy(seed=3, n=256 * 63))
+    S = lr.mel_to_stft(np.exp(lm.T), sr=22050, n_fft=1024, fmin=0, fmax=8000)
+    ph = synth.init_phase(S.shape, seed=3)
+    y8, ang8, tprev8 = lr.griffinlim(S, n_iter=8, hop_length=256, n_fft=1024, init_phase=ph,
+                                     return_state=True)
+    np.savez_compressed(os.path.join(OUT, "gl_small.npz"), logmel=lm, S=S, y8=y8,
+                        sc8=np.array(lr.spectral_convergence(y8, S)))
+    print("golden fixtures written to", OUT)
+    for f in sorted(os.listdir(OUT)):
+        print(f"  {f:28s} {os.path.getsize(os.path.join(OUT, f)):>9d} B")
+
+
+if __name__ == "__main__":
+    main()

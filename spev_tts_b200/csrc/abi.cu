@@ -1,0 +1,417 @@
+// abi.cu -- extern "C" boundary (include/spev_b200.h) and ctx construction.
+//
+// ctx construction restates, in float64 -> float32 exactly as librosa does, the constants the
+// reference path rebuilds on every call: scipy.signal.get_window('hann', 1024, fftbins=True)
+// and librosa.filters.mel(sr, n_fft, n_mels, fmin, fmax, norm='slaney') (reached from
+// /root/reference/spev_real_metrics.py:363 with fmax=None and :730-733 with fmin=0,
+// fmax=8000), plus np.linalg.pinv of the basis (librosa.util.nnls warm start).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+
+#include "spev_internal.cuh"
+
+namespace spev {
+
+static thread_local std::string g_err;
+
+void set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("CUDA error %d (%s) at %s", static_cast<int>(e), cudaGetErrorString(e), what);
+    return SPEV_E_CUDA;
+}
+
+// launchers implemented in spectral.cu / lr.cu / gemm_tc.cu
+int launch_stft_mel(spev_ctx*, const spev_batch*, const float*, float*, bool, int, float, float, float, cudaStream_t);
+int launch_stft_phase(spev_ctx*, const spev_batch*, const float*, const float*, int64_t, void*, void*, int64_t, float, int, bool, cudaStream_t);
+int launch_istft(spev_ctx*, const spev_batch*, const void*, int64_t, float*, cudaStream_t);
+int launch_gl_init(spev_ctx*, const float*, int64_t, const float*, uint64_t, void*, int64_t, int64_t, cudaStream_t);
+int launch_mel_to_mag(spev_ctx*, const spev_batch*, const float*, int, int, float*, int64_t, cudaStream_t);
+int launch_lr_plan(const void*, int, int, int, int32_t*, int64_t*, int64_t*, int64_t*, cudaStream_t);
+int launch_lr_expand(const void*, int64_t, const float*, int, const float*, const float*, const int32_t*, int, int, void*, float*, int64_t, cudaStream_t);
+int launch_duration_rule(const float*, int64_t, float, int64_t*, cudaStream_t);
+int launch_bucketize_embed(const float*, int64_t, const float*, int, int, const float*, int, int64_t*, float*, int, cudaStream_t);
+int launch_mel_project_tc(spev_ctx*, const float*, int64_t, float*, int, float, float, float, cudaStream_t);
+int gemm_tc_init(spev_ctx*);
+void gemm_tc_destroy(spev_ctx*);
+
+// ---- Slaney mel scale (librosa.core.convert) -------------------------------------------------
+static double hz_to_mel(double f) {
+    const double f_sp = 200.0 / 3, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp;
+    const double logstep = std::log(6.4) / 27.0;
+    return f >= min_log_hz ? min_log_mel + std::log(f / min_log_hz) / logstep : f / f_sp;
+}
+static double mel_to_hz(double m) {
+    const double f_sp = 200.0 / 3, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp;
+    const double logstep = std::log(6.4) / 27.0;
+    return m >= min_log_mel ? min_log_hz * std::exp(logstep * (m - min_log_mel)) : f_sp * m;
+}
+
+// librosa.filters.mel: rows computed in float64, stored to float32, Slaney-normalised in place.
+static void build_mel_basis(int sr, int n_fft, int n_mels, double fmin, double fmax, std::vector<float>& w) {
+    const int nb = 1 + n_fft / 2;
+    w.assign(static_cast<size_t>(n_mels) * nb, 0.f);
+    std::vector<double> fftfreqs(nb), mel_f(n_mels + 2);
+    const double val = 1.0 / (n_fft * (1.0 / sr));          // np.fft.rfftfreq(n, d=1/sr)
+    for (int k = 0; k < nb; ++k) fftfreqs[k] = k * val;
+    const double m0 = hz_to_mel(fmin), m1 = hz_to_mel(fmax);
+    const double step = (m1 - m0) / (n_mels + 1);             // np.linspace
+    for (int i = 0; i < n_mels + 2; ++i) mel_f[i] = mel_to_hz(i == n_mels + 1 ? m1 : m0 + i * step);
+    for (int i = 0; i < n_mels; ++i) {
+        const double fd0 = mel_f[i + 1] - mel_f[i], fd1 = mel_f[i + 2] - mel_f[i + 1];
+        const double enorm = 2.0 / (mel_f[i + 2] - mel_f[i]);
+        for (int k = 0; k < nb; ++k) {
+            const double lower = -(mel_f[i] - fftfreqs[k]) / fd0;
+            const double upper = (mel_f[i + 2] - fftfreqs[k]) / fd1;
+            const float tri = static_cast<float>(std::max(0.0, std::min(lower, upper)));
+            w[static_cast<size_t>(i) * nb + k] = static_cast<float>(static_cast<double>(tri) * enorm);
+        }
+    }
+}
+
+// pinv(A) for A [m x n] (m <= n) by one-sided Jacobi SVD of G = A^T in float64.
+static void pinv_jacobi(const std::vector<float>& A, int m, int n, std::vector<float>& P /*[n x m]*/) {
+    std::vector<double> G(static_cast<size_t>(n) * m), V(static_cast<size_t>(m) * m, 0.0);
+    for (int i = 0; i < m; ++i) {
+        V[static_cast<size_t>(i) * m + i] = 1.0;
+        for (int k = 0; k < n; ++k) G[static_cast<size_t>(k) * m + i] = A[static_cast<size_t>(i) * n + k];
+    }
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0.0;
+        for (int p = 0; p < m - 1; ++p)
+            for (int q = p + 1; q < m; ++q) {
+                double a = 0, b = 0, c = 0;
+                for (int k = 0; k < n; ++k) {
+                    const double gp = G[static_cast<size_t>(k) * m + p], gq = G[static_cast<size_t>(k) * m + q];
+                    a += gp * gp; b += gq * gq; c += gp * gq;
+                }
+                if (std::fabs(c) <= 1e-300 || std::fabs(c) <= 1e-17 * std::sqrt(a * b)) continue;
+                off = std::max(off, std::fabs(c) / std::sqrt(a * b));
+                const double zeta = (b - a) / (2.0 * c);
+                const double t = (zeta >= 0 ? 1.0 : -1.0) / (std::fabs(zeta) + std::sqrt(1.0 + zeta * zeta));
+                const double cs = 1.0 / std::sqrt(1.0 + t * t), sn = cs * t;
+                for (int k = 0; k < n; ++k) {
+                    double& gp = G[static_cast<size_t>(k) * m + p];
+                    double& gq = G[static_cast<size_t>(k) * m + q];
+                    const double x = gp, y = gq;
+                    gp = cs * x - sn * y; gq = sn * x + cs * y;
+                }
+                for (int k = 0; k < m; ++k) {
+                    double& vp = V[static_cast<size_t>(k) * m + p];
+                    double& vq = V[static_cast<size_t>(k) * m + q];
+                    const double x = vp, y = vq;
+                    vp = cs * x - sn * y; vq = sn * x + cs * y;
+                }
+            }
+        if (off < 1e-15) break;
+    }
+    std::vector<double> s2(m);
+    double smax2 = 0;
+    for (int j = 0; j < m; ++j) {
+        double a = 0;
+        for (int k = 0; k < n; ++k) a += G[static_cast<size_t>(k) * m + j] * G[static_cast<size_t>(k) * m + j];
+        s2[j] = a; smax2 = std::max(smax2, a);
+    }
+    const double rcond = 1e-15;   // numpy.linalg.pinv default
+    P.assign(static_cast<size_t>(n) * m, 0.f);
+    std::vector<double> acc(static_cast<size_t>(n) * m, 0.0);
+    for (int j = 0; j < m; ++j) {
+        if (std::sqrt(s2[j]) <= rcond * std::sqrt(smax2)) continue;
+        const double inv = 1.0 / s2[j];
+        for (int k = 0; k < n; ++k) {
+            const double g = G[static_cast<size_t>(k) * m + j] * inv;
+            for (int i = 0; i < m; ++i) acc[static_cast<size_t>(k) * m + i] += g * V[static_cast<size_t>(i) * m + j];
+        }
+    }
+    for (size_t i = 0; i < acc.size(); ++i) P[i] = static_cast<float>(acc[i]);
+}
+
+template <class T>
+static int upload(T** dst, const std::vector<T>& src) {
+    SPEV_CUDA(cudaMalloc(reinterpret_cast<void**>(dst), std::max<size_t>(1, src.size()) * sizeof(T)));
+    if (!src.empty())
+        SPEV_CUDA(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return SPEV_OK;
+}
+
+static float tf32_trunc(float x) {
+    uint32_t u;
+    std::memcpy(&u, &x, 4);
+    u &= 0xFFFFE000u;
+    std::memcpy(&x, &u, 4);
+    return x;
+}
+
+}  // namespace spev
+
+using namespace spev;
+
+extern "C" {
+
+int spev_abi_version(void) { return SPEV_ABI_VERSION; }
+const char* spev_last_error(void) { return g_err.c_str(); }
+
+int spev_create(spev_ctx** out, int device, int sr, int n_fft, int hop, int win, int n_mels,
+                float fmin, float fmax) {
+    SPEV_REQUIRE(out, SPEV_E_INVALID, "spev_create: out is null");
+    *out = nullptr;
+    SPEV_REQUIRE(n_fft == kNfft && hop == kHop && (win == kNfft || win <= 0), SPEV_E_UNSUPPORTED,
+                 "spev_create: only n_fft=1024, hop=256, win=1024 are implemented (got %d/%d/%d)", n_fft, hop, win);
+    SPEV_REQUIRE(sr > 0 && n_mels > 0 && n_mels <= 256, SPEV_E_INVALID, "spev_create: bad sr/n_mels");
+    if (fmax <= 0.f) fmax = 0.5f * sr;
+    SPEV_REQUIRE(fmin >= 0.f && fmin < fmax, SPEV_E_INVALID, "spev_create: need 0 <= fmin < fmax");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("spev_create: no CUDA device (this library has no CPU fallback)");
+        return SPEV_E_DEVICE;
+    }
+    SPEV_REQUIRE(device >= 0 && device < ndev, SPEV_E_DEVICE, "spev_create: device %d out of range", device);
+    cudaDeviceProp prop;
+    SPEV_CUDA(cudaGetDeviceProperties(&prop, device));
+    SPEV_REQUIRE(prop.major == 10, SPEV_E_DEVICE, "spev_create: device %d is sm_%d%d; this build is sm_100a only",
+                 device, prop.major, prop.minor);
+    SPEV_CUDA(cudaSetDevice(device));
+
+    spev_ctx* c = new spev_ctx();
+    c->device = device; c->sr = sr; c->n_fft = n_fft; c->hop = hop; c->win = kNfft; c->n_mels = n_mels;
+    c->fmin = fmin; c->fmax = fmax; c->num_sms = prop.multiProcessorCount; c->tma = nullptr;
+    c->d_tw = nullptr; c->d_window = nullptr; c->d_basis_pad = c->d_basis_hi = c->d_basis_lo = nullptr;
+    c->d_pinv_t = c->d_pinv_hi = c->d_pinv_lo = nullptr;
+    c->d_band_start = c->d_band_len = c->d_band_woff = nullptr; c->d_band_w = nullptr;
+
+    // periodic Hann, float64 -> float32
+    c->h_window.resize(kNfft);
+    for (int i = 0; i < kNfft; ++i) c->h_window[i] = static_cast<float>(0.5 - 0.5 * std::cos(2.0 * M_PI * i / kNfft));
+    std::vector<float2> tw(1024);
+    for (int k1 = 0; k1 < 32; ++k1)
+        for (int l = 0; l < 32; ++l) {
+            const double a = -2.0 * M_PI * (k1 * l) / 1024.0;
+            tw[k1 * 32 + l] = make_float2(static_cast<float>(std::cos(a)), static_cast<float>(std::sin(a)));
+        }
+    build_mel_basis(sr, n_fft, n_mels, fmin, fmax, c->h_basis);
+    pinv_jacobi(c->h_basis, n_mels, kBins, c->h_pinv);
+
+    // banded form
+    std::vector<int> bstart(n_mels), blen(n_mels), bwoff(n_mels);
+    std::vector<float> bw;
+    c->band_max_len = 0;
+    for (int m = 0; m < n_mels; ++m) {
+        int lo = kBins, hi = -1;
+        for (int k = 0; k < kBins; ++k)
+            if (c->h_basis[static_cast<size_t>(m) * kBins + k] != 0.f) { lo = std::min(lo, k); hi = std::max(hi, k); }
+        bstart[m] = hi >= lo ? lo : 0;
+        blen[m] = hi >= lo ? hi - lo + 1 : 0;
+        bwoff[m] = static_cast<int>(bw.size());
+        for (int k = 0; k < blen[m]; ++k) bw.push_back(c->h_basis[static_cast<size_t>(m) * kBins + bstart[m] + k]);
+        c->band_max_len = std::max(c->band_max_len, blen[m]);
+    }
+    c->band_nnz = static_cast<int>(bw.size());
+
+    // padded / split operands for the tensor-core GEMMs
+    std::vector<float> basis_pad(static_cast<size_t>(n_mels) * kSpecLd, 0.f), b_hi(basis_pad.size()), b_lo(basis_pad.size());
+    std::vector<float> pinv_t(static_cast<size_t>(n_mels) * kSpecLd, 0.f);
+    for (int m = 0; m < n_mels; ++m)
+        for (int k = 0; k < kBins; ++k) {
+            basis_pad[static_cast<size_t>(m) * kSpecLd + k] = c->h_basis[static_cast<size_t>(m) * kBins + k];
+            pinv_t[static_cast<size_t>(m) * kSpecLd + k] = c->h_pinv[static_cast<size_t>(k) * n_mels + m];
+        }
+    for (size_t i = 0; i < basis_pad.size(); ++i) { b_hi[i] = tf32_trunc(basis_pad[i]); b_lo[i] = basis_pad[i] - b_hi[i]; }
+
+    int rc = SPEV_OK;
+    if ((rc = upload(&c->d_tw, tw)) || (rc = upload(&c->d_window, c->h_window)) ||
+        (rc = upload(&c->d_basis_pad, basis_pad)) || (rc = upload(&c->d_basis_hi, b_hi)) ||
+        (rc = upload(&c->d_basis_lo, b_lo)) || (rc = upload(&c->d_pinv_t, pinv_t)) ||
+        (rc = upload(&c->d_band_start, bstart)) || (rc = upload(&c->d_band_len, blen)) ||
+        (rc = upload(&c->d_band_woff, bwoff)) || (rc = upload(&c->d_band_w, bw)) ||
+        (rc = gemm_tc_init(c))) {
+        spev_destroy(c);
+        return rc;
+    }
+    *out = c;
+    return SPEV_OK;
+}
+
+void spev_destroy(spev_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    gemm_tc_destroy(c);
+    cudaFree(c->d_tw); cudaFree(c->d_window); cudaFree(c->d_basis_pad); cudaFree(c->d_basis_hi);
+    cudaFree(c->d_basis_lo); cudaFree(c->d_pinv_t); cudaFree(c->d_pinv_hi); cudaFree(c->d_pinv_lo);
+    cudaFree(c->d_band_start); cudaFree(c->d_band_len); cudaFree(c->d_band_woff); cudaFree(c->d_band_w);
+    delete c;
+}
+
+int spev_get_mel_basis(const spev_ctx* c, float* dst) {
+    SPEV_REQUIRE(c && dst, SPEV_E_INVALID, "null argument");
+    std::memcpy(dst, c->h_basis.data(), c->h_basis.size() * sizeof(float));
+    return SPEV_OK;
+}
+int spev_get_mel_pinv(const spev_ctx* c, float* dst) {
+    SPEV_REQUIRE(c && dst, SPEV_E_INVALID, "null argument");
+    std::memcpy(dst, c->h_pinv.data(), c->h_pinv.size() * sizeof(float));
+    return SPEV_OK;
+}
+int spev_get_window(const spev_ctx* c, float* dst) {
+    SPEV_REQUIRE(c && dst, SPEV_E_INVALID, "null argument");
+    std::memcpy(dst, c->h_window.data(), c->h_window.size() * sizeof(float));
+    return SPEV_OK;
+}
+
+int spev_host_mel_basis(int sr, int n_fft, int n_mels, float fmin, float fmax, float* basis) {
+    SPEV_REQUIRE(basis && sr > 0 && n_fft > 0 && n_mels > 0, SPEV_E_INVALID, "spev_host_mel_basis: bad argument");
+    if (fmax <= 0.f) fmax = 0.5f * sr;
+    std::vector<float> w;
+    build_mel_basis(sr, n_fft, n_mels, fmin, fmax, w);
+    std::memcpy(basis, w.data(), w.size() * sizeof(float));
+    return SPEV_OK;
+}
+
+int spev_host_pinv(const float* a, int m, int n, float* pinv) {
+    SPEV_REQUIRE(a && pinv && m > 0 && n >= m, SPEV_E_INVALID, "spev_host_pinv: need m <= n");
+    std::vector<float> A(a, a + static_cast<size_t>(m) * n), P;
+    pinv_jacobi(A, m, n, P);
+    std::memcpy(pinv, P.data(), P.size() * sizeof(float));
+    return SPEV_OK;
+}
+
+int spev_tile_frames(void) { return kTileFrames; }
+int spev_tile_chunks(void) { return kTileChunks; }
+
+int64_t spev_plan_tiles(const int64_t* counts, int n, int per_tile, int32_t* tile_item, int32_t* tile_start) {
+    if (!counts || n < 0 || per_tile <= 0) return SPEV_E_INVALID;
+    int64_t nt = 0;
+    for (int i = 0; i < n; ++i) {
+        for (int64_t s = 0; s < counts[i]; s += per_tile, ++nt) {
+            if (tile_item) tile_item[nt] = i;
+            if (tile_start) tile_start[nt] = static_cast<int32_t>(s);
+        }
+    }
+    return nt;
+}
+
+static int with_device(spev_ctx* c) {
+    SPEV_REQUIRE(c, SPEV_E_INVALID, "ctx is null");
+    SPEV_CUDA(cudaSetDevice(c->device));
+    return SPEV_OK;
+}
+
+int spev_logmel(spev_ctx* c, const spev_batch* b, const float* samples, float* out, int mode,
+                float floor_v, float lo, float hi, void* stream) {
+    int rc = with_device(c);
+    if (rc) return rc;
+    SPEV_REQUIRE(mode == 0 || mode == 1, SPEV_E_INVALID, "spev_logmel: mode must be 0 or 1");
+    return launch_stft_mel(c, b, samples, out, false, mode, floor_v, lo, hi, static_cast<cudaStream_t>(stream));
+}
+
+int spev_stft_power(spev_ctx* c, const spev_batch* b, const float* samples, float* power, void* stream) {
+    int rc = with_device(c);
+    if (rc) return rc;
+    return launch_stft_mel(c, b, samples, power, true, 0, 0.f, 0.f, 0.f, static_cast<cudaStream_t>(stream));
+}
+
+int spev_mel_project(spev_ctx* c, const float* power, int64_t n_frames, float* out, int mode,
+                     float floor_v, float lo, float hi, void* stream) {
+    int rc = with_device(c);
+    if (rc) return rc;
+    SPEV_REQUIRE(mode == 0 || mode == 1, SPEV_E_INVALID, "spev_mel_project: mode must be 0 or 1");
+    return launch_mel_project_tc(c, power, n_frames, out, mode, floor_v, lo, hi, static_cast<cudaStream_t>(stream));
+}
+
+int spev_mel_to_mag(spev_ctx* c, const spev_batch* b, const float* mel, int layout, int is_log,
+                    float* S, int64_t ld_s, void* stream) {
+    int rc = with_device(c);
+    if (rc) return rc;
+    return launch_mel_to_mag(c, b, mel, layout, is_log, S, ld_s, static_cast<cudaStream_t>(stream));
+}
+
+int spev_istft(spev_ctx* c, const spev_batch* b, const void* spec, int64_t ld, float* y, void* stream) {
+    int rc = with_device(c);
+    if (rc) return rc;
+    return launch_istft(c, b, spec, ld, y, static_cast<cudaStream_t>(stream));
+}
+
+int spev_stft(spev_ctx* c, const spev_batch* b, const float* y, void* spec, int64_t ld, void* stream) {
+    int rc = with_device(c);
+    if (rc) return rc;
+    return launch_stft_phase(c, b, y, nullptr, 0, spec, nullptr, ld, 0.f, 0, false, static_cast<cudaStream_t>(stream));
+}
+
+int spev_gl_phase_update(spev_ctx* c, const spev_batch* b, const float* y, const float* S, int64_t ld_s,
+                         void* ang, void* tprev, int64_t ld, float alpha, int has_prev, void* stream) {
+    int rc = with_device(c);
+    if (rc) return rc;
+    return launch_stft_phase(c, b, y, S, ld_s, ang, tprev, ld, alpha, has_prev, true, static_cast<cudaStream_t>(stream));
+}
+
+size_t spev_griffinlim_workspace_bytes(int64_t n_frames) {
+    if (n_frames < 0) return 0;
+    return static_cast<size_t>(n_frames) * kSpecLd * 2 * sizeof(float2) + 256;
+}
+
+int spev_griffinlim(spev_ctx* c, const spev_batch* b, const float* S, int64_t ld_s, const float* init_phase,
+                    uint64_t seed, int n_iter, float momentum, float* y, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+    int rc = with_device(c);
+    if (rc) return rc;
+    SPEV_REQUIRE(b, SPEV_E_INVALID, "spev_griffinlim: batch is null");
+    SPEV_REQUIRE(n_iter >= 0 && momentum >= 0.f, SPEV_E_INVALID, "spev_griffinlim: need n_iter >= 0, momentum >= 0");
+    if (b->n_frames == 0) return SPEV_OK;
+    SPEV_REQUIRE(S && y && ld_s >= kBins, SPEV_E_INVALID, "spev_griffinlim: null S/y or ld_s < 513");
+    SPEV_REQUIRE(workspace && workspace_bytes >= spev_griffinlim_workspace_bytes(b->n_frames), SPEV_E_WORKSPACE,
+                 "spev_griffinlim: workspace too small (%zu < %zu)", workspace_bytes,
+                 spev_griffinlim_workspace_bytes(b->n_frames));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~static_cast<uintptr_t>(255);
+    float2* ang = reinterpret_cast<float2*>(base);
+    float2* tprev = ang + b->n_frames * kSpecLd;
+    // librosa: (momentum / (1 + momentum)) is a Python float applied to a complex64 array
+    const float alpha = static_cast<float>(static_cast<double>(momentum) / (1.0 + static_cast<double>(momentum)));
+    if ((rc = launch_gl_init(c, S, ld_s, init_phase, seed, ang, kSpecLd, b->n_frames, st))) return rc;
+    for (int it = 0; it < n_iter; ++it) {
+        if ((rc = launch_istft(c, b, ang, kSpecLd, y, st))) return rc;
+        if ((rc = launch_stft_phase(c, b, y, S, ld_s, ang, tprev, kSpecLd, alpha, it > 0, true, st))) return rc;
+    }
+    return launch_istft(c, b, ang, kSpecLd, y, st);
+}
+
+int spev_lr_plan(const void* dur, int dur_dtype, int B, int T, int32_t* cumsum, int64_t* mel_lens,
+                 int64_t* max_len_dev, int64_t* max_len_host, void* stream) {
+    return launch_lr_plan(dur, dur_dtype, B, T, cumsum, mel_lens, max_len_dev, max_len_host,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int spev_lr_expand(const void* x, int64_t row_bytes, const int32_t* cumsum, int B, int T, void* out,
+                   int64_t max_len, void* stream) {
+    SPEV_REQUIRE(x && out, SPEV_E_INVALID, "spev_lr_expand: null x/out");
+    return launch_lr_expand(x, row_bytes, nullptr, 0, nullptr, nullptr, cumsum, B, T, out, nullptr, max_len,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int spev_lr_expand_fused(const void* x, int64_t row_bytes, const float* feats, int n_feat,
+                         const float* clamp_lo_host, const float* clamp_hi_host, const int32_t* cumsum,
+                         int B, int T, void* out, float* feats_out, int64_t max_len, void* stream) {
+    return launch_lr_expand(x, row_bytes, feats, n_feat, clamp_lo_host, clamp_hi_host, cumsum, B, T, out,
+                            feats_out, max_len, static_cast<cudaStream_t>(stream));
+}
+
+int spev_duration_rule(const float* log_dur, int64_t n, float d_control, int64_t* dur, void* stream) {
+    return launch_duration_rule(log_dur, n, d_control, dur, static_cast<cudaStream_t>(stream));
+}
+
+int spev_bucketize_embed(const float* v, int64_t n, const float* boundaries, int n_boundaries, int right,
+                         const float* table, int H, int64_t* idx_out, float* out, int accumulate, void* stream) {
+    return launch_bucketize_embed(v, n, boundaries, n_boundaries, right, table, H, idx_out, out, accumulate,
+                                  static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

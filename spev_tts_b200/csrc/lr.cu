@@ -1,0 +1,295 @@
+// lr.cu -- LengthRegulator (duration sanitise + warp-scan cumsum + gather-expand), duration
+// rule and bucketize+embedding kernels for sm_100a.  All index arithmetic is integer and
+// bit-exact against the reference; payload rows are copied verbatim.
+//
+// K6 k_lr_plan     replaces the validation loop of LengthRegulator.forward
+//                  (/root/reference/spev_real_metrics.py:126-142) -- which performs one
+//                  .item() device sync per (b,t) -- with one warp-scan per row.
+// K7 k_lr_expand   replaces repeat/cat/pad/stack (:135-146) and the five expand_feat calls
+//                  (:228-236) + post-clamps (:239-243) in the fused variant.
+// K8 k_bucketize   torch.bucketize + F.embedding (SURVEY a-13; no in-tree reference site).
+#include <algorithm>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include "spev_internal.cuh"
+
+namespace spev {
+
+// ---- duration sanitisation: "if not np.isfinite(d) or d < 0 or d > 1000: d = 0; n = int(d)" ----
+__device__ __forceinline__ int sanitize(long long d) { return (d < 0 || d > 1000) ? 0 : static_cast<int>(d); }
+__device__ __forceinline__ int sanitize(int d) { return (d < 0 || d > 1000) ? 0 : d; }
+__device__ __forceinline__ int sanitize(double d) {
+    return (!isfinite(d) || d < 0.0 || d > 1000.0) ? 0 : static_cast<int>(d);   // cast truncates
+}
+__device__ __forceinline__ int sanitize(float d) { return sanitize(static_cast<double>(d)); }
+__device__ __forceinline__ int sanitize(__half d) { return sanitize(static_cast<double>(__half2float(d))); }
+__device__ __forceinline__ int sanitize(__nv_bfloat16 d) { return sanitize(static_cast<double>(__bfloat162float(d))); }
+
+template <class Tdur>
+__global__ void k_lr_plan(const Tdur* __restrict__ dur, int B, int T, int32_t* __restrict__ cumsum,
+                          long long* __restrict__ mel_lens, long long* __restrict__ max_len) {
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    for (int b = blockIdx.x * warps_per_block + (threadIdx.x >> 5); b < B; b += gridDim.x * warps_per_block) {
+        const Tdur* row = dur + static_cast<int64_t>(b) * T;
+        int32_t* crow = cumsum + static_cast<int64_t>(b) * T;
+        int carry = 0;
+        for (int t0 = 0; t0 < T; t0 += 32) {
+            const int t = t0 + lane;
+            int v = t < T ? sanitize(row[t]) : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, v, o);
+                if (lane >= o) v += u;
+            }
+            v += carry;
+            if (t < T) crow[t] = v;
+            carry = __shfl_sync(0xffffffffu, v, 31);
+        }
+        if (lane == 0) {
+            const long long len = carry > 0 ? carry : 1;   // empty row -> one zero frame
+            mel_lens[b] = len;
+            atomicMax(max_len, len);
+        }
+    }
+}
+
+// first i in [0,T) with cs[i] > f   (np.searchsorted(cs, f, side='right')); caller guarantees
+// f < cs[T-1]
+__device__ __forceinline__ int upper_bound_i32(const int32_t* cs, int T, int f) {
+    int lo = 0, hi = T;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (cs[mid] > f) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+constexpr int kLrFrames = 64;     // output frames per CTA
+constexpr int kLrThreads = 256;
+constexpr int kMaxFeat = 16;
+struct ClampParams { int enabled; float lo[kMaxFeat]; float hi[kMaxFeat]; };   // by-value kernel arg
+
+// out[b, f, :] = x[b, idx, :] (row_bytes bytes) or 0; optional n_feat scalar curves.
+__global__ void __launch_bounds__(kLrThreads)
+k_lr_expand(const unsigned char* __restrict__ x, int64_t row_bytes, const float* __restrict__ feats,
+            int n_feat, ClampParams clamp,
+            const int32_t* __restrict__ cumsum, int B, int T, unsigned char* __restrict__ out,
+            float* __restrict__ feats_out, int64_t max_len) {
+    __shared__ int s_idx[kLrFrames];
+    const int b = blockIdx.y;
+    const int64_t f0 = static_cast<int64_t>(blockIdx.x) * kLrFrames;
+    const int32_t* cs = cumsum + static_cast<int64_t>(b) * T;
+    const int total = T > 0 ? cs[T - 1] : 0;
+    if (threadIdx.x < kLrFrames) {
+        const int64_t f = f0 + threadIdx.x;
+        s_idx[threadIdx.x] = (f < total) ? upper_bound_i32(cs, T, static_cast<int>(f)) : -1;
+    }
+    __syncthreads();
+    const int nfr = static_cast<int>(min(static_cast<int64_t>(kLrFrames), max_len - f0));
+    const unsigned char* xb = x + static_cast<int64_t>(b) * T * row_bytes;
+    unsigned char* ob = out + (static_cast<int64_t>(b) * max_len + f0) * row_bytes;
+
+    if (x != nullptr) {
+        const bool vec16 = (row_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
+                           ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+        const bool vec4 = (row_bytes % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 3) == 0) &&
+                          ((reinterpret_cast<uintptr_t>(out) & 3) == 0);
+        if (vec16) {
+            const int per_row = static_cast<int>(row_bytes / 16);
+            const int64_t n = static_cast<int64_t>(nfr) * per_row;
+            for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+                const int fl = static_cast<int>(i / per_row);
+                const int c = static_cast<int>(i - static_cast<int64_t>(fl) * per_row);
+                const int idx = s_idx[fl];
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (idx >= 0) v = __ldg(reinterpret_cast<const uint4*>(xb + idx * row_bytes) + c);
+                reinterpret_cast<uint4*>(ob + fl * row_bytes)[c] = v;
+            }
+        } else if (vec4) {
+            const int per_row = static_cast<int>(row_bytes / 4);
+            const int64_t n = static_cast<int64_t>(nfr) * per_row;
+            for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+                const int fl = static_cast<int>(i / per_row);
+                const int c = static_cast<int>(i - static_cast<int64_t>(fl) * per_row);
+                const int idx = s_idx[fl];
+                uint32_t v = 0;
+                if (idx >= 0) v = __ldg(reinterpret_cast<const uint32_t*>(xb + idx * row_bytes) + c);
+                reinterpret_cast<uint32_t*>(ob + fl * row_bytes)[c] = v;
+            }
+        } else {
+            const int64_t n = static_cast<int64_t>(nfr) * row_bytes;
+            for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+                const int fl = static_cast<int>(i / row_bytes);
+                const int64_t c = i - fl * row_bytes;
+                const int idx = s_idx[fl];
+                ob[i] = idx >= 0 ? xb[idx * row_bytes + c] : 0;
+            }
+        }
+    }
+    // scalar curves: thread <-> (feature j, local frame) -> coalesced in f
+    for (int i = threadIdx.x; i < n_feat * nfr; i += blockDim.x) {
+        const int j = i / nfr, fl = i - j * nfr;
+        const int idx = s_idx[fl];
+        float v = 0.f;
+        if (idx >= 0) v = __ldg(feats + (static_cast<int64_t>(j) * B + b) * T + idx);
+        if (clamp.enabled) v = fminf(fmaxf(v, clamp.lo[j]), clamp.hi[j]);
+        feats_out[(static_cast<int64_t>(j) * B + b) * max_len + f0 + fl] = v;
+    }
+}
+
+// ---- duration rule: clamp((exp(ld)-1)*d_control, 0, 500).round().long(), spev_real_metrics.py:215 ----
+__global__ void k_duration_rule(const float* __restrict__ ld, int64_t n, float d_control,
+                                long long* __restrict__ dur) {
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        // float32 exp evaluated through float64 so that the result is the correctly rounded
+        // float32 value (torch CPU: SLEEF <= 1 ulp); the remaining ops are exact float32.
+        const float e = static_cast<float>(exp(static_cast<double>(ld[i])));
+        float v = (e - 1.0f) * d_control;
+        v = fminf(fmaxf(v, 0.0f), 500.0f);
+        dur[i] = static_cast<long long>(rintf(v));   // round half to even
+    }
+}
+
+// ---- bucketize (+ embedding) ----
+__device__ __forceinline__ int bucket_of(float v, const float* __restrict__ bnd, int nb, int right) {
+    int lo = 0, hi = nb;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const float m = bnd[mid];
+        // same predicates as ATen's lower/upper bound: NaN falls through to nb
+        const bool go_right = right ? !(m > v) : !(m >= v);
+        if (go_right) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256)
+k_bucketize_embed(const float* __restrict__ v, int64_t n, const float* __restrict__ bnd, int nb,
+                  int right, const float* __restrict__ table, int H, long long* __restrict__ idx_out,
+                  float* __restrict__ out, int accumulate) {
+    extern __shared__ float s_bnd[];
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) s_bnd[i] = bnd[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    const bool vec = (H % 4 == 0) && ((reinterpret_cast<uintptr_t>(table) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    for (int64_t e0 = (static_cast<int64_t>(blockIdx.x) * wpb + (threadIdx.x >> 5)) * 32; e0 < n;
+         e0 += static_cast<int64_t>(gridDim.x) * wpb * 32) {
+        // each lane classifies one element, then the warp copies the 32 rows cooperatively
+        const int64_t e = e0 + lane;
+        int my = 0;
+        if (e < n) {
+            my = bucket_of(v[e], s_bnd, nb, right);
+            if (idx_out) idx_out[e] = my;
+        }
+        if (out == nullptr) continue;
+        const int cnt = static_cast<int>(min(static_cast<int64_t>(32), n - e0));
+        for (int r = 0; r < cnt; ++r) {
+            const int idx = __shfl_sync(0xffffffffu, my, r);
+            const float* src = table + static_cast<int64_t>(idx) * H;
+            float* dst = out + (e0 + r) * H;
+            if (vec) {
+                for (int c = lane; c < H / 4; c += 32) {
+                    float4 t = __ldg(reinterpret_cast<const float4*>(src) + c);
+                    if (accumulate) {
+                        const float4 o = reinterpret_cast<float4*>(dst)[c];
+                        t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
+                    }
+                    reinterpret_cast<float4*>(dst)[c] = t;
+                }
+            } else {
+                for (int c = lane; c < H; c += 32) {
+                    float t = __ldg(src + c);
+                    if (accumulate) t += dst[c];
+                    dst[c] = t;
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------
+int launch_lr_plan(const void* dur, int dur_dtype, int B, int T, int32_t* cumsum, int64_t* mel_lens,
+                   int64_t* max_len_dev, int64_t* max_len_host, cudaStream_t st) {
+    SPEV_REQUIRE(B >= 0 && T >= 0, SPEV_E_INVALID, "lr_plan: negative shape");
+    SPEV_REQUIRE(max_len_dev, SPEV_E_INVALID, "lr_plan: max_len_dev is null");
+    SPEV_CUDA(cudaMemsetAsync(max_len_dev, 0, sizeof(int64_t), st));
+    if (B > 0) {
+        SPEV_REQUIRE(mel_lens && (T == 0 || (dur && cumsum)), SPEV_E_INVALID, "lr_plan: null buffer");
+        const int wpb = 4;
+        const int grid = std::min((B + wpb - 1) / wpb, 148 * 8);
+        auto ml = reinterpret_cast<long long*>(mel_lens);
+        auto mx = reinterpret_cast<long long*>(max_len_dev);
+        switch (dur_dtype) {
+            case 0: k_lr_plan<<<grid, wpb * 32, 0, st>>>(static_cast<const long long*>(dur), B, T, cumsum, ml, mx); break;
+            case 1: k_lr_plan<<<grid, wpb * 32, 0, st>>>(static_cast<const int*>(dur), B, T, cumsum, ml, mx); break;
+            case 2: k_lr_plan<<<grid, wpb * 32, 0, st>>>(static_cast<const float*>(dur), B, T, cumsum, ml, mx); break;
+            case 3: k_lr_plan<<<grid, wpb * 32, 0, st>>>(static_cast<const double*>(dur), B, T, cumsum, ml, mx); break;
+            case 4: k_lr_plan<<<grid, wpb * 32, 0, st>>>(static_cast<const __half*>(dur), B, T, cumsum, ml, mx); break;
+            case 5: k_lr_plan<<<grid, wpb * 32, 0, st>>>(static_cast<const __nv_bfloat16*>(dur), B, T, cumsum, ml, mx); break;
+            default: SPEV_REQUIRE(false, SPEV_E_INVALID, "lr_plan: unknown dur_dtype %d", dur_dtype);
+        }
+        SPEV_CUDA(cudaGetLastError());
+    }
+    if (max_len_host)
+        SPEV_CUDA(cudaMemcpyAsync(max_len_host, max_len_dev, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    return SPEV_OK;
+}
+
+int launch_lr_expand(const void* x, int64_t row_bytes, const float* feats, int n_feat,
+                     const float* clamp_lo, const float* clamp_hi, const int32_t* cumsum, int B, int T,
+                     void* out, float* feats_out, int64_t max_len, cudaStream_t st) {
+    SPEV_REQUIRE(B >= 0 && T >= 0 && max_len >= 0 && n_feat >= 0 && n_feat <= 16, SPEV_E_INVALID,
+                 "lr_expand: bad shape");
+    if (B == 0 || max_len == 0) return SPEV_OK;
+    SPEV_REQUIRE(B <= 65535, SPEV_E_UNSUPPORTED, "lr_expand: B > 65535");
+    SPEV_REQUIRE(T == 0 || cumsum, SPEV_E_INVALID, "lr_expand: cumsum is null");
+    SPEV_REQUIRE(!x || (out && row_bytes > 0), SPEV_E_INVALID, "lr_expand: x given but out/row_bytes missing");
+    SPEV_REQUIRE(n_feat == 0 || (feats && feats_out), SPEV_E_INVALID, "lr_expand: feats buffers missing");
+    ClampParams cp;
+    cp.enabled = (n_feat > 0 && clamp_lo && clamp_hi) ? 1 : 0;
+    for (int j = 0; j < kMaxFeat; ++j) {
+        cp.lo[j] = (cp.enabled && j < n_feat) ? clamp_lo[j] : 0.f;
+        cp.hi[j] = (cp.enabled && j < n_feat) ? clamp_hi[j] : 0.f;
+    }
+    dim3 grid(static_cast<unsigned>((max_len + kLrFrames - 1) / kLrFrames), static_cast<unsigned>(B));
+    k_lr_expand<<<grid, kLrThreads, 0, st>>>(static_cast<const unsigned char*>(x), row_bytes, feats, n_feat,
+                                             cp, cumsum, B, T, static_cast<unsigned char*>(out),
+                                             feats_out, max_len);
+    SPEV_CUDA(cudaGetLastError());
+    return SPEV_OK;
+}
+
+int launch_duration_rule(const float* ld, int64_t n, float d_control, int64_t* dur, cudaStream_t st) {
+    SPEV_REQUIRE(n >= 0, SPEV_E_INVALID, "duration_rule: n < 0");
+    if (n == 0) return SPEV_OK;
+    SPEV_REQUIRE(ld && dur, SPEV_E_INVALID, "duration_rule: null buffer");
+    const int grid = static_cast<int>(std::min<int64_t>((n + 255) / 256, 148 * 8));
+    k_duration_rule<<<grid, 256, 0, st>>>(ld, n, d_control, reinterpret_cast<long long*>(dur));
+    SPEV_CUDA(cudaGetLastError());
+    return SPEV_OK;
+}
+
+int launch_bucketize_embed(const float* v, int64_t n, const float* bnd, int nb, int right,
+                           const float* table, int H, int64_t* idx_out, float* out, int accumulate,
+                           cudaStream_t st) {
+    SPEV_REQUIRE(n >= 0 && nb >= 0 && nb <= 12000, SPEV_E_INVALID, "bucketize: bad sizes (n_boundaries <= 12000)");
+    if (n == 0) return SPEV_OK;
+    SPEV_REQUIRE(v && (nb == 0 || bnd), SPEV_E_INVALID, "bucketize: null input");
+    SPEV_REQUIRE(!out || (table && H > 0), SPEV_E_INVALID, "bucketize: out given but table/H missing");
+    const int wpb = 8;
+    const int64_t groups = (n + 31) / 32;
+    const int grid = static_cast<int>(std::min<int64_t>((groups + wpb - 1) / wpb, 148 * 8));
+    k_bucketize_embed<<<grid, wpb * 32, sizeof(float) * nb, st>>>(v, n, bnd, nb, right, table, H,
+                                                                  reinterpret_cast<long long*>(idx_out),
+                                                                  out, accumulate);
+    SPEV_CUDA(cudaGetLastError());
+    return SPEV_OK;
+}
+
+}  // namespace spev

@@ -1,0 +1,593 @@
+// spectral.cu -- STFT / mel / ISTFT / Griffin-Lim kernels for sm_100a.
+//
+// K1 k_stft_mel   : frames -> Hann -> rFFT-1024 (two frames per warp transform) -> |X|^2 ->
+//                   banded Slaney-mel FFMA epilogue -> log/clamp -> [F, n_mels]
+//                   (or, MODE 1, the raw power spectrum [F, 520] for the tcgen05 GEMM path).
+//                   Replaces /root/reference/spev_real_metrics.py:363-367.
+// K4 k_istft      : two Hermitian spectra per warp -> irFFT-1024 -> Hann -> shared memory;
+//                   gather overlap-add (each output sample owner sums its <= 4 frames in
+//                   ascending frame order, no atomics) fused with window-sum-square
+//                   normalisation.            Replaces librosa.istft under :730-733.
+// K5 k_stft_phase : STFT of the rebuilt signal fused with Griffin-Lim's momentum / phase
+//                   normalisation update.     Replaces librosa.stft + the angle update lines of
+//                   librosa.griffinlim under :730-733.
+// K3 k_mel_to_mag : S = sqrt(max(pinv . exp(logmel), 0)) (FFMA version; the tcgen05 version
+//                   lives in gemm_tc.cu).     Replaces librosa mel_to_stft under :730.
+//
+// Shared-memory plan per CTA (16 warps, 32-frame tile, persistent over tiles):
+//   s_tw    float2[32*32]   inter-stage twiddles                     8,192 B
+//   s_win   float [1024]    periodic Hann                            4,096 B
+//   s_stage float [8960]    the tile's samples, read once from HBM  35,840 B  (K1/K5)
+//   s_x     16 x 2114 words warp-private transpose tiles; reused for
+//                           |X|^2 (K1) / windowed frames (K4)      135,296 B
+#include <algorithm>
+#include "spev_internal.cuh"
+
+namespace spev {
+
+struct BatchView {
+    int n_items, n_ftiles, n_ctiles;
+    int64_t n_frames;
+    const int64_t* sample_off;
+    const int64_t* frame_off;
+    const int32_t* ftile_item;
+    const int32_t* ftile_t0;
+    const int32_t* ctile_item;
+    const int32_t* ctile_c0;
+};
+
+static BatchView view_of(const spev_batch* b) {
+    BatchView v;
+    v.n_items = b->n_items; v.n_ftiles = b->n_ftiles; v.n_ctiles = b->n_ctiles;
+    v.n_frames = b->n_frames; v.sample_off = b->sample_off; v.frame_off = b->frame_off;
+    v.ftile_item = b->ftile_item; v.ftile_t0 = b->ftile_t0;
+    v.ctile_item = b->ctile_item; v.ctile_c0 = b->ctile_c0;
+    return v;
+}
+
+constexpr float kTiny = 1.17549435e-38f;   // np.finfo(np.float32).tiny
+
+// ---------------------------------------------------------------------------------------
+// shared helpers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_tables(float2* s_tw, float* s_win, const float2* __restrict__ g_tw,
+                                            const float* __restrict__ g_win) {
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
+        s_tw[i] = g_tw[i];
+        s_win[i] = g_win[i];
+    }
+}
+
+// Stage `count` samples x[first .. first+count) of a signal of length n (zero outside) into
+// shared memory.  `first` may be negative (centre padding).
+__device__ __forceinline__ void stage_samples(float* s_stage, const float* __restrict__ x,
+                                              int64_t n, int64_t first, int count) {
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((first & 3) == 0);
+    if (vec_ok) {
+        for (int i = threadIdx.x * 4; i < count; i += blockDim.x * 4) {
+            const int64_t g = first + i;
+            float4 v;
+            if (g >= 0 && g + 3 < n) {
+                v = __ldg(reinterpret_cast<const float4*>(x + g));
+            } else {
+                v.x = (g >= 0 && g < n) ? __ldg(x + g) : 0.f;
+                v.y = (g + 1 >= 0 && g + 1 < n) ? __ldg(x + g + 1) : 0.f;
+                v.z = (g + 2 >= 0 && g + 2 < n) ? __ldg(x + g + 2) : 0.f;
+                v.w = (g + 3 >= 0 && g + 3 < n) ? __ldg(x + g + 3) : 0.f;
+            }
+            *reinterpret_cast<float4*>(s_stage + i) = v;
+        }
+    } else {
+        for (int i = threadIdx.x; i < count; i += blockDim.x) {
+            const int64_t g = first + i;
+            s_stage[i] = (g >= 0 && g < n) ? __ldg(x + g) : 0.f;
+        }
+    }
+}
+
+// Load the two windowed frames a (real part) and b (imaginary part) of this warp from the
+// staged samples: v[j] = win[32j+lane] * (stage[256a + 32j + lane], stage[256b + 32j + lane]).
+__device__ __forceinline__ void load_frame_pair(float2 (&v)[32], const float* s_stage,
+                                                const float* s_win, int fa, bool b_valid, int lane) {
+    const float* pa = s_stage + fa * kHop + lane;
+    static_for<0, 32>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
+        const float w = s_win[32 * j + lane];
+        const float xa = pa[32 * j];
+        const float xb = b_valid ? pa[kHop + 32 * j] : 0.f;
+        v[j] = make_float2(w * xa, w * xb);
+    });
+}
+
+// ---------------------------------------------------------------------------------------
+// K1: fused STFT -> power -> mel -> log
+// ---------------------------------------------------------------------------------------
+template <int MODE>   // 0: mel epilogue, 1: power-spectrum output
+__global__ void __launch_bounds__(kThreads, 1)
+k_stft_mel(BatchView bv, const float* __restrict__ samples, float* __restrict__ out,
+           const float2* __restrict__ g_tw, const float* __restrict__ g_win, MelBands mb,
+           int log_mode, float floor_v, float lo, float hi) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* s_tw = reinterpret_cast<float2*>(smem_raw);
+    float* s_win = reinterpret_cast<float*>(s_tw + 1024);
+    float* s_stage = s_win + 1024;
+    float* s_x = s_stage + kStageSamples;
+    int* s_bstart = reinterpret_cast<int*>(s_x + kWarps * kWarpRegionWords);
+    int* s_blen = s_bstart + mb.n_mels;
+    int* s_bwoff = s_blen + mb.n_mels;
+    float* s_bw = reinterpret_cast<float*>(s_bwoff + mb.n_mels);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    load_tables(s_tw, s_win, g_tw, g_win);
+    if (MODE == 0) {
+        for (int i = threadIdx.x; i < mb.n_mels; i += blockDim.x) {
+            s_bstart[i] = mb.start[i]; s_blen[i] = mb.len[i]; s_bwoff[i] = mb.woff[i];
+        }
+        for (int i = threadIdx.x; i < mb.nnz; i += blockDim.x) s_bw[i] = mb.w[i];
+    }
+    float* xw = s_x + warp * kWarpRegionWords;
+    const int n_mels = mb.n_mels;
+    const int out_pitch = n_mels + 1;
+
+    for (int tile = blockIdx.x; tile < bv.n_ftiles; tile += gridDim.x) {
+        const int item = bv.ftile_item[tile];
+        const int t0 = bv.ftile_t0[tile];
+        const int64_t fo = bv.frame_off[item];
+        const int T = static_cast<int>(bv.frame_off[item + 1] - fo);
+        const int nf = min(kTileFrames, T - t0);
+        const int64_t so = bv.sample_off[item];
+        const int64_t n = bv.sample_off[item + 1] - so;
+
+        __syncthreads();   // previous tile fully consumed (s_stage alias, s_x); tables loaded
+        stage_samples(s_stage, samples + so, n, static_cast<int64_t>(t0) * kHop - kNfft / 2,
+                      (nf - 1) * kHop + kNfft);
+        __syncthreads();
+
+        const int fa = 2 * warp;
+        if (fa < nf) {
+            const bool b_valid = fa + 1 < nf;
+            float2 v[32];
+            load_frame_pair(v, s_stage, s_win, fa, b_valid, lane);
+            warp_fft1024<-1>(v, reinterpret_cast<float2*>(xw), s_tw, lane);
+            float2 p[16];
+            fetch_mirror(v, p, lane);
+            __syncwarp();   // transpose tile is dead; reuse it for |X|^2
+            float pa512 = v[16].x * v[16].x, pb512 = v[16].y * v[16].y;   // lane 0: bin 512
+            if (MODE == 0) {
+                static_for<0, 16>([&](auto kc) {
+                    constexpr int k2 = decltype(kc)::value;
+                    float2 xa, xb;
+                    split_pair(v[k2], p[k2], xa, xb);
+                    xw[lane + 32 * k2] = fmaf(xa.x, xa.x, xa.y * xa.y);
+                    xw[kBins + lane + 32 * k2] = fmaf(xb.x, xb.x, xb.y * xb.y);
+                });
+                if (lane == 0) { xw[512] = pa512; xw[kBins + 512] = pb512; }
+            } else {
+                float* oa = out + (fo + t0 + fa) * kSpecLd;
+                float* ob = oa + kSpecLd;
+                static_for<0, 16>([&](auto kc) {
+                    constexpr int k2 = decltype(kc)::value;
+                    float2 xa, xb;
+                    split_pair(v[k2], p[k2], xa, xb);
+                    oa[lane + 32 * k2] = fmaf(xa.x, xa.x, xa.y * xa.y);
+                    if (b_valid) ob[lane + 32 * k2] = fmaf(xb.x, xb.x, xb.y * xb.y);
+                });
+                if (lane < kSpecLd - 512) {   // bin 512 + zero pad columns 513..519
+                    oa[512 + lane] = lane == 0 ? pa512 : 0.f;
+                    if (b_valid) ob[512 + lane] = lane == 0 ? pb512 : 0.f;
+                }
+            }
+        }
+        if (MODE == 0) {
+            __syncthreads();   // all |X|^2 written; s_stage no longer read
+            // mel phase: lane <-> frame (conflict-free: bank = frame + bin), warp <-> band set
+            float* s_out = s_stage;
+            if (lane < nf) {
+                const float* pf = s_x + (lane >> 1) * kWarpRegionWords + (lane & 1) * kBins;
+                for (int m = warp; m < n_mels; m += kWarps) {
+                    const float* pw = s_bw + s_bwoff[m];
+                    const float* pp = pf + s_bstart[m];
+                    const int len = s_blen[m];
+                    float acc = 0.f;
+                    for (int j = 0; j < len; ++j) acc = fmaf(pw[j], pp[j], acc);
+                    if (log_mode) acc = fminf(fmaxf(logf(fmaxf(acc, floor_v)), lo), hi);
+                    s_out[lane * out_pitch + m] = acc;
+                }
+            }
+            __syncthreads();
+            float* o = out + (fo + t0) * n_mels;
+            const int total = nf * n_mels;
+            for (int i = threadIdx.x; i < total; i += blockDim.x) {
+                const int f = i / n_mels, m = i - f * n_mels;
+                o[i] = s_out[f * out_pitch + m];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K5: STFT (+ Griffin-Lim phase update)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void phase_update_store(float2 reb, float s, float2* __restrict__ ang,
+                                                   float2* __restrict__ tprev, int64_t idx,
+                                                   float alpha, int has_prev) {
+    float2 a = reb;
+    if (has_prev) {
+        const float2 tp = tprev[idx];
+        a.x = a.x - alpha * tp.x;
+        a.y = a.y - alpha * tp.y;
+    }
+    const float den = sqrtf(fmaf(a.x, a.x, a.y * a.y)) + kTiny;
+    const float r = 1.0f / den;   // numpy complex/real division: multiply by the reciprocal
+    ang[idx] = make_float2(a.x * r * s, a.y * r * s);
+    tprev[idx] = reb;
+}
+
+template <int MODE>   // 0: plain STFT into `ang`; 1: Griffin-Lim phase update
+__global__ void __launch_bounds__(kThreads, 1)
+k_stft_phase(BatchView bv, const float* __restrict__ y, const float* __restrict__ S, int64_t ld_s,
+             float2* __restrict__ ang, float2* __restrict__ tprev, int64_t ld, float alpha,
+             int has_prev, const float2* __restrict__ g_tw, const float* __restrict__ g_win) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* s_tw = reinterpret_cast<float2*>(smem_raw);
+    float* s_win = reinterpret_cast<float*>(s_tw + 1024);
+    float* s_stage = s_win + 1024;
+    float* s_x = s_stage + kStageSamples;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    load_tables(s_tw, s_win, g_tw, g_win);
+    float2* xw = reinterpret_cast<float2*>(s_x + warp * kWarpRegionWords);
+
+    for (int tile = blockIdx.x; tile < bv.n_ftiles; tile += gridDim.x) {
+        const int item = bv.ftile_item[tile];
+        const int t0 = bv.ftile_t0[tile];
+        const int64_t fo = bv.frame_off[item];
+        const int T = static_cast<int>(bv.frame_off[item + 1] - fo);
+        const int nf = min(kTileFrames, T - t0);
+        const int64_t yo = (fo - item) * kHop;
+        const int64_t n = static_cast<int64_t>(T - 1) * kHop;
+
+        __syncthreads();
+        stage_samples(s_stage, y + yo, n, static_cast<int64_t>(t0) * kHop - kNfft / 2,
+                      (nf - 1) * kHop + kNfft);
+        __syncthreads();
+
+        const int fa = 2 * warp;
+        if (fa < nf) {
+            const bool b_valid = fa + 1 < nf;
+            float2 v[32];
+            load_frame_pair(v, s_stage, s_win, fa, b_valid, lane);
+            warp_fft1024<-1>(v, xw, s_tw, lane);
+            float2 p[16];
+            fetch_mirror(v, p, lane);
+            const int64_t ra = (fo + t0 + fa) * ld;        // row of frame a in ang / tprev
+            const int64_t rb = ra + ld;
+            const float* sa = S + (fo + t0 + fa) * ld_s;
+            const float* sb = sa + ld_s;
+            static_for<0, 16>([&](auto kc) {
+                constexpr int k2 = decltype(kc)::value;
+                const int k = lane + 32 * k2;
+                float2 xa, xb;
+                split_pair(v[k2], p[k2], xa, xb);
+                if (MODE == 0) {
+                    ang[ra + k] = xa;
+                    if (b_valid) ang[rb + k] = xb;
+                } else {
+                    phase_update_store(xa, sa[k], ang, tprev, ra + k, alpha, has_prev);
+                    if (b_valid) phase_update_store(xb, sb[k], ang, tprev, rb + k, alpha, has_prev);
+                }
+            });
+            if (lane == 0) {
+                const float2 xa = make_float2(v[16].x, 0.f), xb = make_float2(v[16].y, 0.f);
+                if (MODE == 0) {
+                    ang[ra + 512] = xa;
+                    if (b_valid) ang[rb + 512] = xb;
+                } else {
+                    phase_update_store(xa, sa[512], ang, tprev, ra + 512, alpha, has_prev);
+                    if (b_valid) phase_update_store(xb, sb[512], ang, tprev, rb + 512, alpha, has_prev);
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K4: ISTFT with gather overlap-add and window-sum-square normalisation
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1)
+k_istft(BatchView bv, const float2* __restrict__ spec, int64_t ld, float* __restrict__ y,
+        const float2* __restrict__ g_tw, const float* __restrict__ g_win) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* s_tw = reinterpret_cast<float2*>(smem_raw);
+    float* s_win = reinterpret_cast<float*>(s_tw + 1024);
+    float* s_x = s_win + 1024;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    load_tables(s_tw, s_win, g_tw, g_win);
+    float* xw = s_x + warp * kWarpRegionWords;
+    const int pl = (32 - lane) & 31;
+
+    for (int tile = blockIdx.x; tile < bv.n_ctiles; tile += gridDim.x) {
+        const int item = bv.ctile_item[tile];
+        const int c0 = bv.ctile_c0[tile];
+        const int64_t fo = bv.frame_off[item];
+        const int T = static_cast<int>(bv.frame_off[item + 1] - fo);
+        const int nchunks = min(kTileChunks, (T - 1) - c0);
+        const int64_t yo = (fo - item) * kHop;
+
+        __syncthreads();   // previous tile's gather finished (and tables loaded)
+        // local frame lf <-> item frame t = c0 - 1 + lf ; needed: lf in [0, nchunks + 3)
+        const int lfa = 2 * warp;
+        const int ta = c0 - 1 + lfa, tb = ta + 1;
+        const bool a_valid = lfa < nchunks + 3 && ta >= 0 && ta < T;
+        const bool b_valid = lfa + 1 < nchunks + 3 && tb >= 0 && tb < T;
+        if (a_valid || b_valid) {
+            const float2* A = spec + (fo + ta) * ld;
+            const float2* B = A + ld;
+            float2 v[32];
+            float2 m[16];
+            static_for<0, 16>([&](auto jc) {
+                constexpr int j = decltype(jc)::value;
+                const int k = 32 * j + lane;
+                float2 a = a_valid ? A[k] : make_float2(0.f, 0.f);
+                float2 b = b_valid ? B[k] : make_float2(0.f, 0.f);
+                if (j == 0 && lane == 0) { a.y = 0.f; b.y = 0.f; }   // irfft ignores Im(DC)
+                v[j] = make_float2(a.x - b.y, a.y + b.x);            // A + iB
+                m[j] = make_float2(a.x + b.y, b.x - a.y);            // conj(A) + i conj(B)
+            });
+            // bins 512..1023 of the packed spectrum come from the mirror lane
+            const float nyq_a = a_valid ? A[512].x : 0.f;            // irfft ignores Im(Nyquist)
+            const float nyq_b = b_valid ? B[512].x : 0.f;
+            static_for<0, 16>([&](auto ic) {
+                constexpr int i = decltype(ic)::value;
+                float2 r;
+                r.x = __shfl_sync(0xffffffffu, m[15 - i].x, pl);
+                r.y = __shfl_sync(0xffffffffu, m[15 - i].y, pl);
+                if (lane == 0) {
+                    if constexpr (i == 0) r = make_float2(nyq_a, nyq_b);
+                    else r = m[16 - i];
+                }
+                v[16 + i] = r;
+            });
+            warp_fft1024<1>(v, reinterpret_cast<float2*>(xw), s_tw, lane);
+            __syncwarp();   // transpose tile dead -> reuse for the two windowed real frames
+            static_for<0, 32>([&](auto kc) {
+                constexpr int k2 = decltype(kc)::value;
+                const int nn = lane + 32 * k2;
+                const float w = s_win[nn] * (1.0f / kNfft);
+                xw[nn] = v[k2].x * w;
+                xw[kNfft + nn] = v[k2].y * w;
+            });
+        }
+        __syncthreads();
+        // gather: chunk c = c0 + cl receives frames c-1, c, c+1, c+2 (ascending), local cl..cl+3
+        for (int cl = warp; cl < nchunks; cl += kWarps) {
+            const int c = c0 + cl;
+            float* yo_c = y + yo + static_cast<int64_t>(c) * kHop;
+#pragma unroll
+            for (int ii = 0; ii < kHop / 32; ++ii) {
+                const int i = lane + 32 * ii;
+                float sum = 0.f, wss = 0.f;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int t = c - 1 + q;
+                    if (t >= 0 && t < T) {
+                        const int lf = cl + q;
+                        const int nn = 768 - 256 * q + i;
+                        sum += s_x[(lf >> 1) * kWarpRegionWords + (lf & 1) * kNfft + nn];
+                        const float w = s_win[nn];
+                        wss = fmaf(w, w, wss);
+                    }
+                }
+                yo_c[i] = wss > kTiny ? sum / wss : sum;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Griffin-Lim initial state: ang = S * exp(i * phase)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+__global__ void k_gl_init(const float* __restrict__ S, int64_t ld_s, const float* __restrict__ phase,
+                          uint64_t seed, float2* __restrict__ ang, int64_t ld, int64_t n_frames) {
+    const int64_t total = n_frames * kBins;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t f = i / kBins;
+        const int k = static_cast<int>(i - f * kBins);
+        float sn, cs;
+        if (phase) {
+            sincosf(phase[i], &sn, &cs);
+        } else {
+            const uint64_t r = splitmix64(seed ^ splitmix64(static_cast<uint64_t>(i)));
+            const float u = static_cast<float>(r >> 40) * (1.0f / 16777216.0f);   // [0,1)
+            sincospif(2.0f * u, &sn, &cs);
+        }
+        const float s = S[f * ld_s + k];
+        ang[f * ld + k] = make_float2(s * cs, s * sn);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K3 (FFMA version): S = sqrt(max(pinv . mel, 0))
+// ---------------------------------------------------------------------------------------
+constexpr int kMagFrames = 16;
+__global__ void __launch_bounds__(256)
+k_mel_to_mag(BatchView bv, const float* __restrict__ mel, int layout, int is_log,
+             const float* __restrict__ pinv_t /*[n_mels, 520]*/, int n_mels,
+             float* __restrict__ S, int64_t ld_s) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* s_m = reinterpret_cast<float*>(smem_raw);   // [kMagFrames][n_mels]
+    for (int tile = blockIdx.x; tile < bv.n_ftiles; tile += gridDim.x) {
+        const int item = bv.ftile_item[tile];
+        const int t0 = bv.ftile_t0[tile];
+        const int64_t fo = bv.frame_off[item];
+        const int T = static_cast<int>(bv.frame_off[item + 1] - fo);
+        const int nf = min(kTileFrames, T - t0);
+        for (int h0 = 0; h0 < nf; h0 += kMagFrames) {
+            const int nh = min(kMagFrames, nf - h0);
+            __syncthreads();
+            for (int i = threadIdx.x; i < kMagFrames * n_mels; i += blockDim.x) {
+                int f, m;
+                if (layout == 0) { f = i / n_mels; m = i - f * n_mels; }
+                else { m = i / kMagFrames; f = i - m * kMagFrames; }
+                float val = 0.f;
+                if (f < nh) {
+                    const int t = t0 + h0 + f;
+                    val = layout == 0 ? mel[(fo + t) * n_mels + m]
+                                      : mel[fo * n_mels + static_cast<int64_t>(m) * T + t];
+                    if (is_log) val = expf(val);
+                }
+                s_m[f * n_mels + m] = val;
+            }
+            __syncthreads();
+            for (int k = threadIdx.x; k < kBins; k += blockDim.x) {
+                float acc[kMagFrames];
+#pragma unroll
+                for (int f = 0; f < kMagFrames; ++f) acc[f] = 0.f;
+                for (int m = 0; m < n_mels; ++m) {
+                    const float pv = __ldg(pinv_t + m * kSpecLd + k);
+#pragma unroll
+                    for (int f = 0; f < kMagFrames; ++f) acc[f] = fmaf(pv, s_m[f * n_mels + m], acc[f]);
+                }
+#pragma unroll
+                for (int f = 0; f < kMagFrames; ++f)
+                    if (f < nh) S[(fo + t0 + h0 + f) * ld_s + k] = sqrtf(fmaxf(acc[f], 0.f));
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// host-side launchers
+// ---------------------------------------------------------------------------------------
+static size_t smem_stft(int n_mels, int nnz) {
+    return sizeof(float2) * 1024 + sizeof(float) * 1024 + sizeof(float) * kStageSamples +
+           sizeof(float) * kWarps * kWarpRegionWords + sizeof(int) * 3 * n_mels + sizeof(float) * nnz;
+}
+static size_t smem_istft() {
+    return sizeof(float2) * 1024 + sizeof(float) * 1024 + sizeof(float) * kWarps * kWarpRegionWords;
+}
+
+template <class K>
+static int set_smem(K kernel, size_t bytes) {
+    SPEV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(bytes)));
+    return SPEV_OK;
+}
+
+static int check_batch(const spev_ctx* ctx, const spev_batch* b, bool need_samples, bool need_ctiles) {
+    SPEV_REQUIRE(ctx && b, SPEV_E_INVALID, "null ctx or batch");
+    SPEV_REQUIRE(b->n_items >= 0 && b->n_frames >= 0 && b->n_ftiles >= 0, SPEV_E_INVALID,
+                 "negative batch sizes");
+    if (b->n_items > 0) {
+        SPEV_REQUIRE(b->frame_off && b->ftile_item && b->ftile_t0, SPEV_E_INVALID,
+                     "batch offset/tile tables missing");
+        SPEV_REQUIRE(!need_samples || b->sample_off, SPEV_E_INVALID, "batch.sample_off missing");
+        SPEV_REQUIRE(!need_ctiles || b->n_ctiles == 0 || (b->ctile_item && b->ctile_c0),
+                     SPEV_E_INVALID, "batch chunk-tile tables missing");
+    }
+    return SPEV_OK;
+}
+
+int launch_stft_mel(spev_ctx* ctx, const spev_batch* b, const float* samples, float* out,
+                    bool power_only, int log_mode, float floor_v, float lo, float hi,
+                    cudaStream_t st) {
+    int rc = check_batch(ctx, b, true, false);
+    if (rc) return rc;
+    if (b->n_ftiles == 0) return SPEV_OK;
+    SPEV_REQUIRE(samples && out, SPEV_E_INVALID, "null samples/out");
+    MelBands mb{ctx->n_mels, ctx->band_nnz, ctx->d_band_start, ctx->d_band_len, ctx->d_band_woff,
+                ctx->d_band_w};
+    const size_t smem = smem_stft(ctx->n_mels, ctx->band_nnz);
+    const int grid = std::min<int64_t>(b->n_ftiles, ctx->num_sms);
+    if (power_only) {
+        rc = set_smem(k_stft_mel<1>, smem);
+        if (rc) return rc;
+        k_stft_mel<1><<<grid, kThreads, smem, st>>>(view_of(b), samples, out, ctx->d_tw,
+                                                    ctx->d_window, mb, 0, 0.f, 0.f, 0.f);
+    } else {
+        rc = set_smem(k_stft_mel<0>, smem);
+        if (rc) return rc;
+        k_stft_mel<0><<<grid, kThreads, smem, st>>>(view_of(b), samples, out, ctx->d_tw,
+                                                    ctx->d_window, mb, log_mode, floor_v, lo, hi);
+    }
+    SPEV_CUDA(cudaGetLastError());
+    return SPEV_OK;
+}
+
+int launch_stft_phase(spev_ctx* ctx, const spev_batch* b, const float* y, const float* S,
+                      int64_t ld_s, void* ang, void* tprev, int64_t ld, float alpha, int has_prev,
+                      bool phase, cudaStream_t st) {
+    int rc = check_batch(ctx, b, false, false);
+    if (rc) return rc;
+    if (b->n_ftiles == 0) return SPEV_OK;
+    SPEV_REQUIRE(y && ang && ld >= kBins, SPEV_E_INVALID, "stft: null buffer or ld < 513");
+    const size_t smem = smem_stft(0, 0);
+    const int grid = std::min<int64_t>(b->n_ftiles, ctx->num_sms);
+    if (phase) {
+        SPEV_REQUIRE(S && tprev && ld_s >= kBins, SPEV_E_INVALID, "phase update: null S/tprev");
+        rc = set_smem(k_stft_phase<1>, smem);
+        if (rc) return rc;
+        k_stft_phase<1><<<grid, kThreads, smem, st>>>(view_of(b), y, S, ld_s,
+                                                      static_cast<float2*>(ang),
+                                                      static_cast<float2*>(tprev), ld, alpha,
+                                                      has_prev, ctx->d_tw, ctx->d_window);
+    } else {
+        rc = set_smem(k_stft_phase<0>, smem);
+        if (rc) return rc;
+        k_stft_phase<0><<<grid, kThreads, smem, st>>>(view_of(b), y, nullptr, 0,
+                                                      static_cast<float2*>(ang), nullptr, ld, 0.f, 0,
+                                                      ctx->d_tw, ctx->d_window);
+    }
+    SPEV_CUDA(cudaGetLastError());
+    return SPEV_OK;
+}
+
+int launch_istft(spev_ctx* ctx, const spev_batch* b, const void* spec, int64_t ld, float* y,
+                 cudaStream_t st) {
+    int rc = check_batch(ctx, b, false, true);
+    if (rc) return rc;
+    if (b->n_ctiles == 0) return SPEV_OK;
+    SPEV_REQUIRE(spec && y && ld >= kBins, SPEV_E_INVALID, "istft: null buffer or ld < 513");
+    const size_t smem = smem_istft();
+    rc = set_smem(k_istft, smem);
+    if (rc) return rc;
+    const int grid = std::min<int64_t>(b->n_ctiles, ctx->num_sms);
+    k_istft<<<grid, kThreads, smem, st>>>(view_of(b), static_cast<const float2*>(spec), ld, y,
+                                          ctx->d_tw, ctx->d_window);
+    SPEV_CUDA(cudaGetLastError());
+    return SPEV_OK;
+}
+
+int launch_gl_init(spev_ctx* ctx, const float* S, int64_t ld_s, const float* phase, uint64_t seed,
+                   void* ang, int64_t ld, int64_t n_frames, cudaStream_t st) {
+    if (n_frames == 0) return SPEV_OK;
+    const int64_t total = n_frames * kBins;
+    const int grid = static_cast<int>(std::min<int64_t>((total + 255) / 256, ctx->num_sms * 16));
+    k_gl_init<<<grid, 256, 0, st>>>(S, ld_s, phase, seed, static_cast<float2*>(ang), ld, n_frames);
+    SPEV_CUDA(cudaGetLastError());
+    return SPEV_OK;
+}
+
+int launch_mel_to_mag(spev_ctx* ctx, const spev_batch* b, const float* mel, int layout, int is_log,
+                      float* S, int64_t ld_s, cudaStream_t st) {
+    int rc = check_batch(ctx, b, false, false);
+    if (rc) return rc;
+    if (b->n_ftiles == 0) return SPEV_OK;
+    SPEV_REQUIRE(mel && S && ld_s >= kBins, SPEV_E_INVALID, "mel_to_mag: null buffer or ld < 513");
+    SPEV_REQUIRE(layout == 0 || layout == 1, SPEV_E_INVALID, "mel_to_mag: layout must be 0 or 1");
+    const size_t smem = sizeof(float) * kMagFrames * ctx->n_mels;
+    const int grid = std::min<int64_t>(b->n_ftiles, ctx->num_sms * 4);
+    k_mel_to_mag<<<grid, 256, smem, st>>>(view_of(b), mel, layout, is_log, ctx->d_pinv_t,
+                                          ctx->n_mels, S, ld_s);
+    SPEV_CUDA(cudaGetLastError());
+    return SPEV_OK;
+}
+
+}  // namespace spev

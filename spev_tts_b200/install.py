@@ -1,0 +1,63 @@
+"""``install()``: monkey-patch the reference's call sites so that its scripts run unchanged on
+the B200 path.
+
+Patches, when the modules are importable:
+  * ``librosa.feature.melspectrogram``            (used at ``spev_real_metrics.py:363``)
+  * ``librosa.feature.inverse.mel_to_audio``      (used at ``:730-733``)
+  * ``spev_real_metrics.LengthRegulator``         (``:122-146``; instantiated at ``:160``)
+Calls with parameters outside the implemented configuration (n_fft != 1024, ...) are passed
+through to the original function.
+"""
+from __future__ import annotations
+
+import sys
+
+from . import length_regulator, spectral
+
+_installed = {}
+
+
+def _passthrough(ours, theirs):
+    def wrapper(*args, **kwargs):
+        try:
+            return ours(*args, **kwargs)
+        except NotImplementedError:
+            return theirs(*args, **kwargs)
+    wrapper.__wrapped__ = theirs
+    return wrapper
+
+
+def install(verbose: bool = False) -> dict:
+    done = {}
+    try:
+        import librosa
+        import librosa.feature
+        import librosa.feature.inverse
+        _installed["melspectrogram"] = librosa.feature.melspectrogram
+        _installed["mel_to_audio"] = librosa.feature.inverse.mel_to_audio
+        librosa.feature.melspectrogram = _passthrough(spectral.melspectrogram, _installed["melspectrogram"])
+        librosa.feature.inverse.mel_to_audio = _passthrough(spectral.mel_to_audio, _installed["mel_to_audio"])
+        done["librosa"] = True
+    except ImportError:
+        done["librosa"] = False
+    mod = sys.modules.get("spev_real_metrics")
+    if mod is not None and hasattr(mod, "LengthRegulator"):
+        _installed["LengthRegulator"] = mod.LengthRegulator
+        mod.LengthRegulator = length_regulator.LengthRegulator
+        done["spev_real_metrics.LengthRegulator"] = True
+    if verbose:
+        print("spev_tts_b200.install:", done)
+    return done
+
+
+def patch_model(model) -> int:
+    """Swap the LengthRegulator instances of an already-built reference model
+    (``RealMetricsFastSpeech2.length_regulator``, ``spev_real_metrics.py:160``)."""
+    n = 0
+    for name, child in list(model.named_children()):
+        if type(child).__name__ == "LengthRegulator":
+            setattr(model, name, length_regulator.LengthRegulator())
+            n += 1
+        else:
+            n += patch_model(child)
+    return n

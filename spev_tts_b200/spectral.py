@@ -1,0 +1,277 @@
+"""Host-side mirror of the librosa calls on the reference's spectral hot path.
+
+Same names, argument meaning and return shapes as the calls the reference makes
+(``librosa.feature.melspectrogram`` at ``spev_real_metrics.py:363``;
+``librosa.feature.inverse.mel_to_audio`` at ``:730-733``), but every flop runs in the sm_100a
+kernels behind ``include/spev_b200.h``.  Inputs may be numpy arrays or torch tensors (any
+device); the result comes back as the same kind (numpy -> numpy; torch -> torch on the
+compute device).  Leading batch dimensions broadcast like librosa's.
+
+Ragged batches (the cache build) use the ``*_flat`` functions, which take one flat device
+buffer plus per-item lengths.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+from .batch import HOP, N_FFT, Context, FlatBatch, make_batch, stream_ptr
+
+ArrayLike = Union[np.ndarray, torch.Tensor]
+REF_LOG_FLOOR, REF_LOG_LO, REF_LOG_HI = 1e-5, -10.0, 2.0   # spev_real_metrics.py:364-366
+
+
+def default_device() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("spev_tts_b200 needs a CUDA (sm_100) device; there is no CPU path")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _to_device(a: ArrayLike, device: Optional[torch.device], dtype=torch.float32) -> Tuple[torch.Tensor, bool]:
+    """-> (contiguous device tensor, was_numpy)"""
+    was_numpy = not isinstance(a, torch.Tensor)
+    t = torch.from_numpy(np.ascontiguousarray(a)) if was_numpy else a
+    if device is None:
+        device = t.device if t.is_cuda else default_device()
+    t = t.to(device=device, dtype=dtype, non_blocking=True).contiguous()
+    return t, was_numpy
+
+
+def _ret(t: torch.Tensor, was_numpy: bool):
+    return t.cpu().numpy() if was_numpy else t
+
+
+def _check_fixed(n_fft, hop_length, win_length, window, center, pad_mode, power=2.0):
+    if hop_length is None:
+        hop_length = (win_length or n_fft) // 4
+    if n_fft != N_FFT or hop_length != HOP or (win_length not in (None, N_FFT)):
+        raise NotImplementedError(
+            f"spev_tts_b200 implements the reference CONFIG only (n_fft=1024, hop=256, win=1024); "
+            f"got n_fft={n_fft}, hop_length={hop_length}, win_length={win_length}")
+    if window != "hann" or not center or pad_mode != "constant" or power != 2.0:
+        raise NotImplementedError("only window='hann', center=True, pad_mode='constant', power=2.0 "
+                                  "(the reference's librosa defaults) are implemented")
+
+
+# ---------------------------------------------------------------------------------------------
+# forward: STFT -> power -> mel (-> log)
+# ---------------------------------------------------------------------------------------------
+def logmel_flat(samples: torch.Tensor, n_samples: Sequence[int], *, sr=22050, n_mels=80, fmin=0.0,
+                fmax=None, log=True, floor=REF_LOG_FLOOR, lo=REF_LOG_LO, hi=REF_LOG_HI,
+                sample_off: Optional[np.ndarray] = None, out: Optional[torch.Tensor] = None,
+                batch: Optional[FlatBatch] = None) -> Tuple[torch.Tensor, FlatBatch]:
+    """Ragged batch: ``samples`` is one flat float32 CUDA tensor holding all items.
+    Returns (``[F, n_mels]`` float32 -- the reference's stored cache layout ``mel.T``,
+    ``spev_real_metrics.py:421`` -- and the batch descriptor with ``frame_off``)."""
+    if not (samples.is_cuda and samples.dtype == torch.float32 and samples.is_contiguous()):
+        raise ValueError("samples must be a contiguous float32 CUDA tensor")
+    ctx = Context.get(samples.device, sr=sr, n_mels=n_mels, fmin=fmin, fmax=fmax)
+    if batch is None:
+        batch = make_batch(ctx, n_samples=n_samples, sample_off=sample_off)
+    if out is None:
+        out = torch.empty((batch.n_frames, n_mels), dtype=torch.float32, device=samples.device)
+    _lib.check(ctx.lib.spev_logmel(ctx.handle, batch.desc, samples.data_ptr(), out.data_ptr(),
+                                   1 if log else 0, float(floor), float(lo), float(hi),
+                                   stream_ptr(samples.device)), "spev_logmel")
+    return out, batch
+
+
+def melspectrogram(*, y: ArrayLike, sr=22050, n_fft=2048, hop_length=512, win_length=None,
+                   window="hann", center=True, pad_mode="constant", power=2.0, n_mels=128,
+                   fmin=0.0, fmax=None, device=None):
+    """Drop-in for ``librosa.feature.melspectrogram(y=...)`` -> ``[..., n_mels, T]``."""
+    _check_fixed(n_fft, hop_length, win_length, window, center, pad_mode, power)
+    t, was_numpy = _to_device(y, device)
+    lead, n = t.shape[:-1], t.shape[-1]
+    b = int(np.prod(lead)) if lead else 1
+    mel, fb = logmel_flat(t.reshape(-1), [n] * b, sr=sr, n_mels=n_mels, fmin=fmin, fmax=fmax, log=False)
+    T = 1 + n // HOP
+    mel = mel.view(*lead, T, n_mels).transpose(-1, -2)
+    return _ret(mel, was_numpy)
+
+
+def logmel(y: ArrayLike, *, sr=22050, n_mels=80, device=None):
+    """The reference's four statements ``spev_real_metrics.py:363-367`` + the stored layout
+    of ``:421``: ``[..., N] -> [..., T, n_mels]`` float32 log-mel clamped to [-10, 2]."""
+    t, was_numpy = _to_device(y, device)
+    lead, n = t.shape[:-1], t.shape[-1]
+    b = int(np.prod(lead)) if lead else 1
+    mel, _ = logmel_flat(t.reshape(-1), [n] * b, sr=sr, n_mels=n_mels, log=True)
+    return _ret(mel.view(*lead, 1 + n // HOP, n_mels), was_numpy)
+
+
+def stft_power_flat(samples: torch.Tensor, n_samples: Sequence[int], *, sr=22050):
+    """|STFT|^2 as ``[F, 520]`` (pad columns zero): A operand of the tensor-core mel GEMM."""
+    ctx = Context.get(samples.device, sr=sr)
+    batch = make_batch(ctx, n_samples=n_samples)
+    out = torch.empty((batch.n_frames, _lib.SPEC_LD), dtype=torch.float32, device=samples.device)
+    _lib.check(ctx.lib.spev_stft_power(ctx.handle, batch.desc, samples.data_ptr(), out.data_ptr(),
+                                       stream_ptr(samples.device)), "spev_stft_power")
+    return out, batch
+
+
+def mel_project(power: torch.Tensor, *, sr=22050, n_mels=80, fmin=0.0, fmax=None, log=True,
+                floor=REF_LOG_FLOOR, lo=REF_LOG_LO, hi=REF_LOG_HI):
+    """Tensor-core (tcgen05 3xTF32) mel projection of a ``[F, 520]`` power spectrum."""
+    ctx = Context.get(power.device, sr=sr, n_mels=n_mels, fmin=fmin, fmax=fmax)
+    out = torch.empty((power.shape[0], n_mels), dtype=torch.float32, device=power.device)
+    _lib.check(ctx.lib.spev_mel_project(ctx.handle, power.data_ptr(), power.shape[0], out.data_ptr(),
+                                        1 if log else 0, float(floor), float(lo), float(hi),
+                                        stream_ptr(power.device)), "spev_mel_project")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# STFT / ISTFT (complex, librosa layout [..., 513, T])
+# ---------------------------------------------------------------------------------------------
+def _spec_to_internal(X: torch.Tensor) -> torch.Tensor:
+    """[B, 513, T] complex64 -> [B*T, 520] complex64 (frame-major rows, pitch 520)."""
+    B, nb, T = X.shape
+    buf = torch.zeros((B * T, _lib.SPEC_LD), dtype=torch.complex64, device=X.device)
+    buf[:, :nb] = X.permute(0, 2, 1).reshape(B * T, nb)
+    return buf
+
+
+def stft(y: ArrayLike, *, n_fft=2048, hop_length=None, win_length=None, window="hann", center=True,
+         pad_mode="constant", device=None):
+    """Drop-in for ``librosa.stft`` -> complex64 ``[..., 513, T]``."""
+    _check_fixed(n_fft, hop_length, win_length, window, center, pad_mode)
+    t, was_numpy = _to_device(y, device)
+    lead, n = t.shape[:-1], t.shape[-1]
+    b = int(np.prod(lead)) if lead else 1
+    T = 1 + n // HOP
+    Tc = T
+    if n % HOP:
+        # spev_stft takes the ISTFT-output item layout ((T-1)*hop samples per item).  Zero-extend
+        # to the next multiple of hop -- every one of the first T frames is unchanged because
+        # centre padding is zeros -- compute T+1 frames and drop the last.
+        t = torch.nn.functional.pad(t.reshape(b, n), (0, HOP - n % HOP)).contiguous()
+        Tc = T + 1
+    ctx = Context.get(t.device)
+    batch = make_batch(ctx, n_frames=[Tc] * b)
+    spec = torch.empty((b * Tc, _lib.SPEC_LD), dtype=torch.complex64, device=t.device)
+    _lib.check(ctx.lib.spev_stft(ctx.handle, batch.desc, t.data_ptr(), spec.data_ptr(), _lib.SPEC_LD,
+                                 stream_ptr(t.device)), "spev_stft")
+    out = spec.view(b, Tc, _lib.SPEC_LD)[:, :T, : _lib.N_BINS].permute(0, 2, 1)
+    out = out.reshape(*lead, _lib.N_BINS, T)
+    return _ret(out, was_numpy)
+
+
+def istft(X: ArrayLike, *, hop_length=None, win_length=None, n_fft=None, window="hann", center=True,
+          dtype=None, length=None, device=None):
+    """Drop-in for ``librosa.istft`` -> float32 ``[..., (T-1)*hop]``."""
+    nb = X.shape[-2]
+    _check_fixed(n_fft or 2 * (nb - 1), hop_length, win_length, window, center, "constant")
+    if length is not None:
+        raise NotImplementedError("istft(length=...) is not on the reference path")
+    t, was_numpy = _to_device(X, device, dtype=torch.complex64)
+    lead, T = t.shape[:-2], t.shape[-1]
+    b = int(np.prod(lead)) if lead else 1
+    ctx = Context.get(t.device)
+    batch = make_batch(ctx, n_frames=[T] * b, with_chunks=True)
+    spec = _spec_to_internal(t.reshape(b, nb, T))
+    y = torch.empty(batch.n_out_samples, dtype=torch.float32, device=t.device)
+    _lib.check(ctx.lib.spev_istft(ctx.handle, batch.desc, spec.data_ptr(), _lib.SPEC_LD, y.data_ptr(),
+                                  stream_ptr(t.device)), "spev_istft")
+    return _ret(y.view(*lead, (T - 1) * HOP), was_numpy)
+
+
+# ---------------------------------------------------------------------------------------------
+# inverse: mel -> magnitude -> Griffin-Lim
+# ---------------------------------------------------------------------------------------------
+def mel_to_mag_flat(mel: torch.Tensor, batch: FlatBatch, ctx: Context, *, layout: int, is_log: bool,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    if out is None:
+        out = torch.empty((batch.n_frames, _lib.SPEC_LD), dtype=torch.float32, device=mel.device)
+    _lib.check(ctx.lib.spev_mel_to_mag(ctx.handle, batch.desc, mel.data_ptr(), layout, 1 if is_log else 0,
+                                       out.data_ptr(), _lib.SPEC_LD, stream_ptr(mel.device)),
+               "spev_mel_to_mag")
+    return out
+
+
+def mel_to_stft(M: ArrayLike, *, sr=22050, n_fft=2048, power=2.0, fmin=0.0, fmax=None, device=None):
+    """Drop-in for ``librosa.feature.inverse.mel_to_stft`` -> ``[..., 513, T]`` magnitudes.
+    Computes the NNLS warm start ``clip(pinv(basis) @ M, 0) ** 0.5`` (which librosa's L-BFGS-B
+    returns unchanged for reference-range inputs; see DESIGN.md "NNLS")."""
+    _check_fixed(n_fft, HOP, None, "hann", True, "constant", power)
+    t, was_numpy = _to_device(M, device)
+    lead, n_mels, T = t.shape[:-2], t.shape[-2], t.shape[-1]
+    b = int(np.prod(lead)) if lead else 1
+    ctx = Context.get(t.device, sr=sr, n_mels=n_mels, fmin=fmin, fmax=fmax)
+    batch = make_batch(ctx, n_frames=[T] * b)
+    S = mel_to_mag_flat(t.reshape(-1), batch, ctx, layout=1, is_log=False)
+    out = S.view(b, T, _lib.SPEC_LD)[:, :, : _lib.N_BINS].permute(0, 2, 1).reshape(*lead, _lib.N_BINS, T)
+    return _ret(out, was_numpy)
+
+
+def griffinlim_flat(S: torch.Tensor, batch: FlatBatch, ctx: Context, *, n_iter=32, momentum=0.99,
+                    init_phase: Optional[torch.Tensor] = None, seed: int = 0,
+                    out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None):
+    """``S``: ``[F, 520]`` float32 magnitudes; ``init_phase``: ``[F, 513]`` float32 radians or None.
+    Returns the flat waveform buffer (item i at ``batch.out_sample_off()[i]``)."""
+    lib = ctx.lib
+    need = lib.spev_griffinlim_workspace_bytes(batch.n_frames)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=S.device)
+    if out is None:
+        out = torch.empty(batch.n_out_samples, dtype=torch.float32, device=S.device)
+    _lib.check(lib.spev_griffinlim(ctx.handle, batch.desc, S.data_ptr(), S.shape[1],
+                                   init_phase.data_ptr() if init_phase is not None else None,
+                                   int(seed) & (2 ** 64 - 1), int(n_iter), float(momentum), out.data_ptr(),
+                                   workspace.data_ptr(), workspace.numel(), stream_ptr(S.device)),
+               "spev_griffinlim")
+    return out
+
+
+def _phase_to_internal(init_phase: ArrayLike, b: int, T: int, device) -> torch.Tensor:
+    p, _ = _to_device(init_phase, device)
+    return p.reshape(b, _lib.N_BINS, T).permute(0, 2, 1).contiguous().view(b * T, _lib.N_BINS)
+
+
+def griffinlim(S: ArrayLike, *, n_iter=32, hop_length=None, win_length=None, n_fft=None, window="hann",
+               center=True, dtype=None, length=None, pad_mode="constant", momentum=0.99, init="random",
+               random_state=None, init_phase: Optional[ArrayLike] = None, device=None):
+    """Drop-in for ``librosa.griffinlim`` (``[..., 513, T]`` magnitudes -> ``[..., (T-1)*hop]``).
+    ``init_phase`` (radians, same shape as S) pins the starting phases for parity tests;
+    otherwise phases are drawn on the device from ``random_state`` (None -> OS entropy, like
+    librosa)."""
+    nb = S.shape[-2]
+    _check_fixed(n_fft or 2 * (nb - 1), hop_length, win_length, window, center, pad_mode)
+    if length is not None or init not in ("random",):
+        raise NotImplementedError("griffinlim: only init='random', length=None are on the reference path")
+    t, was_numpy = _to_device(S, device)
+    lead, T = t.shape[:-2], t.shape[-1]
+    b = int(np.prod(lead)) if lead else 1
+    ctx = Context.get(t.device)
+    batch = make_batch(ctx, n_frames=[T] * b, with_chunks=True)
+    Sf = torch.zeros((b * T, _lib.SPEC_LD), dtype=torch.float32, device=t.device)
+    Sf[:, :nb] = t.reshape(b, nb, T).permute(0, 2, 1).reshape(b * T, nb)
+    ph = _phase_to_internal(init_phase, b, T, t.device) if init_phase is not None else None
+    seed = int(np.random.SeedSequence(random_state).generate_state(2, dtype=np.uint32).view(np.uint64)[0])
+    y = griffinlim_flat(Sf, batch, ctx, n_iter=n_iter, momentum=momentum, init_phase=ph, seed=seed)
+    return _ret(y.view(*lead, (T - 1) * HOP), was_numpy)
+
+
+def mel_to_audio(M: ArrayLike, *, sr=22050, n_fft=2048, hop_length=None, win_length=None, window="hann",
+                 center=True, pad_mode="constant", power=2.0, n_iter=32, length=None, dtype=np.float32,
+                 fmin=0.0, fmax=None, momentum=0.99, init_phase: Optional[ArrayLike] = None,
+                 random_state=None, is_log=False, device=None):
+    """Drop-in for ``librosa.feature.inverse.mel_to_audio`` (call site
+    ``spev_real_metrics.py:730-733``): ``[..., n_mels, T]`` mel power -> ``[..., (T-1)*hop]``.
+    ``is_log=True`` fuses the reference's ``np.exp`` (``:729``) into the first kernel."""
+    _check_fixed(n_fft, hop_length, win_length, window, center, pad_mode, power)
+    if length is not None:
+        raise NotImplementedError("mel_to_audio(length=...) is not on the reference path")
+    t, was_numpy = _to_device(M, device)
+    lead, n_mels, T = t.shape[:-2], t.shape[-2], t.shape[-1]
+    b = int(np.prod(lead)) if lead else 1
+    ctx = Context.get(t.device, sr=sr, n_mels=n_mels, fmin=fmin, fmax=fmax)
+    batch = make_batch(ctx, n_frames=[T] * b, with_chunks=True)
+    S = mel_to_mag_flat(t.reshape(-1), batch, ctx, layout=1, is_log=is_log)
+    ph = _phase_to_internal(init_phase, b, T, t.device) if init_phase is not None else None
+    seed = int(np.random.SeedSequence(random_state).generate_state(2, dtype=np.uint32).view(np.uint64)[0])
+    y = griffinlim_flat(S, batch, ctx, n_iter=n_iter, momentum=momentum, init_phase=ph, seed=seed)
+    return _ret(y.view(*lead, (T - 1) * HOP), was_numpy)

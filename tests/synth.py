@@ -1,0 +1,108 @@
+"""Deterministic synthetic inputs shared by the tests, the golden generator and bench.py
+(SURVEY.md section 8(d) "Synthetic inputs").  numpy only."""
+from __future__ import annotations
+
+import numpy as np
+
+SR = 22050
+HOP = 256
+N_FFT = 1024
+
+
+def white(seed: int = 0, n: int = 132300, sigma: float = 0.05) -> np.ndarray:
+    """cfg1 case A: 6 s of white noise, sigma 0.05 (log-mel stays inside the clamps)."""
+    return (sigma * np.random.default_rng(seed).standard_normal(n)).astype(np.float32)
+
+
+def speechy(seed: int = 1, n: int = 132300, sr: int = SR) -> np.ndarray:
+    """cfg1 case B: harmonic stack with vibrato + 3 Hz AM + 1e-4 noise floor.  Exercises
+    both clamps of the reference's log compression (about a quarter of the bins sit on
+    the -10 floor, peaks reach the +2 ceiling)."""
+    r = np.random.default_rng(seed)
+    t = np.arange(n) / sr
+    f0 = 120 + 30 * np.sin(2 * np.pi * 0.7 * t + r.uniform(0, 6))
+    ph = 2 * np.pi * np.cumsum(f0) / sr
+    y = np.zeros(n)
+    for k in range(1, 40):
+        y += k ** -1.5 * np.sin(k * ph)
+    y *= 0.3 * (0.6 + 0.4 * np.sin(2 * np.pi * 3 * t))
+    y += 1e-4 * r.standard_normal(n)
+    return y.astype(np.float32)
+
+
+def utterance_lengths(seed: int, n_utts: int, lo_s: float = 1.0, hi_s: float = 10.0,
+                      sr: int = SR) -> np.ndarray:
+    """cfg4: utterance lengths ~ U[lo, hi] seconds, in samples."""
+    r = np.random.default_rng(seed)
+    return (r.uniform(lo_s, hi_s, n_utts) * sr).astype(np.int64)
+
+
+def lognormal_lengths(seed: int, n_utts: int, median_s: float = 5.0, lo_s: float = 1.0,
+                      hi_s: float = 20.0, sr: int = 24000) -> np.ndarray:
+    """cfg5: LibriTTS-R-like skewed lengths."""
+    r = np.random.default_rng(seed)
+    s = np.clip(r.lognormal(np.log(median_s), 0.6, n_utts), lo_s, hi_s)
+    return (s * sr).astype(np.int64)
+
+
+def cfg2_batch(seed: int = 2, B: int = 32, T: int = 200, H: int = 256):
+    """cfg2: x ~ N(0,1) [B,T,H]; lens ~ U{50..T}; dur ~ U{0..20}, zero beyond lens."""
+    r = np.random.default_rng(seed)
+    lens = r.integers(50, T + 1, B)
+    lens[0] = T
+    x = r.standard_normal((B, T, H)).astype(np.float32)
+    dur = r.integers(0, 21, (B, T)).astype(np.int64)
+    dur[np.arange(T)[None, :] >= lens[:, None]] = 0
+    return x, dur, lens.astype(np.int64)
+
+
+def cfg2_features(seed: int = 2, B: int = 32, T: int = 200, n: int = 5):
+    r = np.random.default_rng(seed + 1000)
+    return [r.standard_normal((B, T)).astype(np.float32) for _ in range(n)]
+
+
+def lr_edge_cases():
+    """Edge semantics of the reference LengthRegulator (SURVEY section 7 hard part 5)."""
+    r = np.random.default_rng(5)
+    H = 6
+    cases = {}
+    x = r.standard_normal((3, 4, H)).astype(np.float32)
+    cases["zero_row"] = (x, np.array([[2, 0, 1, 3], [0, 0, 0, 0], [1, 1, 1, 1]], dtype=np.int64))
+    cases["gt1000"] = (x, np.array([[2, 1001, 1, 0], [1000, 0, 0, 0], [0, 0, 0, 5]], dtype=np.int64))
+    cases["negative"] = (x, np.array([[2, -1, 1, 0], [-5, -5, -5, -5], [3, 0, -2, 1]], dtype=np.int64))
+    cases["float"] = (x, np.array([[1.9, np.nan, 2.0, -1.0], [0.99, 0.0, np.inf, 1000.5],
+                                   [1000.0, 0.5, -np.inf, 3.999]], dtype=np.float32))
+    cases["all_empty"] = (x, np.zeros((3, 4), dtype=np.int64))
+    x1 = r.standard_normal((1, 1, 1)).astype(np.float32)
+    cases["one"] = (x1, np.array([[7]], dtype=np.int64))
+    return cases
+
+
+def log_durations(seed: int = 7, B: int = 32, T: int = 200) -> np.ndarray:
+    r = np.random.default_rng(seed)
+    return np.clip(r.standard_normal((B, T)), -4, 4).astype(np.float32)
+
+
+def bucketize_case(seed: int = 2, B: int = 32, T: int = 200, n_bins: int = 256, H: int = 256):
+    r = np.random.default_rng(seed + 2000)
+    bins = np.linspace(-3, 3, n_bins - 1).astype(np.float32)
+    v = r.standard_normal((B, T)).astype(np.float32)
+    v[0, :8] = [np.nan, np.inf, -np.inf, -3.0, 3.0, bins[10], 3.0001, bins[100]]
+    m = min(T, n_bins - 1)
+    v[1, :m] = bins[:m]  # values exactly on boundaries
+    v[2, :m] = np.nextafter(bins[:m], np.float32(np.inf))
+    v[3, :m] = np.nextafter(bins[:m], np.float32(-np.inf))
+    table = r.standard_normal((n_bins, H)).astype(np.float32)
+    return v, bins, table
+
+
+def init_phase(shape, seed: int = 3) -> np.ndarray:
+    """2*pi*U[0,1) phases shared between the oracle and the CUDA path."""
+    return (2 * np.pi * np.random.default_rng(seed).random(size=shape)).astype(np.float32)
+
+
+def cfg3_logmels(seed: int = 3, B: int = 16, T: int = 800):
+    """cfg3 inputs: log-mels (oracle layout [B,80,T]) of `speechy` signals; built by the
+    caller with the oracle.  Here: just the raw signals."""
+    n = (T - 1) * HOP
+    return [speechy(seed=seed * 100 + b, n=n) for b in range(B)]
