@@ -1,0 +1,469 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the SPEV-TTS spectral hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (our arm: sm_100a kernels)
+    python bench.py --impl reference --gpus N --steps K ...  (reference arm: CPU path)
+
+Metric (BASELINE.json): mel frames/s (STFT -> 80-mel log-spectrogram) on the LJSpeech-shaped
+cache build (configs[3]: 13,100 synthetic utterances of 1-10 s at 22.05 kHz, 6.35 GB of float32
+samples, ~6.2 M frames per GPU -- far larger than the 126 MB L2, so no L2 flush is needed
+between steps).  One "step" = one pass of the fused kernel over the rank's whole shard.
+Scaling is weak: every rank builds the cache of its own 13,100-utterance shard (seed + rank);
+the path has no data-path collective, the NCCL gather of shards is timed separately and
+reported under "gather".
+
+The same JSON line also carries the second half of the metric, Griffin-Lim audio-seconds/s on
+configs[2] (16 x [80,800] log-mels, 60 iterations), with its own roofline, under "griffinlim",
+and the LengthRegulator/bucketize timing on configs[1] under "length_regulator".
+
+The reference arm times the reference's own CPU implementation of the path: the oracle
+restatement of librosa 0.11 (``oracle/librosa_restated.py``; librosa itself is not installable
+here) fanned over all host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SR, HOP, N_MELS = 22050, 256, 80
+ALG_BYTES_PER_FRAME = 1344          # 256 new samples * 4 B read + 80 * 4 B written
+GL_BYTES_PER_FRAME_ITER = 20516
+N_UTTS = 13100
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0=None, t1=None):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ts, line in self.rows:
+            if t0 is not None and not (t0 - 0.05 <= ts <= t1 + 0.15):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU reference path (oracle), fanned over host cores
+# ----------------------------------------------------------------------------------------------
+def _cpu_worker_init():
+    """one BLAS/OpenMP thread per worker process (the pool supplies the parallelism)"""
+    try:
+        from threadpoolctl import threadpool_limits
+        globals()["_tp_limit"] = threadpool_limits(1)
+    except Exception:
+        pass
+
+
+def _cpu_logmel_job(args):
+    seed, n = args
+    from oracle import librosa_restated as lr
+    y = (0.05 * np.random.default_rng(seed).standard_normal(n)).astype(np.float32)
+    t = time.perf_counter()
+    m = lr.reference_logmel(y)
+    return m.shape[0], time.perf_counter() - t
+
+
+def _cpu_gl_job(args):
+    seed, T, n_iter = args
+    from oracle import librosa_restated as lr
+    rng = np.random.default_rng(seed)
+    lm = np.clip(-4 + 2 * rng.standard_normal((80, T)), -10, 2).astype(np.float32)
+    t = time.perf_counter()
+    lr.reference_vocoder_infer(lm, n_iter=n_iter, seed=seed, lbfgs=True)
+    return (T - 1) * HOP / SR, time.perf_counter() - t
+
+
+def cpu_logmel_throughput(n_utts: int, procs: int, seed: int = 4):
+    """frames/s of the restated reference path on `n_utts` cfg4-shaped utterances."""
+    import multiprocessing as mp
+    from tests import synth
+    lens = synth.utterance_lengths(seed=seed, n_utts=N_UTTS)[:n_utts]
+    jobs = [(seed * 100000 + i, int(n)) for i, n in enumerate(lens)]
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    t = time.perf_counter()
+    if procs > 1:
+        with mp.get_context("fork").Pool(procs, initializer=_cpu_worker_init) as pool:
+            res = pool.map(_cpu_logmel_job, jobs, chunksize=4)
+    else:
+        res = [_cpu_logmel_job(j) for j in jobs]
+    wall = time.perf_counter() - t
+    frames = sum(r[0] for r in res)
+    busy = sum(r[1] for r in res) / max(1, procs)    # per-worker compute time (data generation excluded)
+    return frames / busy, frames, wall
+
+
+def cpu_gl_throughput(n_items: int, T: int, n_iter: int, procs: int):
+    import multiprocessing as mp
+    jobs = [(300 + i, T, n_iter) for i in range(n_items)]
+    t = time.perf_counter()
+    if procs > 1:
+        with mp.get_context("fork").Pool(min(procs, n_items), initializer=_cpu_worker_init) as pool:
+            res = pool.map(_cpu_gl_job, jobs)
+    else:
+        res = [_cpu_gl_job(j) for j in jobs]
+    wall = time.perf_counter() - t
+    busy = sum(r[1] for r in res) / max(1, min(procs, n_items))
+    return sum(r[0] for r in res) / busy, wall
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    n_utts = args.ref_utts
+    vals = []
+    for _ in range(args.warmup):
+        cpu_logmel_throughput(max(8, n_utts // 8), cores)
+    t_all = time.perf_counter()
+    for _ in range(args.steps):
+        v, frames, wall = cpu_logmel_throughput(n_utts, cores)
+        vals.append(v)
+    ms = (time.perf_counter() - t_all) * 1e3 / max(1, args.steps)
+    value = float(np.mean(vals))
+    gl_v, gl_wall = cpu_gl_throughput(min(cores, 16), 800, 60, cores)
+    sample = f"{n_utts} of {N_UTTS} cfg4 utterances per step ({frames} frames), {cores} processes"
+    line = {
+        "impl": "reference", "metric": "mel frames/s (STFT->80-mel log, cache build)", "value": value,
+        "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64 FFT / f32 mel (librosa semantics)", "data": "synthetic",
+        "config": {"workload": "cfg4: 13,100 synthetic utterances 1-10 s @22.05 kHz (bounded sample)",
+                   "n_fft": 1024, "hop": 256, "n_mels": 80},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "griffinlim": {"value": gl_v, "unit": "audio-s/s", "n_iter": 60, "cores": cores,
+                       "sample": f"{min(cores, 16)} x [80,800], wall {gl_wall:.1f}s, NNLS L-BFGS-B on"},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import spev_tts_b200 as sp
+    from spev_tts_b200 import cache as spcache
+    from tests import synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py (our arm) needs a B200; there is no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    sp.load()
+    hbm_peak, peak_src = peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---------------- cfg4 shard of this rank (weak scaling: a full 13,100-utterance set) --------
+    lens = synth.utterance_lengths(seed=4 + rank, n_utts=args.utts)
+    total = int(lens.sum())
+    g = torch.Generator(device=dev).manual_seed(4 + rank)
+    samples = torch.empty(total, dtype=torch.float32, device=dev)
+    blk = 1 << 27
+    for s in range(0, total, blk):       # generate in blocks to bound the temporary
+        e = min(total, s + blk)
+        samples[s:e] = torch.randn(e - s, generator=g, device=dev) * 0.05
+    ctx = sp.Context.get(dev, sr=SR, n_mels=N_MELS)
+    batch = sp.make_batch(ctx, n_samples=lens)
+    F = batch.n_frames
+    out = torch.empty((F, N_MELS), dtype=torch.float32, device=dev)
+
+    def step():
+        sp.logmel_flat(samples, lens, out=out, batch=batch)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local).start() if rank == 0 else None
+    time.sleep(0.3)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t0 = time.perf_counter()
+    e_all0 = torch.cuda.Event(enable_timing=True); e_all1 = torch.cuda.Event(enable_timing=True)
+    e_all0.record()
+    for a, b in evs:
+        a.record(); step(); b.record()
+    e_all1.record()
+    barrier()
+    t1 = time.perf_counter()
+    total_ms = e_all0.elapsed_time(e_all1)
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    total_ms = max_over_ranks(total_ms)
+    kern_ms_max = max_over_ranks(kern_ms)
+    frames_all = sum_over_ranks(float(F))
+    ms_per_step = total_ms / args.steps
+    value = frames_all / (ms_per_step * 1e-3)
+    achieved = ALG_BYTES_PER_FRAME * F / (kern_ms * 1e-3) / 1e9      # GB/s, this rank's kernel
+
+    # ---------------- e2e: pinned host samples -> public API -> pinned host cache --------------
+    e2e = None
+    if not args.no_e2e:
+        host = torch.empty(total, dtype=torch.float32).pin_memory()
+        host.copy_(samples)
+        out_host = torch.empty((F, N_MELS), dtype=torch.float32).pin_memory()
+        builder = spcache.LogMelCacheBuilder(dev, sr=SR, n_mels=N_MELS)
+        plan = spcache.plan_chunks(lens, builder.chunk_samples)
+        builder.build(host, lens, out_host=out_host, plan=plan)        # warm-up (allocs, descriptors)
+        torch.cuda.synchronize(dev)
+        n_e2e = max(1, min(args.steps, args.e2e_steps))
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        l0 = builder.launches
+        e0.record()
+        for _ in range(n_e2e):
+            builder.build(host, lens, out_host=out_host, plan=plan)
+        e1.record()
+        barrier()
+        e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / n_e2e
+        e2e_launches = (builder.launches - l0) // n_e2e
+        ok = bool(torch.equal(out_host[: 4096].to(dev), out[: 4096]))
+        e2e = {"value": frames_all / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": total * 4,
+               "d2h_bytes_per_step": F * N_MELS * 4, "ms_per_step": e2e_ms, "steps": n_e2e,
+               "launches_per_step": e2e_launches, "matches_device_result": ok,
+               "api": "spev_tts_b200.cache.LogMelCacheBuilder.build (pinned host in/out, 3-stream pipeline)"}
+        del host, out_host, builder
+    clocks = sampler.stop(t0, t1) if sampler else None
+
+    # ---------------- gather of shards (the one collective; timed separately) -------------------
+    gather = None
+    if world > 1:
+        barrier()
+        g0 = torch.cuda.Event(enable_timing=True); g1 = torch.cuda.Event(enable_timing=True)
+        g0.record()
+        parts, counts = spcache.gather_shards(out, dst=0)
+        g1.record()
+        barrier()
+        gms = max_over_ranks(g0.elapsed_time(g1))
+        nbytes = sum(counts[1:]) * N_MELS * 4
+        gather = {"ms": gms, "bytes_into_root": nbytes, "GBps": nbytes / (gms * 1e-3) / 1e9,
+                  "backend": "nccl send/recv (no gatherv)"}
+        del parts
+
+    # ---------------- second half of the metric: Griffin-Lim on cfg3 (rank 0 reports) ------------
+    gl = lr_res = None
+    if not args.no_gl:
+        gl = bench_griffinlim(sp, dev, hbm_peak, args)
+        lr_res = bench_length_regulator(sp, dev, args)
+    del samples, out
+    torch.cuda.empty_cache()
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            cores = os.cpu_count() or 1
+            v, frames, wall = cpu_logmel_throughput(args.ref_utts, cores)
+            cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
+                   "sample": f"{args.ref_utts} of {N_UTTS} cfg4 utterances ({frames} frames) in {wall:.1f}s, "
+                             f"oracle/librosa_restated.py over {cores} processes"}
+        line = {
+            "metric": "mel frames/s (STFT->80-mel log, cache build)", "value": value, "unit": "frames/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"cfg4: {args.utts} synthetic utterances 1-10 s @22.05 kHz per GPU "
+                                   f"({total * 4 / 1e9:.2f} GB samples, {F} frames); inputs >> L2 (126 MB), no flush needed",
+                       "n_fft": 1024, "hop": 256, "n_mels": 80, "utterances_per_gpu": args.utts,
+                       "frames_per_gpu": F, "parallelism": f"utterance-sharded x{world}, no data-path collective"},
+            "roofline": {"bound": "hbm", "kernel": "k_stft_mel<0>", "achieved": achieved, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": achieved / hbm_peak, "peak_source": peak_src,
+                         "alg_bytes_per_frame": ALG_BYTES_PER_FRAME, "kernel_ms": kern_ms,
+                         "kernel_ms_max_over_ranks": kern_ms_max, "traffic": None,
+                         "note": "fp32-pipe/shared-memory bound by design (SURVEY 0.7): ~25 kFLOP FFT per 1,344 B"},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks,
+            "gather": gather, "griffinlim": gl, "length_regulator": lr_res,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def bench_griffinlim(sp, dev, hbm_peak, args):
+    """cfg3: 16 x [80,800] log-mels, 60 iterations.  audio-seconds per second."""
+    import torch
+    from spev_tts_b200 import _lib
+    B, T, n_iter = 16, 800, 60
+    g = torch.Generator(device=dev).manual_seed(3)
+    lm = (-4 + 2 * torch.randn(B, N_MELS, T, generator=g, device=dev)).clamp(-10, 2)
+    ctx = sp.Context.get(dev, sr=SR, n_mels=N_MELS, fmin=0.0, fmax=8000.0)
+    fb = sp.make_batch(ctx, n_frames=[T] * B, with_chunks=True)
+    S = torch.empty((fb.n_frames, _lib.SPEC_LD), dtype=torch.float32, device=dev)
+    y = torch.empty(fb.n_out_samples, dtype=torch.float32, device=dev)
+    ws = torch.empty(ctx.lib.spev_griffinlim_workspace_bytes(fb.n_frames), dtype=torch.uint8, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step():
+        sp.mel_to_mag_flat(lm.view(-1), fb, ctx, layout=1, is_log=True, out=S)
+        sp.griffinlim_flat(S, fb, ctx, n_iter=n_iter, seed=7, out=y, workspace=ws)
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize(dev)
+    times = []
+    for _ in range(max(3, min(args.steps, 10))):
+        flush.zero_()                      # > L2: evict state between timed steps
+        a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+        a.record(); step(); b.record()
+        torch.cuda.synchronize(dev)
+        times.append(a.elapsed_time(b))
+    ms = float(np.mean(times))
+    audio_s = B * (T - 1) * HOP / SR
+    alg = GL_BYTES_PER_FRAME_ITER * fb.n_frames * n_iter + (2372 + 5128) * fb.n_frames
+    # e2e: host log-mels in, host waveform out through Vocoder.infer
+    voc = sp.Vocoder(n_iter=n_iter, device=dev)
+    lm_host = lm.cpu().pin_memory()
+    voc.infer(lm_host)
+    torch.cuda.synchronize(dev)
+    t = time.perf_counter()
+    n_e = 3
+    for _ in range(n_e):
+        w = voc.infer(lm_host)
+    e2e_ms = (time.perf_counter() - t) * 1e3 / n_e
+    return {"metric": "Griffin-Lim audio-s/s", "value": audio_s / (ms * 1e-3), "unit": "audio-s/s",
+            "config": {"workload": "cfg3: 16 x [80,800] log-mel, 60 iterations, momentum 0.99; L2 flushed between steps"},
+            "ms_per_step": ms, "launches_per_step": 2 * n_iter + 3,
+            "roofline": {"bound": "hbm", "kernels": "k_istft + k_stft_phase<1>", "achieved": alg / (ms * 1e-3) / 1e9,
+                         "peak": hbm_peak, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / hbm_peak,
+                         "alg_bytes_per_frame_iter": GL_BYTES_PER_FRAME_ITER},
+            "e2e": {"value": audio_s / (e2e_ms * 1e-3), "unit": "audio-s/s", "ms_per_step": e2e_ms,
+                    "api": "Vocoder.infer (host log-mel in, numpy waveform out)",
+                    "h2d_bytes_per_step": int(lm.numel() * 4), "d2h_bytes_per_step": int(w.size * 4)}}
+
+
+def bench_length_regulator(sp, dev, args):
+    import torch
+    from tests import synth
+    x, dur, _ = synth.cfg2_batch(seed=2)
+    feats = synth.cfg2_features(seed=2)
+    xd, dd = torch.from_numpy(x).to(dev), torch.from_numpy(dur).to(dev)
+    fd = [torch.from_numpy(f).to(dev) for f in feats]
+    lrm = sp.LengthRegulator()
+    for _ in range(3):
+        o, ml = lrm(xd, dd)
+    p = sp.plan(dd)
+    torch.cuda.synchronize(dev)
+    t = time.perf_counter()
+    n = 20
+    for _ in range(n):
+        o, ml, cv = sp.regulate_variances(xd, dd, fd)
+    torch.cuda.synchronize(dev)
+    wall_ms = (time.perf_counter() - t) * 1e3 / n
+    a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+    ft = torch.stack(fd)
+    a.record()
+    for _ in range(n):
+        sp.expand(xd, p, ft, sp.VARIANCE_CLAMPS)
+    b.record()
+    torch.cuda.synchronize(dev)
+    k_ms = a.elapsed_time(b) / n
+    out_bytes = o.shape[0] * o.shape[1] * (256 + 5) * 4
+    return {"config": {"workload": "cfg2: B=32, T<=200, H=256 + 5 curves (the 6 LengthRegulator calls of one forward)"},
+            "forward_ms_wall_incl_one_sync": wall_ms, "expand_kernel_ms": k_ms,
+            "expand_GBps": out_bytes / (k_ms * 1e-3) / 1e9, "frames": int(o.shape[1]),
+            "reference_cpu_s_per_forward": "6 x 1.42 s (SURVEY App. B)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--utts", type=int, default=N_UTTS, help="utterances per GPU (cfg4: 13100)")
+    ap.add_argument("--ref-utts", type=int, default=2048, help="bounded CPU sample (utterances per step)")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-gl", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

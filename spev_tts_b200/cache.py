@@ -1,0 +1,196 @@
+"""Log-mel training-cache builder: the B200 replacement of the mel lines of the reference's
+cache loop (``/root/reference/spev_real_metrics.py:330-426``; mel statements ``:363-367``,
+stored layout ``'mel': mel.T`` ``:421``).
+
+* ``shard_utterances``  -- length-balanced (greedy LPT) assignment of utterances to ranks.  The
+  path is embarrassingly data-parallel: no collective runs inside or between kernels.
+* ``build_logmel_cache`` -- host buffers in, host buffers out: chunked H2D copy / fused kernel /
+  D2H copy on three streams with double buffering (this is the end-to-end path a caller with
+  wavs in host memory uses; ``bench.py`` times it as ``e2e``).
+* ``gather_shards``      -- the only cross-GPU step: variable-length gather of the ``[F_r, 80]``
+  shards (NCCL on GPUs over NVLink; gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import spectral
+from .batch import HOP, Context, make_batch
+
+
+# ---------------------------------------------------------------------------------------------
+# sharding (host logic; CPU-testable)
+# ---------------------------------------------------------------------------------------------
+def frames_of(n_samples) -> np.ndarray:
+    return 1 + np.asarray(n_samples, dtype=np.int64) // HOP
+
+
+def shard_utterances(n_samples: Sequence[int], world_size: int) -> List[np.ndarray]:
+    """Greedy longest-processing-time assignment balancing the number of frames per rank.
+    Returns, per rank, the sorted utterance indices it owns.  Deterministic."""
+    fr = frames_of(n_samples)
+    order = np.argsort(-fr, kind="stable")
+    loads = np.zeros(world_size, dtype=np.int64)
+    owner = np.empty(len(fr), dtype=np.int64)
+    for i in order:
+        r = int(np.argmin(loads))
+        owner[i] = r
+        loads[r] += fr[i]
+    return [np.sort(np.nonzero(owner == r)[0]) for r in range(world_size)]
+
+
+@dataclass
+class CachePlan:
+    """Chunks of consecutive utterances sized to ~``chunk_samples`` samples."""
+    n_samples: np.ndarray
+    sample_off: np.ndarray      # [U+1] offsets into the packed host buffer
+    frame_off: np.ndarray       # [U+1]
+    chunks: List[Tuple[int, int]]   # (first utt, last utt exclusive)
+
+
+def plan_chunks(n_samples: Sequence[int], chunk_samples: int = 1 << 26) -> CachePlan:
+    ns = np.asarray(n_samples, dtype=np.int64)
+    so = np.concatenate([[0], np.cumsum(ns)])
+    fo = np.concatenate([[0], np.cumsum(frames_of(ns))])
+    chunks, a = [], 0
+    while a < len(ns):
+        b = int(np.searchsorted(so, so[a] + chunk_samples, side="right")) - 1
+        b = max(b, a + 1)
+        b = min(b, len(ns))
+        chunks.append((a, b))
+        a = b
+    return CachePlan(ns, so, fo, chunks)
+
+
+# ---------------------------------------------------------------------------------------------
+# end-to-end builder: pinned host -> device -> pinned host, pipelined
+# ---------------------------------------------------------------------------------------------
+class LogMelCacheBuilder:
+    """Reusable pipelined builder (device staging buffers and streams are allocated once)."""
+
+    def __init__(self, device, *, sr=22050, n_mels=80, chunk_samples: int = 1 << 26, n_buffers: int = 2):
+        self.device = torch.device(device)
+        self.sr, self.n_mels = sr, n_mels
+        self.chunk_samples = chunk_samples
+        self.n_buffers = n_buffers
+        self.ctx = Context.get(self.device, sr=sr, n_mels=n_mels)
+        self.copy_in = torch.cuda.Stream(self.device)
+        self.compute = torch.cuda.Stream(self.device)
+        self.copy_out = torch.cuda.Stream(self.device)
+        self._in: List[Optional[torch.Tensor]] = [None] * n_buffers
+        self._out: List[Optional[torch.Tensor]] = [None] * n_buffers
+        self.launches = 0
+
+    def _buf(self, pool, i, n, dtype=torch.float32):
+        if pool[i] is None or pool[i].numel() < n:
+            pool[i] = torch.empty(max(n, 1), dtype=dtype, device=self.device)
+        return pool[i]
+
+    def build(self, samples_host: torch.Tensor, n_samples: Sequence[int],
+              out_host: Optional[torch.Tensor] = None, plan: Optional[CachePlan] = None):
+        """``samples_host``: flat float32 host tensor (pinned for full copy speed) with the
+        utterances packed back to back; returns ``(out_host [F, n_mels] pinned, frame_off)``."""
+        if plan is None:
+            plan = plan_chunks(n_samples, self.chunk_samples)
+        F = int(plan.frame_off[-1])
+        if out_host is None:
+            out_host = torch.empty((F, self.n_mels), dtype=torch.float32).pin_memory()
+        nb = self.n_buffers
+        in_free = [torch.cuda.Event() for _ in range(nb)]    # compute finished reading buffer i
+        out_free = [torch.cuda.Event() for _ in range(nb)]   # D2H finished reading buffer i
+        max_in = max(int(plan.sample_off[b] - plan.sample_off[a]) for a, b in plan.chunks)
+        max_out = max(int(plan.frame_off[b] - plan.frame_off[a]) for a, b in plan.chunks) * self.n_mels
+        for i in range(nb):
+            self._buf(self._in, i, max_in)
+            self._buf(self._out, i, max_out)
+        # descriptors are tiny; build them all up front so the loop only enqueues
+        batches = [make_batch(self.ctx, n_samples=plan.n_samples[a:b]) for a, b in plan.chunks]
+        tables_up = torch.cuda.Event()
+        tables_up.record(torch.cuda.current_stream(self.device))   # descriptor uploads ran here
+        self.compute.wait_event(tables_up)
+        for ci, (a, b) in enumerate(plan.chunks):
+            i = ci % nb
+            s0, s1 = int(plan.sample_off[a]), int(plan.sample_off[b])
+            f0, f1 = int(plan.frame_off[a]), int(plan.frame_off[b])
+            d_in = self._in[i][: s1 - s0]
+            d_out = self._out[i][: (f1 - f0) * self.n_mels].view(f1 - f0, self.n_mels)
+            with torch.cuda.stream(self.copy_in):
+                if ci >= nb:
+                    self.copy_in.wait_event(in_free[i])
+                d_in.copy_(samples_host[s0:s1], non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(self.copy_in)
+            with torch.cuda.stream(self.compute):
+                self.compute.wait_event(ready)
+                if ci >= nb:
+                    self.compute.wait_event(out_free[i])
+                spectral.logmel_flat(d_in, plan.n_samples[a:b], sr=self.sr, n_mels=self.n_mels,
+                                     out=d_out, batch=batches[ci])
+                self.launches += 1
+                in_free[i].record(self.compute)
+                done = torch.cuda.Event()
+                done.record(self.compute)
+            with torch.cuda.stream(self.copy_out):
+                self.copy_out.wait_event(done)
+                out_host[f0:f1].copy_(d_out, non_blocking=True)
+                out_free[i].record(self.copy_out)
+        fin = torch.cuda.Event()
+        fin.record(self.copy_out)
+        torch.cuda.current_stream(self.device).wait_event(fin)
+        self._keep = batches
+        return out_host, plan.frame_off
+
+
+def build_logmel_cache(samples_host: torch.Tensor, n_samples: Sequence[int], device=None, **kw):
+    """One-shot convenience wrapper around ``LogMelCacheBuilder`` (synchronises before returning)."""
+    device = spectral.default_device() if device is None else torch.device(device)
+    out, fo = LogMelCacheBuilder(device, **kw).build(samples_host, n_samples)
+    torch.cuda.synchronize(device)
+    return out, fo
+
+
+# ---------------------------------------------------------------------------------------------
+# the one cross-rank step: gather the shards
+# ---------------------------------------------------------------------------------------------
+def gather_shards(local: torch.Tensor, dst: int = 0, group=None):
+    """Variable-length gather of ``[F_r, n_mels]`` shards to rank ``dst``.
+    Returns ``(list of per-rank tensors on dst | None elsewhere, frames_per_rank)``.
+    Uses an all_gather of the row counts followed by point-to-point transfers (NCCL has no
+    gatherv); works on the NCCL (GPU, NVLink) and gloo (CPU tests) backends."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    n = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
+    counts = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(counts, n, group=group)
+    counts = [int(c.item()) for c in counts]
+    if rank == dst:
+        parts = [local if r == dst else torch.empty((counts[r], local.shape[1]), dtype=local.dtype,
+                                                    device=local.device) for r in range(world)]
+        reqs = [dist.irecv(parts[r], src=r, group=group) for r in range(world) if r != dst and counts[r]]
+        for q in reqs:
+            q.wait()
+        return parts, counts
+    if local.shape[0]:
+        dist.send(local.contiguous(), dst=dst, group=group)
+    return None, counts
+
+
+def assemble(parts: Sequence[torch.Tensor], shards: Sequence[np.ndarray], n_samples: Sequence[int]):
+    """Re-order gathered shards into corpus order.  Returns ``(cache [F, n_mels], frame_off)``
+    such that utterance ``u`` is ``cache[frame_off[u]:frame_off[u+1]]`` -- i.e. the tensor each
+    ``cache_stable/u_%05d.pt`` would hold under ``'mel'`` (``spev_real_metrics.py:419-425``)."""
+    fr = frames_of(n_samples)
+    fo = np.concatenate([[0], np.cumsum(fr)])
+    out = torch.empty((int(fo[-1]), parts[0].shape[1]), dtype=parts[0].dtype, device=parts[0].device)
+    for part, idx in zip(parts, shards):
+        if len(idx) == 0:
+            continue
+        loc = np.concatenate([[0], np.cumsum(fr[idx])])
+        dest = np.repeat(fo[idx] - loc[:-1], fr[idx]) + np.arange(loc[-1])
+        out[torch.from_numpy(dest).to(out.device)] = part
+    return out, fo

@@ -1,0 +1,121 @@
+"""CPU tests of the oracle: against the committed golden fixtures (LengthRegulator goldens come
+from the REFERENCE's own class), and against independent implementations available here
+(torch.stft/istft, torchaudio Slaney filterbank, scipy L-BFGS-B, torch.bucketize)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import librosa_restated as lr
+from oracle import reference_import
+from tests import synth
+
+
+# ---- LengthRegulator / duration rule / bucketize: pinned by the reference / torch -------------
+def test_lr_restatement_matches_reference_goldens(golden):
+    x, dur, _ = synth.cfg2_batch(seed=2)
+    g = golden("lr_cfg2.npz")
+    out, lens = lr.length_regulator(x, dur)
+    assert np.array_equal(lens, g["mel_lens"]) and tuple(out.shape) == tuple(g["shape"])
+    import hashlib
+    assert hashlib.sha256(out.tobytes()).hexdigest() == str(g["sha256"])
+    s = golden("lr_small.npz")
+    o, l = lr.length_regulator(s["x"], s["dur"])
+    assert np.array_equal(o, s["out"]) and np.array_equal(l, s["mel_lens"])
+    e = golden("lr_edge.npz")
+    for name in synth.lr_edge_cases():
+        o, l = lr.length_regulator(e[name + "_x"], e[name + "_dur"])
+        assert np.array_equal(o, e[name + "_out"]), name
+        assert np.array_equal(l, e[name + "_lens"]), name
+    with pytest.raises(ValueError):
+        lr.length_regulator(np.zeros((0, 3, 2), np.float32), np.zeros((0, 3), np.int64))
+
+
+@pytest.mark.skipif(not reference_import.available(), reason="/root/reference not mounted")
+def test_lr_restatement_vs_live_reference_class():
+    ref = reference_import.load()
+    LR = ref.LengthRegulator()
+    rng = np.random.default_rng(123)
+    for trial in range(6):
+        B, T, H = rng.integers(1, 5), rng.integers(1, 40), rng.integers(1, 9)
+        x = rng.standard_normal((B, T, H)).astype(np.float32)
+        d = rng.integers(-3, 9, (B, T)).astype(np.float64) + rng.choice([0, 0.5, 0.99], (B, T))
+        if trial % 2:
+            d = d.astype(np.int64)
+        o, l = LR(torch.from_numpy(x), torch.from_numpy(d))
+        ro, rl = lr.length_regulator(x, d)
+        assert np.array_equal(o.numpy(), ro) and np.array_equal(l.numpy(), rl)
+
+
+def test_duration_rule_and_bucketize_goldens(golden):
+    g = golden("duration_rule.npz")
+    for dc in (1.0, 0.5, 1.7):
+        assert np.array_equal(lr.duration_rule(g["log_dur"], dc), g[f"d_{dc}"])
+    assert g["half_out"].tolist() == [0, 2, 2, 4, 500, 500, 500, 0]      # half-to-even + clamp
+    v, bins, table = synth.bucketize_case(seed=2)
+    b = golden("bucketize.npz")
+    assert np.array_equal(lr.bucketize(v, bins), b["idx"])
+    assert np.array_equal(lr.bucketize(v, bins, right=True), b["idx_right"])
+    assert np.array_equal(torch.bucketize(torch.from_numpy(v), torch.from_numpy(bins)).numpy(), b["idx"])
+    assert b["idx"][0, :7].tolist() == [255, 255, 0, 0, 254, 10, 255]
+    assert b["idx_right"][0, :7].tolist() == [255, 255, 0, 1, 255, 11, 255]
+
+
+# ---- spectral restatement: frozen fixtures + independent pins -------------------------------
+def test_logmel_goldens_frozen(golden):
+    for name, y in (("white", synth.white(seed=0)), ("speechy", synth.speechy(seed=1))):
+        lm = lr.reference_logmel(y)
+        assert lm.shape == (517, 80) and lm.dtype == np.float32
+        assert np.abs(lm - golden(f"logmel_{name}.npz")["logmel"]).max() < 2e-5
+
+
+def test_mel_basis_vs_torchaudio():
+    import torchaudio
+    for sr, fmax in ((22050, None), (22050, 8000.0), (24000, None)):
+        b = lr.mel_filter(sr=sr, n_fft=1024, n_mels=80, fmin=0.0, fmax=fmax)
+        tb = torchaudio.functional.melscale_fbanks(513, 0.0, fmax or sr / 2, 80, sr, norm="slaney",
+                                                   mel_scale="slaney").T.numpy()
+        assert b.dtype == np.float32 and np.abs(b - tb).max() < 2e-7
+        nnz_per_bin = (b != 0).sum(0)
+        assert nnz_per_bin.max() <= 2 and (b != 0).sum(1).min() >= 1      # banded, no empty filter
+    assert (lr.mel_filter(sr=22050, n_fft=1024, n_mels=80) != 0).sum() == 1000
+
+
+def test_stft_istft_vs_torch_float64():
+    y = synth.white(seed=0)
+    w = torch.hann_window(1024, periodic=True, dtype=torch.float64)
+    S = lr.stft(y, n_fft=1024, hop_length=256)
+    ts = torch.stft(torch.from_numpy(y).double(), 1024, 256, 1024, w, center=True, pad_mode="constant",
+                    return_complex=True).numpy()
+    assert S.shape == (513, 517) and S.dtype == np.complex64
+    assert np.abs(S - ts).max() < 1e-6
+    yi = lr.istft(S, hop_length=256, n_fft=1024)
+    ti = torch.istft(torch.from_numpy(ts), 1024, 256, 1024, w, center=True).numpy()
+    assert yi.shape == ti.shape == (516 * 256,) and yi.dtype == np.float32
+    assert np.abs(yi - ti).max() < 1e-6 and np.abs(yi - y[: yi.shape[0]]).max() < 1e-6
+    # batch dims broadcast like librosa
+    Sb = lr.stft(np.stack([y, -y]), n_fft=1024, hop_length=256)
+    assert Sb.shape == (2, 513, 517) and np.array_equal(Sb[0], S)
+
+
+def test_window_sumsquare_edges():
+    wss = lr.window_sumsquare(n_frames=10, hop_length=256, win_length=1024, n_fft=1024)[512:-512]
+    assert abs(wss[0] - 1.25) < 1e-6 and np.allclose(wss[256:-256], 1.5, atol=1e-6) and wss.min() >= 1.25 - 1e-6
+
+
+def test_nnls_is_pinv_clip_for_reference_range_inputs():
+    lm = lr.reference_logmel(synth.speechy(seed=12, n=256 * 99)).T
+    a = lr.mel_to_stft(np.exp(lm), sr=22050, n_fft=1024, fmin=0, fmax=8000, lbfgs=True)
+    b = lr.mel_to_stft(np.exp(lm), sr=22050, n_fft=1024, fmin=0, fmax=8000, lbfgs=False)
+    assert np.linalg.norm(a - b) / np.linalg.norm(b) < 1e-6
+
+
+def test_griffinlim_golden_and_convergence(golden):
+    g = golden("gl_small.npz")
+    S = g["S"]
+    ph = synth.init_phase(S.shape, seed=3)
+    y = lr.griffinlim(S, n_iter=8, hop_length=256, n_fft=1024, init_phase=ph)
+    assert y.shape == ((S.shape[1] - 1) * 256,) and y.dtype == np.float32
+    assert np.linalg.norm(y - g["y8"]) / np.linalg.norm(g["y8"]) < 1e-3
+    sc0 = lr.spectral_convergence(lr.griffinlim(S, n_iter=0, hop_length=256, n_fft=1024, init_phase=ph), S)
+    sc8 = lr.spectral_convergence(y, S)
+    assert abs(sc8 - float(g["sc8"])) < 1e-4 and sc8 < sc0
