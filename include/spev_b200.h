@@ -14,8 +14,8 @@
  *   - return value 0 = ok, negative = error (SPEV_E_*); text via spev_last_error()
  *     (thread-local).  No C++ exception crosses the ABI.  There is NO CPU fallback: without
  *     an sm_100 device spev_create fails with SPEV_E_DEVICE.
- *   - batches are "flat": items (utterances / spectrograms) are concatenated and described by
- *     prefix-offset arrays plus tile tables built on the host by spev_plan_tiles().
+ *   - batches are "flat": items (utterances / spectrograms) are concatenated and described by a
+ *     frame prefix-offset array plus per-CTA tile tables built on the host by spev_plan_*_tiles().
  */
 #ifndef SPEV_B200_H
 #define SPEV_B200_H
@@ -48,21 +48,35 @@ extern "C" {
 
 typedef struct spev_ctx spev_ctx;
 
-/* Flat batch descriptor.  Item i owns frames [frame_off[i], frame_off[i+1]) and, for waveform
- * inputs, samples [sample_off[i], sample_off[i+1]).  T_i frames <-> N_i samples with
- * T_i = 1 + N_i / hop (librosa center=True framing).  Tile tables come from spev_plan_tiles. */
+/* One CTA tile.  Built on the host (spev_plan_frame_tiles / spev_plan_chunk_tiles) so that a
+ * kernel needs exactly one 48-byte read per tile and no dependent look-ups.
+ *  frame tile (STFT-type kernels): `n` (<= SPEV_TILE_FRAMES) consecutive frames t0.. of one item.
+ *     src0 = absolute index, in the flat sample buffer, of the first staged sample
+ *            (= lo + hop*t0 - n_fft/2; may lie before lo: centre padding reads as zero)
+ *     lo, hi = absolute bounds of the item's samples (zero outside)
+ *     row0 = global index (row of the [F, .] outputs) of frame t0
+ *  chunk tile (ISTFT): `n` (<= SPEV_TILE_CHUNKS) consecutive hop-sized output chunks t0.. .
+ *     src0 = absolute index in y of the first output sample of chunk t0
+ *     row0 = global row of item frame (t0 - 1): the first of the n+3 frames the tile gathers
+ *            (one before the item's first row when t0 == 0; never dereferenced then)
+ *     lo, hi unused. */
+typedef struct spev_tile {
+    int64_t src0, lo, hi, row0;
+    int32_t n, t0, T /* frames in the item */, item;
+} spev_tile;
+
+/* Flat batch descriptor.  Item i owns rows [frame_off[i], frame_off[i+1]) of every [F, .] array.
+ * Framing is librosa center=True: an item of N samples has T = 1 + N / hop frames; an ISTFT
+ * output item has (T-1)*hop samples at offset hop*(frame_off[i] - i). */
 typedef struct spev_batch {
     int32_t n_items;
-    int32_t n_ftiles;          /* tiles of SPEV_TILE_FRAMES frames */
-    int32_t n_ctiles;          /* tiles of SPEV_TILE_CHUNKS output chunks (ISTFT); may be 0 */
+    int32_t n_ftiles;
+    int32_t n_ctiles;          /* may be 0 when no ISTFT is requested */
     int32_t reserved;
     int64_t n_frames;          /* == frame_off[n_items] */
-    const int64_t* sample_off; /* dev [n_items+1]; may be NULL for spectrogram-only calls */
     const int64_t* frame_off;  /* dev [n_items+1] */
-    const int32_t* ftile_item; /* dev [n_ftiles] */
-    const int32_t* ftile_t0;   /* dev [n_ftiles] first frame (item-local) of the tile */
-    const int32_t* ctile_item; /* dev [n_ctiles] */
-    const int32_t* ctile_c0;   /* dev [n_ctiles] first output chunk (item-local) of the tile */
+    const spev_tile* ftiles;   /* dev [n_ftiles] */
+    const spev_tile* ctiles;   /* dev [n_ctiles] */
 } spev_batch;
 
 SPEV_API int spev_abi_version(void);
@@ -91,13 +105,18 @@ SPEV_API int spev_get_window(const spev_ctx* ctx, float* window_host);
 SPEV_API int spev_host_mel_basis(int sr, int n_fft, int n_mels, float fmin, float fmax, float* basis);
 SPEV_API int spev_host_pinv(const float* a, int m, int n, float* pinv);
 
-/* Host helper: split `n` items with `counts[i]` units into tiles of `per_tile` units.
- * Returns the number of tiles; fills tile_item/tile_start when non-NULL (size >= return). */
-SPEV_API int64_t spev_plan_tiles(const int64_t* counts_host, int n, int per_tile, int32_t* tile_item,
-                        int32_t* tile_start);
+/* Host helpers that build the tile tables (call with out == NULL to get the count).
+ *   frames[i]     : frames of item i
+ *   sample_lo[i]  : absolute start of item i's samples in the flat buffer, n_samples[i] its
+ *                   length (waveform batches: spev_logmel / spev_stft_power); pass NULL for both
+ *                   to describe the implicit ISTFT-output layout (spev_stft, spev_gl_*, where
+ *                   item i has (T_i-1)*hop samples at hop*(frame_off[i]-i)). */
+SPEV_API int64_t spev_plan_frame_tiles(const int64_t* frames, const int64_t* sample_lo,
+                                       const int64_t* n_samples, int n_items, spev_tile* out);
+SPEV_API int64_t spev_plan_chunk_tiles(const int64_t* frames, int n_items, spev_tile* out);
 
 /* STFT -> |.|^2 -> mel -> (optional) log compression, fused, one launch.
- *   samples : dev float32, flat; item i at sample_off[i]
+ *   samples : dev float32, flat buffer the frame tiles index into
  *   out     : dev float32 [n_frames, n_mels] row-major  (== the reference's cache layout
  *             `mel.T`, spev_real_metrics.py:421)
  *   mode 0  : mel power            (librosa.feature.melspectrogram, :363)

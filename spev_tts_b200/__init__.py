@@ -12,7 +12,7 @@ CPU, PyTorch-eager or Triton fallback: without the library or without an sm_100 
 raise ``RuntimeError``.
 """
 from ._lib import EXPORTED_SYMBOLS, LIB_PATH, load  # noqa: F401
-from .batch import Context, FlatBatch, make_batch, plan_tiles  # noqa: F401
+from .batch import Context, FlatBatch, make_batch, plan_chunk_tiles, plan_frame_tiles  # noqa: F401
 from .install import install, patch_model  # noqa: F401
 from .length_regulator import (LengthRegulator, VARIANCE_CLAMPS, expand, mel_mask, plan,  # noqa: F401
                                regulate_variances)

@@ -21,14 +21,18 @@ c_i64p = C.POINTER(C.c_int64)
 c_i32p = C.POINTER(C.c_int32)
 
 
+class SpevTile(C.Structure):
+    """``struct spev_tile`` (48 bytes)."""
+    _fields_ = [("src0", C.c_int64), ("lo", C.c_int64), ("hi", C.c_int64), ("row0", C.c_int64),
+                ("n", C.c_int32), ("t0", C.c_int32), ("T", C.c_int32), ("item", C.c_int32)]
+
+
 class SpevBatch(C.Structure):
     """``struct spev_batch`` (include/spev_b200.h)."""
     _fields_ = [
         ("n_items", C.c_int32), ("n_ftiles", C.c_int32), ("n_ctiles", C.c_int32),
         ("reserved", C.c_int32), ("n_frames", C.c_int64),
-        ("sample_off", C.c_void_p), ("frame_off", C.c_void_p),
-        ("ftile_item", C.c_void_p), ("ftile_t0", C.c_void_p),
-        ("ctile_item", C.c_void_p), ("ctile_c0", C.c_void_p),
+        ("frame_off", C.c_void_p), ("ftiles", C.c_void_p), ("ctiles", C.c_void_p),
     ]
 
 
@@ -45,7 +49,8 @@ _SIGS = {
     "spev_get_window": (C.c_int, [C.c_void_p, C.c_void_p]),
     "spev_host_mel_basis": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p]),
     "spev_host_pinv": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
-    "spev_plan_tiles": (C.c_int64, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "spev_plan_frame_tiles": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "spev_plan_chunk_tiles": (C.c_int64, [C.c_void_p, C.c_int, C.c_void_p]),
     "spev_logmel": (C.c_int, [C.c_void_p, C.POINTER(SpevBatch), C.c_void_p, C.c_void_p, C.c_int,
                               C.c_float, C.c_float, C.c_float, C.c_void_p]),
     "spev_stft_power": (C.c_int, [C.c_void_p, C.POINTER(SpevBatch), C.c_void_p, C.c_void_p,

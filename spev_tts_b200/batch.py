@@ -22,15 +22,53 @@ HOP = 256
 N_FFT = 1024
 
 
-def plan_tiles(counts: np.ndarray, per_tile: int):
-    """Split items with ``counts[i]`` units into tiles of ``per_tile`` units.
-    Returns (tile_item int32[n], tile_start int32[n]).  numpy twin of ``spev_plan_tiles``."""
+TILE_DTYPE = np.dtype([("src0", "<i8"), ("lo", "<i8"), ("hi", "<i8"), ("row0", "<i8"),
+                       ("n", "<i4"), ("t0", "<i4"), ("T", "<i4"), ("item", "<i4")])   # struct spev_tile
+assert TILE_DTYPE.itemsize == 48
+
+
+def _split(counts: np.ndarray, per_tile: int):
+    """(tile_item, tile_start) for items with ``counts[i]`` units cut into ``per_tile``-unit tiles."""
     counts = np.asarray(counts, dtype=np.int64)
     nt = (counts + per_tile - 1) // per_tile
-    tile_item = np.repeat(np.arange(len(counts), dtype=np.int32), nt)
+    tile_item = np.repeat(np.arange(len(counts), dtype=np.int64), nt)
     first = np.cumsum(nt) - nt
     tile_start = (np.arange(int(nt.sum()), dtype=np.int64) - np.repeat(first, nt)) * per_tile
-    return tile_item, tile_start.astype(np.int32)
+    return tile_item, tile_start
+
+
+def plan_frame_tiles(frames, sample_lo=None, n_samples=None, tile_frames: int = 32) -> np.ndarray:
+    """numpy twin of ``spev_plan_frame_tiles`` (vectorised): one ``spev_tile`` per <=32-frame tile."""
+    frames = np.asarray(frames, dtype=np.int64)
+    fo = np.concatenate([[0], np.cumsum(frames)])[:-1]
+    if sample_lo is None:
+        lo = HOP * (fo - np.arange(len(frames)))
+        hi = lo + (frames - 1) * HOP
+    else:
+        lo = np.asarray(sample_lo, dtype=np.int64)
+        hi = lo + np.asarray(n_samples, dtype=np.int64)
+    item, t0 = _split(frames, tile_frames)
+    out = np.zeros(len(item), dtype=TILE_DTYPE)
+    out["src0"] = lo[item] + HOP * t0 - N_FFT // 2
+    out["lo"], out["hi"] = lo[item], hi[item]
+    out["row0"] = fo[item] + t0
+    out["n"] = np.minimum(tile_frames, frames[item] - t0)
+    out["t0"], out["T"], out["item"] = t0, frames[item], item
+    return out
+
+
+def plan_chunk_tiles(frames, tile_chunks: int = 29) -> np.ndarray:
+    """numpy twin of ``spev_plan_chunk_tiles``: one ``spev_tile`` per <=29-chunk ISTFT tile."""
+    frames = np.asarray(frames, dtype=np.int64)
+    fo = np.concatenate([[0], np.cumsum(frames)])[:-1]
+    nc = np.maximum(frames - 1, 0)
+    item, c0 = _split(nc, tile_chunks)
+    out = np.zeros(len(item), dtype=TILE_DTYPE)
+    out["src0"] = HOP * (fo[item] - item) + HOP * c0
+    out["row0"] = fo[item] + c0 - 1
+    out["n"] = np.minimum(tile_chunks, nc[item] - c0)
+    out["t0"], out["T"], out["item"] = c0, frames[item], item
+    return out
 
 
 class Context:
@@ -108,11 +146,11 @@ class FlatBatch:
     n_items: int
     n_frames: int
     frames: np.ndarray          # int64 [n_items]  frames per item
-    sample_off: Optional[np.ndarray]   # int64 [n_items+1] or None
+    sample_off: Optional[np.ndarray]   # int64 [n_items] absolute item starts (waveform batches)
     frame_off: np.ndarray       # int64 [n_items+1]
     n_ftiles: int
     n_ctiles: int
-    table: torch.Tensor         # device int64 buffer holding all arrays
+    table: torch.Tensor         # device uint8 buffer holding frame_off + tile tables
     desc: _lib.SpevBatch
     device: torch.device
 
@@ -129,57 +167,47 @@ def make_batch(ctx: Context, *, n_samples: Optional[Sequence[int]] = None,
                n_frames: Optional[Sequence[int]] = None, sample_off: Optional[np.ndarray] = None,
                with_chunks: bool = False, pinned: bool = True) -> FlatBatch:
     """Build the descriptor for items given by sample counts (waveform inputs) or frame counts
-    (spectrogram inputs).  ``sample_off`` overrides the packed offsets (e.g. aligned packing:
-    the gap after an item must be zero-filled, then it reads exactly like centre padding)."""
+    (spectrogram inputs; sample tiles then describe the implicit ISTFT-output layout).
+    ``sample_off[i]`` is the absolute start of item i in the flat sample buffer (default: items
+    packed back to back).  Starts that are multiples of 4 samples take the 16-byte cp.async path;
+    whatever lies between items is never read as signal (explicit [lo, hi) bounds per item)."""
     dev = torch.device("cuda", ctx.device)
     if n_samples is not None:
         ns = np.asarray(n_samples, dtype=np.int64).reshape(-1)
         frames = 1 + ns // HOP
         if sample_off is None:
-            sample_off = np.concatenate([[0], np.cumsum(ns)]).astype(np.int64)
+            sample_off = np.concatenate([[0], np.cumsum(ns)])[:-1].astype(np.int64)
         else:
-            sample_off = np.asarray(sample_off, dtype=np.int64)
-            assert sample_off.shape == (len(ns) + 1,)
+            sample_off = np.asarray(sample_off, dtype=np.int64).reshape(-1)[: len(ns)]
+        ftiles = plan_frame_tiles(frames, sample_off, ns, ctx.tile_frames)
     else:
         frames = np.asarray(n_frames, dtype=np.int64).reshape(-1)
         sample_off = None
+        ftiles = plan_frame_tiles(frames, None, None, ctx.tile_frames)
     n_items = int(len(frames))
     frame_off = np.concatenate([[0], np.cumsum(frames)]).astype(np.int64)
-    ft_item, ft_t0 = plan_tiles(frames, ctx.tile_frames)
-    if with_chunks:
-        ct_item, ct_c0 = plan_tiles(np.maximum(frames - 1, 0), ctx.tile_chunks)
-    else:
-        ct_item = ct_c0 = np.zeros(0, dtype=np.int32)
+    ctiles = plan_chunk_tiles(frames, ctx.tile_chunks) if with_chunks else np.zeros(0, dtype=TILE_DTYPE)
 
-    # one int64 staging buffer: [sample_off | frame_off | ftile_item,ftile_t0 | ctile_item,ctile_c0]
-    def as64(a32):   # pack int32 pairs into int64 words (keeps 8-byte alignment of what follows)
-        n = (len(a32) + 1) // 2 * 2
-        buf = np.zeros(n, dtype=np.int32)
-        buf[: len(a32)] = a32
-        return buf.view(np.int64)
-
-    parts = [sample_off if sample_off is not None else np.zeros(0, np.int64), frame_off,
-             as64(ft_item), as64(ft_t0), as64(ct_item), as64(ct_c0)]
-    sizes = [len(p) for p in parts]
-    host = torch.from_numpy(np.concatenate(parts)) if sum(sizes) else torch.zeros(0, dtype=torch.int64)
-    if pinned and host.numel():
+    # one staging buffer: [ftiles | ctiles | frame_off]; tile tables first (16-byte aligned)
+    parts = [ftiles.view(np.uint8).reshape(-1), ctiles.view(np.uint8).reshape(-1),
+             frame_off.view(np.uint8).reshape(-1)]
+    sizes = [p.size for p in parts]
+    host = torch.from_numpy(np.concatenate(parts))
+    if pinned:
         host = host.pin_memory()
     table = host.to(dev, non_blocking=True)
     base = table.data_ptr()
-    offs = np.concatenate([[0], np.cumsum(sizes)]) * 8
+    assert base % 16 == 0
     d = _lib.SpevBatch()
     d.n_items = n_items
-    d.n_ftiles = len(ft_item)
-    d.n_ctiles = len(ct_item)
+    d.n_ftiles = len(ftiles)
+    d.n_ctiles = len(ctiles)
     d.n_frames = int(frame_off[-1])
-    d.sample_off = base + int(offs[0]) if sample_off is not None else None
-    d.frame_off = base + int(offs[1])
-    d.ftile_item = base + int(offs[2])
-    d.ftile_t0 = base + int(offs[3])
-    d.ctile_item = base + int(offs[4]) if len(ct_item) else None
-    d.ctile_c0 = base + int(offs[5]) if len(ct_item) else None
+    d.ftiles = base if len(ftiles) else None
+    d.ctiles = base + sizes[0] if len(ctiles) else None
+    d.frame_off = base + sizes[0] + sizes[1]
     fb = FlatBatch(n_items=n_items, n_frames=int(frame_off[-1]), frames=frames,
-                   sample_off=sample_off, frame_off=frame_off, n_ftiles=len(ft_item),
-                   n_ctiles=len(ct_item), table=table, desc=d, device=dev)
+                   sample_off=sample_off, frame_off=frame_off, n_ftiles=len(ftiles),
+                   n_ctiles=len(ctiles), table=table, desc=d, device=dev)
     fb._host = host   # keep the pinned staging buffer alive until the async copy is consumed
     return fb

@@ -43,18 +43,29 @@ def shard_utterances(n_samples: Sequence[int], world_size: int) -> List[np.ndarr
     return [np.sort(np.nonzero(owner == r)[0]) for r in range(world_size)]
 
 
+def aligned_offsets(n_samples: Sequence[int], align: int = 4) -> np.ndarray:
+    """Item starts ``[U+1]`` (last entry = buffer size) with every start a multiple of ``align``
+    samples, so that the kernels take the 16-byte cp.async staging path.  The <= align-1 filler
+    samples between items are never read as signal."""
+    ns = np.asarray(n_samples, dtype=np.int64)
+    padded = (ns + align - 1) // align * align
+    return np.concatenate([[0], np.cumsum(padded)]).astype(np.int64)
+
+
 @dataclass
 class CachePlan:
     """Chunks of consecutive utterances sized to ~``chunk_samples`` samples."""
     n_samples: np.ndarray
-    sample_off: np.ndarray      # [U+1] offsets into the packed host buffer
+    sample_off: np.ndarray      # [U+1] item starts in the host buffer (last = end of buffer)
     frame_off: np.ndarray       # [U+1]
     chunks: List[Tuple[int, int]]   # (first utt, last utt exclusive)
 
 
-def plan_chunks(n_samples: Sequence[int], chunk_samples: int = 1 << 26) -> CachePlan:
+def plan_chunks(n_samples: Sequence[int], chunk_samples: int = 1 << 26,
+                sample_off: Optional[np.ndarray] = None) -> CachePlan:
     ns = np.asarray(n_samples, dtype=np.int64)
-    so = np.concatenate([[0], np.cumsum(ns)])
+    so = np.concatenate([[0], np.cumsum(ns)]) if sample_off is None else np.asarray(sample_off, dtype=np.int64)
+    assert so.shape == (len(ns) + 1,) and np.all(so[1:] - so[:-1] >= ns)
     fo = np.concatenate([[0], np.cumsum(frames_of(ns))])
     chunks, a = [], 0
     while a < len(ns):
@@ -91,11 +102,13 @@ class LogMelCacheBuilder:
         return pool[i]
 
     def build(self, samples_host: torch.Tensor, n_samples: Sequence[int],
-              out_host: Optional[torch.Tensor] = None, plan: Optional[CachePlan] = None):
-        """``samples_host``: flat float32 host tensor (pinned for full copy speed) with the
-        utterances packed back to back; returns ``(out_host [F, n_mels] pinned, frame_off)``."""
+              out_host: Optional[torch.Tensor] = None, plan: Optional[CachePlan] = None,
+              sample_off: Optional[np.ndarray] = None):
+        """``samples_host``: flat float32 host tensor (pinned for full copy speed) holding the
+        utterances at ``sample_off`` (default: packed back to back; ``aligned_offsets`` gives the
+        fast layout); returns ``(out_host [F, n_mels] pinned, frame_off)``."""
         if plan is None:
-            plan = plan_chunks(n_samples, self.chunk_samples)
+            plan = plan_chunks(n_samples, self.chunk_samples, sample_off)
         F = int(plan.frame_off[-1])
         if out_host is None:
             out_host = torch.empty((F, self.n_mels), dtype=torch.float32).pin_memory()
@@ -108,7 +121,8 @@ class LogMelCacheBuilder:
             self._buf(self._in, i, max_in)
             self._buf(self._out, i, max_out)
         # descriptors are tiny; build them all up front so the loop only enqueues
-        batches = [make_batch(self.ctx, n_samples=plan.n_samples[a:b]) for a, b in plan.chunks]
+        batches = [make_batch(self.ctx, n_samples=plan.n_samples[a:b],
+                              sample_off=plan.sample_off[a:b] - plan.sample_off[a]) for a, b in plan.chunks]
         tables_up = torch.cuda.Event()
         tables_up.record(torch.cuda.current_stream(self.device))   # descriptor uploads ran here
         self.compute.wait_event(tables_up)
@@ -145,10 +159,11 @@ class LogMelCacheBuilder:
         return out_host, plan.frame_off
 
 
-def build_logmel_cache(samples_host: torch.Tensor, n_samples: Sequence[int], device=None, **kw):
+def build_logmel_cache(samples_host: torch.Tensor, n_samples: Sequence[int], device=None,
+                       sample_off: Optional[np.ndarray] = None, **kw):
     """One-shot convenience wrapper around ``LogMelCacheBuilder`` (synchronises before returning)."""
     device = spectral.default_device() if device is None else torch.device(device)
-    out, fo = LogMelCacheBuilder(device, **kw).build(samples_host, n_samples)
+    out, fo = LogMelCacheBuilder(device, **kw).build(samples_host, n_samples, sample_off=sample_off)
     torch.cuda.synchronize(device)
     return out, fo
 

@@ -287,14 +287,40 @@ int spev_host_pinv(const float* a, int m, int n, float* pinv) {
 int spev_tile_frames(void) { return kTileFrames; }
 int spev_tile_chunks(void) { return kTileChunks; }
 
-int64_t spev_plan_tiles(const int64_t* counts, int n, int per_tile, int32_t* tile_item, int32_t* tile_start) {
-    if (!counts || n < 0 || per_tile <= 0) return SPEV_E_INVALID;
-    int64_t nt = 0;
-    for (int i = 0; i < n; ++i) {
-        for (int64_t s = 0; s < counts[i]; s += per_tile, ++nt) {
-            if (tile_item) tile_item[nt] = i;
-            if (tile_start) tile_start[nt] = static_cast<int32_t>(s);
+int64_t spev_plan_frame_tiles(const int64_t* frames, const int64_t* sample_lo, const int64_t* n_samples,
+                              int n_items, spev_tile* out) {
+    if (!frames || n_items < 0 || ((sample_lo == nullptr) != (n_samples == nullptr))) return SPEV_E_INVALID;
+    int64_t nt = 0, fo = 0;
+    for (int i = 0; i < n_items; ++i) {
+        const int64_t T = frames[i];
+        // implicit layout: the ISTFT output of item i, (T-1)*hop samples at hop*(frame_off - i)
+        const int64_t lo = sample_lo ? sample_lo[i] : kHop * (fo - i);
+        const int64_t hi = lo + (n_samples ? n_samples[i] : (T - 1) * kHop);
+        for (int64_t t0 = 0; t0 < T; t0 += kTileFrames, ++nt) {
+            if (!out) continue;
+            spev_tile& d = out[nt];
+            d.src0 = lo + kHop * t0 - kNfft / 2; d.lo = lo; d.hi = hi; d.row0 = fo + t0;
+            d.n = static_cast<int32_t>(std::min<int64_t>(kTileFrames, T - t0));
+            d.t0 = static_cast<int32_t>(t0); d.T = static_cast<int32_t>(T); d.item = i;
         }
+        fo += T;
+    }
+    return nt;
+}
+
+int64_t spev_plan_chunk_tiles(const int64_t* frames, int n_items, spev_tile* out) {
+    if (!frames || n_items < 0) return SPEV_E_INVALID;
+    int64_t nt = 0, fo = 0;
+    for (int i = 0; i < n_items; ++i) {
+        const int64_t T = frames[i], nc = T - 1;
+        for (int64_t c0 = 0; c0 < nc; c0 += kTileChunks, ++nt) {
+            if (!out) continue;
+            spev_tile& d = out[nt];
+            d.src0 = kHop * (fo - i) + kHop * c0; d.lo = 0; d.hi = 0; d.row0 = fo + c0 - 1;
+            d.n = static_cast<int32_t>(std::min<int64_t>(kTileChunks, nc - c0));
+            d.t0 = static_cast<int32_t>(c0); d.T = static_cast<int32_t>(T); d.item = i;
+        }
+        fo += T;
     }
     return nt;
 }

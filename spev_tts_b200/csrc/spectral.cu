@@ -14,42 +14,64 @@
 // K3 k_mel_to_mag : S = sqrt(max(pinv . exp(logmel), 0)) (FFMA version; the tcgen05 version
 //                   lives in gemm_tc.cu).     Replaces librosa mel_to_stft under :730.
 //
-// Shared-memory plan per CTA (16 warps, 32-frame tile, persistent over tiles):
-//   s_tw    float2[32*32]   inter-stage twiddles                     8,192 B
-//   s_win   float [1024]    periodic Hann                            4,096 B
-//   s_stage float [8960]    the tile's samples, read once from HBM  35,840 B  (K1/K5)
+// All three FFT kernels are persistent (grid = #SMs, one 16-warp CTA per SM, static round-robin
+// over host-built 48-byte tile descriptors).  Nothing on the per-tile critical path waits on
+// global memory: tile descriptors travel through a 4-slot cp.async ring three tiles ahead, and
+// the samples of tile i+1 are cp.async-staged into the second half of a double buffer while
+// tile i is transformed.
+//
+// Shared-memory plan per CTA:
+//   s_tw    float2[32*32]   inter-stage twiddles                       8,192 B
+//   s_win   float [1024]    periodic Hann                              4,096 B
+//   s_ring  spev_tile[4]    descriptor ring                              192 B
+//   s_stage float [2][8960] double-buffered tile samples (K1/K5)      71,680 B
 //   s_x     16 x 2114 words warp-private transpose tiles; reused for
-//                           |X|^2 (K1) / windowed frames (K4)      135,296 B
+//                           |X|^2 (K1) / windowed frames (K4)        135,296 B
+//   bands   CSR form of the mel basis (K1)                            ~5,000 B
 #include <algorithm>
 #include "spev_internal.cuh"
 
 namespace spev {
 
 struct BatchView {
-    int n_items, n_ftiles, n_ctiles;
-    int64_t n_frames;
-    const int64_t* sample_off;
-    const int64_t* frame_off;
-    const int32_t* ftile_item;
-    const int32_t* ftile_t0;
-    const int32_t* ctile_item;
-    const int32_t* ctile_c0;
+    int n_ftiles, n_ctiles;
+    const spev_tile* ftiles;
+    const spev_tile* ctiles;
 };
 
 static BatchView view_of(const spev_batch* b) {
     BatchView v;
-    v.n_items = b->n_items; v.n_ftiles = b->n_ftiles; v.n_ctiles = b->n_ctiles;
-    v.n_frames = b->n_frames; v.sample_off = b->sample_off; v.frame_off = b->frame_off;
-    v.ftile_item = b->ftile_item; v.ftile_t0 = b->ftile_t0;
-    v.ctile_item = b->ctile_item; v.ctile_c0 = b->ctile_c0;
+    v.n_ftiles = b->n_ftiles; v.n_ctiles = b->n_ctiles;
+    v.ftiles = b->ftiles; v.ctiles = b->ctiles;
     return v;
 }
 
 constexpr float kTiny = 1.17549435e-38f;   // np.finfo(np.float32).tiny
+constexpr int kRing = 4;
 
 // ---------------------------------------------------------------------------------------
-// shared helpers
+// cp.async helpers (LDGSTS): zero-fill through the src-size operand
 // ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
+    const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem, int src_bytes) {
+    const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+__device__ __forceinline__ void fetch_desc(spev_tile* slot, const spev_tile* g) {
+    static_assert(sizeof(spev_tile) == 48, "spev_tile must be 48 bytes");
+    if (threadIdx.x == 0) {
+        cp_async16(reinterpret_cast<char*>(slot), reinterpret_cast<const char*>(g), 16);
+        cp_async16(reinterpret_cast<char*>(slot) + 16, reinterpret_cast<const char*>(g) + 16, 16);
+        cp_async16(reinterpret_cast<char*>(slot) + 32, reinterpret_cast<const char*>(g) + 32, 16);
+    }
+}
+
 __device__ __forceinline__ void load_tables(float2* s_tw, float* s_win, const float2* __restrict__ g_tw,
                                             const float* __restrict__ g_win) {
     for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
@@ -58,29 +80,24 @@ __device__ __forceinline__ void load_tables(float2* s_tw, float* s_win, const fl
     }
 }
 
-// Stage `count` samples x[first .. first+count) of a signal of length n (zero outside) into
-// shared memory.  `first` may be negative (centre padding).
-__device__ __forceinline__ void stage_samples(float* s_stage, const float* __restrict__ x,
-                                              int64_t n, int64_t first, int count) {
-    const bool vec_ok = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((first & 3) == 0);
-    if (vec_ok) {
+// Asynchronously stage samples x[src0 .. src0+count) (zero outside [lo, hi)) into shared memory.
+__device__ __forceinline__ void stage_async(float* s_stage, const float* __restrict__ x,
+                                            const spev_tile& d) {
+    const int count = (d.n - 1) * kHop + kNfft;
+    const int64_t first = d.src0, lo = d.lo, hi = d.hi;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((lo & 3) == 0);
+    if (vec_ok) {   // lo % 4 == 0 and first == lo (mod 4): a float4 never straddles `lo`
         for (int i = threadIdx.x * 4; i < count; i += blockDim.x * 4) {
             const int64_t g = first + i;
-            float4 v;
-            if (g >= 0 && g + 3 < n) {
-                v = __ldg(reinterpret_cast<const float4*>(x + g));
-            } else {
-                v.x = (g >= 0 && g < n) ? __ldg(x + g) : 0.f;
-                v.y = (g + 1 >= 0 && g + 1 < n) ? __ldg(x + g + 1) : 0.f;
-                v.z = (g + 2 >= 0 && g + 2 < n) ? __ldg(x + g + 2) : 0.f;
-                v.w = (g + 3 >= 0 && g + 3 < n) ? __ldg(x + g + 3) : 0.f;
-            }
-            *reinterpret_cast<float4*>(s_stage + i) = v;
+            int64_t nb = g < lo ? 0 : (hi - g) * 4;
+            nb = nb < 0 ? 0 : (nb > 16 ? 16 : nb);
+            cp_async16(s_stage + i, nb > 0 ? x + g : x, static_cast<int>(nb));
         }
     } else {
         for (int i = threadIdx.x; i < count; i += blockDim.x) {
             const int64_t g = first + i;
-            s_stage[i] = (g >= 0 && g < n) ? __ldg(x + g) : 0.f;
+            const bool ok = g >= lo && g < hi;
+            cp_async4(s_stage + i, ok ? x + g : x, ok ? 4 : 0);
         }
     }
 }
@@ -99,6 +116,17 @@ __device__ __forceinline__ void load_frame_pair(float2 (&v)[32], const float* s_
     });
 }
 
+// Persistent-loop bookkeeping shared by the kernels: prologue of the descriptor ring.
+__device__ __forceinline__ int ring_prologue(spev_tile* s_ring, const spev_tile* tiles, int n_tiles) {
+    const int first = blockIdx.x, stride = gridDim.x;
+    const int my_n = first < n_tiles ? (n_tiles - first + stride - 1) / stride : 0;
+    for (int j = 0; j < 3 && j < my_n; ++j) fetch_desc(s_ring + j, tiles + first + j * stride);
+    cp_async_commit();
+    cp_async_wait_all();
+    __syncthreads();
+    return my_n;
+}
+
 // ---------------------------------------------------------------------------------------
 // K1: fused STFT -> power -> mel -> log
 // ---------------------------------------------------------------------------------------
@@ -110,8 +138,9 @@ k_stft_mel(BatchView bv, const float* __restrict__ samples, float* __restrict__ 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* s_tw = reinterpret_cast<float2*>(smem_raw);
     float* s_win = reinterpret_cast<float*>(s_tw + 1024);
-    float* s_stage = s_win + 1024;
-    float* s_x = s_stage + kStageSamples;
+    spev_tile* s_ring = reinterpret_cast<spev_tile*>(s_win + 1024);
+    float* s_stage = reinterpret_cast<float*>(s_ring + kRing);
+    float* s_x = s_stage + 2 * kStageSamples;
     int* s_bstart = reinterpret_cast<int*>(s_x + kWarps * kWarpRegionWords);
     int* s_blen = s_bstart + mb.n_mels;
     int* s_bwoff = s_blen + mb.n_mels;
@@ -128,31 +157,35 @@ k_stft_mel(BatchView bv, const float* __restrict__ samples, float* __restrict__ 
     float* xw = s_x + warp * kWarpRegionWords;
     const int n_mels = mb.n_mels;
     const int out_pitch = n_mels + 1;
+    // output copy mapping: thread <-> (frame residue, mel bin), fixed for the whole kernel
+    const int rows_per_pass = kThreads / n_mels;
+    const int cp_m = threadIdx.x % n_mels, cp_f0 = threadIdx.x / n_mels;
 
-    for (int tile = blockIdx.x; tile < bv.n_ftiles; tile += gridDim.x) {
-        const int item = bv.ftile_item[tile];
-        const int t0 = bv.ftile_t0[tile];
-        const int64_t fo = bv.frame_off[item];
-        const int T = static_cast<int>(bv.frame_off[item + 1] - fo);
-        const int nf = min(kTileFrames, T - t0);
-        const int64_t so = bv.sample_off[item];
-        const int64_t n = bv.sample_off[item + 1] - so;
+    const int stride = gridDim.x;
+    const int my_n = ring_prologue(s_ring, bv.ftiles, bv.n_ftiles);
+    if (my_n > 0) stage_async(s_stage, samples, s_ring[0]);
+    cp_async_commit();
 
-        __syncthreads();   // previous tile fully consumed (s_stage alias, s_x); tables loaded
-        stage_samples(s_stage, samples + so, n, static_cast<int64_t>(t0) * kHop - kNfft / 2,
-                      (nf - 1) * kHop + kNfft);
-        __syncthreads();
+    for (int i = 0; i < my_n; ++i) {
+        cp_async_wait_all();
+        __syncthreads();   // B1: tile i staged + visible; previous tile fully consumed
+        const int nf = s_ring[i & 3].n;
+        const int64_t row0 = s_ring[i & 3].row0;
+        if (i + 1 < my_n) stage_async(s_stage + ((i + 1) & 1) * kStageSamples, samples, s_ring[(i + 1) & 3]);
+        if (i + 3 < my_n) fetch_desc(s_ring + ((i + 3) & 3), bv.ftiles + blockIdx.x + (i + 3) * stride);
+        cp_async_commit();
+        float* stage = s_stage + (i & 1) * kStageSamples;
 
         const int fa = 2 * warp;
         if (fa < nf) {
             const bool b_valid = fa + 1 < nf;
             float2 v[32];
-            load_frame_pair(v, s_stage, s_win, fa, b_valid, lane);
+            load_frame_pair(v, stage, s_win, fa, b_valid, lane);
             warp_fft1024<-1>(v, reinterpret_cast<float2*>(xw), s_tw, lane);
             float2 p[16];
             fetch_mirror(v, p, lane);
             __syncwarp();   // transpose tile is dead; reuse it for |X|^2
-            float pa512 = v[16].x * v[16].x, pb512 = v[16].y * v[16].y;   // lane 0: bin 512
+            const float pa512 = v[16].x * v[16].x, pb512 = v[16].y * v[16].y;   // lane 0: bin 512
             if (MODE == 0) {
                 static_for<0, 16>([&](auto kc) {
                     constexpr int k2 = decltype(kc)::value;
@@ -163,7 +196,7 @@ k_stft_mel(BatchView bv, const float* __restrict__ samples, float* __restrict__ 
                 });
                 if (lane == 0) { xw[512] = pa512; xw[kBins + 512] = pb512; }
             } else {
-                float* oa = out + (fo + t0 + fa) * kSpecLd;
+                float* oa = out + (row0 + fa) * kSpecLd;
                 float* ob = oa + kSpecLd;
                 static_for<0, 16>([&](auto kc) {
                     constexpr int k2 = decltype(kc)::value;
@@ -179,9 +212,9 @@ k_stft_mel(BatchView bv, const float* __restrict__ samples, float* __restrict__ 
             }
         }
         if (MODE == 0) {
-            __syncthreads();   // all |X|^2 written; s_stage no longer read
+            __syncthreads();   // B2: all |X|^2 written; this tile's samples no longer read
             // mel phase: lane <-> frame (conflict-free: bank = frame + bin), warp <-> band set
-            float* s_out = s_stage;
+            float* s_out = stage;
             if (lane < nf) {
                 const float* pf = s_x + (lane >> 1) * kWarpRegionWords + (lane & 1) * kBins;
                 for (int m = warp; m < n_mels; m += kWarps) {
@@ -189,18 +222,16 @@ k_stft_mel(BatchView bv, const float* __restrict__ samples, float* __restrict__ 
                     const float* pp = pf + s_bstart[m];
                     const int len = s_blen[m];
                     float acc = 0.f;
+#pragma unroll 4
                     for (int j = 0; j < len; ++j) acc = fmaf(pw[j], pp[j], acc);
                     if (log_mode) acc = fminf(fmaxf(logf(fmaxf(acc, floor_v)), lo), hi);
                     s_out[lane * out_pitch + m] = acc;
                 }
             }
-            __syncthreads();
-            float* o = out + (fo + t0) * n_mels;
-            const int total = nf * n_mels;
-            for (int i = threadIdx.x; i < total; i += blockDim.x) {
-                const int f = i / n_mels, m = i - f * n_mels;
-                o[i] = s_out[f * out_pitch + m];
-            }
+            __syncthreads();   // B3
+            float* o = out + row0 * n_mels;
+            if (cp_f0 < rows_per_pass)
+                for (int f = cp_f0; f < nf; f += rows_per_pass) o[f * n_mels + cp_m] = s_out[f * out_pitch + cp_m];
         }
     }
 }
@@ -208,73 +239,93 @@ k_stft_mel(BatchView bv, const float* __restrict__ samples, float* __restrict__ 
 // ---------------------------------------------------------------------------------------
 // K5: STFT (+ Griffin-Lim phase update)
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void phase_update_store(float2 reb, float s, float2* __restrict__ ang,
-                                                   float2* __restrict__ tprev, int64_t idx,
-                                                   float alpha, int has_prev) {
+__device__ __forceinline__ float2 phase_of(float2 reb, float s, float2 tp, float alpha, int has_prev) {
     float2 a = reb;
     if (has_prev) {
-        const float2 tp = tprev[idx];
         a.x = a.x - alpha * tp.x;
         a.y = a.y - alpha * tp.y;
     }
     const float den = sqrtf(fmaf(a.x, a.x, a.y * a.y)) + kTiny;
-    const float r = 1.0f / den;   // numpy complex/real division: multiply by the reciprocal
-    ang[idx] = make_float2(a.x * r * s, a.y * r * s);
-    tprev[idx] = reb;
+    const float r = 1.0f / den;   // numpy complex/real division multiplies by the reciprocal
+    return make_float2(a.x * r * s, a.y * r * s);
 }
 
 template <int MODE>   // 0: plain STFT into `ang`; 1: Griffin-Lim phase update
 __global__ void __launch_bounds__(kThreads, 1)
 k_stft_phase(BatchView bv, const float* __restrict__ y, const float* __restrict__ S, int64_t ld_s,
-             float2* __restrict__ ang, float2* __restrict__ tprev, int64_t ld, float alpha,
+             float2* __restrict__ ang, float2* tprev, int64_t ld, float alpha,
              int has_prev, const float2* __restrict__ g_tw, const float* __restrict__ g_win) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* s_tw = reinterpret_cast<float2*>(smem_raw);
     float* s_win = reinterpret_cast<float*>(s_tw + 1024);
-    float* s_stage = s_win + 1024;
-    float* s_x = s_stage + kStageSamples;
+    spev_tile* s_ring = reinterpret_cast<spev_tile*>(s_win + 1024);
+    float* s_stage = reinterpret_cast<float*>(s_ring + kRing);
+    float* s_x = s_stage + 2 * kStageSamples;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     load_tables(s_tw, s_win, g_tw, g_win);
     float2* xw = reinterpret_cast<float2*>(s_x + warp * kWarpRegionWords);
 
-    for (int tile = blockIdx.x; tile < bv.n_ftiles; tile += gridDim.x) {
-        const int item = bv.ftile_item[tile];
-        const int t0 = bv.ftile_t0[tile];
-        const int64_t fo = bv.frame_off[item];
-        const int T = static_cast<int>(bv.frame_off[item + 1] - fo);
-        const int nf = min(kTileFrames, T - t0);
-        const int64_t yo = (fo - item) * kHop;
-        const int64_t n = static_cast<int64_t>(T - 1) * kHop;
+    const int stride = gridDim.x;
+    const int my_n = ring_prologue(s_ring, bv.ftiles, bv.n_ftiles);
+    if (my_n > 0) stage_async(s_stage, y, s_ring[0]);
+    cp_async_commit();
 
+    for (int i = 0; i < my_n; ++i) {
+        cp_async_wait_all();
         __syncthreads();
-        stage_samples(s_stage, y + yo, n, static_cast<int64_t>(t0) * kHop - kNfft / 2,
-                      (nf - 1) * kHop + kNfft);
-        __syncthreads();
+        const int nf = s_ring[i & 3].n;
+        const int64_t row0 = s_ring[i & 3].row0;
+        if (i + 1 < my_n) stage_async(s_stage + ((i + 1) & 1) * kStageSamples, y, s_ring[(i + 1) & 3]);
+        if (i + 3 < my_n) fetch_desc(s_ring + ((i + 3) & 3), bv.ftiles + blockIdx.x + (i + 3) * stride);
+        cp_async_commit();
+        const float* stage = s_stage + (i & 1) * kStageSamples;
 
         const int fa = 2 * warp;
         if (fa < nf) {
             const bool b_valid = fa + 1 < nf;
             float2 v[32];
-            load_frame_pair(v, s_stage, s_win, fa, b_valid, lane);
+            load_frame_pair(v, stage, s_win, fa, b_valid, lane);
             warp_fft1024<-1>(v, xw, s_tw, lane);
             float2 p[16];
             fetch_mirror(v, p, lane);
-            const int64_t ra = (fo + t0 + fa) * ld;        // row of frame a in ang / tprev
+            const int64_t ra = (row0 + fa) * ld;        // row of frame a in ang / tprev
             const int64_t rb = ra + ld;
-            const float* sa = S + (fo + t0 + fa) * ld_s;
+            const float* sa = S + (row0 + fa) * ld_s;
             const float* sb = sa + ld_s;
-            static_for<0, 16>([&](auto kc) {
-                constexpr int k2 = decltype(kc)::value;
-                const int k = lane + 32 * k2;
-                float2 xa, xb;
-                split_pair(v[k2], p[k2], xa, xb);
-                if (MODE == 0) {
-                    ang[ra + k] = xa;
-                    if (b_valid) ang[rb + k] = xb;
-                } else {
-                    phase_update_store(xa, sa[k], ang, tprev, ra + k, alpha, has_prev);
-                    if (b_valid) phase_update_store(xb, sb[k], ang, tprev, rb + k, alpha, has_prev);
+            // four groups of four bins-per-lane: all loads of a group are issued before its
+            // arithmetic so that 16 independent requests per thread are in flight
+            static_for<0, 4>([&](auto gc) {
+                constexpr int g = decltype(gc)::value;
+                float2 tpa[4], tpb[4];
+                float s_a[4], s_b[4];
+                if (MODE == 1) {
+                    static_for<0, 4>([&](auto qc) {
+                        constexpr int q = decltype(qc)::value;
+                        const int k = lane + 32 * (4 * g + q);
+                        s_a[q] = sa[k];
+                        s_b[q] = b_valid ? sb[k] : 0.f;
+                        tpa[q] = has_prev ? tprev[ra + k] : make_float2(0.f, 0.f);
+                        tpb[q] = (has_prev && b_valid) ? tprev[rb + k] : make_float2(0.f, 0.f);
+                    });
                 }
+                static_for<0, 4>([&](auto qc) {
+                    constexpr int q = decltype(qc)::value;
+                    constexpr int k2 = 4 * g + q;
+                    const int k = lane + 32 * k2;
+                    float2 xa, xb;
+                    split_pair(v[k2], p[k2], xa, xb);
+                    if (MODE == 0) {
+                        ang[ra + k] = xa;
+                        if (b_valid) ang[rb + k] = xb;
+                    } else {
+                        ang[ra + k] = phase_of(xa, s_a[q], tpa[q], alpha, has_prev);
+                        tprev[ra + k] = xa;
+                        if (b_valid) {
+                            ang[rb + k] = phase_of(xb, s_b[q], tpb[q], alpha, has_prev);
+                            tprev[rb + k] = xb;
+                        }
+                    }
+                });
             });
             if (lane == 0) {
                 const float2 xa = make_float2(v[16].x, 0.f), xb = make_float2(v[16].y, 0.f);
@@ -282,8 +333,13 @@ k_stft_phase(BatchView bv, const float* __restrict__ y, const float* __restrict_
                     ang[ra + 512] = xa;
                     if (b_valid) ang[rb + 512] = xb;
                 } else {
-                    phase_update_store(xa, sa[512], ang, tprev, ra + 512, alpha, has_prev);
-                    if (b_valid) phase_update_store(xb, sb[512], ang, tprev, rb + 512, alpha, has_prev);
+                    const float2 z = make_float2(0.f, 0.f);
+                    ang[ra + 512] = phase_of(xa, sa[512], has_prev ? tprev[ra + 512] : z, alpha, has_prev);
+                    tprev[ra + 512] = xa;
+                    if (b_valid) {
+                        ang[rb + 512] = phase_of(xb, sb[512], has_prev ? tprev[rb + 512] : z, alpha, has_prev);
+                        tprev[rb + 512] = xb;
+                    }
                 }
             }
         }
@@ -299,28 +355,31 @@ k_istft(BatchView bv, const float2* __restrict__ spec, int64_t ld, float* __rest
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* s_tw = reinterpret_cast<float2*>(smem_raw);
     float* s_win = reinterpret_cast<float*>(s_tw + 1024);
-    float* s_x = s_win + 1024;
+    spev_tile* s_ring = reinterpret_cast<spev_tile*>(s_win + 1024);
+    float* s_x = reinterpret_cast<float*>(s_ring + kRing);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     load_tables(s_tw, s_win, g_tw, g_win);
     float* xw = s_x + warp * kWarpRegionWords;
     const int pl = (32 - lane) & 31;
 
-    for (int tile = blockIdx.x; tile < bv.n_ctiles; tile += gridDim.x) {
-        const int item = bv.ctile_item[tile];
-        const int c0 = bv.ctile_c0[tile];
-        const int64_t fo = bv.frame_off[item];
-        const int T = static_cast<int>(bv.frame_off[item + 1] - fo);
-        const int nchunks = min(kTileChunks, (T - 1) - c0);
-        const int64_t yo = (fo - item) * kHop;
+    const int stride = gridDim.x;
+    const int my_n = ring_prologue(s_ring, bv.ctiles, bv.n_ctiles);
 
-        __syncthreads();   // previous tile's gather finished (and tables loaded)
+    for (int i = 0; i < my_n; ++i) {
+        cp_async_wait_all();
+        __syncthreads();   // previous tile's gather finished; descriptor i visible
+        const spev_tile d = s_ring[i & 3];
+        if (i + 3 < my_n) fetch_desc(s_ring + ((i + 3) & 3), bv.ctiles + blockIdx.x + (i + 3) * stride);
+        cp_async_commit();
+        const int c0 = d.t0, T = d.T, nchunks = d.n;
+
         // local frame lf <-> item frame t = c0 - 1 + lf ; needed: lf in [0, nchunks + 3)
         const int lfa = 2 * warp;
         const int ta = c0 - 1 + lfa, tb = ta + 1;
         const bool a_valid = lfa < nchunks + 3 && ta >= 0 && ta < T;
         const bool b_valid = lfa + 1 < nchunks + 3 && tb >= 0 && tb < T;
         if (a_valid || b_valid) {
-            const float2* A = spec + (fo + ta) * ld;
+            const float2* A = spec + (d.row0 + lfa) * ld;
             const float2* B = A + ld;
             float2 v[32];
             float2 m[16];
@@ -337,15 +396,15 @@ k_istft(BatchView bv, const float2* __restrict__ spec, int64_t ld, float* __rest
             const float nyq_a = a_valid ? A[512].x : 0.f;            // irfft ignores Im(Nyquist)
             const float nyq_b = b_valid ? B[512].x : 0.f;
             static_for<0, 16>([&](auto ic) {
-                constexpr int i = decltype(ic)::value;
+                constexpr int ii = decltype(ic)::value;
                 float2 r;
-                r.x = __shfl_sync(0xffffffffu, m[15 - i].x, pl);
-                r.y = __shfl_sync(0xffffffffu, m[15 - i].y, pl);
+                r.x = __shfl_sync(0xffffffffu, m[15 - ii].x, pl);
+                r.y = __shfl_sync(0xffffffffu, m[15 - ii].y, pl);
                 if (lane == 0) {
-                    if constexpr (i == 0) r = make_float2(nyq_a, nyq_b);
-                    else r = m[16 - i];
+                    if constexpr (ii == 0) r = make_float2(nyq_a, nyq_b);
+                    else r = m[16 - ii];
                 }
-                v[16 + i] = r;
+                v[16 + ii] = r;
             });
             warp_fft1024<1>(v, reinterpret_cast<float2*>(xw), s_tw, lane);
             __syncwarp();   // transpose tile dead -> reuse for the two windowed real frames
@@ -361,23 +420,23 @@ k_istft(BatchView bv, const float2* __restrict__ spec, int64_t ld, float* __rest
         // gather: chunk c = c0 + cl receives frames c-1, c, c+1, c+2 (ascending), local cl..cl+3
         for (int cl = warp; cl < nchunks; cl += kWarps) {
             const int c = c0 + cl;
-            float* yo_c = y + yo + static_cast<int64_t>(c) * kHop;
+            float* yo_c = y + d.src0 + static_cast<int64_t>(cl) * kHop;
 #pragma unroll
             for (int ii = 0; ii < kHop / 32; ++ii) {
-                const int i = lane + 32 * ii;
+                const int s = lane + 32 * ii;
                 float sum = 0.f, wss = 0.f;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int t = c - 1 + q;
                     if (t >= 0 && t < T) {
                         const int lf = cl + q;
-                        const int nn = 768 - 256 * q + i;
+                        const int nn = 768 - 256 * q + s;
                         sum += s_x[(lf >> 1) * kWarpRegionWords + (lf & 1) * kNfft + nn];
                         const float w = s_win[nn];
                         wss = fmaf(w, w, wss);
                     }
                 }
-                yo_c[i] = wss > kTiny ? sum / wss : sum;
+                yo_c[s] = wss > kTiny ? sum / wss : sum;
             }
         }
     }
@@ -424,11 +483,9 @@ k_mel_to_mag(BatchView bv, const float* __restrict__ mel, int layout, int is_log
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* s_m = reinterpret_cast<float*>(smem_raw);   // [kMagFrames][n_mels]
     for (int tile = blockIdx.x; tile < bv.n_ftiles; tile += gridDim.x) {
-        const int item = bv.ftile_item[tile];
-        const int t0 = bv.ftile_t0[tile];
-        const int64_t fo = bv.frame_off[item];
-        const int T = static_cast<int>(bv.frame_off[item + 1] - fo);
-        const int nf = min(kTileFrames, T - t0);
+        const spev_tile d = bv.ftiles[tile];
+        const int t0 = d.t0, T = d.T, nf = d.n;
+        const int64_t fo = d.row0 - t0;   // first row of the item
         for (int h0 = 0; h0 < nf; h0 += kMagFrames) {
             const int nh = min(kMagFrames, nf - h0);
             __syncthreads();
@@ -457,7 +514,7 @@ k_mel_to_mag(BatchView bv, const float* __restrict__ mel, int layout, int is_log
                 }
 #pragma unroll
                 for (int f = 0; f < kMagFrames; ++f)
-                    if (f < nh) S[(fo + t0 + h0 + f) * ld_s + k] = sqrtf(fmaxf(acc[f], 0.f));
+                    if (f < nh) S[(d.row0 + h0 + f) * ld_s + k] = sqrtf(fmaxf(acc[f], 0.f));
             }
         }
     }
@@ -466,13 +523,12 @@ k_mel_to_mag(BatchView bv, const float* __restrict__ mel, int layout, int is_log
 // ---------------------------------------------------------------------------------------
 // host-side launchers
 // ---------------------------------------------------------------------------------------
+static size_t smem_common() { return sizeof(float2) * 1024 + sizeof(float) * 1024 + sizeof(spev_tile) * kRing; }
 static size_t smem_stft(int n_mels, int nnz) {
-    return sizeof(float2) * 1024 + sizeof(float) * 1024 + sizeof(float) * kStageSamples +
-           sizeof(float) * kWarps * kWarpRegionWords + sizeof(int) * 3 * n_mels + sizeof(float) * nnz;
+    return smem_common() + sizeof(float) * 2 * kStageSamples + sizeof(float) * kWarps * kWarpRegionWords +
+           sizeof(int) * 3 * n_mels + sizeof(float) * nnz;
 }
-static size_t smem_istft() {
-    return sizeof(float2) * 1024 + sizeof(float) * 1024 + sizeof(float) * kWarps * kWarpRegionWords;
-}
+static size_t smem_istft() { return smem_common() + sizeof(float) * kWarps * kWarpRegionWords; }
 
 template <class K>
 static int set_smem(K kernel, size_t bytes) {
@@ -481,30 +537,28 @@ static int set_smem(K kernel, size_t bytes) {
     return SPEV_OK;
 }
 
-static int check_batch(const spev_ctx* ctx, const spev_batch* b, bool need_samples, bool need_ctiles) {
+static int check_batch(const spev_ctx* ctx, const spev_batch* b, bool need_ctiles) {
     SPEV_REQUIRE(ctx && b, SPEV_E_INVALID, "null ctx or batch");
-    SPEV_REQUIRE(b->n_items >= 0 && b->n_frames >= 0 && b->n_ftiles >= 0, SPEV_E_INVALID,
+    SPEV_REQUIRE(b->n_items >= 0 && b->n_frames >= 0 && b->n_ftiles >= 0 && b->n_ctiles >= 0, SPEV_E_INVALID,
                  "negative batch sizes");
-    if (b->n_items > 0) {
-        SPEV_REQUIRE(b->frame_off && b->ftile_item && b->ftile_t0, SPEV_E_INVALID,
-                     "batch offset/tile tables missing");
-        SPEV_REQUIRE(!need_samples || b->sample_off, SPEV_E_INVALID, "batch.sample_off missing");
-        SPEV_REQUIRE(!need_ctiles || b->n_ctiles == 0 || (b->ctile_item && b->ctile_c0),
-                     SPEV_E_INVALID, "batch chunk-tile tables missing");
-    }
+    SPEV_REQUIRE(b->n_ftiles == 0 || b->ftiles, SPEV_E_INVALID, "batch.ftiles missing");
+    SPEV_REQUIRE(!need_ctiles || b->n_ctiles == 0 || b->ctiles, SPEV_E_INVALID, "batch.ctiles missing");
+    SPEV_REQUIRE((reinterpret_cast<uintptr_t>(b->ftiles) & 15) == 0 && (reinterpret_cast<uintptr_t>(b->ctiles) & 15) == 0,
+                 SPEV_E_INVALID, "tile tables must be 16-byte aligned");
     return SPEV_OK;
 }
 
 int launch_stft_mel(spev_ctx* ctx, const spev_batch* b, const float* samples, float* out,
                     bool power_only, int log_mode, float floor_v, float lo, float hi,
                     cudaStream_t st) {
-    int rc = check_batch(ctx, b, true, false);
+    int rc = check_batch(ctx, b, false);
     if (rc) return rc;
     if (b->n_ftiles == 0) return SPEV_OK;
     SPEV_REQUIRE(samples && out, SPEV_E_INVALID, "null samples/out");
     MelBands mb{ctx->n_mels, ctx->band_nnz, ctx->d_band_start, ctx->d_band_len, ctx->d_band_woff,
                 ctx->d_band_w};
     const size_t smem = smem_stft(ctx->n_mels, ctx->band_nnz);
+    SPEV_REQUIRE(smem <= 232448, SPEV_E_UNSUPPORTED, "mel basis too large for the fused kernel (%zu B smem)", smem);
     const int grid = std::min<int64_t>(b->n_ftiles, ctx->num_sms);
     if (power_only) {
         rc = set_smem(k_stft_mel<1>, smem);
@@ -524,7 +578,7 @@ int launch_stft_mel(spev_ctx* ctx, const spev_batch* b, const float* samples, fl
 int launch_stft_phase(spev_ctx* ctx, const spev_batch* b, const float* y, const float* S,
                       int64_t ld_s, void* ang, void* tprev, int64_t ld, float alpha, int has_prev,
                       bool phase, cudaStream_t st) {
-    int rc = check_batch(ctx, b, false, false);
+    int rc = check_batch(ctx, b, false);
     if (rc) return rc;
     if (b->n_ftiles == 0) return SPEV_OK;
     SPEV_REQUIRE(y && ang && ld >= kBins, SPEV_E_INVALID, "stft: null buffer or ld < 513");
@@ -551,7 +605,7 @@ int launch_stft_phase(spev_ctx* ctx, const spev_batch* b, const float* y, const 
 
 int launch_istft(spev_ctx* ctx, const spev_batch* b, const void* spec, int64_t ld, float* y,
                  cudaStream_t st) {
-    int rc = check_batch(ctx, b, false, true);
+    int rc = check_batch(ctx, b, true);
     if (rc) return rc;
     if (b->n_ctiles == 0) return SPEV_OK;
     SPEV_REQUIRE(spec && y && ld >= kBins, SPEV_E_INVALID, "istft: null buffer or ld < 513");
@@ -577,7 +631,7 @@ int launch_gl_init(spev_ctx* ctx, const float* S, int64_t ld_s, const float* pha
 
 int launch_mel_to_mag(spev_ctx* ctx, const spev_batch* b, const float* mel, int layout, int is_log,
                       float* S, int64_t ld_s, cudaStream_t st) {
-    int rc = check_batch(ctx, b, false, false);
+    int rc = check_batch(ctx, b, false);
     if (rc) return rc;
     if (b->n_ftiles == 0) return SPEV_OK;
     SPEV_REQUIRE(mel && S && ld_s >= kBins, SPEV_E_INVALID, "mel_to_mag: null buffer or ld < 513");

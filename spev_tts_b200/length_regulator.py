@@ -29,6 +29,18 @@ class LengthPlan:
         self.cumsum, self.mel_lens, self.max_len, self.B, self.T = cumsum, mel_lens, max_len, B, T
 
 
+_pinned_scalars: dict = {}
+
+
+def _pinned_scalar(dev: torch.device) -> torch.Tensor:
+    """one pinned int64 per device, reused (cudaHostAlloc costs more than the two kernels)"""
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    t = _pinned_scalars.get(key)
+    if t is None:
+        t = _pinned_scalars[key] = torch.empty((1,), dtype=torch.int64).pin_memory()
+    return t
+
+
 def _require_cuda(t: torch.Tensor, what: str):
     if not t.is_cuda:
         raise RuntimeError(f"spev_tts_b200.LengthRegulator: {what} must be a CUDA tensor "
@@ -51,7 +63,7 @@ def plan(durations: torch.Tensor) -> LengthPlan:
     cumsum = torch.empty((B, T), dtype=torch.int32, device=dev)
     mel_lens = torch.empty((B,), dtype=torch.int64, device=dev)
     max_dev = torch.empty((1,), dtype=torch.int64, device=dev)
-    max_host = torch.empty((1,), dtype=torch.int64).pin_memory()
+    max_host = _pinned_scalar(dev)
     st = torch.cuda.current_stream(dev)
     with torch.cuda.device(dev):
         _lib.check(lib.spev_lr_plan(durations.data_ptr(), _DUR_DTYPES[durations.dtype], B, T,

@@ -57,17 +57,33 @@ def test_host_constants_match_oracle():
 
 
 def test_plan_tiles_c_vs_numpy():
+    """spev_plan_frame_tiles / spev_plan_chunk_tiles (C) == the vectorised numpy twins."""
     import spev_tts_b200 as sp
+    from spev_tts_b200 import batch as B
     lib = sp.load()
     rng = np.random.default_rng(0)
-    counts = rng.integers(0, 200, 50).astype(np.int64)
-    for per in (32, 29, 1):
-        n = lib.spev_plan_tiles(counts.ctypes.data, len(counts), per, None, None)
-        ti = np.empty(n, np.int32); ts = np.empty(n, np.int32)
-        assert lib.spev_plan_tiles(counts.ctypes.data, len(counts), per, ti.ctypes.data, ts.ctypes.data) == n
-        pi, ps = sp.plan_tiles(counts, per)
-        assert np.array_equal(ti, pi) and np.array_equal(ts, ps)
-        assert n == int(((counts + per - 1) // per).sum())
+    ns = rng.integers(0, 200 * 256, 50).astype(np.int64)
+    ns[:4] = [0, 255, 256, 32 * 256]
+    frames = 1 + ns // 256
+    starts = np.concatenate([[0], np.cumsum((ns + 3) // 4 * 4)])[:-1].astype(np.int64)
+    for lo, n in ((starts, ns), (None, None)):
+        cnt = lib.spev_plan_frame_tiles(frames.ctypes.data, lo.ctypes.data if lo is not None else None,
+                                        n.ctypes.data if n is not None else None, len(frames), None)
+        out = np.zeros(cnt, dtype=B.TILE_DTYPE)
+        assert lib.spev_plan_frame_tiles(frames.ctypes.data, lo.ctypes.data if lo is not None else None,
+                                         n.ctypes.data if n is not None else None, len(frames),
+                                         out.ctypes.data) == cnt
+        ref = B.plan_frame_tiles(frames, lo, n, 32)
+        assert cnt == len(ref) == int(((frames + 31) // 32).sum())
+        assert out.tobytes() == ref.tobytes()
+    cnt = lib.spev_plan_chunk_tiles(frames.ctypes.data, len(frames), None)
+    out = np.zeros(cnt, dtype=B.TILE_DTYPE)
+    assert lib.spev_plan_chunk_tiles(frames.ctypes.data, len(frames), out.ctypes.data) == cnt
+    ref = B.plan_chunk_tiles(frames, 29)
+    assert out.tobytes() == ref.tobytes() and cnt == int(((frames - 1 + 28) // 29).sum())
+    # every frame / chunk covered exactly once
+    assert B.plan_frame_tiles(frames)["n"].sum() == frames.sum()
+    assert ref["n"].sum() == (frames - 1).sum()
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")

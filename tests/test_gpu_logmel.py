@@ -72,13 +72,36 @@ def test_ragged_batch_edges(cuda):
         got = out[fb.frame_off[i]: fb.frame_off[i + 1]]
         assert got.shape == ref.shape
         assert np.abs(got - ref).max() <= TOL_LOGMEL, (i, lens[i])
-    # aligned packing (zero-filled gaps, every item start % 4 == 0) takes the float4 path
-    starts = np.concatenate([[0], np.cumsum([(n + 3) // 4 * 4 for n in lens])]).astype(np.int64)
-    buf = np.zeros(starts[-1], dtype=np.float32)
+    # aligned packing (every item start % 4 == 0) takes the 16-byte cp.async path; the filler
+    # between items is garbage on purpose: explicit [lo, hi) bounds keep it out of the signal
+    from spev_tts_b200 import cache
+    starts = cache.aligned_offsets(lens)
+    buf = np.full(starts[-1] + 8, 1e6, dtype=np.float32)
     for s, y in zip(starts[:-1], ys):
         buf[s: s + len(y)] = y
     out2, _ = sp.logmel_flat(torch.from_numpy(buf).to(cuda), lens, sample_off=starts)
     assert np.array_equal(out2.cpu().numpy(), out)
+
+
+def test_pipelined_host_builder_matches_device_path(cuda):
+    """LogMelCacheBuilder (pinned host in -> chunked H2D/kernel/D2H -> pinned host out) must give
+    exactly the one-launch device result, for aligned and back-to-back packing."""
+    import spev_tts_b200 as sp
+    from spev_tts_b200 import cache
+    lens = synth.utterance_lengths(seed=14, n_utts=300)
+    rng = np.random.default_rng(14)
+    ys = [(0.05 * rng.standard_normal(int(n))).astype(np.float32) for n in lens]
+    flat = torch.from_numpy(np.concatenate(ys))
+    ref, fb = sp.logmel_flat(flat.to(cuda), lens)
+    out, fo = cache.build_logmel_cache(flat.pin_memory(), lens, device=cuda, chunk_samples=1 << 20)
+    assert np.array_equal(fo, fb.frame_off) and torch.equal(out.to(cuda), ref)
+    starts = cache.aligned_offsets(lens)
+    buf = torch.full((int(starts[-1]),), 7.0)
+    for s, y in zip(starts[:-1], ys):
+        buf[s: s + len(y)] = torch.from_numpy(y)
+    out2, _ = cache.build_logmel_cache(buf.pin_memory(), lens, device=cuda, chunk_samples=1 << 20,
+                                       sample_off=starts)
+    assert torch.equal(out2, out)
 
 
 def test_cfg4_scale_properties(cuda):
