@@ -63,6 +63,15 @@ __device__ __forceinline__ void cp_async4(void* smem, const void* gmem, int src_
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
+// Warp-cooperative L2 prefetch of [p, p+bytes): moves DRAM->L2 traffic off the critical path
+// (issued at tile start, consumed after the FFT phase), no registers or shared memory needed.
+__device__ __forceinline__ void warp_prefetch_l2(const void* p, int bytes, int lane) {
+    const uintptr_t base = reinterpret_cast<uintptr_t>(p) & ~static_cast<uintptr_t>(127);
+    const int n = static_cast<int>((reinterpret_cast<uintptr_t>(p) + bytes - base + 127) >> 7);
+    for (int i = lane; i < n; i += 32)
+        asm volatile("prefetch.global.L2 [%0];\n" ::"l"(base + (static_cast<uintptr_t>(i) << 7)));
+}
+
 __device__ __forceinline__ void fetch_desc(spev_tile* slot, const spev_tile* g) {
     static_assert(sizeof(spev_tile) == 48, "spev_tile must be 48 bytes");
     if (threadIdx.x == 0) {
@@ -283,6 +292,12 @@ k_stft_phase(BatchView bv, const float* __restrict__ y, const float* __restrict_
         const int fa = 2 * warp;
         if (fa < nf) {
             const bool b_valid = fa + 1 < nf;
+            if (MODE == 1) {   // start pulling this pair's epilogue operands into L2 now
+                const int rows = b_valid ? 2 : 1;
+                warp_prefetch_l2(S + (row0 + fa) * ld_s, static_cast<int>((rows - 1) * ld_s + kBins) * 4, lane);
+                if (has_prev)
+                    warp_prefetch_l2(tprev + (row0 + fa) * ld, static_cast<int>((rows - 1) * ld + kBins) * 8, lane);
+            }
             float2 v[32];
             load_frame_pair(v, stage, s_win, fa, b_valid, lane);
             warp_fft1024<-1>(v, xw, s_tw, lane);
@@ -372,9 +387,19 @@ k_istft(BatchView bv, const float2* __restrict__ spec, int64_t ld, float* __rest
         if (i + 3 < my_n) fetch_desc(s_ring + ((i + 3) & 3), bv.ctiles + blockIdx.x + (i + 3) * stride);
         cp_async_commit();
         const int c0 = d.t0, T = d.T, nchunks = d.n;
+        const int lfa = 2 * warp;
+        if (i + 1 < my_n) {   // pull the next tile's spectra of this warp into L2 during this tile's FFT
+            const spev_tile& nx = s_ring[(i + 1) & 3];
+            const int nta = nx.t0 - 1 + lfa;
+            int r0 = lfa, r1 = lfa + 2;                       // local rows [r0, r1) to prefetch
+            if (nta < 0) r0 += 1;
+            if (r1 > nx.n + 3) r1 = nx.n + 3;
+            if (nta + (r1 - lfa) > nx.T) r1 = lfa + (nx.T - nta);
+            if (r1 > r0)
+                warp_prefetch_l2(spec + (nx.row0 + r0) * ld, static_cast<int>((r1 - r0 - 1) * ld + kBins) * 8, lane);
+        }
 
         // local frame lf <-> item frame t = c0 - 1 + lf ; needed: lf in [0, nchunks + 3)
-        const int lfa = 2 * warp;
         const int ta = c0 - 1 + lfa, tb = ta + 1;
         const bool a_valid = lfa < nchunks + 3 && ta >= 0 && ta < T;
         const bool b_valid = lfa + 1 < nchunks + 3 && tb >= 0 && tb < T;
