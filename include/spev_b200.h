@@ -141,11 +141,16 @@ SPEV_API int spev_mel_project(spev_ctx* ctx, const float* power, int64_t n_frame
  *   mel     : dev float32.  layout 0: [n_frames, n_mels] frame-major flat;
  *             layout 1: per item [n_mels, T_i] at element offset frame_off[i]*n_mels
  *             (the reference's Vocoder.infer input, :725-733)
+ *             layout 0 runs on the tensor cores (TMA + tcgen05 3xTF32, TMEM accumulators);
+ *             layout 1 on an FFMA kernel
  *   is_log  : 1 -> apply exp() first (:729)
  *   S       : dev float32 [n_frames, ld_s]
  * Replaces librosa.feature.inverse.mel_to_stft under :730. */
 SPEV_API int spev_mel_to_mag(spev_ctx* ctx, const spev_batch* batch, const float* mel, int layout,
                     int is_log, float* S, int64_t ld_s, void* stream);
+
+/* A/B switch for the tensor-core path of spev_mel_to_mag (default on): 0 forces the FFMA kernel. */
+SPEV_API int spev_set_tensor_core(spev_ctx* ctx, int enable);
 
 /* ISTFT (irFFT-1024, Hann, gather overlap-add, window-sum-square normalisation).
  *   spec : dev float2 [n_frames, ld] ; y : dev float32, item i at 256*(frame_off[i]-i),

@@ -112,6 +112,10 @@ class Context:
                 cls._cache[key] = ctx
         return ctx
 
+    def set_tensor_core(self, enable: bool) -> None:
+        """A/B switch: False forces the FFMA kernel for the mel->magnitude projection."""
+        _lib.check(self.lib.spev_set_tensor_core(self.handle, 1 if enable else 0), "spev_set_tensor_core")
+
     def mel_basis(self) -> np.ndarray:
         out = np.empty((self.n_mels, _lib.N_BINS), dtype=np.float32)
         _lib.check(self.lib.spev_get_mel_basis(self.handle, out.ctypes.data), "spev_get_mel_basis")

@@ -41,6 +41,7 @@ int launch_lr_expand(const void*, int64_t, const float*, int, const float*, cons
 int launch_duration_rule(const float*, int64_t, float, int64_t*, cudaStream_t);
 int launch_bucketize_embed(const float*, int64_t, const float*, int, int, const float*, int, int64_t*, float*, int, cudaStream_t);
 int launch_mel_project_tc(spev_ctx*, const float*, int64_t, float*, int, float, float, float, cudaStream_t);
+int launch_mel_to_mag_tc(spev_ctx*, const float*, int64_t, int, float*, int64_t, cudaStream_t);
 int gemm_tc_init(spev_ctx*);
 void gemm_tc_destroy(spev_ctx*);
 
@@ -184,7 +185,7 @@ int spev_create(spev_ctx** out, int device, int sr, int n_fft, int hop, int win,
 
     spev_ctx* c = new spev_ctx();
     c->device = device; c->sr = sr; c->n_fft = n_fft; c->hop = hop; c->win = kNfft; c->n_mels = n_mels;
-    c->fmin = fmin; c->fmax = fmax; c->num_sms = prop.multiProcessorCount; c->tma = nullptr;
+    c->fmin = fmin; c->fmax = fmax; c->num_sms = prop.multiProcessorCount; c->tma = nullptr; c->use_tc = 1;
     c->d_tw = nullptr; c->d_window = nullptr; c->d_basis_pad = c->d_basis_hi = c->d_basis_lo = nullptr;
     c->d_pinv_t = c->d_pinv_hi = c->d_pinv_lo = nullptr;
     c->d_band_start = c->d_band_len = c->d_band_woff = nullptr; c->d_band_w = nullptr;
@@ -284,6 +285,12 @@ int spev_host_pinv(const float* a, int m, int n, float* pinv) {
     return SPEV_OK;
 }
 
+int spev_set_tensor_core(spev_ctx* c, int enable) {
+    SPEV_REQUIRE(c, SPEV_E_INVALID, "ctx is null");
+    c->use_tc = enable ? 1 : 0;
+    return SPEV_OK;
+}
+
 int spev_tile_frames(void) { return kTileFrames; }
 int spev_tile_chunks(void) { return kTileChunks; }
 
@@ -357,6 +364,12 @@ int spev_mel_to_mag(spev_ctx* c, const spev_batch* b, const float* mel, int layo
                     float* S, int64_t ld_s, void* stream) {
     int rc = with_device(c);
     if (rc) return rc;
+    SPEV_REQUIRE(b, SPEV_E_INVALID, "spev_mel_to_mag: batch is null");
+    // frame-major input: TMA-staged tcgen05 (3xTF32) GEMM; [n_mels, T] items: FFMA kernel
+    const bool tc_ok = c->use_tc && layout == 0 && c->n_mels % 4 == 0 && ld_s % 4 == 0 && b->n_frames > 0 &&
+                       (reinterpret_cast<uintptr_t>(mel) & 15) == 0 && (reinterpret_cast<uintptr_t>(S) & 15) == 0 &&
+                       ld_s >= kSpecLd;
+    if (tc_ok) return launch_mel_to_mag_tc(c, mel, b->n_frames, is_log, S, ld_s, static_cast<cudaStream_t>(stream));
     return launch_mel_to_mag(c, b, mel, layout, is_log, S, ld_s, static_cast<cudaStream_t>(stream));
 }
 
@@ -392,7 +405,8 @@ int spev_griffinlim(spev_ctx* c, const spev_batch* b, const float* S, int64_t ld
     SPEV_REQUIRE(b, SPEV_E_INVALID, "spev_griffinlim: batch is null");
     SPEV_REQUIRE(n_iter >= 0 && momentum >= 0.f, SPEV_E_INVALID, "spev_griffinlim: need n_iter >= 0, momentum >= 0");
     if (b->n_frames == 0) return SPEV_OK;
-    SPEV_REQUIRE(S && y && ld_s >= kBins, SPEV_E_INVALID, "spev_griffinlim: null S/y or ld_s < 513");
+    SPEV_REQUIRE(S && ld_s >= kBins, SPEV_E_INVALID, "spev_griffinlim: null S or ld_s < 513");
+    SPEV_REQUIRE(y || b->n_ctiles == 0, SPEV_E_INVALID, "spev_griffinlim: y is null");
     SPEV_REQUIRE(workspace && workspace_bytes >= spev_griffinlim_workspace_bytes(b->n_frames), SPEV_E_WORKSPACE,
                  "spev_griffinlim: workspace too small (%zu < %zu)", workspace_bytes,
                  spev_griffinlim_workspace_bytes(b->n_frames));

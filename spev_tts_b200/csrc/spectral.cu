@@ -606,7 +606,9 @@ int launch_stft_phase(spev_ctx* ctx, const spev_batch* b, const float* y, const 
     int rc = check_batch(ctx, b, false);
     if (rc) return rc;
     if (b->n_ftiles == 0) return SPEV_OK;
-    SPEV_REQUIRE(y && ang && ld >= kBins, SPEV_E_INVALID, "stft: null buffer or ld < 513");
+    SPEV_REQUIRE(ang && ld >= kBins, SPEV_E_INVALID, "stft: null buffer or ld < 513");
+    SPEV_REQUIRE(y || b->n_frames == b->n_items, SPEV_E_INVALID, "stft: y is null");
+    if (!y) y = reinterpret_cast<const float*>(ang);   // every item has T == 1 (empty signal): never dereferenced as signal
     const size_t smem = smem_stft(0, 0);
     const int grid = std::min<int64_t>(b->n_ftiles, ctx->num_sms);
     if (phase) {

@@ -71,4 +71,5 @@ struct spev_ctx {
     int band_nnz;
     int band_max_len;
     void* tma;           // opaque: tensor-map cache (gemm_tc.cu)
+    int use_tc;          // mel->magnitude on frame-major input uses the tcgen05 GEMM
 };

@@ -202,7 +202,9 @@ def mel_to_stft(M: ArrayLike, *, sr=22050, n_fft=2048, power=2.0, fmin=0.0, fmax
     b = int(np.prod(lead)) if lead else 1
     ctx = Context.get(t.device, sr=sr, n_mels=n_mels, fmin=fmin, fmax=fmax)
     batch = make_batch(ctx, n_frames=[T] * b)
-    S = mel_to_mag_flat(t.reshape(-1), batch, ctx, layout=1, is_log=False)
+    # [b, n_mels, T] -> frame-major [b*T, n_mels]: the layout the tcgen05 GEMM path takes
+    tm = t.reshape(b, n_mels, T).transpose(1, 2).contiguous().view(-1)
+    S = mel_to_mag_flat(tm, batch, ctx, layout=0, is_log=False)
     out = S.view(b, T, _lib.SPEC_LD)[:, :, : _lib.N_BINS].permute(0, 2, 1).reshape(*lead, _lib.N_BINS, T)
     return _ret(out, was_numpy)
 
@@ -270,7 +272,8 @@ def mel_to_audio(M: ArrayLike, *, sr=22050, n_fft=2048, hop_length=None, win_len
     b = int(np.prod(lead)) if lead else 1
     ctx = Context.get(t.device, sr=sr, n_mels=n_mels, fmin=fmin, fmax=fmax)
     batch = make_batch(ctx, n_frames=[T] * b, with_chunks=True)
-    S = mel_to_mag_flat(t.reshape(-1), batch, ctx, layout=1, is_log=is_log)
+    tm = t.reshape(b, n_mels, T).transpose(1, 2).contiguous().view(-1)   # frame-major -> tensor-core GEMM
+    S = mel_to_mag_flat(tm, batch, ctx, layout=0, is_log=is_log)
     ph = _phase_to_internal(init_phase, b, T, t.device) if init_phase is not None else None
     seed = int(np.random.SeedSequence(random_state).generate_state(2, dtype=np.uint32).view(np.uint64)[0])
     y = griffinlim_flat(S, batch, ctx, n_iter=n_iter, momentum=momentum, init_phase=ph, seed=seed)
