@@ -313,6 +313,7 @@ def run_ours(args):
     # ---------------- gather of shards (the one collective; timed separately) -------------------
     gather = None
     if world > 1:
+        spcache.gather_shards(out[:1024], dst=0)     # warm-up: NCCL P2P connections are set up lazily
         barrier()
         g0 = torch.cuda.Event(enable_timing=True); g1 = torch.cuda.Event(enable_timing=True)
         g0.record()
@@ -326,8 +327,9 @@ def run_ours(args):
         del parts
 
     # ---------------- second half of the metric: Griffin-Lim on cfg3 (rank 0 reports) ------------
-    gl = lr_res = None
+    gl = lr_res = tc = None
     if not args.no_gl:
+        tc = bench_mel_gemm_tc(sp, dev, samples, lens, starts, hbm_peak, out)
         gl = bench_griffinlim(sp, dev, hbm_peak, args)
         lr_res = bench_length_regulator(sp, dev, args)
     del samples, out
@@ -355,12 +357,56 @@ def run_ours(args):
                          "kernel_ms_max_over_ranks": kern_ms_max, "traffic": None,
                          "note": "fp32-pipe/shared-memory bound by design (SURVEY 0.7): ~25 kFLOP FFT per 1,344 B"},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks,
-            "gather": gather, "griffinlim": gl, "length_regulator": lr_res,
+            "gather": gather, "mel_gemm_tc": tc, "griffinlim": gl, "length_regulator": lr_res,
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def bench_mel_gemm_tc(sp, dev, samples, lens, starts, hbm_peak, fused_out):
+    """A/B: the two-kernel tensor-core path (K1' power spectrum -> TMA/tcgen05 3xTF32 mel GEMM) on the
+    same cfg4 shard as the fused kernel.  Tensor 'peak' = measured cuBLAS bf16 / 2 (tf32 rate)."""
+    import torch
+    from spev_tts_b200 import _lib
+    ctx = sp.Context.get(dev, sr=SR, n_mels=N_MELS)
+    batch = sp.make_batch(ctx, n_samples=lens, sample_off=starts)
+    F = batch.n_frames
+    power = torch.empty((F, _lib.SPEC_LD), dtype=torch.float32, device=dev)
+    out = torch.empty((F, N_MELS), dtype=torch.float32, device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+
+    def k1():
+        _lib.check(ctx.lib.spev_stft_power(ctx.handle, batch.desc, samples.data_ptr(), power.data_ptr(), st))
+
+    def k2():
+        _lib.check(ctx.lib.spev_mel_project(ctx.handle, power.data_ptr(), F, out.data_ptr(), 1, 1e-5, -10.0, 2.0, st))
+
+    def t(fn, n=5):
+        for _ in range(3):
+            fn()
+        a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record(); torch.cuda.synchronize(dev)
+        return a.elapsed_time(b) / n
+    ms1, ms2 = t(k1), t(k2)
+    err = float((out - fused_out).abs().max())
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    tf32_peak = (json.load(open(p))["bf16_tflops"] / 2) if os.path.exists(p) else 795.0
+    flops = 2.0 * F * 513 * 80 * 3
+    bytes_gemm = F * (513 * 4 + 80 * 4)
+    return {"config": {"workload": "cfg4 shard, two-kernel tensor-core path (A/B against the fused kernel)"},
+            "stft_power_ms": ms1, "mel_project_ms": ms2, "frames_per_s_two_kernel": F / ((ms1 + ms2) * 1e-3),
+            "max_abs_diff_vs_fused_logmel": err,
+            "roofline": {"bound": "hbm", "kernel": "k_gemm_tf32x3<80,MEL>", "achieved": bytes_gemm / (ms2 * 1e-3) / 1e9,
+                         "peak": hbm_peak, "unit": "GB/s", "frac": bytes_gemm / (ms2 * 1e-3) / 1e9 / hbm_peak,
+                         "alg_bytes_per_frame": 513 * 4 + 320},
+            "tensor": {"achieved_tflops_3xtf32": flops / (ms2 * 1e-3) / 1e12, "peak_tflops_tf32": tf32_peak,
+                       "frac": flops / (ms2 * 1e-3) / 1e12 / tf32_peak,
+                       "note": "arithmetic intensity 103 FLOP/B (3 passes) < ridge ~125: the projection is HBM-bound"}}
 
 
 def bench_griffinlim(sp, dev, hbm_peak, args):

@@ -186,12 +186,14 @@ def gather_shards(local: torch.Tensor, dst: int = 0, group=None):
     if rank == dst:
         parts = [local if r == dst else torch.empty((counts[r], local.shape[1]), dtype=local.dtype,
                                                     device=local.device) for r in range(world)]
-        reqs = [dist.irecv(parts[r], src=r, group=group) for r in range(world) if r != dst and counts[r]]
-        for q in reqs:
-            q.wait()
+        ops = [dist.P2POp(dist.irecv, parts[r], r, group) for r in range(world) if r != dst and counts[r]]
+        if ops:
+            for q in dist.batch_isend_irecv(ops):   # one grouped NCCL launch: transfers run concurrently
+                q.wait()
         return parts, counts
     if local.shape[0]:
-        dist.send(local.contiguous(), dst=dst, group=group)
+        for q in dist.batch_isend_irecv([dist.P2POp(dist.isend, local.contiguous(), dst, group)]):
+            q.wait()
     return None, counts
 
 

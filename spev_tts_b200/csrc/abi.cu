@@ -188,7 +188,7 @@ int spev_create(spev_ctx** out, int device, int sr, int n_fft, int hop, int win,
     c->fmin = fmin; c->fmax = fmax; c->num_sms = prop.multiProcessorCount; c->tma = nullptr; c->use_tc = 1;
     c->d_tw = nullptr; c->d_window = nullptr; c->d_basis_pad = c->d_basis_hi = c->d_basis_lo = nullptr;
     c->d_pinv_t = c->d_pinv_hi = c->d_pinv_lo = nullptr;
-    c->d_band_start = c->d_band_len = c->d_band_woff = nullptr; c->d_band_w = nullptr;
+    c->d_prog_w = nullptr; c->d_prog_i = nullptr;
 
     // periodic Hann, float64 -> float32
     c->h_window.resize(kNfft);
@@ -202,21 +202,51 @@ int spev_create(spev_ctx** out, int device, int sr, int n_fft, int hop, int win,
     build_mel_basis(sr, n_fft, n_mels, fmin, fmax, c->h_basis);
     pinv_jacobi(c->h_basis, n_mels, kBins, c->h_pinv);
 
-    // banded form
-    std::vector<int> bstart(n_mels), blen(n_mels), bwoff(n_mels);
-    std::vector<float> bw;
-    c->band_max_len = 0;
+    // mel program of the fused kernel (see MelProgram): float4 groups, LPT-balanced over 16 warps
+    std::vector<int> bstart(n_mels), bn4(n_mels);
+    c->band_max_len = 0; c->band_nnz = 0;
     for (int m = 0; m < n_mels; ++m) {
         int lo = kBins, hi = -1;
         for (int k = 0; k < kBins; ++k)
-            if (c->h_basis[static_cast<size_t>(m) * kBins + k] != 0.f) { lo = std::min(lo, k); hi = std::max(hi, k); }
-        bstart[m] = hi >= lo ? lo : 0;
-        blen[m] = hi >= lo ? hi - lo + 1 : 0;
-        bwoff[m] = static_cast<int>(bw.size());
-        for (int k = 0; k < blen[m]; ++k) bw.push_back(c->h_basis[static_cast<size_t>(m) * kBins + bstart[m] + k]);
-        c->band_max_len = std::max(c->band_max_len, blen[m]);
+            if (c->h_basis[static_cast<size_t>(m) * kBins + k] != 0.f) { lo = std::min(lo, k); hi = std::max(hi, k); ++c->band_nnz; }
+        bstart[m] = hi >= lo ? (lo / 4) * 4 : 0;
+        bn4[m] = hi >= lo ? (hi - bstart[m] + 4) / 4 : 1;   // an empty filter still emits (a zero)
+        c->band_max_len = std::max(c->band_max_len, hi >= lo ? hi - lo + 1 : 0);
     }
-    c->band_nnz = static_cast<int>(bw.size());
+    std::vector<std::vector<int>> warp_bands(kWarps);
+    {
+        std::vector<int> by_len(n_mels), load(kWarps, 0);
+        for (int m = 0; m < n_mels; ++m) by_len[m] = m;
+        std::stable_sort(by_len.begin(), by_len.end(), [&](int a, int b) { return bn4[a] > bn4[b]; });
+        for (int m : by_len) {
+            const int w = static_cast<int>(std::min_element(load.begin(), load.end()) - load.begin());
+            warp_bands[w].push_back(m);
+            load[w] += bn4[m] + 1;   // +1: emit cost
+        }
+    }
+    int gmax = 1;
+    for (int w = 0; w < kWarps; ++w) {
+        int g = 0;
+        for (int m : warp_bands[w]) g += bn4[m];
+        gmax = std::max(gmax, g);
+    }
+    gmax = (gmax + 3) & ~3;   // unroll-friendly
+    std::vector<float4> prog_w(static_cast<size_t>(kWarps) * gmax, make_float4(0.f, 0.f, 0.f, 0.f));
+    std::vector<int2> prog_i(static_cast<size_t>(kWarps) * gmax, make_int2(0, -1));
+    for (int w = 0; w < kWarps; ++w) {
+        int g = w * gmax;
+        for (int m : warp_bands[w])
+            for (int j = 0; j < bn4[m]; ++j, ++g) {
+                float wv[4];
+                for (int q = 0; q < 4; ++q) {
+                    const int bin = bstart[m] + 4 * j + q;   // bins 513..515 of a slot are kept at zero
+                    wv[q] = bin < kBins ? c->h_basis[static_cast<size_t>(m) * kBins + bin] : 0.f;
+                }
+                prog_w[g] = make_float4(wv[0], wv[1], wv[2], wv[3]);
+                prog_i[g] = make_int2(bstart[m] + 4 * j, j == bn4[m] - 1 ? m : -1);
+            }
+    }
+    c->prog_gmax = gmax;
 
     // padded / split operands for the tensor-core GEMMs
     std::vector<float> basis_pad(static_cast<size_t>(n_mels) * kSpecLd, 0.f), b_hi(basis_pad.size()), b_lo(basis_pad.size());
@@ -232,8 +262,7 @@ int spev_create(spev_ctx** out, int device, int sr, int n_fft, int hop, int win,
     if ((rc = upload(&c->d_tw, tw)) || (rc = upload(&c->d_window, c->h_window)) ||
         (rc = upload(&c->d_basis_pad, basis_pad)) || (rc = upload(&c->d_basis_hi, b_hi)) ||
         (rc = upload(&c->d_basis_lo, b_lo)) || (rc = upload(&c->d_pinv_t, pinv_t)) ||
-        (rc = upload(&c->d_band_start, bstart)) || (rc = upload(&c->d_band_len, blen)) ||
-        (rc = upload(&c->d_band_woff, bwoff)) || (rc = upload(&c->d_band_w, bw)) ||
+        (rc = upload(&c->d_prog_w, prog_w)) || (rc = upload(&c->d_prog_i, prog_i)) ||
         (rc = gemm_tc_init(c))) {
         spev_destroy(c);
         return rc;
@@ -248,7 +277,7 @@ void spev_destroy(spev_ctx* c) {
     gemm_tc_destroy(c);
     cudaFree(c->d_tw); cudaFree(c->d_window); cudaFree(c->d_basis_pad); cudaFree(c->d_basis_hi);
     cudaFree(c->d_basis_lo); cudaFree(c->d_pinv_t); cudaFree(c->d_pinv_hi); cudaFree(c->d_pinv_lo);
-    cudaFree(c->d_band_start); cudaFree(c->d_band_len); cudaFree(c->d_band_woff); cudaFree(c->d_band_w);
+    cudaFree(c->d_prog_w); cudaFree(c->d_prog_i);
     delete c;
 }
 

@@ -36,7 +36,11 @@ constexpr int kHop = 256;
 constexpr int kBins = 513;
 constexpr int kXPitch = 33;                       // float2 per row of the transpose tile
 constexpr int kXWords = 32 * kXPitch * 2;         // 2112 32-bit words
-constexpr int kWarpRegionWords = kXWords + 2;     // == 2 (mod 32): lane<->frame bank spread
+// Warp-private region stride and second-frame offset of the |X|^2 slots (K1): in 16-byte units they
+// are == 2 and == 1 (mod 8), so that lane f's float4 reads land in 16-byte bank group f % 8 --
+// conflict-free for every quarter-warp (LDS.128) and for scalar accesses alike.
+constexpr int kWarpRegionWords = kXWords + 8;     // 2120
+constexpr int kPSlot = 516;                       // frame b's |X|^2 slot starts here (513 bins + 3 zero words)
 
 // cos/sin(2*pi*e/32), e = 0..31 (float-rounded from float64)
 constexpr float kCos32[32] = {
@@ -194,6 +198,12 @@ SPEV_D void fetch_mirror(const float2 (&v)[32], float2 (&p)[16], int lane) {
 }
 
 #endif  // __CUDACC__
+
+// Hermitian split when the 1/2 has been folded into the window (exact: power of two)
+SPEV_HD void split_pair_prescaled(float2 z, float2 zm, float2& xa, float2& xb) {
+    xa = make_float2(z.x + zm.x, z.y - zm.y);
+    xb = make_float2(z.y + zm.y, zm.x - z.x);
+}
 
 // Hermitian split: Z[k] = (a,b), Z[N-k] = (c,d)  ->  Xa[k], Xb[k]
 SPEV_HD void split_pair(float2 z, float2 zm, float2& xa, float2& xb) {

@@ -81,11 +81,13 @@ __device__ __forceinline__ void fetch_desc(spev_tile* slot, const spev_tile* g) 
     }
 }
 
+// s_win holds win_scale * Hann: 0.5 for the forward kernels (folds the 1/2 of the Hermitian split
+// into the window -- exact, a power of two), 1 for the inverse kernel.
 __device__ __forceinline__ void load_tables(float2* s_tw, float* s_win, const float2* __restrict__ g_tw,
-                                            const float* __restrict__ g_win) {
+                                            const float* __restrict__ g_win, float win_scale) {
     for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
         s_tw[i] = g_tw[i];
-        s_win[i] = g_win[i];
+        s_win[i] = win_scale * g_win[i];
     }
 }
 
@@ -93,36 +95,51 @@ __device__ __forceinline__ void load_tables(float2* s_tw, float* s_win, const fl
 __device__ __forceinline__ void stage_async(float* s_stage, const float* __restrict__ x,
                                             const spev_tile& d) {
     const int count = (d.n - 1) * kHop + kNfft;
-    const int64_t first = d.src0, lo = d.lo, hi = d.hi;
-    const bool vec_ok = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((lo & 3) == 0);
+    const int64_t first = d.src0;
+    // tile-local valid range [i_lo, i_hi): 32-bit from here on
+    const int i_lo = static_cast<int>(max(static_cast<int64_t>(0), d.lo - first));
+    const int i_hi = static_cast<int>(min(static_cast<int64_t>(count), d.hi - first));
+    const float* xs = x + first;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((d.lo & 3) == 0);
     if (vec_ok) {   // lo % 4 == 0 and first == lo (mod 4): a float4 never straddles `lo`
         for (int i = threadIdx.x * 4; i < count; i += blockDim.x * 4) {
-            const int64_t g = first + i;
-            int64_t nb = g < lo ? 0 : (hi - g) * 4;
-            nb = nb < 0 ? 0 : (nb > 16 ? 16 : nb);
-            cp_async16(s_stage + i, nb > 0 ? x + g : x, static_cast<int>(nb));
+            int nb = i >= i_lo ? (i_hi - i) * 4 : 0;
+            nb = max(0, min(16, nb));
+            cp_async16(s_stage + i, nb > 0 ? xs + i : x, nb);
         }
     } else {
         for (int i = threadIdx.x; i < count; i += blockDim.x) {
-            const int64_t g = first + i;
-            const bool ok = g >= lo && g < hi;
-            cp_async4(s_stage + i, ok ? x + g : x, ok ? 4 : 0);
+            const bool ok = i >= i_lo && i < i_hi;
+            cp_async4(s_stage + i, ok ? xs + i : x, ok ? 4 : 0);
         }
     }
 }
 
 // Load the two windowed frames a (real part) and b (imaginary part) of this warp from the
 // staged samples: v[j] = win[32j+lane] * (stage[256a + 32j + lane], stage[256b + 32j + lane]).
+// Frame b of an odd tile tail does not exist: its slot must be exactly zero (anything else would
+// leak rounding error into frame a through the packed transform), hence the warp-uniform branch.
 __device__ __forceinline__ void load_frame_pair(float2 (&v)[32], const float* s_stage,
                                                 const float* s_win, int fa, bool b_valid, int lane) {
     const float* pa = s_stage + fa * kHop + lane;
-    static_for<0, 32>([&](auto jc) {
-        constexpr int j = decltype(jc)::value;
-        const float w = s_win[32 * j + lane];
-        const float xa = pa[32 * j];
-        const float xb = b_valid ? pa[kHop + 32 * j] : 0.f;
-        v[j] = make_float2(w * xa, w * xb);
-    });
+    if (b_valid) {
+        // frame b = frame a shifted by one hop (8 rows of 32): 40 loads serve both frames
+        float x[40];
+        static_for<0, 40>([&](auto jc) {
+            constexpr int j = decltype(jc)::value;
+            x[j] = pa[32 * j];
+        });
+        static_for<0, 32>([&](auto jc) {
+            constexpr int j = decltype(jc)::value;
+            const float w = s_win[32 * j + lane];
+            v[j] = make_float2(w * x[j], w * x[j + 8]);
+        });
+    } else {
+        static_for<0, 32>([&](auto jc) {
+            constexpr int j = decltype(jc)::value;
+            v[j] = make_float2(s_win[32 * j + lane] * pa[32 * j], 0.f);
+        });
+    }
 }
 
 // Persistent-loop bookkeeping shared by the kernels: prologue of the descriptor ring.
@@ -142,7 +159,7 @@ __device__ __forceinline__ int ring_prologue(spev_tile* s_ring, const spev_tile*
 template <int MODE>   // 0: mel epilogue, 1: power-spectrum output
 __global__ void __launch_bounds__(kThreads, 1)
 k_stft_mel(BatchView bv, const float* __restrict__ samples, float* __restrict__ out,
-           const float2* __restrict__ g_tw, const float* __restrict__ g_win, MelBands mb,
+           const float2* __restrict__ g_tw, const float* __restrict__ g_win, MelProgram mb,
            int log_mode, float floor_v, float lo, float hi) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* s_tw = reinterpret_cast<float2*>(smem_raw);
@@ -150,18 +167,13 @@ k_stft_mel(BatchView bv, const float* __restrict__ samples, float* __restrict__ 
     spev_tile* s_ring = reinterpret_cast<spev_tile*>(s_win + 1024);
     float* s_stage = reinterpret_cast<float*>(s_ring + kRing);
     float* s_x = s_stage + 2 * kStageSamples;
-    int* s_bstart = reinterpret_cast<int*>(s_x + kWarps * kWarpRegionWords);
-    int* s_blen = s_bstart + mb.n_mels;
-    int* s_bwoff = s_blen + mb.n_mels;
-    float* s_bw = reinterpret_cast<float*>(s_bwoff + mb.n_mels);
+    float4* s_gw = reinterpret_cast<float4*>(s_x + kWarps * kWarpRegionWords);   // [16*gmax], 16-B aligned
+    int2* s_gi = reinterpret_cast<int2*>(s_gw + kWarps * mb.gmax);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    load_tables(s_tw, s_win, g_tw, g_win);
+    load_tables(s_tw, s_win, g_tw, g_win, 0.5f);
     if (MODE == 0) {
-        for (int i = threadIdx.x; i < mb.n_mels; i += blockDim.x) {
-            s_bstart[i] = mb.start[i]; s_blen[i] = mb.len[i]; s_bwoff[i] = mb.woff[i];
-        }
-        for (int i = threadIdx.x; i < mb.nnz; i += blockDim.x) s_bw[i] = mb.w[i];
+        for (int i = threadIdx.x; i < kWarps * mb.gmax; i += blockDim.x) { s_gw[i] = mb.gw[i]; s_gi[i] = mb.gi[i]; }
     }
     float* xw = s_x + warp * kWarpRegionWords;
     const int n_mels = mb.n_mels;
@@ -194,23 +206,27 @@ k_stft_mel(BatchView bv, const float* __restrict__ samples, float* __restrict__ 
             float2 p[16];
             fetch_mirror(v, p, lane);
             __syncwarp();   // transpose tile is dead; reuse it for |X|^2
-            const float pa512 = v[16].x * v[16].x, pb512 = v[16].y * v[16].y;   // lane 0: bin 512
+            // lane 0: bin 512 (the window carries a factor 1/2: X[512] = 2 * Z'[512])
+            const float pa512 = 4.f * v[16].x * v[16].x, pb512 = 4.f * v[16].y * v[16].y;
             if (MODE == 0) {
                 static_for<0, 16>([&](auto kc) {
                     constexpr int k2 = decltype(kc)::value;
                     float2 xa, xb;
-                    split_pair(v[k2], p[k2], xa, xb);
+                    split_pair_prescaled(v[k2], p[k2], xa, xb);
                     xw[lane + 32 * k2] = fmaf(xa.x, xa.x, xa.y * xa.y);
-                    xw[kBins + lane + 32 * k2] = fmaf(xb.x, xb.x, xb.y * xb.y);
+                    xw[kPSlot + lane + 32 * k2] = fmaf(xb.x, xb.x, xb.y * xb.y);
                 });
-                if (lane == 0) { xw[512] = pa512; xw[kBins + 512] = pb512; }
+                if (lane < 4) {   // bin 512 + three zero words so that padded float4 band reads stay clean
+                    xw[512 + lane] = lane == 0 ? pa512 : 0.f;
+                    xw[kPSlot + 512 + lane] = lane == 0 ? pb512 : 0.f;
+                }
             } else {
                 float* oa = out + (row0 + fa) * kSpecLd;
                 float* ob = oa + kSpecLd;
                 static_for<0, 16>([&](auto kc) {
                     constexpr int k2 = decltype(kc)::value;
                     float2 xa, xb;
-                    split_pair(v[k2], p[k2], xa, xb);
+                    split_pair_prescaled(v[k2], p[k2], xa, xb);
                     oa[lane + 32 * k2] = fmaf(xa.x, xa.x, xa.y * xa.y);
                     if (b_valid) ob[lane + 32 * k2] = fmaf(xb.x, xb.x, xb.y * xb.y);
                 });
@@ -223,18 +239,32 @@ k_stft_mel(BatchView bv, const float* __restrict__ samples, float* __restrict__ 
         if (MODE == 0) {
             __syncthreads();   // B2: all |X|^2 written; this tile's samples no longer read
             // mel phase: lane <-> frame (conflict-free: bank = frame + bin), warp <-> band set
+            // mel phase: lane <-> frame (conflict-free: bank group = frame), warp <-> band program.
+            // Results are staged in shared memory (the consumed half of the sample double buffer) and
+            // copied out as contiguous rows; storing 4-byte values straight from this loop was
+            // measured slower (650 vs 702 M frames/s: 32 sectors per store instruction).
             float* s_out = stage;
-            if (lane < nf) {
-                const float* pf = s_x + (lane >> 1) * kWarpRegionWords + (lane & 1) * kBins;
-                for (int m = warp; m < n_mels; m += kWarps) {
-                    const float* pw = s_bw + s_bwoff[m];
-                    const float* pp = pf + s_bstart[m];
-                    const int len = s_blen[m];
-                    float acc = 0.f;
+            {   // lanes >= nf run on stale slots; their rows are never copied out (no divergence)
+                const float* pf = s_x + (lane >> 1) * kWarpRegionWords + (lane & 1) * kPSlot;
+                const float4* gw = s_gw + warp * mb.gmax;
+                const int2* gi = s_gi + warp * mb.gmax;
+                float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll 4
-                    for (int j = 0; j < len; ++j) acc = fmaf(pw[j], pp[j], acc);
-                    if (log_mode) acc = fminf(fmaxf(logf(fmaxf(acc, floor_v)), lo), hi);
-                    s_out[lane * out_pitch + m] = acc;
+                for (int g = 0; g < mb.gmax; ++g) {
+                    const float4 w = gw[g];                 // warp-uniform: broadcast
+                    const int2 inf = gi[g];
+                    const float4 x = *reinterpret_cast<const float4*>(pf + inf.x);   // conflict-free LDS.128
+                    acc0 = fmaf(w.x, x.x, acc0);
+                    acc1 = fmaf(w.y, x.y, acc1);
+                    acc0 = fmaf(w.z, x.z, acc0);
+                    acc1 = fmaf(w.w, x.w, acc1);
+                    if (inf.y >= 0) {                       // last group of band inf.y: emit (warp-uniform)
+                        float acc = acc0 + acc1;
+                        // __logf: <= 3 ulp (2^-21.4 abs in [0.5,2]) -- far inside the 1e-4 tolerance
+                        if (log_mode) acc = fminf(fmaxf(__logf(fmaxf(acc, floor_v)), lo), hi);
+                        s_out[lane * out_pitch + inf.y] = acc;
+                        acc0 = 0.f; acc1 = 0.f;
+                    }
                 }
             }
             __syncthreads();   // B3
@@ -271,7 +301,7 @@ k_stft_phase(BatchView bv, const float* __restrict__ y, const float* __restrict_
     float* s_stage = reinterpret_cast<float*>(s_ring + kRing);
     float* s_x = s_stage + 2 * kStageSamples;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    load_tables(s_tw, s_win, g_tw, g_win);
+    load_tables(s_tw, s_win, g_tw, g_win, 0.5f);
     float2* xw = reinterpret_cast<float2*>(s_x + warp * kWarpRegionWords);
 
     const int stride = gridDim.x;
@@ -328,7 +358,7 @@ k_stft_phase(BatchView bv, const float* __restrict__ y, const float* __restrict_
                     constexpr int k2 = 4 * g + q;
                     const int k = lane + 32 * k2;
                     float2 xa, xb;
-                    split_pair(v[k2], p[k2], xa, xb);
+                    split_pair_prescaled(v[k2], p[k2], xa, xb);
                     if (MODE == 0) {
                         ang[ra + k] = xa;
                         if (b_valid) ang[rb + k] = xb;
@@ -343,7 +373,8 @@ k_stft_phase(BatchView bv, const float* __restrict__ y, const float* __restrict_
                 });
             });
             if (lane == 0) {
-                const float2 xa = make_float2(v[16].x, 0.f), xb = make_float2(v[16].y, 0.f);
+                // the window carries a factor 1/2: X[512] = 2 * Z'[512]
+                const float2 xa = make_float2(2.f * v[16].x, 0.f), xb = make_float2(2.f * v[16].y, 0.f);
                 if (MODE == 0) {
                     ang[ra + 512] = xa;
                     if (b_valid) ang[rb + 512] = xb;
@@ -371,9 +402,17 @@ k_istft(BatchView bv, const float2* __restrict__ spec, int64_t ld, float* __rest
     float2* s_tw = reinterpret_cast<float2*>(smem_raw);
     float* s_win = reinterpret_cast<float*>(s_tw + 1024);
     spev_tile* s_ring = reinterpret_cast<spev_tile*>(s_win + 1024);
-    float* s_x = reinterpret_cast<float*>(s_ring + kRing);
+    float* s_iw = reinterpret_cast<float*>(s_ring + kRing);   // [256] 1 / sum_q w^2 for interior chunks
+    float* s_x = s_iw + kHop;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    load_tables(s_tw, s_win, g_tw, g_win);
+    load_tables(s_tw, s_win, g_tw, g_win, 1.0f);
+    __syncthreads();
+    for (int s = threadIdx.x; s < kHop; s += blockDim.x) {
+        float wss = 0.f;   // same ascending-frame fmaf chain as the edge path below
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const float w = s_win[768 - 256 * q + s]; wss = fmaf(w, w, wss); }
+        s_iw[s] = 1.0f / wss;
+    }
     float* xw = s_x + warp * kWarpRegionWords;
     const int pl = (32 - lane) & 31;
 
@@ -446,6 +485,19 @@ k_istft(BatchView bv, const float2* __restrict__ spec, int64_t ld, float* __rest
         for (int cl = warp; cl < nchunks; cl += kWarps) {
             const int c = c0 + cl;
             float* yo_c = y + d.src0 + static_cast<int64_t>(cl) * kHop;
+            if (c >= 1 && c + 2 < T) {   // all four frames exist: table-driven normalisation
+                const float* f0 = s_x + (cl >> 1) * kWarpRegionWords + (cl & 1) * kNfft + lane;
+                const float* f1 = s_x + ((cl + 1) >> 1) * kWarpRegionWords + ((cl + 1) & 1) * kNfft + lane;
+                const float* f2 = s_x + ((cl + 2) >> 1) * kWarpRegionWords + ((cl + 2) & 1) * kNfft + lane;
+                const float* f3 = s_x + ((cl + 3) >> 1) * kWarpRegionWords + ((cl + 3) & 1) * kNfft + lane;
+#pragma unroll
+                for (int ii = 0; ii < kHop / 32; ++ii) {
+                    const int o = 32 * ii;
+                    const float sum = ((f0[768 + o] + f1[512 + o]) + f2[256 + o]) + f3[o];
+                    yo_c[lane + o] = sum * s_iw[lane + o];
+                }
+                continue;
+            }
 #pragma unroll
             for (int ii = 0; ii < kHop / 32; ++ii) {
                 const int s = lane + 32 * ii;
@@ -549,11 +601,11 @@ k_mel_to_mag(BatchView bv, const float* __restrict__ mel, int layout, int is_log
 // host-side launchers
 // ---------------------------------------------------------------------------------------
 static size_t smem_common() { return sizeof(float2) * 1024 + sizeof(float) * 1024 + sizeof(spev_tile) * kRing; }
-static size_t smem_stft(int n_mels, int nnz) {
+static size_t smem_stft(int gmax) {
     return smem_common() + sizeof(float) * 2 * kStageSamples + sizeof(float) * kWarps * kWarpRegionWords +
-           sizeof(int) * 3 * n_mels + sizeof(float) * nnz;
+           (sizeof(float4) + sizeof(int2)) * kWarps * gmax;
 }
-static size_t smem_istft() { return smem_common() + sizeof(float) * kWarps * kWarpRegionWords; }
+static size_t smem_istft() { return smem_common() + sizeof(float) * kHop + sizeof(float) * kWarps * kWarpRegionWords; }
 
 template <class K>
 static int set_smem(K kernel, size_t bytes) {
@@ -580,9 +632,8 @@ int launch_stft_mel(spev_ctx* ctx, const spev_batch* b, const float* samples, fl
     if (rc) return rc;
     if (b->n_ftiles == 0) return SPEV_OK;
     SPEV_REQUIRE(samples && out, SPEV_E_INVALID, "null samples/out");
-    MelBands mb{ctx->n_mels, ctx->band_nnz, ctx->d_band_start, ctx->d_band_len, ctx->d_band_woff,
-                ctx->d_band_w};
-    const size_t smem = smem_stft(ctx->n_mels, ctx->band_nnz);
+    MelProgram mb{ctx->n_mels, ctx->prog_gmax, ctx->d_prog_w, ctx->d_prog_i};
+    const size_t smem = smem_stft(ctx->prog_gmax);
     SPEV_REQUIRE(smem <= 232448, SPEV_E_UNSUPPORTED, "mel basis too large for the fused kernel (%zu B smem)", smem);
     const int grid = std::min<int64_t>(b->n_ftiles, ctx->num_sms);
     if (power_only) {
@@ -609,7 +660,7 @@ int launch_stft_phase(spev_ctx* ctx, const spev_batch* b, const float* y, const 
     SPEV_REQUIRE(ang && ld >= kBins, SPEV_E_INVALID, "stft: null buffer or ld < 513");
     SPEV_REQUIRE(y || b->n_frames == b->n_items, SPEV_E_INVALID, "stft: y is null");
     if (!y) y = reinterpret_cast<const float*>(ang);   // every item has T == 1 (empty signal): never dereferenced as signal
-    const size_t smem = smem_stft(0, 0);
+    const size_t smem = smem_stft(0);
     const int grid = std::min<int64_t>(b->n_ftiles, ctx->num_sms);
     if (phase) {
         SPEV_REQUIRE(S && tprev && ld_s >= kBins, SPEV_E_INVALID, "phase update: null S/tprev");

@@ -35,15 +35,16 @@ int cuda_fail(cudaError_t e, const char* what);
         }                                                                      \
     } while (0)
 
-// Banded (CSR-by-band) form of the mel basis: band m covers bins [start, start+len) with
-// weights w[woff .. woff+len).
-struct MelBands {
+// Mel projection of the fused kernel as a flat per-warp "program" built on the host: warp w runs
+// groups [w*gmax, (w+1)*gmax).  A group is four consecutive bins (start multiple of 4) of one
+// band: weights gw[g] (zero padded), first bin gi[g].x, and gi[g].y = mel index if this is the
+// band's last group (emit), else -1.  Bands are LPT-balanced over the 16 warps; short warps are
+// padded with zero-weight groups so that the trip count is uniform.
+struct MelProgram {
     int n_mels;
-    int nnz;
-    const int* start;   // dev [n_mels]
-    const int* len;     // dev [n_mels]
-    const int* woff;    // dev [n_mels]
-    const float* w;     // dev [nnz]
+    int gmax;            // groups per warp
+    const float4* gw;    // dev [16*gmax]
+    const int2* gi;      // dev [16*gmax]
 };
 
 }  // namespace spev
@@ -64,11 +65,10 @@ struct spev_ctx {
     float* d_pinv_t;     // [n_mels, 520]: pinv transposed (pinv_t[m][k] = pinv[k][m])
     float* d_pinv_hi;    // [528, n_mels_pad]: pinv rows (K-major B operand), tf32 hi
     float* d_pinv_lo;    //   residual
-    int* d_band_start;
-    int* d_band_len;
-    int* d_band_woff;
-    float* d_band_w;
-    int band_nnz;
+    float4* d_prog_w;    // mel program of the fused kernel (MelProgram)
+    int2* d_prog_i;
+    int prog_gmax;
+    int band_nnz;        // nnz of the basis (diagnostics)
     int band_max_len;
     void* tma;           // opaque: tensor-map cache (gemm_tc.cu)
     int use_tc;          // mel->magnitude on frame-major input uses the tcgen05 GEMM
