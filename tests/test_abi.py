@@ -128,3 +128,32 @@ def test_host_fft_building_blocks():
                            "-I" + os.path.join(ROOT, "spev_tts_b200", "csrc"),
                            os.path.join(ROOT, "tests", "host", "fft_check.cpp"), "-o", exe])
     assert subprocess.call([exe]) == 0
+
+
+def test_header_is_valid_c99_and_struct_layout():
+    """include/spev_b200.h compiles as strict C99 and spev_tile is 48 bytes (what the kernels assume)."""
+    obj = os.path.join(ROOT, "tests", "host", "abi_c99.o")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                           "-c", os.path.join(ROOT, "tests", "host", "abi_c99.c"), "-o", obj])
+    from spev_tts_b200 import _lib, batch
+    assert C.sizeof(_lib.SpevTile) == 48 == batch.TILE_DTYPE.itemsize
+    assert C.sizeof(_lib.SpevBatch) == 48
+    # every header symbol is referenced by the C probe
+    src = open(os.path.join(ROOT, "tests", "host", "abi_c99.c")).read()
+    for sym in header_symbols():
+        assert f"USE({sym})" in src, sym
+
+
+def test_host_entry_points_reject_bad_arguments():
+    import spev_tts_b200 as sp
+    lib = sp.load()
+    assert lib.spev_plan_frame_tiles(None, None, None, 3, None) == -1
+    assert lib.spev_plan_chunk_tiles(None, 3, None) == -1
+    assert lib.spev_host_mel_basis(0, 1024, 80, 0.0, 0.0, None) == -1
+    assert lib.spev_griffinlim_workspace_bytes(-5) == 0
+    assert lib.spev_griffinlim_workspace_bytes(10) >= 10 * 520 * 16
+    h = C.c_void_p()
+    assert lib.spev_create(C.byref(h), 0, 22050, 1024, 256, 1024, 0, 0.0, 0.0) in (-1, -3)      # n_mels = 0
+    assert lib.spev_create(None, 0, 22050, 1024, 256, 1024, 80, 0.0, 0.0) == -1
+    assert lib.spev_logmel(None, None, None, None, 1, 1e-5, -10.0, 2.0, None) == -1             # null ctx
+    assert b"ctx is null" in lib.spev_last_error()
