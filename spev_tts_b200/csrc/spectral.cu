@@ -142,6 +142,12 @@ __device__ __forceinline__ void load_frame_pair(float2 (&v)[32], const float* s_
     }
 }
 
+// Programmatic dependent launch: a kernel launched with the stream-serialization attribute may
+// start while its predecessor is still draining; everything before pdl_wait() must only touch
+// data the predecessor does not write (constant tables, tile descriptors).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+
 // Persistent-loop bookkeeping shared by the kernels: prologue of the descriptor ring.
 __device__ __forceinline__ int ring_prologue(spev_tile* s_ring, const spev_tile* tiles, int n_tiles) {
     const int first = blockIdx.x, stride = gridDim.x;
@@ -305,7 +311,9 @@ k_stft_phase(BatchView bv, const float* __restrict__ y, const float* __restrict_
     float2* xw = reinterpret_cast<float2*>(s_x + warp * kWarpRegionWords);
 
     const int stride = gridDim.x;
+    pdl_launch_dependents();
     const int my_n = ring_prologue(s_ring, bv.ftiles, bv.n_ftiles);
+    pdl_wait();   // y (and ang/tprev) come from the previous kernel
     if (my_n > 0) stage_async(s_stage, y, s_ring[0]);
     cp_async_commit();
 
@@ -417,7 +425,9 @@ k_istft(BatchView bv, const float2* __restrict__ spec, int64_t ld, float* __rest
     const int pl = (32 - lane) & 31;
 
     const int stride = gridDim.x;
+    pdl_launch_dependents();
     const int my_n = ring_prologue(s_ring, bv.ctiles, bv.n_ctiles);
+    pdl_wait();   // the spectra come from the previous kernel
 
     for (int i = 0; i < my_n; ++i) {
         cp_async_wait_all();
@@ -531,6 +541,8 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
 
 __global__ void k_gl_init(const float* __restrict__ S, int64_t ld_s, const float* __restrict__ phase,
                           uint64_t seed, float2* __restrict__ ang, int64_t ld, int64_t n_frames) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int64_t total = n_frames * kBins;
     for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -607,6 +619,23 @@ static size_t smem_stft(int gmax) {
 }
 static size_t smem_istft() { return smem_common() + sizeof(float) * kHop + sizeof(float) * kWarps * kWarpRegionWords; }
 
+// Launch with the programmatic-stream-serialization attribute (PDL).
+template <class... KArgs, class... Args>
+static int launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(grid));
+    cfg.blockDim = dim3(static_cast<unsigned>(block));
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SPEV_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+    return SPEV_OK;
+}
+
 template <class K>
 static int set_smem(K kernel, size_t bytes) {
     SPEV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -666,16 +695,17 @@ int launch_stft_phase(spev_ctx* ctx, const spev_batch* b, const float* y, const 
         SPEV_REQUIRE(S && tprev && ld_s >= kBins, SPEV_E_INVALID, "phase update: null S/tprev");
         rc = set_smem(k_stft_phase<1>, smem);
         if (rc) return rc;
-        k_stft_phase<1><<<grid, kThreads, smem, st>>>(view_of(b), y, S, ld_s,
-                                                      static_cast<float2*>(ang),
-                                                      static_cast<float2*>(tprev), ld, alpha,
-                                                      has_prev, ctx->d_tw, ctx->d_window);
+        rc = launch_pdl(k_stft_phase<1>, grid, kThreads, smem, st, view_of(b), y, S, ld_s, static_cast<float2*>(ang),
+                        static_cast<float2*>(tprev), ld, alpha, has_prev, static_cast<const float2*>(ctx->d_tw),
+                        static_cast<const float*>(ctx->d_window));
+        if (rc) return rc;
     } else {
         rc = set_smem(k_stft_phase<0>, smem);
         if (rc) return rc;
-        k_stft_phase<0><<<grid, kThreads, smem, st>>>(view_of(b), y, nullptr, 0,
-                                                      static_cast<float2*>(ang), nullptr, ld, 0.f, 0,
-                                                      ctx->d_tw, ctx->d_window);
+        rc = launch_pdl(k_stft_phase<0>, grid, kThreads, smem, st, view_of(b), y, static_cast<const float*>(nullptr),
+                        static_cast<int64_t>(0), static_cast<float2*>(ang), static_cast<float2*>(nullptr), ld, 0.f, 0,
+                        static_cast<const float2*>(ctx->d_tw), static_cast<const float*>(ctx->d_window));
+        if (rc) return rc;
     }
     SPEV_CUDA(cudaGetLastError());
     return SPEV_OK;
@@ -691,9 +721,9 @@ int launch_istft(spev_ctx* ctx, const spev_batch* b, const void* spec, int64_t l
     rc = set_smem(k_istft, smem);
     if (rc) return rc;
     const int grid = std::min<int64_t>(b->n_ctiles, ctx->num_sms);
-    k_istft<<<grid, kThreads, smem, st>>>(view_of(b), static_cast<const float2*>(spec), ld, y,
-                                          ctx->d_tw, ctx->d_window);
-    SPEV_CUDA(cudaGetLastError());
+    rc = launch_pdl(k_istft, grid, kThreads, smem, st, view_of(b), static_cast<const float2*>(spec), ld, y,
+                    static_cast<const float2*>(ctx->d_tw), static_cast<const float*>(ctx->d_window));
+    if (rc) return rc;
     return SPEV_OK;
 }
 
@@ -702,8 +732,8 @@ int launch_gl_init(spev_ctx* ctx, const float* S, int64_t ld_s, const float* pha
     if (n_frames == 0) return SPEV_OK;
     const int64_t total = n_frames * kBins;
     const int grid = static_cast<int>(std::min<int64_t>((total + 255) / 256, ctx->num_sms * 16));
-    k_gl_init<<<grid, 256, 0, st>>>(S, ld_s, phase, seed, static_cast<float2*>(ang), ld, n_frames);
-    SPEV_CUDA(cudaGetLastError());
+    int rc = launch_pdl(k_gl_init, grid, 256, 0, st, S, ld_s, phase, seed, static_cast<float2*>(ang), ld, n_frames);
+    if (rc) return rc;
     return SPEV_OK;
 }
 

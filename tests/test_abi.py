@@ -33,7 +33,7 @@ def test_library_builds_and_exports_header_symbols():
     out = subprocess.check_output(["nm", "-D", "--defined-only", sp.LIB_PATH], text=True)
     exported = sorted(l.split()[-1] for l in out.splitlines() if " T " in l)
     assert exported == syms, "library exports symbols outside the header (or misses some)"
-    assert lib.spev_abi_version() == 1 and lib.spev_tile_frames() == 32 and lib.spev_tile_chunks() == 29
+    assert lib.spev_abi_version() == 1 and lib.spev_tile_chunks() == lib.spev_tile_frames() - 3
 
 
 def test_sass_is_sm100a():
@@ -73,14 +73,16 @@ def test_plan_tiles_c_vs_numpy():
         assert lib.spev_plan_frame_tiles(frames.ctypes.data, lo.ctypes.data if lo is not None else None,
                                          n.ctypes.data if n is not None else None, len(frames),
                                          out.ctypes.data) == cnt
-        ref = B.plan_frame_tiles(frames, lo, n, 32)
-        assert cnt == len(ref) == int(((frames + 31) // 32).sum())
+        tf = lib.spev_tile_frames()
+        ref = B.plan_frame_tiles(frames, lo, n, tf)
+        assert cnt == len(ref) == int(((frames + tf - 1) // tf).sum())
         assert out.tobytes() == ref.tobytes()
     cnt = lib.spev_plan_chunk_tiles(frames.ctypes.data, len(frames), None)
     out = np.zeros(cnt, dtype=B.TILE_DTYPE)
     assert lib.spev_plan_chunk_tiles(frames.ctypes.data, len(frames), out.ctypes.data) == cnt
-    ref = B.plan_chunk_tiles(frames, 29)
-    assert out.tobytes() == ref.tobytes() and cnt == int(((frames - 1 + 28) // 29).sum())
+    tc = lib.spev_tile_chunks()
+    ref = B.plan_chunk_tiles(frames, tc)
+    assert out.tobytes() == ref.tobytes() and cnt == int(((frames - 1 + tc - 1) // tc).sum())
     # every frame / chunk covered exactly once
     assert B.plan_frame_tiles(frames)["n"].sum() == frames.sum()
     assert ref["n"].sum() == (frames - 1).sum()
