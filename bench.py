@@ -327,8 +327,9 @@ def run_ours(args):
         del parts
 
     # ---------------- second half of the metric: Griffin-Lim on cfg3 (rank 0 reports) ------------
-    gl = lr_res = tc = None
+    gl = lr_res = tc = cfg5 = None
     if not args.no_gl:
+        cfg5 = bench_logmel_cfg5(sp, dev, hbm_peak, spcache)
         tc = bench_mel_gemm_tc(sp, dev, samples, lens, starts, hbm_peak, out)
         gl = bench_griffinlim(sp, dev, hbm_peak, args)
         lr_res = bench_length_regulator(sp, dev, args)
@@ -357,12 +358,39 @@ def run_ours(args):
                          "kernel_ms_max_over_ranks": kern_ms_max, "traffic": None,
                          "note": "fp32-pipe/shared-memory bound by design (SURVEY 0.7): ~25 kFLOP FFT per 1,344 B"},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks,
-            "gather": gather, "mel_gemm_tc": tc, "griffinlim": gl, "length_regulator": lr_res,
+            "gather": gather, "logmel_cfg5": cfg5, "mel_gemm_tc": tc, "griffinlim": gl, "length_regulator": lr_res,
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def bench_logmel_cfg5(sp, dev, hbm_peak, spcache):
+    """cfg5-shaped cache build: 24 kHz (mel basis fmax 12 kHz), LibriTTS-R-like log-normal lengths
+    1-20 s, 4,096 utterances per GPU in one ragged launch."""
+    import torch
+    from tests import synth
+    lens = synth.lognormal_lengths(seed=5, n_utts=4096, sr=24000)
+    starts = spcache.aligned_offsets(lens)
+    g = torch.Generator(device=dev).manual_seed(5)
+    x = torch.randn(int(starts[-1]), generator=g, device=dev) * 0.05
+    ctx = sp.Context.get(dev, sr=24000, n_mels=N_MELS)
+    batch = sp.make_batch(ctx, n_samples=lens, sample_off=starts)
+    out = torch.empty((batch.n_frames, N_MELS), dtype=torch.float32, device=dev)
+    for _ in range(3):
+        sp.logmel_flat(x, lens, sr=24000, out=out, batch=batch)
+    a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(5):
+        sp.logmel_flat(x, lens, sr=24000, out=out, batch=batch)
+    b.record(); torch.cuda.synchronize(dev)
+    ms = a.elapsed_time(b) / 5
+    F = batch.n_frames
+    return {"config": {"workload": f"cfg5: 4096 utterances 1-20 s @24 kHz per GPU ({x.numel() * 4 / 1e9:.2f} GB, {F} frames)"},
+            "value": F / (ms * 1e-3), "unit": "frames/s", "ms_per_step": ms,
+            "roofline": {"bound": "hbm", "achieved": ALG_BYTES_PER_FRAME * F / (ms * 1e-3) / 1e9, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": ALG_BYTES_PER_FRAME * F / (ms * 1e-3) / 1e9 / hbm_peak}}
 
 
 def bench_mel_gemm_tc(sp, dev, samples, lens, starts, hbm_peak, fused_out):
@@ -450,7 +478,8 @@ def bench_griffinlim(sp, dev, hbm_peak, args):
     for _ in range(n_e):
         w = voc.infer(lm_host)
     e2e_ms = (time.perf_counter() - t) * 1e3 / n_e
-    return {"metric": "Griffin-Lim audio-s/s", "value": audio_s / (ms * 1e-3), "unit": "audio-s/s",
+    scale = bench_griffinlim_cfg5(sp, dev, hbm_peak)
+    return {"metric": "Griffin-Lim audio-s/s", "value": audio_s / (ms * 1e-3), "unit": "audio-s/s", "cfg5_subset": scale,
             "config": {"workload": "cfg3: 16 x [80,800] log-mel, 60 iterations, momentum 0.99; L2 flushed between steps"},
             "ms_per_step": ms, "launches_per_step": 2 * n_iter + 3,
             "roofline": {"bound": "hbm", "kernels": "k_istft + k_stft_phase<1>", "achieved": alg / (ms * 1e-3) / 1e9,
@@ -459,6 +488,44 @@ def bench_griffinlim(sp, dev, hbm_peak, args):
             "e2e": {"value": audio_s / (e2e_ms * 1e-3), "unit": "audio-s/s", "ms_per_step": e2e_ms,
                     "api": "Vocoder.infer (host log-mel in, numpy waveform out)",
                     "h2d_bytes_per_step": int(lm.numel() * 4), "d2h_bytes_per_step": int(w.size * 4)}}
+
+
+def bench_griffinlim_cfg5(sp, dev, hbm_peak):
+    """cfg5-shaped Griffin-Lim: 256 variable-length utterances per GPU (LibriTTS-R-like log-normal
+    lengths 1-20 s at 24 kHz), 60 iterations, one ragged flat batch."""
+    import torch
+    from spev_tts_b200 import _lib
+    from tests import synth
+    sr, n_iter = 24000, 60
+    lens = synth.lognormal_lengths(seed=5, n_utts=256, sr=sr)
+    frames = 1 + lens // HOP
+    ctx = sp.Context.get(dev, sr=sr, n_mels=N_MELS, fmin=0.0, fmax=8000.0)
+    fb = sp.make_batch(ctx, n_frames=frames, with_chunks=True)
+    g = torch.Generator(device=dev).manual_seed(5)
+    lm = (-4 + 2 * torch.randn(fb.n_frames, N_MELS, generator=g, device=dev)).clamp(-10, 2)   # frame-major
+    S = torch.empty((fb.n_frames, _lib.SPEC_LD), dtype=torch.float32, device=dev)
+    y = torch.empty(fb.n_out_samples, dtype=torch.float32, device=dev)
+    ws = torch.empty(ctx.lib.spev_griffinlim_workspace_bytes(fb.n_frames), dtype=torch.uint8, device=dev)
+
+    def step():
+        sp.mel_to_mag_flat(lm.view(-1), fb, ctx, layout=0, is_log=True, out=S)     # tcgen05 GEMM path
+        sp.griffinlim_flat(S, fb, ctx, n_iter=n_iter, seed=11, out=y, workspace=ws)
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize(dev)
+    a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(3):
+        step()
+    b.record(); torch.cuda.synchronize(dev)
+    ms = a.elapsed_time(b) / 3
+    alg = GL_BYTES_PER_FRAME_ITER * fb.n_frames * n_iter + (2372 + 5128) * fb.n_frames
+    return {"config": {"workload": f"cfg5 subset: 256 utterances 1-20 s @24 kHz ({fb.n_frames} frames, state "
+                                   f"{fb.n_frames * 10400 / 1e6:.0f} MB >> L2), 60 iterations, ragged flat batch"},
+            "value": float(fb.n_out_samples) / sr / (ms * 1e-3), "unit": "audio-s/s", "ms_per_step": ms,
+            "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": alg / (ms * 1e-3) / 1e9 / hbm_peak}}
 
 
 def bench_length_regulator(sp, dev, args):

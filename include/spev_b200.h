@@ -181,6 +181,23 @@ SPEV_API int spev_griffinlim(spev_ctx* ctx, const spev_batch* batch, const float
                     const float* init_phase, uint64_t seed, int n_iter, float momentum, float* y,
                     void* workspace, size_t workspace_bytes, void* stream);
 
+/* Frame-level energy / brightness.  For every frame t (hop 256) of the centre-padded
+ * 2048-sample window:  rms[t] = sqrt(mean(x^2))  and  centroid[t] = sum_k f_k|X_k| / sum_k|X_k|,
+ * X = rFFT-2048(hann * x), f_k = k*sr/2048.  Same flat waveform batch as spev_logmel; outputs [n_frames].
+ * Replaces librosa.feature.rms(y, hop_length=256) and librosa.feature.spectral_centroid(y, sr,
+ * hop_length=256) at spev_real_metrics.py:370-371 (the caller takes the logs). */
+SPEV_API int spev_frame_features(spev_ctx* ctx, const spev_batch* batch, const float* samples, float* rms,
+                                 float* centroid, void* stream);
+
+/* Per-phoneme pooling of a frame-level curve: for phoneme p of item i with duration d_p frames,
+ *   out[p] = clamp((mean(curve[frame_off[i] + start_p .. + d_p)) - mu) / sigma, lo, hi)
+ * where start_p is the running sum of the item's earlier durations.  durs: dev int64 flat, item i
+ * owns [phone_off[i], phone_off[i+1]).  Replaces the e / bri (and, with mu=1, sigma=-1, br) lines of
+ * the per-phone loop, spev_real_metrics.py:400-417. */
+SPEV_API int spev_segment_pool(const float* curve, const int64_t* frame_off, const int64_t* durs,
+                               const int64_t* phone_off, int n_items, float mu, float sigma, float lo, float hi,
+                               float* out, void* stream);
+
 /* LengthRegulator, phase 1: sanitise durations (non-finite / <0 / >1000 -> 0, truncate),
  * inclusive row cumsum, mel_lens = max(total, 1), max_len = max(mel_lens).
  *   dur       : dev [B,T], dur_dtype 0=int64 1=int32 2=float32 3=float64 4=float16 5=bfloat16

@@ -26,7 +26,7 @@ The reference ships **no tests, golden vectors or fixtures** (SURVEY.md section 
 librosa itself cannot run here, so for the spectral functions parity is
 **unpinned by the reference**.  The restatement is instead pinned against
 independent implementations that *are* available in the container
-(``tests/test_oracle_pins.py``): ``torchaudio.functional.melscale_fbanks`` (Slaney
+(``tests/test_oracle.py``): ``torchaudio.functional.melscale_fbanks`` (Slaney
 basis), ``torch.stft`` / ``torch.istft`` in float64 (framing, padding, window,
 overlap-add, window-sum-square normalisation), ``scipy.optimize.fmin_l_bfgs_b``
 (the very routine librosa's NNLS calls) and ``torch.bucketize``.
@@ -420,3 +420,43 @@ def bucketize(v, boundaries, right=False):
 def bucketize_embed(v, boundaries, table, right=False):
     idx = bucketize(v, boundaries, right=right)
     return idx, np.asarray(table)[idx]
+
+
+# ----------------------------------------------------------------------------------
+# frame-level energy / brightness and per-phoneme pooling
+#   reference: spev_real_metrics.py:370-371 (rms, spectral_centroid) and :400-417 (pooling)
+# ----------------------------------------------------------------------------------
+def rms(*, y, frame_length=2048, hop_length=512, center=True, pad_mode="constant"):
+    """librosa.feature.rms(y=...) -> ``[..., 1, T]`` float32: sqrt(mean(frame**2)) over
+    centre-padded frames; squares and the mean (reduction over the frame axis) in float32."""
+    y = np.asarray(y)
+    if center:
+        pad = [(0, 0)] * (y.ndim - 1) + [(frame_length // 2, frame_length // 2)]
+        y = np.pad(y, pad, mode=pad_mode)
+    n_frames = 1 + (y.shape[-1] - frame_length) // hop_length
+    idx = (np.arange(n_frames) * hop_length)[None, :] + np.arange(frame_length)[:, None]
+    x = y[..., idx]                                    # [..., frame_length, T]
+    power = np.mean(np.abs(x).astype(np.float32) ** 2, axis=-2, keepdims=True)
+    return np.sqrt(power)
+
+
+def spectral_centroid(*, y, sr=22050, n_fft=2048, hop_length=512, center=True, pad_mode="constant"):
+    """librosa.feature.spectral_centroid(y=...) -> ``[..., 1, T]`` float64:
+    sum(freq * normalize(|STFT|, norm=1)), columns with an l1 norm below tiny left unscaled."""
+    S = np.abs(stft(y, n_fft=n_fft, hop_length=hop_length, center=center, pad_mode=pad_mode))
+    freq = np.fft.rfftfreq(n=n_fft, d=1.0 / sr)
+    length = np.sum(np.abs(S), axis=-2, keepdims=True)
+    length = np.where(length < np.finfo(S.dtype).tiny, 1.0, length).astype(S.dtype)
+    Snorm = S / length
+    return np.sum(freq[:, None] * Snorm, axis=-2, keepdims=True)
+
+
+def phoneme_pool(curve, durs, mu, sigma, lo, hi):
+    """One of the per-phone lines of ``spev_real_metrics.py:400-417``:
+    ``np.clip((np.mean(curve[curr:curr+d]) - mu) / sigma, lo, hi)`` for consecutive durations."""
+    out, curr = [], 0
+    for d in durs:
+        sl = slice(curr, curr + int(d))
+        out.append(np.clip((np.mean(curve[sl]) - mu) / sigma, lo, hi))
+        curr += int(d)
+    return np.array(out, dtype=np.float32)

@@ -71,6 +71,9 @@ _SIGS = {
     "spev_griffinlim": (C.c_int, [C.c_void_p, C.POINTER(SpevBatch), C.c_void_p, C.c_int64,
                                   C.c_void_p, C.c_uint64, C.c_int, C.c_float, C.c_void_p,
                                   C.c_void_p, C.c_size_t, C.c_void_p]),
+    "spev_frame_features": (C.c_int, [C.c_void_p, C.POINTER(SpevBatch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "spev_segment_pool": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float,
+                                    C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
     "spev_lr_plan": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                C.c_void_p, C.c_void_p, C.c_void_p]),
     "spev_lr_expand": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_void_p,

@@ -40,6 +40,8 @@ int launch_lr_plan(const void*, int, int, int, int32_t*, int64_t*, int64_t*, int
 int launch_lr_expand(const void*, int64_t, const float*, int, const float*, const float*, const int32_t*, int, int, void*, float*, int64_t, cudaStream_t);
 int launch_duration_rule(const float*, int64_t, float, int64_t*, cudaStream_t);
 int launch_bucketize_embed(const float*, int64_t, const float*, int, int, const float*, int, int64_t*, float*, int, cudaStream_t);
+int launch_frame_features(spev_ctx*, const spev_batch*, const float*, float*, float*, cudaStream_t);
+int launch_segment_pool(const float*, const int64_t*, const int64_t*, const int64_t*, int, float, float, float, float, float*, cudaStream_t);
 int launch_mel_project_tc(spev_ctx*, const float*, int64_t, float*, int, float, float, float, cudaStream_t);
 int launch_mel_to_mag_tc(spev_ctx*, const float*, int64_t, int, float*, int64_t, cudaStream_t);
 int gemm_tc_init(spev_ctx*);
@@ -186,7 +188,7 @@ int spev_create(spev_ctx** out, int device, int sr, int n_fft, int hop, int win,
     spev_ctx* c = new spev_ctx();
     c->device = device; c->sr = sr; c->n_fft = n_fft; c->hop = hop; c->win = kNfft; c->n_mels = n_mels;
     c->fmin = fmin; c->fmax = fmax; c->num_sms = prop.multiProcessorCount; c->tma = nullptr; c->use_tc = 1;
-    c->d_tw = nullptr; c->d_window = nullptr; c->d_basis_pad = c->d_basis_hi = c->d_basis_lo = nullptr;
+    c->d_tw = nullptr; c->d_window = nullptr; c->d_win2048 = nullptr; c->d_tw2048 = nullptr; c->d_basis_pad = c->d_basis_hi = c->d_basis_lo = nullptr;
     c->d_pinv_t = c->d_pinv_hi = c->d_pinv_lo = nullptr;
     c->d_prog_w = nullptr; c->d_prog_i = nullptr;
 
@@ -199,6 +201,15 @@ int spev_create(spev_ctx** out, int device, int sr, int n_fft, int hop, int win,
             const double a = -2.0 * M_PI * (k1 * l) / 1024.0;
             tw[k1 * 32 + l] = make_float2(static_cast<float>(std::cos(a)), static_cast<float>(std::sin(a)));
         }
+    std::vector<float2> win2048(1024), tw2048(512);
+    for (int n = 0; n < 1024; ++n) {
+        const double w0 = 0.5 - 0.5 * std::cos(2.0 * M_PI * (2 * n) / 2048.0), w1 = 0.5 - 0.5 * std::cos(2.0 * M_PI * (2 * n + 1) / 2048.0);
+        win2048[n] = make_float2(0.5f * static_cast<float>(w0), 0.5f * static_cast<float>(w1));
+    }
+    for (int k = 0; k < 512; ++k) {
+        const double a = -2.0 * M_PI * k / 2048.0;
+        tw2048[k] = make_float2(static_cast<float>(std::cos(a)), static_cast<float>(std::sin(a)));
+    }
     build_mel_basis(sr, n_fft, n_mels, fmin, fmax, c->h_basis);
     pinv_jacobi(c->h_basis, n_mels, kBins, c->h_pinv);
 
@@ -260,6 +271,7 @@ int spev_create(spev_ctx** out, int device, int sr, int n_fft, int hop, int win,
 
     int rc = SPEV_OK;
     if ((rc = upload(&c->d_tw, tw)) || (rc = upload(&c->d_window, c->h_window)) ||
+        (rc = upload(&c->d_win2048, win2048)) || (rc = upload(&c->d_tw2048, tw2048)) ||
         (rc = upload(&c->d_basis_pad, basis_pad)) || (rc = upload(&c->d_basis_hi, b_hi)) ||
         (rc = upload(&c->d_basis_lo, b_lo)) || (rc = upload(&c->d_pinv_t, pinv_t)) ||
         (rc = upload(&c->d_prog_w, prog_w)) || (rc = upload(&c->d_prog_i, prog_i)) ||
@@ -275,7 +287,7 @@ void spev_destroy(spev_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     gemm_tc_destroy(c);
-    cudaFree(c->d_tw); cudaFree(c->d_window); cudaFree(c->d_basis_pad); cudaFree(c->d_basis_hi);
+    cudaFree(c->d_tw); cudaFree(c->d_window); cudaFree(c->d_win2048); cudaFree(c->d_tw2048); cudaFree(c->d_basis_pad); cudaFree(c->d_basis_hi);
     cudaFree(c->d_basis_lo); cudaFree(c->d_pinv_t); cudaFree(c->d_pinv_hi); cudaFree(c->d_pinv_lo);
     cudaFree(c->d_prog_w); cudaFree(c->d_prog_i);
     delete c;
@@ -451,6 +463,18 @@ int spev_griffinlim(spev_ctx* c, const spev_batch* b, const float* S, int64_t ld
         if ((rc = launch_stft_phase(c, b, y, S, ld_s, ang, tprev, kSpecLd, alpha, it > 0, true, st))) return rc;
     }
     return launch_istft(c, b, ang, kSpecLd, y, st);
+}
+
+int spev_frame_features(spev_ctx* c, const spev_batch* b, const float* samples, float* rms, float* centroid, void* stream) {
+    int rc = with_device(c);
+    if (rc) return rc;
+    return launch_frame_features(c, b, samples, rms, centroid, static_cast<cudaStream_t>(stream));
+}
+
+int spev_segment_pool(const float* curve, const int64_t* frame_off, const int64_t* durs, const int64_t* phone_off,
+                      int n_items, float mu, float sigma, float lo, float hi, float* out, void* stream) {
+    return launch_segment_pool(curve, frame_off, durs, phone_off, n_items, mu, sigma, lo, hi, out,
+                               static_cast<cudaStream_t>(stream));
 }
 
 int spev_lr_plan(const void* dur, int dur_dtype, int B, int T, int32_t* cumsum, int64_t* mel_lens,

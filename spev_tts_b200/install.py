@@ -4,6 +4,7 @@ the B200 path.
 Patches, when the modules are importable:
   * ``librosa.feature.melspectrogram``            (used at ``spev_real_metrics.py:363``)
   * ``librosa.feature.inverse.mel_to_audio``      (used at ``:730-733``)
+  * ``librosa.feature.rms`` / ``librosa.feature.spectral_centroid``   (``:370-371``, stats pass ``:314-316``)
   * ``spev_real_metrics.LengthRegulator``         (``:122-146``; instantiated at ``:160``)
 Calls with parameters outside the implemented configuration (n_fft != 1024, ...) are passed
 through to the original function.
@@ -12,7 +13,7 @@ from __future__ import annotations
 
 import sys
 
-from . import length_regulator, spectral
+from . import features, length_regulator, spectral
 
 _installed = {}
 
@@ -37,6 +38,10 @@ def install(verbose: bool = False) -> dict:
         _installed["mel_to_audio"] = librosa.feature.inverse.mel_to_audio
         librosa.feature.melspectrogram = _passthrough(spectral.melspectrogram, _installed["melspectrogram"])
         librosa.feature.inverse.mel_to_audio = _passthrough(spectral.mel_to_audio, _installed["mel_to_audio"])
+        _installed["rms"] = librosa.feature.rms
+        _installed["spectral_centroid"] = librosa.feature.spectral_centroid
+        librosa.feature.rms = _passthrough(features.rms, _installed["rms"])
+        librosa.feature.spectral_centroid = _passthrough(features.spectral_centroid, _installed["spectral_centroid"])
         done["librosa"] = True
     except ImportError:
         done["librosa"] = False

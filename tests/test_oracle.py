@@ -119,3 +119,22 @@ def test_griffinlim_golden_and_convergence(golden):
     sc0 = lr.spectral_convergence(lr.griffinlim(S, n_iter=0, hop_length=256, n_fft=1024, init_phase=ph), S)
     sc8 = lr.spectral_convergence(y, S)
     assert abs(sc8 - float(g["sc8"])) < 1e-4 and sc8 < sc0
+
+
+def test_rms_and_centroid_vs_torch():
+    """8(f) row 1 restatements pinned against torch (float64 STFT magnitude, unfold)."""
+    y = synth.speechy(seed=9, n=30000)
+    yt = torch.from_numpy(y).double()
+    frames = torch.nn.functional.pad(yt, (1024, 1024)).unfold(0, 2048, 256)          # [T, 2048]
+    r_t = frames.pow(2).mean(1).sqrt().numpy()
+    r = lr.rms(y=y, hop_length=256)[0]
+    assert r.shape == r_t.shape == (1 + 30000 // 256,) and np.abs(r - r_t).max() < 1e-6
+    w = torch.hann_window(2048, periodic=True, dtype=torch.float64)
+    S = torch.stft(yt, 2048, 256, 2048, w, center=True, pad_mode="constant", return_complex=True).abs().numpy()
+    f = np.arange(1025) * 22050 / 2048
+    c_t = (f[:, None] * S).sum(0) / S.sum(0)
+    c = lr.spectral_centroid(y=y, sr=22050, hop_length=256)[0]
+    assert np.abs(c - c_t).max() / c_t.max() < 1e-6
+    assert lr.spectral_centroid(y=np.zeros(4096, np.float32), sr=22050)[0].max() == 0.0    # silent columns
+    pooled = lr.phoneme_pool(np.arange(10, dtype=np.float32), [2, 3, 5], 1.0, 2.0, -1.0, 1.5)
+    assert np.allclose(pooled, np.clip((np.array([0.5, 3.0, 7.0]) - 1) / 2, -1, 1.5))
