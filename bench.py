@@ -327,10 +327,11 @@ def run_ours(args):
         del parts
 
     # ---------------- second half of the metric: Griffin-Lim on cfg3 (rank 0 reports) ------------
-    gl = lr_res = tc = cfg5 = None
+    gl = lr_res = tc = cfg5 = feat = None
     if not args.no_gl:
         cfg5 = bench_logmel_cfg5(sp, dev, hbm_peak, spcache)
         tc = bench_mel_gemm_tc(sp, dev, samples, lens, starts, hbm_peak, out)
+        feat = bench_frame_features(sp, dev, samples, lens, starts, hbm_peak)
         gl = bench_griffinlim(sp, dev, hbm_peak, args)
         lr_res = bench_length_regulator(sp, dev, args)
     del samples, out
@@ -358,7 +359,7 @@ def run_ours(args):
                          "kernel_ms_max_over_ranks": kern_ms_max, "traffic": None,
                          "note": "fp32-pipe/shared-memory bound by design (SURVEY 0.7): ~25 kFLOP FFT per 1,344 B"},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks,
-            "gather": gather, "logmel_cfg5": cfg5, "mel_gemm_tc": tc, "griffinlim": gl, "length_regulator": lr_res,
+            "gather": gather, "logmel_cfg5": cfg5, "mel_gemm_tc": tc, "frame_features": feat, "griffinlim": gl, "length_regulator": lr_res,
         }
         print(json.dumps(line))
     if world > 1:
@@ -435,6 +436,28 @@ def bench_mel_gemm_tc(sp, dev, samples, lens, starts, hbm_peak, fused_out):
             "tensor": {"achieved_tflops_3xtf32": flops / (ms2 * 1e-3) / 1e12, "peak_tflops_tf32": tf32_peak,
                        "frac": flops / (ms2 * 1e-3) / 1e12 / tf32_peak,
                        "note": "arithmetic intensity 103 FLOP/B (3 passes) < ridge ~125: the projection is HBM-bound"}}
+
+
+def bench_frame_features(sp, dev, samples, lens, starts, hbm_peak):
+    """SURVEY 8(f) row 1 on the cfg4 shard: RMS + spectral centroid (2048-point STFT), one launch."""
+    import torch
+    ctx = sp.Context.get(dev, sr=SR, n_mels=N_MELS)
+    batch = sp.make_batch(ctx, n_samples=lens, sample_off=starts)
+    for _ in range(2):
+        sp.frame_features_flat(samples, lens, batch=batch)
+    a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(3):
+        sp.frame_features_flat(samples, lens, batch=batch)
+    b.record(); torch.cuda.synchronize(dev)
+    ms = a.elapsed_time(b) / 3
+    F = batch.n_frames
+    return {"config": {"workload": "cfg4 shard: rms + spectral centroid per frame (n_fft=2048, hop=256)"},
+            "value": F / (ms * 1e-3), "unit": "frames/s", "ms_per_step": ms,
+            "roofline": {"bound": "hbm", "kernel": "k_frame_features", "achieved": 1032.0 * F / (ms * 1e-3) / 1e9,
+                         "peak": hbm_peak, "unit": "GB/s", "frac": 1032.0 * F / (ms * 1e-3) / 1e9 / hbm_peak,
+                         "alg_bytes_per_frame": 1032,
+                         "note": "one full 1024-complex warp FFT per frame (2x the STFT kernel's FFT work): issue-bound"}}
 
 
 def bench_griffinlim(sp, dev, hbm_peak, args):

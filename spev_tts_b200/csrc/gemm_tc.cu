@@ -111,7 +111,8 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n) {
 
 template <int BN>
 struct TcSmem {
-    static constexpr int kStages = BN > 128 ? 2 : 3;   // 227 KB budget
+    static constexpr int kStages = 2;                  // 2 x 52 KB (BN=80): two CTAs per SM keep 4 stages of loads in flight
+    static constexpr int kCtas = BN > 128 ? 1 : 2;
     static constexpr uint32_t kBBytes = BN * kBK * 4;
     static constexpr uint32_t kStage = 2 * kABytes + 2 * kBBytes;
     static constexpr uint32_t kBars = 1024;
@@ -120,7 +121,7 @@ struct TcSmem {
 };
 
 template <int BN, int EPI>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kTcThreads, TcSmem<BN>::kCtas)
 k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
               const __grid_constant__ CUtensorMap map_blo, float* __restrict__ out, TcParams p) {
     using L = TcSmem<BN>;
