@@ -125,6 +125,11 @@ SPEV_API int64_t spev_plan_chunk_tiles(const int64_t* frames, int n_items, spev_
 SPEV_API int spev_logmel(spev_ctx* ctx, const spev_batch* batch, const float* samples, float* out,
                 int mode, float floor, float lo, float hi, void* stream);
 
+/* 16-bit PCM -> float32, out[i] = pcm[i] / 32768 (exact): the values soundfile / librosa.load hand to
+ * melspectrogram for a 16-bit wav (spev_real_metrics.py:332 -> :363).  Lets a cache build ship PCM
+ * over PCIe (half the bytes) and widen on the device. */
+SPEV_API int spev_pcm16_to_f32(const int16_t* pcm, int64_t n, float* out, void* stream);
+
 /* Same front end, but writes the power spectrum |STFT|^2 as [n_frames, SPEV_SPEC_LD] (pad
  * columns zero) -- the A operand of spev_mel_project. */
 SPEV_API int spev_stft_power(spev_ctx* ctx, const spev_batch* batch, const float* samples, float* power,

@@ -53,6 +53,7 @@ _SIGS = {
     "spev_plan_chunk_tiles": (C.c_int64, [C.c_void_p, C.c_int, C.c_void_p]),
     "spev_logmel": (C.c_int, [C.c_void_p, C.POINTER(SpevBatch), C.c_void_p, C.c_void_p, C.c_int,
                               C.c_float, C.c_float, C.c_float, C.c_void_p]),
+    "spev_pcm16_to_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "spev_stft_power": (C.c_int, [C.c_void_p, C.POINTER(SpevBatch), C.c_void_p, C.c_void_p,
                                   C.c_void_p]),
     "spev_mel_project": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int,

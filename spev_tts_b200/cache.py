@@ -18,7 +18,7 @@ from typing import List, Optional, Sequence, Tuple
 import numpy as np
 import torch
 
-from . import spectral
+from . import _lib, spectral
 from .batch import HOP, Context, make_batch
 
 
@@ -92,6 +92,7 @@ class LogMelCacheBuilder:
         self.copy_in = torch.cuda.Stream(self.device)
         self.compute = torch.cuda.Stream(self.device)
         self.copy_out = torch.cuda.Stream(self.device)
+        self._pcm: List[Optional[torch.Tensor]] = [None] * n_buffers
         self._in: List[Optional[torch.Tensor]] = [None] * n_buffers
         self._out: List[Optional[torch.Tensor]] = [None] * n_buffers
         self.launches = 0
@@ -104,9 +105,14 @@ class LogMelCacheBuilder:
     def build(self, samples_host: torch.Tensor, n_samples: Sequence[int],
               out_host: Optional[torch.Tensor] = None, plan: Optional[CachePlan] = None,
               sample_off: Optional[np.ndarray] = None):
-        """``samples_host``: flat float32 host tensor (pinned for full copy speed) holding the
-        utterances at ``sample_off`` (default: packed back to back; ``aligned_offsets`` gives the
-        fast layout); returns ``(out_host [F, n_mels] pinned, frame_off)``."""
+        """``samples_host``: flat host tensor (pinned for full copy speed) holding the utterances at
+        ``sample_off`` (default: packed back to back; ``aligned_offsets`` gives the fast layout),
+        either float32 or **int16 PCM** (shipped as 2 bytes/sample and widened to ``pcm/32768`` on the
+        device -- the exact values a 16-bit wav decodes to); returns ``(out_host [F, n_mels] pinned,
+        frame_off)``."""
+        pcm = samples_host.dtype == torch.int16
+        if not pcm and samples_host.dtype != torch.float32:
+            raise ValueError("samples_host must be float32 or int16 PCM")
         if plan is None:
             plan = plan_chunks(n_samples, self.chunk_samples, sample_off)
         F = int(plan.frame_off[-1])
@@ -120,6 +126,8 @@ class LogMelCacheBuilder:
         for i in range(nb):
             self._buf(self._in, i, max_in)
             self._buf(self._out, i, max_out)
+            if pcm:
+                self._buf(self._pcm, i, max_in, torch.int16)
         # descriptors are tiny; build them all up front so the loop only enqueues
         batches = [make_batch(self.ctx, n_samples=plan.n_samples[a:b],
                               sample_off=plan.sample_off[a:b] - plan.sample_off[a]) for a, b in plan.chunks]
@@ -135,13 +143,17 @@ class LogMelCacheBuilder:
             with torch.cuda.stream(self.copy_in):
                 if ci >= nb:
                     self.copy_in.wait_event(in_free[i])
-                d_in.copy_(samples_host[s0:s1], non_blocking=True)
+                (self._pcm[i][: s1 - s0] if pcm else d_in).copy_(samples_host[s0:s1], non_blocking=True)
                 ready = torch.cuda.Event()
                 ready.record(self.copy_in)
             with torch.cuda.stream(self.compute):
                 self.compute.wait_event(ready)
                 if ci >= nb:
                     self.compute.wait_event(out_free[i])
+                if pcm:
+                    _lib.check(self.ctx.lib.spev_pcm16_to_f32(self._pcm[i].data_ptr(), s1 - s0, d_in.data_ptr(),
+                                                              self.compute.cuda_stream), "spev_pcm16_to_f32")
+                    self.launches += 1
                 spectral.logmel_flat(d_in, plan.n_samples[a:b], sr=self.sr, n_mels=self.n_mels,
                                      out=d_out, batch=batches[ci])
                 self.launches += 1

@@ -211,9 +211,45 @@ k_bucketize_embed(const float* __restrict__ v, int64_t n, const float* __restric
     }
 }
 
+// ---- 16-bit PCM -> float32 (x / 32768): what soundfile/librosa.load produce from a 16-bit wav ----
+__global__ void k_pcm16_to_f32(const short* __restrict__ in, int64_t n, float* __restrict__ out) {
+    const int64_t n8 = n >> 3;
+    const bool vec = ((reinterpret_cast<uintptr_t>(in) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    const int64_t nthr = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    int64_t done = 0;
+    if (vec) {
+        for (int64_t i = tid; i < n8; i += nthr) {
+            const int4 v = __ldg(reinterpret_cast<const int4*>(in) + i);   // 8 samples
+            const int w[4] = {v.x, v.y, v.z, v.w};
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                f[2 * j] = static_cast<float>(static_cast<short>(w[j] & 0xffff)) * (1.0f / 32768.0f);
+                f[2 * j + 1] = static_cast<float>(static_cast<short>(w[j] >> 16)) * (1.0f / 32768.0f);
+            }
+            float4* o = reinterpret_cast<float4*>(out) + 2 * i;
+            o[0] = make_float4(f[0], f[1], f[2], f[3]);
+            o[1] = make_float4(f[4], f[5], f[6], f[7]);
+        }
+        done = n8 << 3;
+    }
+    for (int64_t i = done + tid; i < n; i += nthr) out[i] = static_cast<float>(in[i]) * (1.0f / 32768.0f);
+}
+
 // ---------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------
+int launch_pcm16_to_f32(const int16_t* in, int64_t n, float* out, cudaStream_t st) {
+    SPEV_REQUIRE(n >= 0, SPEV_E_INVALID, "pcm16_to_f32: n < 0");
+    if (n == 0) return SPEV_OK;
+    SPEV_REQUIRE(in && out, SPEV_E_INVALID, "pcm16_to_f32: null buffer");
+    const int grid = static_cast<int>(std::min<int64_t>((n / 8 + 255) / 256 + 1, 148 * 16));
+    k_pcm16_to_f32<<<grid, 256, 0, st>>>(reinterpret_cast<const short*>(in), n, out);
+    SPEV_CUDA(cudaGetLastError());
+    return SPEV_OK;
+}
+
 int launch_lr_plan(const void* dur, int dur_dtype, int B, int T, int32_t* cumsum, int64_t* mel_lens,
                    int64_t* max_len_dev, int64_t* max_len_host, cudaStream_t st) {
     SPEV_REQUIRE(B >= 0 && T >= 0, SPEV_E_INVALID, "lr_plan: negative shape");

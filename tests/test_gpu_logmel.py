@@ -104,6 +104,25 @@ def test_pipelined_host_builder_matches_device_path(cuda):
     assert torch.equal(out2, out)
 
 
+def test_pcm16_host_path_is_exact(cuda):
+    """int16 PCM shipped over PCIe and widened on the device == float32(pcm / 32768) shipped directly."""
+    import spev_tts_b200 as sp
+    from spev_tts_b200 import cache
+    lens = synth.utterance_lengths(seed=15, n_utts=120)
+    rng = np.random.default_rng(15)
+    starts = cache.aligned_offsets(lens)
+    pcm = rng.integers(-32768, 32768, int(starts[-1]), dtype=np.int16)
+    f32 = (pcm.astype(np.float32) / 32768.0)
+    out_f, _ = cache.build_logmel_cache(torch.from_numpy(f32).pin_memory(), lens, device=cuda, sample_off=starts,
+                                        chunk_samples=1 << 20)
+    out_p, _ = cache.build_logmel_cache(torch.from_numpy(pcm).pin_memory(), lens, device=cuda, sample_off=starts,
+                                        chunk_samples=1 << 20)
+    assert torch.equal(out_f, out_p)
+    ref = lr.reference_logmel(f32[starts[3]: starts[3] + lens[3]])
+    fo = np.concatenate([[0], np.cumsum(1 + lens // 256)])
+    assert np.abs(out_p[fo[3]: fo[4]].numpy() - ref).max() <= TOL_LOGMEL
+
+
 def test_cfg4_scale_properties(cuda):
     """Full-size shaped run (device-generated, ~0.6 M frames here; bench.py runs all 6.2 M):
     batch result == per-utterance result (checksum of checksums), spot checks vs oracle,
