@@ -216,6 +216,7 @@ def run_ours(args):
     assert torch.cuda.is_available(), "bench.py (our arm) needs a B200; there is no CPU fallback"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = spcache.bind_to_gpu_numa_node(dev) if world > 1 else {"bound": False}   # before any pinned allocation
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     sp.load()
@@ -307,7 +308,8 @@ def run_ours(args):
         e2e = {"value": frames_all / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": total * 4,
                "d2h_bytes_per_step": F * N_MELS * 4, "ms_per_step": e2e_ms, "steps": n_e2e,
                "launches_per_step": e2e_launches, "matches_device_result": ok,
-               "api": "spev_tts_b200.cache.LogMelCacheBuilder.build (pinned host in/out, 3-stream pipeline)"}
+               "api": "spev_tts_b200.cache.LogMelCacheBuilder.build (pinned host in/out, 3-stream pipeline)",
+               "host_numa_binding_rank0": numa}
         # extra: the same corpus as 16-bit PCM on the host (the on-disk format of LJSpeech-style
         # corpora; pcm/32768 is exactly what the reference's loader produces) -> half the H2D bytes
         pcm = (samples.clamp(-1, 1) * 32767).to(torch.int16)

@@ -203,6 +203,24 @@ SPEV_API int spev_segment_pool(const float* curve, const int64_t* frame_off, con
                                const int64_t* phone_off, int n_items, float mu, float sigma, float lo, float hi,
                                float* out, void* stream);
 
+/* GPU-side batching of a resident cache: ragged -> zero-padded copies, i.e. the
+ * pad_sequence(..., batch_first=True) calls of the reference's collate_fn (spev_real_metrics.py:449-462)
+ * for up to 12 arrays in one launch.  Array k holds rows of row_bytes bytes, indexed per frame
+ * (per_phone = 0: item i owns rows [frame_off[i], frame_off[i+1])) or per phoneme (per_phone = 1:
+ * phone_off).  For batch entry b (item sel[b], or b when sel is NULL):
+ *   dst_k[b, r, :] = src_k[off[item] + r, :]  for r < len(item),  0 for len(item) <= r < t_max / p_max.
+ * Rows are copied verbatim: bit-exact for every dtype. */
+typedef struct spev_pad_array {
+    const void* src;     /* dev: flat [rows, row_bytes] */
+    void* dst;           /* dev: [B, t_max or p_max, row_bytes] */
+    int64_t row_bytes;
+    int32_t per_phone;
+    int32_t reserved;
+} spev_pad_array;
+SPEV_API int spev_collate(const spev_pad_array* arrays_host, int n_arrays, const int64_t* frame_off,
+                          const int64_t* phone_off, const int64_t* sel, int B, int64_t t_max, int64_t p_max,
+                          void* stream);
+
 /* LengthRegulator, phase 1: sanitise durations (non-finite / <0 / >1000 -> 0, truncate),
  * inclusive row cumsum, mel_lens = max(total, 1), max_len = max(mel_lens).
  *   dur       : dev [B,T], dur_dtype 0=int64 1=int32 2=float32 3=float64 4=float16 5=bfloat16

@@ -13,8 +13,12 @@ Run in the build container (where ``/root/reference`` is mounted):
 * ``logmel_*.npz``, ``gl_*.npz`` -- produced by ``oracle.librosa_restated`` (the reference's
                        librosa is not installable: parity for these is unpinned by the
                        reference; the fixtures freeze the restatement so that it cannot
-                       drift silently, and ``tests/test_oracle_pins.py`` checks it against
+                       drift silently, and ``tests/test_oracle.py`` checks it against
                        torch / torchaudio / scipy independently).
+
+* ``collate.npz``   -- produced by the REFERENCE'S OWN ``RealMetricsDataset`` (constructor early-return
+                       path ``:291-298``, ``__getitem__`` ``:433-447``) and ``collate_fn`` (``:449-462``) on a
+                       cache written by ``spev_tts_b200.dataset.write_reference_cache``.
 
 Inputs are regenerated from seeds by ``tests/synth.py``; large outputs are stored as
 SHA-256 digests plus a decimated slice so that the fixtures stay small.
@@ -111,6 +115,23 @@ def main() -> None:
                                      return_state=True)
     np.savez_compressed(os.path.join(OUT, "gl_small.npz"), logmel=lm, S=S, y8=y8,
                         sc8=np.array(lr.spectral_convergence(y8, S)))
+    # ---- cache consumer: the reference's own Dataset.__getitem__ + collate_fn (:433-462) ----------
+    import tempfile
+    from spev_tts_b200.dataset import write_reference_cache
+    recs, stats, vocab = synth.cache_records(seed=8)
+    with tempfile.TemporaryDirectory() as tmp:
+        write_reference_cache(tmp, recs, stats, vocab)
+        # the reference's own constructor takes its early-return path (:291-298: > 10 records and a
+        # metadata.json) -- i.e. it accepts the cache we wrote
+        ds = ref.RealMetricsDataset("unused_data_dir", cache_dir=tmp, force_rebuild=False)
+        assert len(ds) == len(recs) and ds.vocab == vocab and ds.stats == stats
+        gold = {}
+        for name, idx in (("a", [0, 5, 2, 7]), ("b", list(range(len(recs)))), ("c", [3])):
+            batch = ref.collate_fn([ds[i] for i in idx])
+            gold[name + "_idx"] = np.array(idx)
+            for k, v in batch.items():
+                gold[f"{name}_{k}"] = v.numpy()
+    np.savez_compressed(os.path.join(OUT, "collate.npz"), **gold)
     print("golden fixtures written to", OUT)
     for f in sorted(os.listdir(OUT)):
         print(f"  {f:28s} {os.path.getsize(os.path.join(OUT, f)):>9d} B")

@@ -27,6 +27,12 @@ class SpevTile(C.Structure):
                 ("n", C.c_int32), ("t0", C.c_int32), ("T", C.c_int32), ("item", C.c_int32)]
 
 
+class SpevPadArray(C.Structure):
+    """``struct spev_pad_array``."""
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("row_bytes", C.c_int64),
+                ("per_phone", C.c_int32), ("reserved", C.c_int32)]
+
+
 class SpevBatch(C.Structure):
     """``struct spev_batch`` (include/spev_b200.h)."""
     _fields_ = [
@@ -75,6 +81,8 @@ _SIGS = {
     "spev_frame_features": (C.c_int, [C.c_void_p, C.POINTER(SpevBatch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "spev_segment_pool": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float,
                                     C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
+    "spev_collate": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64,
+                               C.c_void_p]),
     "spev_lr_plan": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                C.c_void_p, C.c_void_p, C.c_void_p]),
     "spev_lr_expand": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_void_p,

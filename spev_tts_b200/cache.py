@@ -23,6 +23,46 @@ from .batch import HOP, Context, make_batch
 
 
 # ---------------------------------------------------------------------------------------------
+# host placement: pinned staging buffers should live on the NUMA node the GPU hangs off
+# ---------------------------------------------------------------------------------------------
+def _parse_cpulist(text: str):
+    cpus = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        cpus.extend(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(device) -> dict:
+    """Pin the calling process to the CPUs of the NUMA node that `device`'s PCIe root belongs to
+    (Linux sysfs).  Call it BEFORE allocating pinned host buffers: first-touch then places them on
+    that node, so that H2D/D2H copies of several ranks do not cross sockets.  Best effort: returns
+    what it did and never raises."""
+    import os
+    info = {"bound": False}
+    try:
+        dev = torch.device(device)
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        props = torch.cuda.get_device_properties(idx)
+        bdf = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        info.update(pci=bdf, numa_node=node)
+        if node < 0:
+            return info
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set(_parse_cpulist(f.read())) & set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info.update(bound=True, n_cpus=len(cpus))
+    except Exception as e:   # sysfs layout / permissions differ: keep going unbound
+        info["error"] = repr(e)
+    return info
+
+
+# ---------------------------------------------------------------------------------------------
 # sharding (host logic; CPU-testable)
 # ---------------------------------------------------------------------------------------------
 def frames_of(n_samples) -> np.ndarray:

@@ -40,6 +40,7 @@ int launch_lr_plan(const void*, int, int, int, int32_t*, int64_t*, int64_t*, int
 int launch_lr_expand(const void*, int64_t, const float*, int, const float*, const float*, const int32_t*, int, int, void*, float*, int64_t, cudaStream_t);
 int launch_duration_rule(const float*, int64_t, float, int64_t*, cudaStream_t);
 int launch_pcm16_to_f32(const int16_t*, int64_t, float*, cudaStream_t);
+int launch_collate(const spev_pad_array*, int, const int64_t*, const int64_t*, const int64_t*, int, int64_t, int64_t, cudaStream_t);
 int launch_bucketize_embed(const float*, int64_t, const float*, int, int, const float*, int, int64_t*, float*, int, cudaStream_t);
 int launch_frame_features(spev_ctx*, const spev_batch*, const float*, float*, float*, cudaStream_t);
 int launch_segment_pool(const float*, const int64_t*, const int64_t*, const int64_t*, int, float, float, float, float, float*, cudaStream_t);
@@ -476,6 +477,11 @@ int spev_segment_pool(const float* curve, const int64_t* frame_off, const int64_
                       int n_items, float mu, float sigma, float lo, float hi, float* out, void* stream) {
     return launch_segment_pool(curve, frame_off, durs, phone_off, n_items, mu, sigma, lo, hi, out,
                                static_cast<cudaStream_t>(stream));
+}
+
+int spev_collate(const spev_pad_array* arrays, int n_arrays, const int64_t* frame_off, const int64_t* phone_off,
+                 const int64_t* sel, int B, int64_t t_max, int64_t p_max, void* stream) {
+    return launch_collate(arrays, n_arrays, frame_off, phone_off, sel, B, t_max, p_max, static_cast<cudaStream_t>(stream));
 }
 
 int spev_lr_plan(const void* dur, int dur_dtype, int B, int T, int32_t* cumsum, int64_t* mel_lens,

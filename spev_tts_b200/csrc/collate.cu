@@ -1,0 +1,81 @@
+// collate.cu -- GPU-side batching of a resident cache: the ragged -> padded
+// copies of the reference's collate_fn (/root/reference/spev_real_metrics.py:449-462:
+// pad_sequence(..., batch_first=True) over ids, durs, mel and the six per-phone float curves) as
+// ONE launch.  Because every item's rows are contiguous in the flat cache, padding item b of an
+// array is a contiguous copy of len_b * row_bytes followed by a zero fill: pure HBM byte work,
+// 16-byte vectorised when alignment allows, bit-exact for every dtype.
+#include <algorithm>
+#include "spev_internal.cuh"
+
+namespace spev {
+
+constexpr int kMaxPadArrays = 12;
+struct PadParams {
+    int n_arrays, B;
+    int64_t t_max, p_max;
+    const int64_t* frame_off;
+    const int64_t* phone_off;
+    const int64_t* sel;
+    spev_pad_array a[kMaxPadArrays];
+};
+
+constexpr int kPadThreads = 256;
+constexpr int kPadBytesPerCta = kPadThreads * 16 * 4;   // 16 KB of output per CTA
+
+__global__ void __launch_bounds__(kPadThreads)
+k_pad_ragged(PadParams p) {
+    const spev_pad_array arr = p.a[blockIdx.z];
+    const int b = blockIdx.y;
+    const int64_t item = p.sel ? p.sel[b] : b;
+    const int64_t* off = arr.per_phone ? p.phone_off : p.frame_off;
+    const int64_t lmax = arr.per_phone ? p.p_max : p.t_max;
+    const int64_t row = arr.row_bytes;
+    const int64_t valid = (off[item + 1] - off[item]) * row;          // bytes to copy
+    const int64_t total = lmax * row;                                 // bytes of the padded block
+    const unsigned char* src = static_cast<const unsigned char*>(arr.src) + off[item] * row;
+    unsigned char* dst = static_cast<unsigned char*>(arr.dst) + static_cast<int64_t>(b) * total;
+    const int64_t lo = static_cast<int64_t>(blockIdx.x) * kPadBytesPerCta;
+    const int64_t hi = min(total, lo + kPadBytesPerCta);
+    if (lo >= total) return;
+    const bool vec = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) | static_cast<uintptr_t>(valid)) & 15) == 0;
+    if (vec) {
+        for (int64_t i = lo + threadIdx.x * 16; i < hi; i += kPadThreads * 16) {
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (i < valid) v = __ldg(reinterpret_cast<const uint4*>(src + i));
+            if (i + 16 <= total) *reinterpret_cast<uint4*>(dst + i) = v;
+            else for (int64_t j = i; j < total; ++j) dst[j] = j < valid ? src[j] : 0;
+        }
+    } else if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) | static_cast<uintptr_t>(row)) & 3) == 0) {
+        for (int64_t i = lo + threadIdx.x * 4; i < hi; i += kPadThreads * 4)
+            *reinterpret_cast<uint32_t*>(dst + i) = i < valid ? __ldg(reinterpret_cast<const uint32_t*>(src + i)) : 0u;
+    } else {
+        for (int64_t i = lo + threadIdx.x; i < hi; i += kPadThreads) dst[i] = i < valid ? src[i] : 0;
+    }
+}
+
+int launch_collate(const spev_pad_array* arrays, int n_arrays, const int64_t* frame_off, const int64_t* phone_off,
+                   const int64_t* sel, int B, int64_t t_max, int64_t p_max, cudaStream_t st) {
+    SPEV_REQUIRE(n_arrays >= 0 && n_arrays <= kMaxPadArrays && B >= 0 && t_max >= 0 && p_max >= 0, SPEV_E_INVALID,
+                 "collate: bad sizes (at most %d arrays)", kMaxPadArrays);
+    if (n_arrays == 0 || B == 0) return SPEV_OK;
+    SPEV_REQUIRE(arrays && B <= 65535, SPEV_E_INVALID, "collate: null arrays or B > 65535");
+    PadParams p{};
+    p.n_arrays = n_arrays; p.B = B; p.t_max = t_max; p.p_max = p_max;
+    p.frame_off = frame_off; p.phone_off = phone_off; p.sel = sel;
+    int64_t max_bytes = 0;
+    for (int i = 0; i < n_arrays; ++i) {
+        SPEV_REQUIRE(arrays[i].src && arrays[i].dst && arrays[i].row_bytes > 0, SPEV_E_INVALID, "collate: array %d incomplete", i);
+        SPEV_REQUIRE(arrays[i].per_phone ? phone_off != nullptr : frame_off != nullptr, SPEV_E_INVALID,
+                     "collate: array %d needs an offset table that was not given", i);
+        p.a[i] = arrays[i];
+        max_bytes = std::max(max_bytes, (arrays[i].per_phone ? p_max : t_max) * arrays[i].row_bytes);
+    }
+    if (max_bytes == 0) return SPEV_OK;
+    dim3 grid(static_cast<unsigned>((max_bytes + kPadBytesPerCta - 1) / kPadBytesPerCta), static_cast<unsigned>(B),
+              static_cast<unsigned>(n_arrays));
+    k_pad_ragged<<<grid, kPadThreads, 0, st>>>(p);
+    SPEV_CUDA(cudaGetLastError());
+    return SPEV_OK;
+}
+
+}  // namespace spev

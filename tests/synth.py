@@ -106,3 +106,23 @@ def cfg3_logmels(seed: int = 3, B: int = 16, T: int = 800):
     caller with the oracle.  Here: just the raw signals."""
     n = (T - 1) * HOP
     return [speechy(seed=seed * 100 + b, n=n) for b in range(B)]
+
+
+def cache_records(seed: int = 8, n: int = 12, n_mels: int = 80):
+    """Synthetic cache records in the reference's format (spev_real_metrics.py:419-425) + vocab/stats."""
+    import torch
+    r = np.random.default_rng(seed)
+    vocab = sorted(["<PAD>", "<UNK>", "<SIL>"] + [chr(97 + i) for i in range(20)])
+    recs = []
+    for _ in range(n):
+        P = int(r.integers(3, 14))
+        durs = r.integers(1, 9, P)
+        T = int(durs.sum())
+        phs = ["<SIL>"] + [str(x) for x in r.choice(vocab + ["zz"], P - 2)] + ["<SIL>"]      # "zz": out of vocab -> id 0
+        recs.append({"phs": phs, "durs": [int(d) for d in durs],
+                     "mel": torch.from_numpy(np.clip(r.standard_normal((T, n_mels)) * 2 - 4, -10, 2).astype(np.float32)),
+                     "pitch": np.clip(r.standard_normal(P), -2.5, 2.5), "energy": np.clip(r.standard_normal(P), -2.5, 2.5),
+                     "breath": np.clip(r.random(P), 0, 0.8), "rough": np.clip(r.random(P) * 2, 0, 1.5),
+                     "bright": np.clip(r.standard_normal(P), -2.5, 2.5)})
+    stats = {"p_mean": 5.0, "p_std": 0.3, "e_mean": -3.0, "e_std": 1.0, "c_mean": 7.0, "c_std": 0.5}
+    return recs, stats, vocab

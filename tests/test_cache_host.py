@@ -84,3 +84,9 @@ def test_gather_shards_world2_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res == {0: True, 1: True}
+
+
+def test_cpulist_parser():
+    from spev_tts_b200 import cache
+    assert cache._parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert cache._parse_cpulist("") == []
