@@ -350,11 +350,12 @@ def run_ours(args):
         del parts
 
     # ---------------- second half of the metric: Griffin-Lim on cfg3 (rank 0 reports) ------------
-    gl = lr_res = tc = cfg5 = feat = None
+    gl = lr_res = tc = cfg5 = feat = coll = None
     if not args.no_gl:
         cfg5 = bench_logmel_cfg5(sp, dev, hbm_peak, spcache)
         tc = bench_mel_gemm_tc(sp, dev, samples, lens, starts, hbm_peak, out)
         feat = bench_frame_features(sp, dev, samples, lens, starts, hbm_peak)
+        coll = bench_collate(sp, dev, out, batch, hbm_peak)
         gl = bench_griffinlim(sp, dev, hbm_peak, args)
         lr_res = bench_length_regulator(sp, dev, args)
     del samples, out
@@ -385,7 +386,7 @@ def run_ours(args):
                                          "note": "co-limited by issue slots and the shared-memory pipe, not HBM"},
                          "note": "fp32-pipe/shared-memory bound by design (SURVEY 0.7): ~25 kFLOP FFT per 1,344 B"},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks,
-            "gather": gather, "logmel_cfg5": cfg5, "mel_gemm_tc": tc, "frame_features": feat, "griffinlim": gl, "length_regulator": lr_res,
+            "gather": gather, "logmel_cfg5": cfg5, "mel_gemm_tc": tc, "frame_features": feat, "collate": coll, "griffinlim": gl, "length_regulator": lr_res,
         }
         print(json.dumps(line))
     if world > 1:
@@ -484,6 +485,39 @@ def bench_frame_features(sp, dev, samples, lens, starts, hbm_peak):
                          "peak": hbm_peak, "unit": "GB/s", "frac": 1032.0 * F / (ms * 1e-3) / 1e9 / hbm_peak,
                          "alg_bytes_per_frame": 1032,
                          "note": "one full 1024-complex warp FFT per frame (2x the STFT kernel's FFT work): issue-bound"}}
+
+
+def bench_collate(sp, dev, mel, batch, hbm_peak):
+    """serve training batches from the GPU-resident cfg4 cache (the reference does
+    torch.load per item + pad_sequence on the CPU + one H2D copy per batch, spev_real_metrics.py:433-462)."""
+    import torch
+    rng = np.random.default_rng(9)
+    U = batch.n_items
+    frames = batch.frames
+    phones = np.maximum(2, frames // 9)                       # ~9 frames per phone
+    po = np.concatenate([[0], np.cumsum(phones)])
+    P = int(po[-1])
+    g = torch.Generator(device=dev).manual_seed(9)
+    ids = torch.randint(0, 60, (P,), generator=g, device=dev)
+    durs = torch.randint(1, 18, (P,), generator=g, device=dev)
+    curves = {k: torch.randn(P, generator=g, device=dev) for k in ("pitch", "energy", "breath", "rough", "bright")}
+    cache = sp.ResidentCache.from_flat(mel, batch.frame_off, ids, durs, po, curves)
+    res = {}
+    for B in (16, 256):
+        idx = rng.choice(U, B, replace=False)
+        for _ in range(3):
+            b = cache.collate(idx)
+        torch.cuda.synchronize(dev)
+        t = time.perf_counter()
+        n = 20
+        for _ in range(n):
+            b = cache.collate(idx)
+        torch.cuda.synchronize(dev)
+        wall_ms = (time.perf_counter() - t) * 1e3 / n
+        nbytes = sum(v.numel() * v.element_size() for v in b.values())
+        res[f"B{B}"] = {"wall_ms_per_batch": wall_ms, "output_bytes": nbytes, "GBps_wall": nbytes / (wall_ms * 1e-3) / 1e9,
+                        "mel_shape": list(b["mel"].shape)}
+    return {"config": {"workload": "cfg4 cache resident on the GPU; collate == reference collate_fn output, one launch"}, **res}
 
 
 def bench_griffinlim(sp, dev, hbm_peak, args):

@@ -599,7 +599,10 @@ int launch_stft_mel(spev_ctx* ctx, const spev_batch* b, const float* samples, fl
     SPEV_REQUIRE(samples && out, SPEV_E_INVALID, "null samples/out");
     MelProgram mb{ctx->n_mels, ctx->prog_gmax, ctx->d_prog_w, ctx->d_prog_i};
     const size_t smem = smem_stft(ctx->prog_gmax);
-    SPEV_REQUIRE(smem <= 232448, SPEV_E_UNSUPPORTED, "mel basis too large for the fused kernel (%zu B smem)", smem);
+    SPEV_REQUIRE(smem <= 232448, SPEV_E_UNSUPPORTED,
+                 "this mel basis (n_mels=%d: %d float4 groups per warp program) does not fit the fused kernel's shared memory "
+                 "(%zu B > 232448); bands wider than ~128 bins (n_mels below ~24 at 22 kHz) are not supported",
+                 ctx->n_mels, ctx->prog_gmax, smem);
     const int grid = std::min<int64_t>(b->n_ftiles, ctx->num_sms);
     if (power_only) {
         rc = set_smem(k_stft_mel<1>, smem);

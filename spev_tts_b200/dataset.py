@@ -76,6 +76,26 @@ class ResidentCache:
         self.d_phone_off = torch.from_numpy(self.phone_off).to(dev)
 
     @classmethod
+    def from_flat(cls, mel: torch.Tensor, frame_off, ids: torch.Tensor, durs: torch.Tensor, phone_off,
+                  curves: Dict[str, torch.Tensor], vocab: Sequence[str] = (), stats: Optional[dict] = None):
+        """Adopt device-resident flat arrays directly (e.g. the ``[F,80]`` output of ``logmel_flat`` /
+        ``gather_shards``) without a round trip through per-utterance records."""
+        self = cls.__new__(cls)
+        self.device = mel.device
+        self.vocab, self.stats = list(vocab), stats
+        self.frame_off = np.asarray(frame_off, dtype=np.int64)
+        self.phone_off = np.asarray(phone_off, dtype=np.int64)
+        self.n_frames_per_item = np.diff(self.frame_off)
+        self.n_phones_per_item = np.diff(self.phone_off)
+        self.n_mels = int(mel.shape[1])
+        self.mel, self.ids, self.durs = mel.contiguous(), ids.contiguous(), durs.contiguous()
+        self.log_durs = torch.log(torch.clamp(durs.float(), min=1) + 1)
+        self.curves = {k: curves[k].to(torch.float32).contiguous() for k in CURVES}
+        self.d_frame_off = torch.from_numpy(self.frame_off).to(self.device)
+        self.d_phone_off = torch.from_numpy(self.phone_off).to(self.device)
+        return self
+
+    @classmethod
     def load(cls, cache_dir: str, device=None) -> "ResidentCache":
         records, stats, vocab = read_reference_cache(cache_dir)
         return cls(records, vocab, stats, device)

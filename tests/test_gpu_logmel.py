@@ -57,6 +57,32 @@ def test_inverse_basis_and_sr24k(cuda):
         assert np.array_equal(ctx.mel_basis(), ob)
 
 
+@pytest.mark.parametrize("n_mels,sr,fmin,fmax", [(128, 22050, 0.0, None), (40, 16000, 50.0, 7600.0), (96, 24000, 0.0, 8000.0), (32, 22050, 0.0, None)])
+def test_other_mel_configurations(cuda, n_mels, sr, fmin, fmax):
+    """The fused kernel's mel program is built at ctx creation for any (sr, n_mels, fmin, fmax)."""
+    import spev_tts_b200 as sp
+    y = synth.speechy(seed=n_mels, n=40000, sr=sr)
+    ref = lr.melspectrogram(y=y, sr=sr, n_fft=1024, hop_length=256, n_mels=n_mels, fmin=fmin, fmax=fmax)
+    got = sp.melspectrogram(y=y, sr=sr, n_fft=1024, hop_length=256, n_mels=n_mels, fmin=fmin, fmax=fmax)
+    assert got.shape == ref.shape == (n_mels, 1 + 40000 // 256)
+    rel = np.abs(got - ref) / (np.abs(ref) + 1e-6 * ref.max())
+    assert rel.max() < 2e-4, rel.max()
+    lm_ref = np.clip(np.log(np.clip(ref, 1e-5, None)), -10, 2).T
+    flat, _ = sp.logmel_flat(torch.from_numpy(y).to(cuda), [len(y)], sr=sr, n_mels=n_mels, fmin=fmin, fmax=fmax)
+    assert np.abs(flat.cpu().numpy() - lm_ref).max() <= TOL_LOGMEL
+    # mel -> magnitude for the same basis (tcgen05 path when n_mels % 4 == 0)
+    S_ref = lr.mel_to_stft(ref[:, :64], sr=sr, n_fft=1024, fmin=fmin, fmax=fmax, lbfgs=False)
+    S = sp.mel_to_stft(ref[:, :64], sr=sr, n_fft=1024, fmin=fmin, fmax=fmax)
+    assert np.linalg.norm(S - S_ref) / np.linalg.norm(S_ref) < 2e-5
+
+
+def test_too_wide_bands_are_a_clear_error(cuda):
+    """Very few, very wide bands exceed the fused kernel's shared-memory program: explicit error, no fallback."""
+    import spev_tts_b200 as sp
+    with pytest.raises(RuntimeError, match="does not fit the fused kernel"):
+        sp.melspectrogram(y=synth.white(seed=1, n=4096), sr=22050, n_fft=1024, hop_length=256, n_mels=12)
+
+
 def test_ragged_batch_edges(cuda):
     """empty / sub-hop / exact-multiple / odd lengths, aligned and unaligned packing."""
     import spev_tts_b200 as sp
