@@ -43,7 +43,7 @@ def install(verbose: bool = False) -> dict:
         librosa.feature.rms = _passthrough(features.rms, _installed["rms"])
         librosa.feature.spectral_centroid = _passthrough(features.spectral_centroid, _installed["spectral_centroid"])
         done["librosa"] = True
-    except ImportError:
+    except (ImportError, AttributeError):   # absent, or a partial stub without the functions
         done["librosa"] = False
     mod = sys.modules.get("spev_real_metrics")
     if mod is not None and hasattr(mod, "LengthRegulator"):

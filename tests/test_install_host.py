@@ -1,0 +1,65 @@
+"""CPU tests of the zero-edit integration: install() patches the reference's
+call sites and passes calls with unsupported parameters through to the original function."""
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import reference_import
+
+
+@pytest.fixture()
+def fake_librosa(monkeypatch):
+    calls = []
+    lib = types.ModuleType("librosa")
+    feat = types.ModuleType("librosa.feature")
+    inv = types.ModuleType("librosa.feature.inverse")
+    for mod, names in ((feat, ("melspectrogram", "rms", "spectral_centroid")), (inv, ("mel_to_audio",))):
+        for n in names:
+            def f(*a, _n=n, **k):
+                calls.append(_n)
+                return ("original", _n)
+            setattr(mod, n, f)
+    lib.feature, feat.inverse = feat, inv
+    monkeypatch.setitem(sys.modules, "librosa", lib)
+    monkeypatch.setitem(sys.modules, "librosa.feature", feat)
+    monkeypatch.setitem(sys.modules, "librosa.feature.inverse", inv)
+    return lib, calls
+
+
+def test_install_patches_and_passes_through(fake_librosa):
+    import spev_tts_b200 as sp
+    lib, calls = fake_librosa
+    done = sp.install()
+    assert done["librosa"] is True
+    for fn in (lib.feature.melspectrogram, lib.feature.rms, lib.feature.spectral_centroid, lib.feature.inverse.mel_to_audio):
+        assert hasattr(fn, "__wrapped__")
+    y = np.zeros(4096, np.float32)
+    # parameters outside the implemented configuration -> NotImplementedError inside the shim -> original
+    assert lib.feature.melspectrogram(y=y, sr=22050, n_fft=2048, hop_length=512) == ("original", "melspectrogram")
+    assert lib.feature.rms(y=y, frame_length=1024, hop_length=256) == ("original", "rms")
+    assert lib.feature.spectral_centroid(y=y, sr=22050, n_fft=1024) == ("original", "spectral_centroid")
+    assert calls == ["melspectrogram", "rms", "spectral_centroid"]
+    if not torch.cuda.is_available():
+        # supported parameters reach the CUDA path, which fails loudly without a GPU (no silent fallback)
+        with pytest.raises(RuntimeError):
+            lib.feature.melspectrogram(y=y, sr=22050, n_fft=1024, hop_length=256, n_mels=80)
+        assert calls == ["melspectrogram", "rms", "spectral_centroid"]
+
+
+@pytest.mark.skipif(not reference_import.available(), reason="/root/reference not mounted")
+def test_patch_model_swaps_length_regulator():
+    import spev_tts_b200 as sp
+    ref = reference_import.load()
+    model = ref.RealMetricsFastSpeech2(vocab_size=30)
+    assert type(model.length_regulator).__module__ == "spev_real_metrics"
+    assert sp.patch_model(model) == 1
+    assert isinstance(model.length_regulator, sp.LengthRegulator)
+    orig = ref.LengthRegulator
+    try:
+        sp.install()
+        assert ref.LengthRegulator is sp.LengthRegulator
+    finally:
+        ref.LengthRegulator = orig
