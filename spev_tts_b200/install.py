@@ -55,6 +55,23 @@ def install(verbose: bool = False) -> dict:
     return done
 
 
+def uninstall() -> None:
+    """Restore everything ``install()`` replaced."""
+    try:
+        import librosa
+        for name in ("melspectrogram", "rms", "spectral_centroid"):
+            if name in _installed:
+                setattr(librosa.feature, name, _installed.pop(name))
+        if "mel_to_audio" in _installed:
+            librosa.feature.inverse.mel_to_audio = _installed.pop("mel_to_audio")
+    except (ImportError, AttributeError):
+        pass
+    mod = sys.modules.get("spev_real_metrics")
+    if mod is not None and "LengthRegulator" in _installed:
+        mod.LengthRegulator = _installed.pop("LengthRegulator")
+    _installed.clear()
+
+
 def patch_model(model) -> int:
     """Swap the LengthRegulator instances of an already-built reference model
     (``RealMetricsFastSpeech2.length_regulator``, ``spev_real_metrics.py:160``)."""

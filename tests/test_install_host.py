@@ -26,7 +26,9 @@ def fake_librosa(monkeypatch):
     monkeypatch.setitem(sys.modules, "librosa", lib)
     monkeypatch.setitem(sys.modules, "librosa.feature", feat)
     monkeypatch.setitem(sys.modules, "librosa.feature.inverse", inv)
-    return lib, calls
+    yield lib, calls
+    import spev_tts_b200
+    spev_tts_b200.uninstall()
 
 
 def test_install_patches_and_passes_through(fake_librosa):
@@ -62,4 +64,5 @@ def test_patch_model_swaps_length_regulator():
         sp.install()
         assert ref.LengthRegulator is sp.LengthRegulator
     finally:
-        ref.LengthRegulator = orig
+        sp.uninstall()
+    assert ref.LengthRegulator is orig
