@@ -282,7 +282,8 @@ k_stft_phase(BatchView bv, const float* __restrict__ y, const float* __restrict_
             const float* sa = S + (row0 + fa) * ld_s;
             const float* sb = sa + ld_s;
             // four groups of four bins-per-lane: all loads of a group are issued before its
-            // arithmetic so that 16 independent requests per thread are in flight
+            // arithmetic so that 16 independent requests per thread are in flight (eight-bin groups
+            // were measured: no gain, and they spill)
             static_for<0, 4>([&](auto gc) {
                 constexpr int g = decltype(gc)::value;
                 float2 tpa[4], tpb[4];
@@ -333,6 +334,171 @@ k_stft_phase(BatchView bv, const float* __restrict__ y, const float* __restrict_
                 }
             }
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K5w: warp-independent STFT (+ Griffin-Lim phase update)
+//
+// The phase update has no cross-warp data dependence, so here every warp is its own worker:
+// it walks the (tile, slot) pairs with a grid-wide stride, cp.async-stages the 1280 samples of
+// its NEXT pair into its own transpose tile as soon as the current transform has read the tile
+// back (the copy lands during the second 32-point DFT and the memory epilogue), and never meets
+// a CTA barrier.  Warps drift out of phase, so the FFTs of some overlap the L2/HBM epilogues of
+// others instead of the whole SM alternating between "compute only" and "memory only".
+// ---------------------------------------------------------------------------------------
+struct PairInfo {
+    int64_t row;      // global row of frame a
+    int valid;        // 0: no such pair
+    int b_valid;
+};
+
+__device__ __forceinline__ PairInfo stage_pair(float* region, const float* __restrict__ x, const spev_tile* __restrict__ tiles,
+                                               int64_t p, int64_t n_pairs, int lane) {
+    PairInfo pi{0, 0, 0};
+    if (p >= n_pairs) return pi;
+    const spev_tile* d = tiles + (p >> 4);
+    const int fa = 2 * static_cast<int>(p & 15);
+    const int n = __ldg(&d->n);
+    if (fa >= n) return pi;
+    const int64_t src0 = __ldg(&d->src0), lo = __ldg(&d->lo), hi = __ldg(&d->hi);
+    pi.row = __ldg(&d->row0) + fa;
+    pi.valid = 1;
+    pi.b_valid = fa + 1 < n;
+    const int count = kNfft + kHop;                       // samples of frames a and a+1
+    const int64_t first = src0 + static_cast<int64_t>(fa) * kHop;
+    const int i_lo = static_cast<int>(max(static_cast<int64_t>(0), lo - first));
+    const int i_hi = static_cast<int>(min(static_cast<int64_t>(count), hi - first));
+    const float* xs = x + first;
+    if (((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((lo & 3) == 0)) {
+#pragma unroll
+        for (int j = 0; j < count / 128; ++j) {
+            const int i = lane * 4 + 128 * j;
+            int nb = i >= i_lo ? (i_hi - i) * 4 : 0;
+            nb = max(0, min(16, nb));
+            cp_async16(region + i, nb > 0 ? xs + i : x, nb);
+        }
+    } else {
+        for (int i = lane; i < count; i += 32) {
+            const bool ok = i >= i_lo && i < i_hi;
+            cp_async4(region + i, ok ? xs + i : x, ok ? 4 : 0);
+        }
+    }
+    return pi;
+}
+
+template <int MODE>   // 0: plain STFT into `ang`; 1: Griffin-Lim phase update
+__global__ void __launch_bounds__(kThreads, 1)
+k_stft_phase_w(BatchView bv, const float* __restrict__ y, const float* __restrict__ S, int64_t ld_s,
+               float2* __restrict__ ang, float2* tprev, int64_t ld, float alpha, int has_prev,
+               const float2* __restrict__ g_tw, const float* __restrict__ g_win) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* s_tw = reinterpret_cast<float2*>(smem_raw);
+    float* s_win = reinterpret_cast<float*>(s_tw + 1024);
+    float* s_x = s_win + 1024;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    pdl_launch_dependents();
+    load_tables(s_tw, s_win, g_tw, g_win, 0.5f);
+    __syncthreads();                                     // the only CTA-wide barrier
+    pdl_wait();                                          // y / ang / tprev come from the previous kernel
+    float* region = s_x + warp * kWarpRegionWords;       // staging for 1280 samples, then transpose tile
+    float2* xb = reinterpret_cast<float2*>(region);
+
+    const int64_t n_pairs = static_cast<int64_t>(bv.n_ftiles) * kWarps;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * kWarps;
+    int64_t p = static_cast<int64_t>(blockIdx.x) * kWarps + warp;
+    PairInfo cur = stage_pair(region, y, bv.ftiles, p, n_pairs, lane);
+    while (!cur.valid && p < n_pairs) { p += stride; cur = stage_pair(region, y, bv.ftiles, p, n_pairs, lane); }
+    cp_async_commit();
+
+    while (cur.valid) {
+        cp_async_wait_all();
+        __syncwarp();
+        float2 v[32];
+        load_frame_pair(v, region, s_win, 0, cur.b_valid != 0, lane);
+        __syncwarp();                                    // staging fully consumed: tile may be overwritten
+        // ---- first half of the transform: 32-point DFTs, inter-stage twiddles, transpose ----
+        dft32<-1>(v);
+        static_for<1, 32>([&](auto k1c) {
+            constexpr int k1 = decltype(k1c)::value;
+            v[k1] = cmul(v[k1], s_tw[k1 * 32 + lane]);
+        });
+        static_for<0, 32>([&](auto k1c) {
+            constexpr int k1 = decltype(k1c)::value;
+            xb[k1 * kXPitch + lane] = v[k1];
+        });
+        __syncwarp();
+        static_for<0, 32>([&](auto n2c) {
+            constexpr int n2 = decltype(n2c)::value;
+            v[n2] = xb[lane * kXPitch + n2];
+        });
+        __syncwarp();                                    // tile read back: free for the next pair's samples
+        // ---- stage the next pair (lands during the second DFT and the epilogue) ----
+        PairInfo nxt{0, 0, 0};
+        do { p += stride; nxt = stage_pair(region, y, bv.ftiles, p, n_pairs, lane); } while (!nxt.valid && p < n_pairs);
+        cp_async_commit();
+        if (MODE == 1 && nxt.valid) {                    // and pull its epilogue operands into L2
+            const int rows = nxt.b_valid ? 2 : 1;
+            warp_prefetch_l2(S + nxt.row * ld_s, static_cast<int>((rows - 1) * ld_s + kBins) * 4, lane);
+            if (has_prev) warp_prefetch_l2(tprev + nxt.row * ld, static_cast<int>((rows - 1) * ld + kBins) * 8, lane);
+        }
+        dft32<-1>(v);
+        float2 pm[16];
+        fetch_mirror(v, pm, lane);
+        const bool b_valid = cur.b_valid != 0;
+        const int64_t ra = cur.row * ld, rb = ra + ld;
+        const float* sa = S + cur.row * ld_s;
+        const float* sb = sa + ld_s;
+        static_for<0, 4>([&](auto gc) {
+            constexpr int g = decltype(gc)::value;
+            float2 tpa[4], tpb[4];
+            float s_a[4], s_b[4];
+            if (MODE == 1) {
+                static_for<0, 4>([&](auto qc) {
+                    constexpr int q = decltype(qc)::value;
+                    const int k = lane + 32 * (4 * g + q);
+                    s_a[q] = sa[k];
+                    s_b[q] = b_valid ? sb[k] : 0.f;
+                    tpa[q] = has_prev ? tprev[ra + k] : make_float2(0.f, 0.f);
+                    tpb[q] = (has_prev && b_valid) ? tprev[rb + k] : make_float2(0.f, 0.f);
+                });
+            }
+            static_for<0, 4>([&](auto qc) {
+                constexpr int q = decltype(qc)::value;
+                constexpr int k2 = 4 * g + q;
+                const int k = lane + 32 * k2;
+                float2 xa, xbv;
+                split_pair_prescaled(v[k2], pm[k2], xa, xbv);
+                if (MODE == 0) {
+                    ang[ra + k] = xa;
+                    if (b_valid) ang[rb + k] = xbv;
+                } else {
+                    ang[ra + k] = phase_of(xa, s_a[q], tpa[q], alpha, has_prev);
+                    tprev[ra + k] = xa;
+                    if (b_valid) {
+                        ang[rb + k] = phase_of(xbv, s_b[q], tpb[q], alpha, has_prev);
+                        tprev[rb + k] = xbv;
+                    }
+                }
+            });
+        });
+        if (lane == 0) {
+            // the window carries a factor 1/2: X[512] = 2 * Z'[512]
+            const float2 xa = make_float2(2.f * v[16].x, 0.f), xbv = make_float2(2.f * v[16].y, 0.f);
+            if (MODE == 0) {
+                ang[ra + 512] = xa;
+                if (b_valid) ang[rb + 512] = xbv;
+            } else {
+                const float2 z = make_float2(0.f, 0.f);
+                ang[ra + 512] = phase_of(xa, sa[512], has_prev ? tprev[ra + 512] : z, alpha, has_prev);
+                tprev[ra + 512] = xa;
+                if (b_valid) {
+                    ang[rb + 512] = phase_of(xbv, sb[512], has_prev ? tprev[rb + 512] : z, alpha, has_prev);
+                    tprev[rb + 512] = xbv;
+                }
+            }
+        }
+        cur = nxt;
     }
 }
 
@@ -628,8 +794,12 @@ int launch_stft_phase(spev_ctx* ctx, const spev_batch* b, const float* y, const 
     SPEV_REQUIRE(ang && ld >= kBins, SPEV_E_INVALID, "stft: null buffer or ld < 513");
     SPEV_REQUIRE(y || b->n_frames == b->n_items, SPEV_E_INVALID, "stft: y is null");
     if (!y) y = reinterpret_cast<const float*>(ang);   // every item has T == 1 (empty signal): never dereferenced as signal
+    // Plain STFT: warp-independent kernel (measured 18.0 vs 19.9 us at cfg3, 128 vs 156 us on 120 k frames).
+    // Phase update: tile kernel (the warp-independent variant is not faster there -- 51.7 vs 50.6 us, and
+    // 444 vs 372 us at scale: that path is bound by bytes in flight against L2/HBM latency, not by lock-step).
+    const size_t smem_w = sizeof(float2) * 1024 + sizeof(float) * 1024 + sizeof(float) * kWarps * kWarpRegionWords;
     const size_t smem = smem_stft(0);
-    const int grid = std::min<int64_t>(b->n_ftiles, ctx->num_sms);
+    const int grid = static_cast<int>(std::min<int64_t>(b->n_ftiles, ctx->num_sms));
     if (phase) {
         SPEV_REQUIRE(S && tprev && ld_s >= kBins, SPEV_E_INVALID, "phase update: null S/tprev");
         rc = set_smem(k_stft_phase<1>, smem);
@@ -639,9 +809,9 @@ int launch_stft_phase(spev_ctx* ctx, const spev_batch* b, const float* y, const 
                         static_cast<const float*>(ctx->d_window));
         if (rc) return rc;
     } else {
-        rc = set_smem(k_stft_phase<0>, smem);
+        rc = set_smem(k_stft_phase_w<0>, smem_w);
         if (rc) return rc;
-        rc = launch_pdl(k_stft_phase<0>, grid, kThreads, smem, st, view_of(b), y, static_cast<const float*>(nullptr),
+        rc = launch_pdl(k_stft_phase_w<0>, grid, kThreads, smem_w, st, view_of(b), y, static_cast<const float*>(nullptr),
                         static_cast<int64_t>(0), static_cast<float2*>(ang), static_cast<float2*>(nullptr), ld, 0.f, 0,
                         static_cast<const float2*>(ctx->d_tw), static_cast<const float*>(ctx->d_window));
         if (rc) return rc;

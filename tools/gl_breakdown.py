@@ -30,6 +30,7 @@ def t_loop(fn, n=60, reps=5):
     return best
 k4 = t_loop(lambda: lib.spev_istft(ctx.handle, fb.desc, ang.data_ptr(), 520, y.data_ptr(), st))
 k5 = t_loop(lambda: lib.spev_gl_phase_update(ctx.handle, fb.desc, y.data_ptr(), S.data_ptr(), 520, ang.data_ptr(), tprev.data_ptr(), 520, 0.4975, 1, st))
+k5n = t_loop(lambda: lib.spev_gl_phase_update(ctx.handle, fb.desc, y.data_ptr(), S.data_ptr(), 520, ang.data_ptr(), tprev.data_ptr(), 520, 0.4975, 0, st))
 k5s = t_loop(lambda: lib.spev_stft(ctx.handle, fb.desc, y.data_ptr(), ang.data_ptr(), 520, st))
 def both():
     lib.spev_istft(ctx.handle, fb.desc, ang.data_ptr(), 520, y.data_ptr(), st)
@@ -38,5 +39,6 @@ kb = t_loop(both)
 print(f"B={B} T={T} frames={F} ftiles={fb.n_ftiles} ctiles={fb.n_ctiles}")
 print(f"istft          {k4:8.2f} us/launch   {F*(4104+1024)/k4/1e3:8.1f} GB/s")
 print(f"phase_update   {k5:8.2f} us/launch   {F*15388/k5/1e3:8.1f} GB/s")
-print(f"stft only      {k5s:8.2f} us/launch")
+print(f"phase no-prev   {k5n:8.2f} us/launch   (no tprev loads: S 2 KB read, ang+tprev 8 KB written per frame)")
+print(f"stft only      {k5s:8.2f} us/launch   (no loads, 4 KB written per frame)")
 print(f"istft+phase    {kb:8.2f} us/iter     {F*20516/kb/1e3:8.1f} GB/s")
