@@ -648,6 +648,34 @@ def bench_length_regulator(sp, dev, args):
     torch.cuda.synchronize(dev)
     k_ms = a.elapsed_time(b) / n
     out_bytes = o.shape[0] * o.shape[1] * (256 + 5) * 4
+    # fused variance adaptor (expand + clamp + 5 Conv1d(1,256,3) embeddings + sum, :226-252) vs expand + torch convs
+    embs = [torch.nn.Conv1d(1, 256, 3, padding=1).to(dev) for _ in range(5)]
+    for _ in range(3):
+        sp.variance_adaptor(xd, dd, fd, embs)
+    a3 = torch.cuda.Event(enable_timing=True); b3 = torch.cuda.Event(enable_timing=True)
+    a3.record()
+    for _ in range(n):
+        sp.variance_adaptor(xd, dd, fd, embs)
+    b3.record()
+    torch.cuda.synchronize(dev)
+    fused_ms = a3.elapsed_time(b3) / n
+
+    def unfused():
+        xe, ml_, ce = sp.regulate_variances(xd, dd, fd)
+        di = xe.transpose(1, 2)
+        for e_, c_ in zip(embs, ce):
+            di = di + e_(c_)
+        return di.transpose(1, 2)
+    with torch.no_grad():
+        for _ in range(3):
+            unfused()
+        a4 = torch.cuda.Event(enable_timing=True); b4 = torch.cuda.Event(enable_timing=True)
+        a4.record()
+        for _ in range(n):
+            unfused()
+        b4.record()
+        torch.cuda.synchronize(dev)
+    unfused_ms = a4.elapsed_time(b4) / n
     # larger batch ("also measure at B=512"): the expand kernel leaves the latency regime
     rng = np.random.default_rng(12)
     xb = torch.from_numpy(rng.standard_normal((512, 200, 256)).astype(np.float32)).to(dev)
@@ -666,7 +694,7 @@ def bench_length_regulator(sp, dev, args):
     big_bytes = ob.shape[0] * ob.shape[1] * (256 + 5) * 4
     big = {"B": 512, "frames": int(ob.shape[1]), "expand_kernel_ms": kb_ms, "expand_GBps": big_bytes / (kb_ms * 1e-3) / 1e9,
            "output_GB": big_bytes / 1e9}
-    return {"B512": big,"config": {"workload": "cfg2: B=32, T<=200, H=256 + 5 curves (the 6 LengthRegulator calls of one forward)"},
+    return {"B512": big, "variance_adaptor_fused_ms": fused_ms, "variance_adaptor_expand_plus_cudnn_ms": unfused_ms,"config": {"workload": "cfg2: B=32, T<=200, H=256 + 5 curves (the 6 LengthRegulator calls of one forward)"},
             "forward_ms_wall_incl_one_sync": wall_ms, "expand_kernel_ms": k_ms,
             "expand_GBps": out_bytes / (k_ms * 1e-3) / 1e9, "frames": int(o.shape[1]),
             "reference_cpu_s_per_forward": "6 x 1.42 s (SURVEY App. B)"}

@@ -248,6 +248,17 @@ SPEV_API int spev_lr_expand_fused(const void* x, int64_t row_bytes, const float*
                          const int32_t* cumsum, int B, int T, void* out, float* feats_out,
                          int64_t max_len, void* stream);
 
+/* Fused variance adaptor: the whole block spev_real_metrics.py:226-252 in one launch --
+ * expand x by the durations, expand + clamp the n_feat scalar curves, apply each curve's
+ * Conv1d(1 -> H, kernel 3, padding 1) embedding and add the embeddings to the expanded hidden states:
+ *   out[b,f,:] = x[b,idx(b,f),:] + sum_j ( bias_j + w_j[:,0]*cv_j[b,f-1] + w_j[:,1]*cv_j[b,f] + w_j[:,2]*cv_j[b,f+1] )
+ *   x [B,T,H] float32; feats [n_feat,B,T]; conv_w [n_feat,H,3] (= nn.Conv1d.weight[:,0,:] per curve);
+ *   conv_b [n_feat,H]; cumsum from spev_lr_plan; out [B,max_len,H]; feats_out [n_feat,B,max_len] or NULL. */
+SPEV_API int spev_variance_fuse(const float* x, const float* feats, int n_feat, const float* clamp_lo_host,
+                                const float* clamp_hi_host, const float* conv_w, const float* conv_b,
+                                const int32_t* cumsum, int B, int T, int H, float* out, float* feats_out,
+                                int64_t max_len, void* stream);
+
 /* Inference duration rule, spev_real_metrics.py:215:
  *   dur = (int64) rint(clamp((exp(log_dur) - 1) * d_control, 0, 500))   (round-half-even) */
 SPEV_API int spev_duration_rule(const float* log_dur, int64_t n, float d_control, int64_t* dur,

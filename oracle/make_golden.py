@@ -20,6 +20,9 @@ Run in the build container (where ``/root/reference`` is mounted):
                        path ``:291-298``, ``__getitem__`` ``:433-447``) and ``collate_fn`` (``:449-462``) on a
                        cache written by ``spev_tts_b200.dataset.write_reference_cache``.
 
+* ``variance_adaptor.npz`` -- the block ``:226-252`` executed with the reference model's own
+                       ``length_regulator`` and ``*_embedding`` Conv1d modules (weights stored in the fixture).
+
 Inputs are regenerated from seeds by ``tests/synth.py``; large outputs are stored as
 SHA-256 digests plus a decimated slice so that the fixtures stay small.
 """
@@ -132,6 +135,40 @@ def main() -> None:
             for k, v in batch.items():
                 gold[f"{name}_{k}"] = v.numpy()
     np.savez_compressed(os.path.join(OUT, "collate.npz"), **gold)
+
+    # ---- variance adaptor block, run through the reference model's OWN modules (:226-252) -------------
+    torch.manual_seed(11)
+    model = ref.RealMetricsFastSpeech2(vocab_size=40).eval()
+    rng = np.random.default_rng(11)
+    B, T, H = 3, 15, 256
+    xv = torch.from_numpy(rng.standard_normal((B, T, H)).astype(np.float32))
+    dv = torch.from_numpy(rng.integers(0, 7, (B, T)).astype(np.int64))
+    dv[1, 9:] = 0                                                   # a shorter row -> padded frames
+    curves = [torch.from_numpy((3 * rng.standard_normal((B, T))).astype(np.float32)) for _ in range(5)]
+    with torch.no_grad():                                           # the statements of :226-252, verbatim
+        x_expanded, mel_len = model.length_regulator(xv, dv)
+
+        def expand_feat(f, d):
+            expanded, _ = model.length_regulator(f.unsqueeze(-1), d)
+            return expanded.transpose(1, 2)
+        pitch, energy, breath, rough, bright = [expand_feat(c, dv) for c in curves]
+        pitch = torch.clamp(pitch, -3.0, 3.0)
+        energy = torch.clamp(energy, -3.0, 3.0)
+        breath = torch.clamp(breath, 0.0, 1.0)
+        rough = torch.clamp(rough, 0.0, 2.0)
+        bright = torch.clamp(bright, -3.0, 3.0)
+        dec_input = x_expanded.transpose(1, 2)
+        dec_input = dec_input + model.pitch_embedding(pitch) + model.energy_embedding(energy) + \
+            model.breath_embedding(breath) + model.rough_embedding(rough) + model.bright_embedding(bright)
+        dec_input = dec_input.transpose(1, 2)
+    embs = [model.pitch_embedding, model.energy_embedding, model.breath_embedding, model.rough_embedding,
+            model.bright_embedding]
+    np.savez_compressed(os.path.join(OUT, "variance_adaptor.npz"), x=xv.numpy(), dur=dv.numpy(),
+                        curves=np.stack([c.numpy() for c in curves]),
+                        conv_w=np.stack([e.weight.detach().numpy() for e in embs]),      # [5, 256, 1, 3]
+                        conv_b=np.stack([e.bias.detach().numpy() for e in embs]),
+                        dec_input=dec_input.numpy(), mel_len=mel_len.numpy(),
+                        curves_expanded=np.stack([t[:, 0].numpy() for t in (pitch, energy, breath, rough, bright)]))
     print("golden fixtures written to", OUT)
     for f in sorted(os.listdir(OUT)):
         print(f"  {f:28s} {os.path.getsize(os.path.join(OUT, f)):>9d} B")

@@ -17,7 +17,7 @@ from .dataset import ResidentCache, read_reference_cache, write_reference_cache 
 from .features import frame_features_flat, rms, segment_pool, spectral_centroid  # noqa: F401
 from .install import install, patch_model, uninstall  # noqa: F401
 from .length_regulator import (LengthRegulator, VARIANCE_CLAMPS, expand, mel_mask, plan,  # noqa: F401
-                               regulate_variances)
+                               regulate_variances, variance_adaptor)
 from .spectral import (griffinlim, griffinlim_flat, istft, logmel, logmel_flat, mel_project,  # noqa: F401
                        mel_to_audio, mel_to_mag_flat, mel_to_stft, melspectrogram, stft,
                        stft_power_flat)

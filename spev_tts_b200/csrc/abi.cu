@@ -39,6 +39,7 @@ int launch_mel_to_mag(spev_ctx*, const spev_batch*, const float*, int, int, floa
 int launch_lr_plan(const void*, int, int, int, int32_t*, int64_t*, int64_t*, int64_t*, cudaStream_t);
 int launch_lr_expand(const void*, int64_t, const float*, int, const float*, const float*, const int32_t*, int, int, void*, float*, int64_t, cudaStream_t);
 int launch_duration_rule(const float*, int64_t, float, int64_t*, cudaStream_t);
+int launch_variance_fuse(const float*, const float*, int, const float*, const float*, const float*, const float*, const int32_t*, int, int, int, float*, float*, int64_t, cudaStream_t);
 int launch_pcm16_to_f32(const int16_t*, int64_t, float*, cudaStream_t);
 int launch_collate(const spev_pad_array*, int, const int64_t*, const int64_t*, const int64_t*, int, int64_t, int64_t, cudaStream_t);
 int launch_bucketize_embed(const float*, int64_t, const float*, int, int, const float*, int, int64_t*, float*, int, cudaStream_t);
@@ -506,6 +507,13 @@ int spev_lr_expand_fused(const void* x, int64_t row_bytes, const float* feats, i
 
 int spev_pcm16_to_f32(const int16_t* pcm, int64_t n, float* out, void* stream) {
     return launch_pcm16_to_f32(pcm, n, out, static_cast<cudaStream_t>(stream));
+}
+
+int spev_variance_fuse(const float* x, const float* feats, int n_feat, const float* clamp_lo_host, const float* clamp_hi_host,
+                       const float* conv_w, const float* conv_b, const int32_t* cumsum, int B, int T, int H, float* out,
+                       float* feats_out, int64_t max_len, void* stream) {
+    return launch_variance_fuse(x, feats, n_feat, clamp_lo_host, clamp_hi_host, conv_w, conv_b, cumsum, B, T, H, out,
+                                feats_out, max_len, static_cast<cudaStream_t>(stream));
 }
 
 int spev_duration_rule(const float* log_dur, int64_t n, float d_control, int64_t* dur, void* stream) {

@@ -138,6 +138,78 @@ k_lr_expand(const unsigned char* __restrict__ x, int64_t row_bytes, const float*
     }
 }
 
+// ---- fused variance adaptor: expand + n_feat Conv1d(1->H, k=3, pad=1) embeddings + sum -----------------
+// out[b,f,c] = x[b,idx(b,f),c] (0 past the row's length)
+//            + sum_j ( bias_j[c] + w_j[c,0]*cv_j[b,f-1] + w_j[c,1]*cv_j[b,f] + w_j[c,2]*cv_j[b,f+1] )
+// with cv_j[b,f] = clamp(curve_j[b,idx(b,f)], lo_j, hi_j) inside the row, 0 outside [0, max_len) and past
+// the row's length -- i.e. spev_real_metrics.py:226-252 (six LengthRegulator calls, five clamps, five
+// Conv1d embeddings, their sum) in one launch; x_expanded and the expanded curves never reach HBM.
+// Thread <-> channel (weights of the thread's channel live in registers), CTA <-> 64 frames of one row.
+constexpr int kVaFrames = 64;
+constexpr int kVaMaxFeat = 8;
+__global__ void __launch_bounds__(256)
+k_variance_fuse(const float* __restrict__ x, const float* __restrict__ feats, int n_feat, ClampParams clamp,
+                const float* __restrict__ conv_w /*[n_feat,H,3]*/, const float* __restrict__ conv_b /*[n_feat,H]*/,
+                const int32_t* __restrict__ cumsum, int B, int T, int H, float* __restrict__ out,
+                float* __restrict__ feats_out /*nullable [n_feat,B,max_len]*/, int64_t max_len) {
+    __shared__ int s_idx[kVaFrames + 2];
+    __shared__ float s_cv[kVaMaxFeat][kVaFrames + 2];
+    const int b = blockIdx.y;
+    const int64_t f0 = static_cast<int64_t>(blockIdx.x) * kVaFrames;
+    const int32_t* cs = cumsum + static_cast<int64_t>(b) * T;
+    const int total = T > 0 ? cs[T - 1] : 0;
+    for (int i = threadIdx.x; i < kVaFrames + 2; i += blockDim.x) {
+        const int64_t f = f0 - 1 + i;                         // halo of one frame on each side
+        s_idx[i] = (f >= 0 && f < total) ? upper_bound_i32(cs, T, static_cast<int>(f)) : -1;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_feat * (kVaFrames + 2); i += blockDim.x) {
+        const int j = i / (kVaFrames + 2), fl = i - j * (kVaFrames + 2);
+        const int idx = s_idx[fl];
+        const int64_t f = f0 - 1 + fl;
+        float v = 0.f;
+        if (idx >= 0) v = __ldg(feats + (static_cast<int64_t>(j) * B + b) * T + idx);
+        // the reference clamps the zero-padded tensor: positions past the row's length hold clamp(0),
+        // positions outside [0, max_len) are the convolution's zero padding
+        if (clamp.enabled) v = fminf(fmaxf(v, clamp.lo[j]), clamp.hi[j]);
+        if (f < 0 || f >= max_len) v = 0.f;
+        s_cv[j][fl] = v;
+        if (feats_out && fl >= 1 && fl <= kVaFrames && f < max_len)
+            feats_out[(static_cast<int64_t>(j) * B + b) * max_len + f] = v;
+    }
+    __syncthreads();
+    const int nfr = static_cast<int>(min(static_cast<int64_t>(kVaFrames), max_len - f0));
+    const float* xb = x + static_cast<int64_t>(b) * T * H;
+    float* ob = out + (static_cast<int64_t>(b) * max_len + f0) * H;
+    for (int c = threadIdx.x; c < H; c += blockDim.x) {
+        float w0[kVaMaxFeat], w1[kVaMaxFeat], w2[kVaMaxFeat], bs[kVaMaxFeat];
+#pragma unroll
+        for (int j = 0; j < kVaMaxFeat; ++j) {
+            if (j < n_feat) {
+                const float* w = conv_w + (static_cast<int64_t>(j) * H + c) * 3;
+                w0[j] = __ldg(w); w1[j] = __ldg(w + 1); w2[j] = __ldg(w + 2);
+                bs[j] = __ldg(conv_b + static_cast<int64_t>(j) * H + c);
+            }
+        }
+        for (int fl = 0; fl < nfr; ++fl) {
+            const int idx = s_idx[fl + 1];
+            float acc = idx >= 0 ? __ldg(xb + static_cast<int64_t>(idx) * H + c) : 0.f;
+#pragma unroll
+            for (int j = 0; j < kVaMaxFeat; ++j) {
+                if (j < n_feat) {
+                    // one embedding: bias + 3-tap correlation, then added to the running sum in the
+                    // reference's left-to-right order (dec_input + pitch + energy + breath + rough + bright)
+                    float e = fmaf(w0[j], s_cv[j][fl], bs[j]);
+                    e = fmaf(w1[j], s_cv[j][fl + 1], e);
+                    e = fmaf(w2[j], s_cv[j][fl + 2], e);
+                    acc += e;
+                }
+            }
+            ob[static_cast<int64_t>(fl) * H + c] = acc;
+        }
+    }
+}
+
 // ---- duration rule: clamp((exp(ld)-1)*d_control, 0, 500).round().long(), spev_real_metrics.py:215 ----
 __global__ void k_duration_rule(const float* __restrict__ ld, int64_t n, float d_control,
                                 long long* __restrict__ dur) {
@@ -297,6 +369,27 @@ int launch_lr_expand(const void* x, int64_t row_bytes, const float* feats, int n
     k_lr_expand<<<grid, kLrThreads, 0, st>>>(static_cast<const unsigned char*>(x), row_bytes, feats, n_feat,
                                              cp, cumsum, B, T, static_cast<unsigned char*>(out),
                                              feats_out, max_len);
+    SPEV_CUDA(cudaGetLastError());
+    return SPEV_OK;
+}
+
+int launch_variance_fuse(const float* x, const float* feats, int n_feat, const float* clamp_lo, const float* clamp_hi,
+                         const float* conv_w, const float* conv_b, const int32_t* cumsum, int B, int T, int H, float* out,
+                         float* feats_out, int64_t max_len, cudaStream_t st) {
+    SPEV_REQUIRE(B >= 0 && T >= 0 && H > 0 && max_len >= 0 && n_feat >= 0 && n_feat <= kVaMaxFeat, SPEV_E_INVALID,
+                 "variance_fuse: bad shape (n_feat <= %d)", kVaMaxFeat);
+    if (B == 0 || max_len == 0) return SPEV_OK;
+    SPEV_REQUIRE(B <= 65535, SPEV_E_UNSUPPORTED, "variance_fuse: B > 65535");
+    SPEV_REQUIRE(x && out && (T == 0 || cumsum) && (n_feat == 0 || (feats && conv_w && conv_b)), SPEV_E_INVALID,
+                 "variance_fuse: null buffer");
+    ClampParams cp;
+    cp.enabled = (n_feat > 0 && clamp_lo && clamp_hi) ? 1 : 0;
+    for (int j = 0; j < kMaxFeat; ++j) {
+        cp.lo[j] = (cp.enabled && j < n_feat) ? clamp_lo[j] : 0.f;
+        cp.hi[j] = (cp.enabled && j < n_feat) ? clamp_hi[j] : 0.f;
+    }
+    dim3 grid(static_cast<unsigned>((max_len + kVaFrames - 1) / kVaFrames), static_cast<unsigned>(B));
+    k_variance_fuse<<<grid, 256, 0, st>>>(x, feats, n_feat, cp, conv_w, conv_b, cumsum, B, T, H, out, feats_out, max_len);
     SPEV_CUDA(cudaGetLastError());
     return SPEV_OK;
 }

@@ -133,6 +133,38 @@ def regulate_variances(x: torch.Tensor, durations: torch.Tensor, curves: Sequenc
     return out, p.mel_lens, [fo[j].unsqueeze(1) for j in range(fo.shape[0])]
 
 
+def variance_adaptor(x: torch.Tensor, durations: torch.Tensor, curves: Sequence[torch.Tensor],
+                     embeddings: Sequence[nn.Module], clamps: Optional[Sequence[Tuple[float, float]]] = VARIANCE_CLAMPS,
+                     return_curves: bool = False):
+    """``spev_real_metrics.py:226-252`` in ONE kernel after the plan: expand ``x`` and the curves by
+    ``durations``, clamp, apply each curve's ``nn.Conv1d(1, H, 3, padding=1)`` embedding and sum.
+    ``embeddings``: the model's ``pitch_embedding, energy_embedding, breath_embedding, rough_embedding,
+    bright_embedding`` (weights are read, not copied).  Returns ``(dec_input [B,maxF,H], mel_len [B])``
+    (+ the expanded clamped curves ``[n,B,maxF]`` if ``return_curves``).  Forward only (inference)."""
+    import ctypes as C
+    _require_cuda(x, "x")
+    p = plan(durations)
+    x = x.to(torch.float32).contiguous()
+    B, T, H = x.shape
+    feats = torch.stack([c.to(torch.float32) for c in curves]).contiguous()
+    n = feats.shape[0]
+    w = torch.stack([e.weight.detach().reshape(H, 3) for e in embeddings]).to(torch.float32).contiguous()
+    bias = torch.stack([e.bias.detach() for e in embeddings]).to(torch.float32).contiguous()
+    out = torch.empty((B, p.max_len, H), dtype=torch.float32, device=x.device)
+    fo = torch.empty((n, B, p.max_len), dtype=torch.float32, device=x.device) if return_curves else None
+    lo = hi = None
+    if clamps is not None:
+        lo = (C.c_float * n)(*[float(c[0]) for c in clamps])
+        hi = (C.c_float * n)(*[float(c[1]) for c in clamps])
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().spev_variance_fuse(
+            x.data_ptr(), feats.data_ptr(), n, C.cast(lo, C.c_void_p) if lo is not None else None,
+            C.cast(hi, C.c_void_p) if hi is not None else None, w.data_ptr(), bias.data_ptr(), p.cumsum.data_ptr(),
+            B, T, H, out.data_ptr(), fo.data_ptr() if fo is not None else None, p.max_len, stream_ptr(x.device)),
+            "spev_variance_fuse")
+    return (out, p.mel_lens, fo) if return_curves else (out, p.mel_lens)
+
+
 def mel_mask(mel_len: torch.Tensor, max_len: int) -> torch.Tensor:
     """``spev_real_metrics.py:259``: ``arange(maxF)[None,:] >= mel_len[:,None]``."""
     return torch.arange(max_len, device=mel_len.device)[None, :] >= mel_len[:, None]

@@ -136,3 +136,36 @@ def test_bucketize_embed_vs_torch(cuda, golden):
     assert np.array_equal(acc.cpu().numpy(), 1.0 + table[g["idx"]])
     t3 = torch.from_numpy(table[:, :7].copy()).to(cuda)
     assert np.array_equal(sp.bucketize_embed(vt, bt, t3).cpu().numpy(), table[:, :7][g["idx"]])
+
+
+def test_fused_variance_adaptor_vs_reference_modules(cuda, golden):
+    """expand + clamp + five Conv1d(1,256,3) embeddings + sum in one kernel == the reference model's own
+    modules on the same weights (spev_real_metrics.py:226-252); float32 sums: tolerance 2e-6 abs."""
+    import spev_tts_b200 as sp
+    g = golden("variance_adaptor.npz")
+    embs = []
+    for j in range(5):
+        e = torch.nn.Conv1d(1, 256, kernel_size=3, padding=1)
+        with torch.no_grad():
+            e.weight.copy_(torch.from_numpy(g["conv_w"][j])); e.bias.copy_(torch.from_numpy(g["conv_b"][j]))
+        embs.append(e.to(cuda))
+    x = torch.from_numpy(g["x"]).to(cuda)
+    d = torch.from_numpy(g["dur"]).to(cuda)
+    curves = [torch.from_numpy(c).to(cuda) for c in g["curves"]]
+    out, mel_len, cv = sp.variance_adaptor(x, d, curves, embs, return_curves=True)
+    assert np.array_equal(mel_len.cpu().numpy(), g["mel_len"])
+    assert out.shape == g["dec_input"].shape
+    assert np.array_equal(cv.cpu().numpy(), g["curves_expanded"])                 # expanded + clamped curves: exact
+    err = np.abs(out.cpu().numpy() - g["dec_input"]).max()
+    assert err <= 2e-6 * max(1.0, np.abs(g["dec_input"]).max()), err
+    # larger shape against torch's own conv1d on the GPU (cfg2 sizes)
+    xb, db, _ = synth.cfg2_batch(seed=2)
+    feats = [torch.from_numpy(f).to(cuda) * 2 for f in synth.cfg2_features(seed=2)]
+    xe, ml, ce = sp.regulate_variances(torch.from_numpy(xb).to(cuda), torch.from_numpy(db).to(cuda), feats)
+    ref = xe.transpose(1, 2)
+    with torch.no_grad():
+        for e, c in zip(embs, ce):
+            ref = ref + e(c)
+    ref = ref.transpose(1, 2)
+    out2, ml2 = sp.variance_adaptor(torch.from_numpy(xb).to(cuda), torch.from_numpy(db).to(cuda), feats, embs)
+    assert torch.equal(ml, ml2) and float((out2 - ref).abs().max()) < 1e-5
