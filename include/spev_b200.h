@@ -272,6 +272,43 @@ SPEV_API int spev_bucketize_embed(const float* v, int64_t n, const float* bounda
                          int right, const float* table, int H, int64_t* idx_out, float* out,
                          int accumulate, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * pYIN  (SURVEY 8(f) "next" row 2)
+ * Replaces  f0, _, voiced_prob = librosa.pyin(y, fmin=60, fmax=500, sr=22050, hop_length=256)
+ * at /root/reference/spev_real_metrics.py:369 (cache build) and :311 (statistics pass): librosa defaults
+ * frame_length=2048, win_length=1024, 100 thresholds, beta(2,18), Boltzmann(2), 10-cent bins,
+ * max_transition_rate=35.92 octaves/s, switch_prob=0.01, no_trough_prob=0.01, centre zero padding.
+ * Three stages so that each can be checked on its own; frames are addressed through the same
+ * spev_batch frame tiles as spev_logmel (item i has 1 + len_i/256 frames).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct spev_pyin spev_pyin;
+/* beta_probs_host: optional host array [100] = diff(beta(2,18).cdf(linspace(0,1,101))) as the caller's own
+ * statistics library rounds it (the Python shim passes scipy's, i.e. librosa's exact table); NULL = built-in
+ * closed form (equal to ~1e-16 absolute). */
+SPEV_API int spev_pyin_create(spev_pyin** out, int device, int sr, float fmin, float fmax,
+                              const double* beta_probs_host);
+SPEV_API void spev_pyin_destroy(spev_pyin* ctx);
+/* n_bins: voiced pitch bins (states = 2*n_bins); lags min_period..max_period (n_lags of them). */
+SPEV_API int spev_pyin_info(const spev_pyin* ctx, int* n_bins, int* min_period, int* max_period, int* n_lags);
+/* Host copies of the model tables: dense log(transition + tiny) [2*n_bins, 2*n_bins] (row = from-state),
+ * bin frequencies [n_bins], beta-distributed threshold weights [100].  Any pointer may be NULL. */
+SPEV_API int spev_pyin_host_tables(const spev_pyin* ctx, double* log_transition, double* freqs, double* beta_probs);
+/* Stage 1: cumulative-mean-normalised difference.  samples: device f32 (flat batch), yin: device f32
+ * [n_frames, n_lags]  (librosa.core.pitch._cumulative_mean_normalized_difference). */
+SPEV_API int spev_pyin_cmnd(spev_pyin* ctx, const spev_batch* batch, const float* samples, float* yin, void* stream);
+/* Stage 2: trough statistics -> log observation probabilities (librosa.core.pitch.__pyin_helper).
+ * logobs f32 [n_frames, n_bins] = log(P(voiced bin) + tiny); log_unvoiced f32 [n_frames] = the (uniform)
+ * log-probability of each unvoiced state; voiced_prob f32 [n_frames]. */
+SPEV_API int spev_pyin_observe(spev_pyin* ctx, const float* yin, int64_t n_frames, float* logobs,
+                               float* log_unvoiced, float* voiced_prob, void* stream);
+/* Stage 3: Viterbi decode per item (librosa.sequence.viterbi) + state -> (f0, voiced_flag).
+ * frame_off: device int64 [n_items+1]; states int32 [n_frames]; f0 f32 [n_frames] (NaN where unvoiced)
+ * and voiced_flag u8 [n_frames] may be NULL.  workspace: device, >= spev_pyin_decode_workspace_bytes. */
+SPEV_API size_t spev_pyin_decode_workspace_bytes(const spev_pyin* ctx, int64_t n_frames);
+SPEV_API int spev_pyin_decode(spev_pyin* ctx, const float* logobs, const float* log_unvoiced, const int64_t* frame_off,
+                              int n_items, int64_t n_frames, int32_t* states, float* f0, uint8_t* voiced_flag,
+                              void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

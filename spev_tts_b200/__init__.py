@@ -16,6 +16,7 @@ from .batch import Context, FlatBatch, make_batch, plan_chunk_tiles, plan_frame_
 from .dataset import ResidentCache, read_reference_cache, write_reference_cache  # noqa: F401
 from .features import frame_features_flat, rms, segment_pool, spectral_centroid  # noqa: F401
 from .install import install, patch_model, uninstall  # noqa: F401
+from .pitch import PyinContext, pyin, pyin_flat  # noqa: F401
 from .length_regulator import (LengthRegulator, VARIANCE_CLAMPS, expand, mel_mask, plan,  # noqa: F401
                                regulate_variances, variance_adaptor)
 from .spectral import (griffinlim, griffinlim_flat, istft, logmel, logmel_flat, mel_project,  # noqa: F401

@@ -1,0 +1,667 @@
+// pyin.cu -- probabilistic YIN (pYIN) on sm_100a: SURVEY 8(f) "next" row 2.
+// Replaces librosa.pyin(y, fmin=60, fmax=500, sr=22050, hop_length=256) at
+// /root/reference/spev_real_metrics.py:369 (and :311) -- the serial CPU bottleneck of the reference's
+// cache build (seconds per utterance: YIN difference function, 100-threshold trough statistics and a
+// 736-state Viterbi decode per utterance).
+//
+//   P1 k_yin_cmnd     frame -> cumulative-mean-normalised difference for lags min_period..max_period.
+//                     d(tau) = e(0) + e(tau) - 2 acf(tau) with the autocorrelation summed directly
+//                     (one lag per thread, four accumulators), energies from a block prefix sum, the
+//                     reference's |.| < 1e-6 -> 0 clean-ups, block scan for the cumulative mean.
+//   P2 k_pyin_observe frame -> troughs, parabolic refinement, for each of the 100 thresholds the
+//                     Boltzmann prior over the troughs below it (bitmask + popcount ranks, float64),
+//                     beta-weighted sum, global-minimum bonus, mapping to 10-cent pitch bins ->
+//                     float32 log observation probabilities [F, n_bins] + voiced probability [F].
+//   P3 k_pyin_viterbi utterance -> state path.  One CTA per utterance, one thread per state
+//                     (2 x n_bins), float64 log-domain recursion over the banded transition
+//                     (kron(switch 2x2, triangular local band)); predecessors outside the band carry
+//                     log(tiny) exactly as in the dense reference, so the best of them is the previous
+//                     step's global maximum, found by a block arg-max.  Backpointers go to a
+//                     caller-provided workspace; ties resolve to the lowest state index like np.argmax.
+#include <algorithm>
+#include <cmath>
+#include <vector>
+#include "spev_internal.cuh"
+#include "tile_pipe.cuh"
+
+struct spev_pyin {
+    int device, sr;
+    double fmin, fmax;
+    int frame_length, win_length, hop, min_period, max_period, n_lags;
+    int n_thresholds, n_bins, bins_per_semitone, trans_width;
+    double no_trough_prob;
+    double* d_thresholds;     // [n_thresholds+1]
+    double* d_beta_probs;     // [n_thresholds]
+    double* d_beta_cum;       // [n_thresholds+1] prefix sums of beta_probs (sequential, like np.sum of a slice... see note)
+    double* d_boltz_exp;      // [kMaxTroughs] exp(-lambda k)
+    double* d_boltz_fact;     // [kMaxTroughs+1] (1-exp(-lambda)) / (1-exp(-lambda N))
+    double* d_ltrans;         // [2][2][n_classes][trans_width] log(t_switch * t_local + tiny)
+    double* d_freqs;          // [n_bins]
+    int n_classes;
+    std::vector<double> h_freqs, h_ltrans, h_beta;
+};
+
+namespace spev {
+
+constexpr int kMaxTroughs = 192;          // 325 lags -> at most 163 local minima
+constexpr int kMaskWords = kMaxTroughs / 32;
+constexpr double kTiny64 = 2.2250738585072014e-308;
+constexpr double kLogTiny64 = -708.3964185322641;   // log(DBL_MIN)
+
+// ----------------------------------------------------------------------------------------------
+// P1: cumulative mean normalised difference
+// ----------------------------------------------------------------------------------------------
+constexpr int kCmndThreads = 384;
+constexpr int kQuads = 96;                 // lag quads per frame (lags 0..383), x 4 segments of the window
+
+__device__ __forceinline__ float block_incl_scan(float v, float* s_w) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const float t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+    if (lane == 31) s_w[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        float w = lane < (kCmndThreads / 32) ? s_w[lane] : 0.f;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const float t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+        if (lane < (kCmndThreads / 32)) s_w[lane] = w;
+    }
+    __syncthreads();
+    if (wid > 0) v += s_w[wid - 1];
+    __syncthreads();
+    return v;
+}
+
+__global__ void __launch_bounds__(kCmndThreads)
+k_yin_cmnd(BatchView bv, const float* __restrict__ samples, float* __restrict__ yin, int frame_length, int win,
+           int min_period, int max_period) {
+    extern __shared__ __align__(16) float sm[];
+    float* s_x = sm + 3;                               // s_x[1] is 16-byte aligned (the window starts at sample 1)
+    float* s_e = sm + 2056;                            // inclusive prefix sums of x^2
+    float* s_part = s_e + 2048;                        // [4][384] partial autocorrelations
+    float* s_w = s_part + 4 * kCmndThreads;            // [16]
+    const int need = win + 4 * kQuads + 4;             // samples the lag quads touch (<= frame_length)
+    const int n_lags = max_period - min_period + 1;
+    const int64_t slots = static_cast<int64_t>(bv.n_ftiles) * kTileFrames;
+    for (int64_t fidx = blockIdx.x; fidx < slots; fidx += gridDim.x) {
+        const int64_t tile = fidx / kTileFrames;
+        const spev_tile d = bv.ftiles[tile];
+        const int fl = static_cast<int>(fidx - tile * kTileFrames);
+        if (fl >= d.n) continue;                       // (uniform per CTA)
+        // the frame_length window starts frame_length/2 before the frame centre; src0 is n_fft/2 before it
+        const int64_t first = d.src0 - (frame_length / 2 - kNfft / 2) + static_cast<int64_t>(fl) * kHop;
+        __syncthreads();
+        for (int i = threadIdx.x; i < need; i += blockDim.x) {
+            const int64_t g = first + i;
+            s_x[i] = (g >= d.lo && g < d.hi) ? __ldg(samples + g) : 0.f;
+        }
+        __syncthreads();
+        {   // inclusive prefix sums of x^2 (numpy: cumsum in the input dtype)
+            const int per = (need + kCmndThreads - 1) / kCmndThreads;
+            const int b0 = threadIdx.x * per, b1 = min(need, b0 + per);
+            float loc = 0.f;
+            for (int i = b0; i < b1; ++i) loc = fmaf(s_x[i], s_x[i], loc);
+            float run = block_incl_scan(loc, s_w) - loc;
+            for (int i = b0; i < b1; ++i) { run = fmaf(s_x[i], s_x[i], run); s_e[i] = run; }
+        }
+        {   // acf(tau) = sum_{j=1..W} x_j x_{j+tau}: thread = (lag quad q, window segment g), 4x4 register tile
+            const int q = threadIdx.x % kQuads, g = threadIdx.x / kQuads;
+            const float4* x4 = reinterpret_cast<const float4*>(s_x + 1);
+            const int seg = win / 16;                   // float4 per segment
+            float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+#pragma unroll 4
+            for (int i = g * seg; i < (g + 1) * seg; ++i) {
+                const float4 a = x4[i], b0 = x4[i + q], b1 = x4[i + q + 1];
+                c0 = fmaf(a.x, b0.x, c0); c0 = fmaf(a.y, b0.y, c0); c0 = fmaf(a.z, b0.z, c0); c0 = fmaf(a.w, b0.w, c0);
+                c1 = fmaf(a.x, b0.y, c1); c1 = fmaf(a.y, b0.z, c1); c1 = fmaf(a.z, b0.w, c1); c1 = fmaf(a.w, b1.x, c1);
+                c2 = fmaf(a.x, b0.z, c2); c2 = fmaf(a.y, b0.w, c2); c2 = fmaf(a.z, b1.x, c2); c2 = fmaf(a.w, b1.y, c2);
+                c3 = fmaf(a.x, b0.w, c3); c3 = fmaf(a.y, b1.x, c3); c3 = fmaf(a.z, b1.y, c3); c3 = fmaf(a.w, b1.z, c3);
+            }
+            float* o = s_part + g * kCmndThreads + 4 * q;
+            o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
+        }
+        __syncthreads();
+        const int tau = threadIdx.x;                    // one lag per thread from here on
+        float dval = 0.f;
+        if (tau >= 1 && tau <= max_period) {
+            float acf = (s_part[tau] + s_part[kCmndThreads + tau]) + (s_part[2 * kCmndThreads + tau] + s_part[3 * kCmndThreads + tau]);
+            float e_tau = s_e[tau + win] - s_e[tau];    // samples tau+1 .. tau+W
+            float e_0 = s_e[win] - s_e[0];
+            if (fabsf(acf) < 1e-6f) acf = 0.f;          // the reference's clean-ups
+            if (fabsf(e_tau) < 1e-6f) e_tau = 0.f;
+            if (fabsf(e_0) < 1e-6f) e_0 = 0.f;
+            dval = e_0 + e_tau - 2.f * acf;
+        }
+        const float cum = block_incl_scan(dval, s_w);   // sum of d(1..tau)
+        if (tau >= min_period && tau <= max_period) {
+            const float cm = cum / static_cast<float>(tau);
+            yin[(d.row0 + fl) * n_lags + (tau - min_period)] = dval / (cm + 1.17549435e-38f);
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// P2: observation probabilities
+// ----------------------------------------------------------------------------------------------
+struct ObsParams {
+    int n_lags, min_period, n_thresholds, n_bins, bins_per_semitone, sr;
+    double fmin, no_trough_prob;
+    const double* thresholds;
+    const double* beta_probs;
+    const double* beta_cum;
+    const double* boltz_exp;
+    const double* boltz_fact;
+};
+
+constexpr int kObsThreads = 128;
+__global__ void __launch_bounds__(kObsThreads)
+k_pyin_observe(const float* __restrict__ yin, int64_t n_frames, ObsParams p, float* __restrict__ logobs,
+               float* __restrict__ log_unvoiced, float* __restrict__ voiced_prob) {
+    __shared__ float s_y[512];
+    __shared__ int s_tidx[kMaxTroughs];
+    __shared__ int s_ithr[kMaxTroughs];
+    __shared__ double s_prob[kMaxTroughs];
+    __shared__ unsigned s_mask[128][kMaskWords];     // [threshold][word]: troughs below that threshold
+    __shared__ int s_count[128];
+    __shared__ int s_wcnt[kObsThreads / 32];
+    __shared__ double s_wsum[kObsThreads / 32];
+    __shared__ double s_obs[512];
+    __shared__ double s_thr[104], s_beta[104], s_bcum[104], s_bexp[kMaxTroughs], s_bfact[kMaxTroughs + 1];
+    const int L = p.n_lags, NT = p.n_thresholds;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i <= NT; i += blockDim.x) { s_thr[i] = p.thresholds[i]; s_bcum[i] = p.beta_cum[i]; }
+    for (int i = threadIdx.x; i < NT; i += blockDim.x) s_beta[i] = p.beta_probs[i];
+    for (int i = threadIdx.x; i < kMaxTroughs; i += blockDim.x) { s_bexp[i] = p.boltz_exp[i]; s_bfact[i + 1] = p.boltz_fact[i + 1]; }
+    const float log_tiny_f = static_cast<float>(kLogTiny64);
+    for (int64_t f = blockIdx.x; f < n_frames; f += gridDim.x) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < L; i += blockDim.x) s_y[i] = yin[f * L + i];
+        for (int i = threadIdx.x; i < p.n_bins; i += blockDim.x) s_obs[i] = 0.0;
+        for (int i = threadIdx.x; i < NT * kMaskWords; i += blockDim.x) (&s_mask[0][0])[i] = 0u;
+        __syncthreads();
+        // troughs: localmin (x[i] < x[i-1] && x[i] <= x[i+1], edge-padded); first element: x[0] < x[1].
+        // ordered compaction, kObsThreads lags per round
+        int K = 0;
+        for (int base = 0; base < L; base += kObsThreads) {
+            const int i = base + threadIdx.x;
+            bool tr = false;
+            if (i < L) {
+                const float c = s_y[i];
+                if (i == 0) tr = L > 1 && c < s_y[1];
+                else tr = (c < s_y[i - 1]) && (c <= (i + 1 < L ? s_y[i + 1] : c));
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, tr);
+            if (lane == 0) s_wcnt[wid] = __popc(bal);
+            __syncthreads();
+            int off = K;
+            for (int w = 0; w < wid; ++w) off += s_wcnt[w];
+            if (tr) { const int k = off + __popc(bal & ((1u << lane) - 1u)); if (k < kMaxTroughs) s_tidx[k] = i; }
+            for (int w = 0; w < kObsThreads / 32; ++w) K += s_wcnt[w];
+            __syncthreads();
+        }
+        K = min(K, kMaxTroughs);
+        if (K == 0) {                                    // (uniform) no trough: all mass on the unvoiced states
+            if (threadIdx.x == 0) {
+                voiced_prob[f] = 0.f;
+                log_unvoiced[f] = static_cast<float>(log(1.0 / p.n_bins + kTiny64));
+            }
+            for (int i = threadIdx.x; i < p.n_bins; i += blockDim.x) logobs[f * p.n_bins + i] = log_tiny_f;
+            continue;
+        }
+        // first threshold index each trough lies below (thresholds[i+1] > h); NT if none
+        for (int k = threadIdx.x; k < K; k += blockDim.x) {
+            const double h = static_cast<double>(s_y[s_tidx[k]]);
+            int lo = 0, hi = NT;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (h < s_thr[mid + 1]) hi = mid; else lo = mid + 1; }
+            s_ithr[k] = lo;
+            if (lo < NT) atomicOr(&s_mask[lo][k >> 5], 1u << (k & 31));
+        }
+        __syncthreads();
+        if (threadIdx.x < kMaskWords) {                 // prefix-OR over thresholds
+            unsigned run = 0u;
+            for (int i = 0; i < NT; ++i) { run |= s_mask[i][threadIdx.x]; s_mask[i][threadIdx.x] = run; }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < NT; i += blockDim.x) {
+            int c = 0;
+#pragma unroll
+            for (int w = 0; w < kMaskWords; ++w) c += __popc(s_mask[i][w]);
+            s_count[i] = c;
+        }
+        __syncthreads();
+        // probs[k] = sum_i boltzmann.pmf(rank_{k,i}, lambda, n_i) * beta_probs[i]   (i >= ithr[k]);
+        // four threads per trough (thresholds interleaved), partials combined in a fixed order
+        for (int kb = 0; kb < K; kb += kObsThreads / 4) {
+            const int k = kb + (threadIdx.x >> 2), sub = threadIdx.x & 3;
+            double acc = 0.0;
+            if (k < K) {
+                const int w0 = k >> 5;
+                const unsigned below = (1u << (k & 31)) - 1u;
+                for (int i = s_ithr[k] + sub; i < NT; i += 4) {
+                    int rank = __popc(s_mask[i][w0] & below);
+                    for (int w = 0; w < w0; ++w) rank += __popc(s_mask[i][w]);
+                    acc += (s_bfact[s_count[i]] * s_bexp[rank]) * s_beta[i];
+                }
+            }
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            if (k < K && sub == 0) s_prob[k] = acc;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            // global minimum bonus (np.argmin: first minimum)
+            int gm = 0;
+            float hmin = s_y[s_tidx[0]];
+            for (int k = 1; k < K; ++k) { const float h = s_y[s_tidx[k]]; if (h < hmin) { hmin = h; gm = k; } }
+            s_prob[gm] += p.no_trough_prob * s_bcum[s_ithr[gm]];
+            // candidates -> pitch bins, ascending lag (later entries overwrite earlier ones in the same bin)
+            for (int k = 0; k < K; ++k) {
+                const float prf = static_cast<float>(s_prob[k]);   // yin_probs takes the curve's dtype (float32)
+                if (prf == 0.f) continue;                // np.nonzero
+                const int i = s_tidx[k];
+                double shift = 0.0;                      // parabolic interpolation on the float32 curve
+                if (i >= 1 && i + 1 < L) {
+                    const float a = s_y[i + 1] + s_y[i - 1] - 2.f * s_y[i];
+                    const float b = (s_y[i + 1] - s_y[i - 1]) / 2.f;
+                    if (fabsf(b) < fabsf(a)) shift = static_cast<double>(-b / a);
+                }
+                const double period = static_cast<double>(p.min_period + i) + shift;
+                const double f0 = static_cast<double>(p.sr) / period;
+                double bi = rint(12.0 * p.bins_per_semitone * log2(f0 / p.fmin));
+                bi = fmin(fmax(bi, 0.0), static_cast<double>(p.n_bins));
+                const int bin = static_cast<int>(bi);
+                if (bin < p.n_bins) s_obs[bin] = static_cast<double>(prf);   // bin == n_bins falls in the unvoiced half, overwritten there
+            }
+        }
+        __syncthreads();
+        {   // voiced probability = clip(sum of the voiced bins, 0, 1)
+            double part = 0.0;
+            for (int i = threadIdx.x; i < p.n_bins; i += blockDim.x) part += s_obs[i];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            if (lane == 0) s_wsum[wid] = part;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double vsum = (s_wsum[0] + s_wsum[1]) + (s_wsum[2] + s_wsum[3]);
+                vsum = fmin(fmax(vsum, 0.0), 1.0);
+                voiced_prob[f] = static_cast<float>(vsum);
+                log_unvoiced[f] = static_cast<float>(log((1.0 - vsum) / p.n_bins + kTiny64));
+            }
+        }
+        for (int i = threadIdx.x; i < p.n_bins; i += blockDim.x) {
+            const double o = s_obs[i];
+            logobs[f * p.n_bins + i] = o == 0.0 ? log_tiny_f : static_cast<float>(log(o + kTiny64));
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// P3: Viterbi
+// ----------------------------------------------------------------------------------------------
+struct VitParams {
+    int n_bins, width, n_classes;
+    const double* ltrans;     // [2][2][n_classes][width]
+};
+
+__device__ __forceinline__ int row_class(int b, int n_bins, int half) {
+    return b < half ? b : (b >= n_bins - half ? half + 1 + (b - (n_bins - half)) : half);
+}
+
+constexpr int kVitThreads = 384;                 // one thread per pitch bin: it owns the voiced AND the unvoiced state of that bin
+struct ArgMax { double v; int i; };
+__device__ __forceinline__ ArgMax warp_argmax(ArgMax a) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, a.v, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, a.i, o);
+        if (ov > a.v || (ov == a.v && oi < a.i)) { a.v = ov; a.i = oi; }
+    }
+    return a;
+}
+
+__global__ void __launch_bounds__(kVitThreads, 2)
+k_pyin_viterbi(const float* __restrict__ logobs, const float* __restrict__ log_unvoiced,
+               const int64_t* __restrict__ frame_off, int n_items, VitParams p, unsigned short* __restrict__ ptr,
+               int* __restrict__ states, unsigned* __restrict__ work_counter) {
+    extern __shared__ double smd[];
+    double* s_val = smd;                                   // [2][S]
+    double* s_lt = smd + 2 * 2 * p.n_bins;                 // [2][2][n_classes][width]
+    __shared__ double s_red_v[kVitThreads / 32];
+    __shared__ int s_red_i[kVitThreads / 32];
+    __shared__ double s_gmax;
+    __shared__ int s_garg;
+    __shared__ int s_item;
+    const int nb = p.n_bins, S = 2 * nb, W = p.width, half = W / 2;
+    const int lt_n = 4 * p.n_classes * W;
+    for (int i = threadIdx.x; i < lt_n; i += blockDim.x) s_lt[i] = p.ltrans[i];
+    const int b = threadIdx.x;
+    const bool act = b < nb;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int blo = max(0, b - half), bhi = min(nb - 1, b + half);
+    const double log_init_unv = log(1.0 / nb + kTiny64);
+    const int cstride = p.n_classes * W;                   // s_lt stride between the four (vp, v) tables
+
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_item = static_cast<int>(atomicAdd(work_counter, 1u));
+        __syncthreads();
+        const int u = s_item;
+        if (u >= n_items) break;
+        const int64_t f0 = frame_off[u];
+        const int T = static_cast<int>(frame_off[u + 1] - f0);
+        if (T <= 0) continue;
+        // t = 0: log_prob[0] + log(p_init): p_init = 0 on voiced states, 1/n_bins on unvoiced ones
+        double cur0 = -INFINITY, cur1 = -INFINITY;
+        if (act) {
+            cur0 = static_cast<double>(logobs[f0 * nb + b]) + kLogTiny64;
+            cur1 = static_cast<double>(log_unvoiced[f0]) + log_init_unv;
+            s_val[b] = cur0;
+            s_val[nb + b] = cur1;
+        }
+        for (int t = 1; t < T; ++t) {
+            const int64_t ft = f0 + t;
+            // this step's observations (issued early: the loads overlap the arg-max reduction)
+            const float lp0f = act ? logobs[ft * nb + b] : 0.f;
+            const float lp1f = log_unvoiced[ft];
+            // block arg-max of the previous values (lowest index on ties)
+            ArgMax m;
+            if (act) { if (cur1 > cur0) { m.v = cur1; m.i = nb + b; } else { m.v = cur0; m.i = b; } }
+            else { m.v = -INFINITY; m.i = 0x7fffffff; }
+            m = warp_argmax(m);
+            if (lane == 0) { s_red_v[wid] = m.v; s_red_i[wid] = m.i; }
+            __syncthreads();                               // also publishes s_val[prev]
+            if (wid == 0) {
+                if (lane < kVitThreads / 32) { m.v = s_red_v[lane]; m.i = s_red_i[lane]; }
+                else { m.v = -INFINITY; m.i = 0x7fffffff; }
+                m = warp_argmax(m);
+                if (lane == 0) { s_gmax = m.v; s_garg = m.i; }
+            }
+            __syncthreads();
+            const double* prev = s_val + ((t - 1) & 1) * S;
+            double* next = s_val + (t & 1) * S;
+            if (act) {
+                // four independent running maxima: (from voiced | unvoiced) x (to voiced | unvoiced), ascending bin
+                double m00 = -INFINITY, m01 = -INFINITY, m10 = -INFINITY, m11 = -INFINITY;
+                int a00 = 0, a01 = 0, a10 = 0, a11 = 0;
+                const double* pv0 = prev;
+                const double* pv1 = prev + nb;
+                const double* l00 = s_lt;                       // [vp=0][v=0]
+                const double* l01 = l00 + cstride;              // [vp=0][v=1]
+                const double* l10 = l00 + 2 * cstride;          // [vp=1][v=0]
+                const double* l11 = l00 + 3 * cstride;          // [vp=1][v=1]
+#pragma unroll 2
+                for (int bp = blo; bp <= bhi; ++bp) {
+                    // row class of the predecessor: its own index near the edges, `half` in the interior
+                    const int cls = min(bp, half) + max(0, bp - nb + half + 1);
+                    const int off = cls * W + (b - bp + half);
+                    const double x0 = pv0[bp], x1 = pv1[bp];
+                    const double s00 = x0 + l00[off], s01 = x0 + l01[off], s10 = x1 + l10[off], s11 = x1 + l11[off];
+                    if (s00 > m00) { m00 = s00; a00 = bp; }
+                    if (s01 > m01) { m01 = s01; a01 = bp; }
+                    if (s10 > m10) { m10 = s10; a10 = bp; }
+                    if (s11 > m11) { m11 = s11; a11 = bp; }
+                }
+                // merge the two source halves; the voiced half holds the lower state indices and wins ties
+                double best0 = m00, best1 = m01;
+                int arg0 = a00, arg1 = a01;
+                if (m10 > best0) { best0 = m10; arg0 = nb + a10; }
+                if (m11 > best1) { best1 = m11; arg1 = nb + a11; }
+                // predecessors outside the band have transition probability 0 -> log(0 + tiny); the best
+                // of them is the global maximum when that state is itself outside the band
+                const int ga = s_garg;
+                const int gb = ga >= nb ? ga - nb : ga;
+                if (gb < blo || gb > bhi) {
+                    const double sc = s_gmax + kLogTiny64;
+                    if (sc > best0 || (sc == best0 && ga < arg0)) { best0 = sc; arg0 = ga; }
+                    if (sc > best1 || (sc == best1 && ga < arg1)) { best1 = sc; arg1 = ga; }
+                }
+                cur0 = static_cast<double>(lp0f) + best0;
+                cur1 = static_cast<double>(lp1f) + best1;
+                next[b] = cur0;
+                next[nb + b] = cur1;
+                ptr[ft * S + b] = static_cast<unsigned short>(arg0);
+                ptr[ft * S + nb + b] = static_cast<unsigned short>(arg1);
+            }
+            // (the __syncthreads at the top of the next iteration orders next[] before it is read)
+        }
+        // final arg-max and backtrace
+        {
+            ArgMax m;
+            if (act) { if (cur1 > cur0) { m.v = cur1; m.i = nb + b; } else { m.v = cur0; m.i = b; } }
+            else { m.v = -INFINITY; m.i = 0x7fffffff; }
+            m = warp_argmax(m);
+            if (lane == 0) { s_red_v[wid] = m.v; s_red_i[wid] = m.i; }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double bv = -INFINITY;
+                int bi = 0x7fffffff;
+                for (int w = 0; w < kVitThreads / 32; ++w)
+                    if (s_red_v[w] > bv || (s_red_v[w] == bv && s_red_i[w] < bi)) { bv = s_red_v[w]; bi = s_red_i[w]; }
+                int st = bi;
+                states[f0 + T - 1] = st;
+                for (int t = T - 2; t >= 0; --t) {
+                    st = ptr[(f0 + t + 1) * S + st];
+                    states[f0 + t] = st;
+                }
+            }
+        }
+    }
+}
+
+__global__ void k_pyin_finish(const int* __restrict__ states, int64_t n, int n_bins, const double* __restrict__ freqs,
+                              float* __restrict__ f0, unsigned char* __restrict__ voiced) {
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int s = states[i];
+        const bool vflag = s < n_bins;
+        if (voiced) voiced[i] = vflag ? 1 : 0;
+        if (f0) f0[i] = vflag ? static_cast<float>(freqs[s % n_bins]) : __int_as_float(0x7fc00000);
+    }
+}
+
+}  // namespace spev
+
+using namespace spev;
+
+// ----------------------------------------------------------------------------------------------
+// host side: tables (restating librosa.pyin's set-up) and the C ABI
+// ----------------------------------------------------------------------------------------------
+static double beta_cdf_int(double x, int a, int b) {
+    // I_x(a, b) for integer a, b = 1 - sum_{j<a} C(n, j) x^j (1-x)^(n-j), n = a+b-1 (the short, accurate side)
+    const int n = a + b - 1;
+    double s = 0.0;
+    const bool upper = x >= 0.25;                          // sum the side with the smaller total
+    for (int j = upper ? 0 : a; j <= (upper ? a - 1 : n); ++j) {
+        double c = 1.0;
+        for (int q = 1; q <= j; ++q) c = c * (n - j + q) / q;
+        s += c * std::pow(x, j) * std::pow(1.0 - x, n - j);
+    }
+    return upper ? 1.0 - s : s;
+}
+
+template <class T>
+static int up(T** dst, const std::vector<T>& src) {
+    SPEV_CUDA(cudaMalloc(reinterpret_cast<void**>(dst), std::max<size_t>(1, src.size()) * sizeof(T)));
+    if (!src.empty()) SPEV_CUDA(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return SPEV_OK;
+}
+
+extern "C" {
+
+int spev_pyin_create(spev_pyin** out, int device, int sr, float fmin, float fmax, const double* beta_probs_host) {
+    SPEV_REQUIRE(out, SPEV_E_INVALID, "spev_pyin_create: out is null");
+    *out = nullptr;
+    SPEV_REQUIRE(sr > 0 && fmin > 0.f && fmax > fmin, SPEV_E_INVALID, "spev_pyin_create: need sr > 0, 0 < fmin < fmax");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("spev_pyin_create: no CUDA device (this library has no CPU fallback)");
+        return SPEV_E_DEVICE;
+    }
+    SPEV_REQUIRE(device >= 0 && device < ndev, SPEV_E_DEVICE, "spev_pyin_create: device out of range");
+    SPEV_CUDA(cudaSetDevice(device));
+    spev_pyin* c = new spev_pyin();
+    c->device = device; c->sr = sr; c->fmin = fmin; c->fmax = fmax;
+    c->frame_length = 2048; c->win_length = 1024; c->hop = kHop;
+    c->min_period = static_cast<int>(std::floor(static_cast<double>(sr) / fmax));
+    c->max_period = std::min(static_cast<int>(std::ceil(static_cast<double>(sr) / fmin)), c->frame_length - c->win_length - 1);
+    c->n_lags = c->max_period - c->min_period + 1;
+    c->n_thresholds = 100; c->no_trough_prob = 0.01;
+    c->bins_per_semitone = 10;                                     // ceil(1 / resolution), resolution = 0.1
+    c->n_bins = static_cast<int>(std::floor(12.0 * c->bins_per_semitone * std::log2(static_cast<double>(fmax) / fmin))) + 1;
+    const int max_semitones = static_cast<int>(std::nearbyint(35.92 * 12.0 * c->hop / sr));
+    c->trans_width = max_semitones * c->bins_per_semitone + 1;
+    c->d_thresholds = c->d_beta_probs = c->d_beta_cum = c->d_boltz_exp = c->d_boltz_fact = c->d_ltrans = c->d_freqs = nullptr;
+    if (!(c->n_lags > 2 && c->n_lags <= 512 && c->max_period < 384 && c->n_bins >= 2 * c->trans_width && c->n_bins <= 384 &&
+          c->trans_width >= 3 && (c->trans_width & 1))) {
+        delete c;
+        set_error("spev_pyin_create: (sr, fmin, fmax) outside what the kernels support");
+        return SPEV_E_UNSUPPORTED;
+    }
+    // thresholds = linspace(0, 1, 101); beta_probs = diff(beta(2, 18).cdf(thresholds))
+    std::vector<double> thr(c->n_thresholds + 1), cdf(c->n_thresholds + 1), bp(c->n_thresholds), bc(c->n_thresholds + 1, 0.0);
+    const double step = 1.0 / c->n_thresholds;
+    for (int i = 0; i <= c->n_thresholds; ++i) { thr[i] = i == c->n_thresholds ? 1.0 : i * step; cdf[i] = beta_cdf_int(thr[i], 2, 18); }
+    for (int i = 0; i < c->n_thresholds; ++i) bp[i] = beta_probs_host ? beta_probs_host[i] : cdf[i + 1] - cdf[i];
+    for (int i = 0; i < c->n_thresholds; ++i) bc[i + 1] = bc[i] + bp[i];
+    // boltzmann.pmf(k, lambda=2, N) = (1 - e^-lambda) e^(-lambda k) / (1 - e^(-lambda N))
+    const double lam = 2.0;
+    std::vector<double> bexp(kMaxTroughs), bfact(kMaxTroughs + 1, 0.0);
+    for (int k = 0; k < kMaxTroughs; ++k) bexp[k] = std::exp(-lam * k);
+    for (int N = 1; N <= kMaxTroughs; ++N) bfact[N] = (1.0 - std::exp(-lam)) / (1.0 - std::exp(-lam * N));
+    // transition = kron(transition_loop(2, 0.99), transition_local(n_bins, width, 'triangle')); log(. + tiny)
+    const int W = c->trans_width, half = W / 2, nb = c->n_bins;
+    c->n_classes = 2 * half + 1;
+    std::vector<double> tri(W);
+    for (int n = 0; n <= W / 2; ++n) tri[n] = tri[W - 1 - n] = 2.0 * (n + 1) / (W + 1.0);       // scipy.signal.triang(odd M)
+    const double stay = 1.0 - 0.01, leave = (1.0 - stay) / 1.0;        // transition_loop(2, 1 - switch_prob)
+    const double sw[2][2] = {{stay, leave}, {leave, stay}};
+    std::vector<double> lt(static_cast<size_t>(4) * c->n_classes * W, kLogTiny64);
+    for (int cls = 0; cls < c->n_classes; ++cls) {
+        const int bprow = cls < half ? cls : (cls == half ? half : nb - half + (cls - half - 1));   // a representative row
+        double rowsum = 0.0;
+        for (int d = 0; d < W; ++d) { const int bcol = bprow + d - half; if (bcol >= 0 && bcol < nb) rowsum += tri[d]; }
+        for (int vp = 0; vp < 2; ++vp)
+            for (int v = 0; v < 2; ++v)
+                for (int d = 0; d < W; ++d) {
+                    // entry (from bp = bprow, to b = bprow + d' ) is stored at index (b - bp + half)
+                    const int bcol = bprow + d - half;
+                    if (bcol < 0 || bcol >= nb) continue;
+                    const double tl = tri[d] / rowsum;
+                    lt[((static_cast<size_t>(vp) * 2 + v) * c->n_classes + cls) * W + d] = std::log(sw[vp][v] * tl + kTiny64);
+                }
+    }
+    c->h_ltrans = lt;
+    c->h_beta = bp;
+    c->h_freqs.resize(nb);
+    for (int i = 0; i < nb; ++i) c->h_freqs[i] = fmin * std::pow(2.0, static_cast<double>(i) / (12.0 * c->bins_per_semitone));
+    int rc;
+    if ((rc = up(&c->d_thresholds, thr)) || (rc = up(&c->d_beta_probs, bp)) || (rc = up(&c->d_beta_cum, bc)) ||
+        (rc = up(&c->d_boltz_exp, bexp)) || (rc = up(&c->d_boltz_fact, bfact)) || (rc = up(&c->d_ltrans, lt)) ||
+        (rc = up(&c->d_freqs, c->h_freqs))) {
+        spev_pyin_destroy(c);
+        return rc;
+    }
+    *out = c;
+    return SPEV_OK;
+}
+
+void spev_pyin_destroy(spev_pyin* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaFree(c->d_thresholds); cudaFree(c->d_beta_probs); cudaFree(c->d_beta_cum); cudaFree(c->d_boltz_exp);
+    cudaFree(c->d_boltz_fact); cudaFree(c->d_ltrans); cudaFree(c->d_freqs);
+    delete c;
+}
+
+int spev_pyin_info(const spev_pyin* c, int* n_bins, int* min_period, int* max_period, int* n_lags) {
+    SPEV_REQUIRE(c, SPEV_E_INVALID, "pyin ctx is null");
+    if (n_bins) *n_bins = c->n_bins;
+    if (min_period) *min_period = c->min_period;
+    if (max_period) *max_period = c->max_period;
+    if (n_lags) *n_lags = c->n_lags;
+    return SPEV_OK;
+}
+
+int spev_pyin_host_tables(const spev_pyin* c, double* log_transition, double* freqs, double* beta_probs) {
+    SPEV_REQUIRE(c, SPEV_E_INVALID, "pyin ctx is null");
+    const int nb = c->n_bins, S = 2 * nb, W = c->trans_width, half = W / 2;
+    if (log_transition) {                                  // dense [S, S], row = from-state
+        for (int from = 0; from < S; ++from)
+            for (int to = 0; to < S; ++to) {
+                const int vp = from >= nb, bp = from - vp * nb, v = to >= nb, b = to - v * nb;
+                double val = kLogTiny64;
+                if (std::abs(b - bp) <= half) {
+                    const int cls = bp < half ? bp : (bp >= nb - half ? half + 1 + (bp - (nb - half)) : half);
+                    val = c->h_ltrans[((static_cast<size_t>(vp) * 2 + v) * c->n_classes + cls) * W + (b - bp + half)];
+                }
+                log_transition[static_cast<size_t>(from) * S + to] = val;
+            }
+    }
+    if (freqs) std::copy(c->h_freqs.begin(), c->h_freqs.end(), freqs);
+    if (beta_probs) std::copy(c->h_beta.begin(), c->h_beta.end(), beta_probs);
+    return SPEV_OK;
+}
+
+int spev_pyin_cmnd(spev_pyin* c, const spev_batch* b, const float* samples, float* yin, void* stream) {
+    SPEV_REQUIRE(c && b, SPEV_E_INVALID, "spev_pyin_cmnd: null ctx/batch");
+    SPEV_CUDA(cudaSetDevice(c->device));
+    if (b->n_frames == 0) return SPEV_OK;
+    SPEV_REQUIRE(samples && yin && b->ftiles, SPEV_E_INVALID, "spev_pyin_cmnd: null buffer");
+    const int64_t slots = static_cast<int64_t>(b->n_ftiles) * kTileFrames;
+    const int grid = static_cast<int>(std::min<int64_t>(slots, 148 * 64));
+    k_yin_cmnd<<<grid, kCmndThreads, sizeof(float) * (2056 + 2048 + 4 * kCmndThreads + 16), static_cast<cudaStream_t>(stream)>>>(
+        view_of(b), samples, yin, c->frame_length, c->win_length, c->min_period, c->max_period);
+    SPEV_CUDA(cudaGetLastError());
+    return SPEV_OK;
+}
+
+int spev_pyin_observe(spev_pyin* c, const float* yin, int64_t n_frames, float* logobs, float* log_unvoiced,
+                      float* voiced_prob, void* stream) {
+    SPEV_REQUIRE(c, SPEV_E_INVALID, "spev_pyin_observe: null ctx");
+    SPEV_CUDA(cudaSetDevice(c->device));
+    SPEV_REQUIRE(n_frames >= 0, SPEV_E_INVALID, "spev_pyin_observe: n_frames < 0");
+    if (n_frames == 0) return SPEV_OK;
+    SPEV_REQUIRE(yin && logobs && log_unvoiced && voiced_prob, SPEV_E_INVALID, "spev_pyin_observe: null buffer");
+    ObsParams p{c->n_lags, c->min_period, c->n_thresholds, c->n_bins, c->bins_per_semitone, c->sr, c->fmin,
+                c->no_trough_prob, c->d_thresholds, c->d_beta_probs, c->d_beta_cum, c->d_boltz_exp, c->d_boltz_fact};
+    const int grid = static_cast<int>(std::min<int64_t>(n_frames, 148 * 64));
+    k_pyin_observe<<<grid, kObsThreads, 0, static_cast<cudaStream_t>(stream)>>>(yin, n_frames, p, logobs, log_unvoiced, voiced_prob);
+    SPEV_CUDA(cudaGetLastError());
+    return SPEV_OK;
+}
+
+size_t spev_pyin_decode_workspace_bytes(const spev_pyin* c, int64_t n_frames) {
+    if (!c || n_frames < 0) return 0;
+    return static_cast<size_t>(n_frames) * 2 * c->n_bins * sizeof(unsigned short) + 512;
+}
+
+int spev_pyin_decode(spev_pyin* c, const float* logobs, const float* log_unvoiced, const int64_t* frame_off, int n_items,
+                     int64_t n_frames, int32_t* states, float* f0, uint8_t* voiced_flag, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+    SPEV_REQUIRE(c, SPEV_E_INVALID, "spev_pyin_decode: null ctx");
+    SPEV_CUDA(cudaSetDevice(c->device));
+    SPEV_REQUIRE(n_items >= 0 && n_frames >= 0, SPEV_E_INVALID, "spev_pyin_decode: negative sizes");
+    if (n_items == 0 || n_frames == 0) return SPEV_OK;
+    SPEV_REQUIRE(logobs && log_unvoiced && frame_off && states, SPEV_E_INVALID, "spev_pyin_decode: null buffer");
+    SPEV_REQUIRE(workspace && workspace_bytes >= spev_pyin_decode_workspace_bytes(c, n_frames), SPEV_E_WORKSPACE,
+                 "spev_pyin_decode: workspace too small");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned* counter = reinterpret_cast<unsigned*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+    unsigned short* ptr = reinterpret_cast<unsigned short*>(counter + 64);
+    SPEV_REQUIRE(c->n_bins <= kVitThreads, SPEV_E_UNSUPPORTED, "spev_pyin_decode: too many pitch bins");
+    VitParams p{c->n_bins, c->trans_width, c->n_classes, c->d_ltrans};
+    const size_t smem = sizeof(double) * (static_cast<size_t>(4) * c->n_bins + static_cast<size_t>(4) * c->n_classes * c->trans_width);
+    SPEV_CUDA(cudaFuncSetAttribute(k_pyin_viterbi, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    SPEV_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned), st));
+    const int grid = std::min(n_items, 148 * 2);
+    k_pyin_viterbi<<<grid, kVitThreads, smem, st>>>(logobs, log_unvoiced, frame_off, n_items, p, ptr, states, counter);
+    SPEV_CUDA(cudaGetLastError());
+    if (f0 || voiced_flag) {
+        const int g2 = static_cast<int>(std::min<int64_t>((n_frames + 255) / 256, 148 * 8));
+        k_pyin_finish<<<g2, 256, 0, st>>>(states, n_frames, c->n_bins, c->d_freqs, f0, voiced_flag);
+        SPEV_CUDA(cudaGetLastError());
+    }
+    return SPEV_OK;
+}
+
+}  // extern "C"

@@ -5,6 +5,7 @@ Patches, when the modules are importable:
   * ``librosa.feature.melspectrogram``            (used at ``spev_real_metrics.py:363``)
   * ``librosa.feature.inverse.mel_to_audio``      (used at ``:730-733``)
   * ``librosa.feature.rms`` / ``librosa.feature.spectral_centroid``   (``:370-371``, stats pass ``:314-316``)
+  * ``librosa.pyin``                              (``:369``, stats pass ``:311``)
   * ``spev_real_metrics.LengthRegulator``         (``:122-146``; instantiated at ``:160``)
 Calls with parameters outside the implemented configuration (n_fft != 1024, ...) are passed
 through to the original function.
@@ -13,7 +14,7 @@ from __future__ import annotations
 
 import sys
 
-from . import features, length_regulator, spectral
+from . import features, length_regulator, pitch, spectral
 
 _installed = {}
 
@@ -42,6 +43,9 @@ def install(verbose: bool = False) -> dict:
         _installed["spectral_centroid"] = librosa.feature.spectral_centroid
         librosa.feature.rms = _passthrough(features.rms, _installed["rms"])
         librosa.feature.spectral_centroid = _passthrough(features.spectral_centroid, _installed["spectral_centroid"])
+        if hasattr(librosa, "pyin"):
+            _installed["pyin"] = librosa.pyin
+            librosa.pyin = _passthrough(pitch.pyin, _installed["pyin"])
         done["librosa"] = True
     except (ImportError, AttributeError):   # absent, or a partial stub without the functions
         done["librosa"] = False
@@ -62,6 +66,8 @@ def uninstall() -> None:
         for name in ("melspectrogram", "rms", "spectral_centroid"):
             if name in _installed:
                 setattr(librosa.feature, name, _installed.pop(name))
+        if "pyin" in _installed:
+            librosa.pyin = _installed.pop("pyin")
         if "mel_to_audio" in _installed:
             librosa.feature.inverse.mel_to_audio = _installed.pop("mel_to_audio")
     except (ImportError, AttributeError):

@@ -126,3 +126,33 @@ def cache_records(seed: int = 8, n: int = 12, n_mels: int = 80):
                      "bright": np.clip(r.standard_normal(P), -2.5, 2.5)})
     stats = {"p_mean": 5.0, "p_std": 0.3, "e_mean": -3.0, "e_std": 1.0, "c_mean": 7.0, "c_std": 0.5}
     return recs, stats, vocab
+
+
+def voiced_unvoiced(seed: int = 0, n: int = 3 * SR, sr: int = SR):
+    """Speech-like pitch test signal: harmonic segments with gliding f0 (80-400 Hz), separated by noise
+    bursts and silences.  -> (y float32 [n], f0_true float64 [n] with 0 where unvoiced)."""
+    r = np.random.default_rng(seed)
+    y = np.zeros(n)
+    f_true = np.zeros(n)
+    pos = 0
+    kind = int(r.integers(0, 3))
+    while pos < n:
+        seg = int(r.uniform(0.08, 0.45) * sr)
+        e = min(n, pos + seg)
+        m = e - pos
+        if kind == 0:                                      # voiced
+            fa, fb = r.uniform(80, 400, 2)
+            fb = float(np.clip(fb, fa / 1.5, fa * 1.5))
+            f = np.linspace(fa, fb, m)
+            ph = 2 * np.pi * np.cumsum(f) / sr
+            amp = r.uniform(0.05, 0.4) * np.hanning(m + 2)[1:-1] ** 0.25
+            nh = int(r.integers(2, 12))
+            y[pos:e] = amp * sum(np.sin(k * ph + r.uniform(0, 6)) / k for k in range(1, nh + 1))
+            f_true[pos:e] = f
+        elif kind == 1:                                    # fricative-like noise
+            y[pos:e] = r.uniform(0.01, 0.1) * r.standard_normal(m)
+        # kind == 2: silence
+        pos = e
+        kind = int((kind + r.integers(1, 3)) % 3)
+    y += 1e-4 * r.standard_normal(n)
+    return y.astype(np.float32), f_true

@@ -23,6 +23,11 @@ def fake_librosa(monkeypatch):
                 return ("original", _n)
             setattr(mod, n, f)
     lib.feature, feat.inverse = feat, inv
+
+    def orig_pyin(*a, **k):
+        calls.append("pyin")
+        return ("original", "pyin")
+    lib.pyin = orig_pyin
     monkeypatch.setitem(sys.modules, "librosa", lib)
     monkeypatch.setitem(sys.modules, "librosa.feature", feat)
     monkeypatch.setitem(sys.modules, "librosa.feature.inverse", inv)
@@ -43,12 +48,15 @@ def test_install_patches_and_passes_through(fake_librosa):
     assert lib.feature.melspectrogram(y=y, sr=22050, n_fft=2048, hop_length=512) == ("original", "melspectrogram")
     assert lib.feature.rms(y=y, frame_length=1024, hop_length=256) == ("original", "rms")
     assert lib.feature.spectral_centroid(y=y, sr=22050, n_fft=1024) == ("original", "spectral_centroid")
-    assert calls == ["melspectrogram", "rms", "spectral_centroid"]
+    assert lib.pyin(y, fmin=60, fmax=500, sr=22050, hop_length=512) == ("original", "pyin")
+    assert calls == ["melspectrogram", "rms", "spectral_centroid", "pyin"]
     if not torch.cuda.is_available():
         # supported parameters reach the CUDA path, which fails loudly without a GPU (no silent fallback)
         with pytest.raises(RuntimeError):
             lib.feature.melspectrogram(y=y, sr=22050, n_fft=1024, hop_length=256, n_mels=80)
-        assert calls == ["melspectrogram", "rms", "spectral_centroid"]
+        with pytest.raises(RuntimeError):
+            lib.pyin(y, fmin=60, fmax=500, sr=22050, hop_length=256)
+        assert calls == ["melspectrogram", "rms", "spectral_centroid", "pyin"]
 
 
 @pytest.mark.skipif(not reference_import.available(), reason="/root/reference not mounted")
