@@ -282,10 +282,13 @@ SPEV_API int spev_bucketize_embed(const float* v, int64_t n, const float* bounda
  * spev_batch frame tiles as spev_logmel (item i has 1 + len_i/256 frames).
  * ---------------------------------------------------------------------------------------------- */
 typedef struct spev_pyin spev_pyin;
-/* beta_probs_host: optional host array [100] = diff(beta(2,18).cdf(linspace(0,1,101))) as the caller's own
+/* hop_length: 256 (cache loop, :369) or 512 (librosa's default frame_length/4, used by the statistics pass
+ * :311).  It sets the transition band (max_transition_rate * hop / sr); stages 1-2 run on the hop-256 frame
+ * grid and the caller keeps every (hop_length/256)-th frame before stage 3.
+ * beta_probs_host: optional host array [100] = diff(beta(2,18).cdf(linspace(0,1,101))) as the caller's own
  * statistics library rounds it (the Python shim passes scipy's, i.e. librosa's exact table); NULL = built-in
  * closed form (equal to ~1e-16 absolute). */
-SPEV_API int spev_pyin_create(spev_pyin** out, int device, int sr, float fmin, float fmax,
+SPEV_API int spev_pyin_create(spev_pyin** out, int device, int sr, int hop_length, float fmin, float fmax,
                               const double* beta_probs_host);
 SPEV_API void spev_pyin_destroy(spev_pyin* ctx);
 /* n_bins: voiced pitch bins (states = 2*n_bins); lags min_period..max_period (n_lags of them). */
@@ -308,6 +311,15 @@ SPEV_API size_t spev_pyin_decode_workspace_bytes(const spev_pyin* ctx, int64_t n
 SPEV_API int spev_pyin_decode(spev_pyin* ctx, const float* logobs, const float* log_unvoiced, const int64_t* frame_off,
                               int n_items, int64_t n_frames, int32_t* states, float* f0, uint8_t* voiced_flag,
                               void* workspace, size_t workspace_bytes, void* stream);
+
+/* Per-phoneme pitch statistics from the decoded states, spev_real_metrics.py:399-414 (float64 like numpy):
+ *   f0_log = log(f0 + 1e-8) on voiced frames (state < n_bins); unvoiced frames are masked (the reference's
+ *   log(1e-8 + 1e-8) < -5 test);  pitch[p] = clip((mean - p_mean) / p_std, lo, hi), or clip(0) without voiced
+ *   frames;  rough[p] = clip(population std, 0, rough_hi), 0 without voiced frames.
+ *   states int32 [F]; frame_off / phone_off int64 [n_items+1]; durs int64 [P]; pitch, rough f32 [P]. */
+SPEV_API int spev_pitch_pool(const spev_pyin* ctx, const int32_t* states, const int64_t* frame_off, const int64_t* durs,
+                             const int64_t* phone_off, int n_items, double p_mean, double p_std, float lo, float hi,
+                             float rough_hi, float* pitch, float* rough, void* stream);
 
 #ifdef __cplusplus
 }

@@ -50,6 +50,82 @@ def sha(a: np.ndarray) -> str:
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
+def run_reference_cache_build(ref, corpus, workdir):
+    """Execute the REFERENCE'S OWN ``RealMetricsDataset.__init__`` build path (``spev_real_metrics.py:300-430``)
+    on an in-memory corpus.  Its third-party calls are bound to the restated oracle (librosa.load / pyin /
+    feature.*), an identity ``phonemize`` and a JSON-backed ``textgrid`` -- everything else (statistics,
+    duration re-scaling, per-phone pooling, clipping, file naming, metadata) is the reference's code."""
+    import contextlib
+    import io
+    import json
+    import types
+    from oracle import pyin_restated as po
+    data_dir, tg_dir, cache_dir = (os.path.join(workdir, d) for d in ("data", "tg", "cache"))
+    os.makedirs(data_dir), os.makedirs(tg_dir)
+    for it in corpus:
+        np.asarray(it["y"], dtype=np.float32).tofile(os.path.join(data_dir, it["name"] + ".wav"))
+        if it["text"] is not None:
+            with open(os.path.join(data_dir, it["name"] + ".txt"), "w") as f:
+                f.write(it["text"])
+        if it["intervals"] is not None:
+            with open(os.path.join(tg_dir, it["name"] + ".TextGrid"), "w") as f:
+                json.dump(it["intervals"], f)
+
+    class _Tier(list):
+        name = "phones"
+
+    class _TextGrid:
+        @staticmethod
+        def fromFile(path):
+            with open(path) as f:
+                return [_Tier(types.SimpleNamespace(minTime=a, maxTime=b, mark=m) for a, b, m in json.load(f))]
+
+    L = ref.librosa
+    saved = {k: getattr(L, k, None) for k in ("load", "pyin", "feature")}
+    saved_mod = {k: getattr(ref, k, None) for k in ("phonemize", "textgrid", "TEXTGRID_AVAILABLE", "tqdm")}
+    L.load = lambda path, sr=None: (np.fromfile(path, dtype=np.float32), sr)
+    L.pyin = lambda y, fmin, fmax, sr=22050, hop_length=None, **k: po.pyin(
+        y, fmin=fmin, fmax=fmax, sr=sr, hop_length=hop_length or 512)
+    L.feature = types.SimpleNamespace(rms=lr.rms, spectral_centroid=lr.spectral_centroid,
+                                      melspectrogram=lr.melspectrogram)
+    ref.phonemize = lambda text, **k: text
+    ref.textgrid = types.SimpleNamespace(TextGrid=_TextGrid)
+    ref.TEXTGRID_AVAILABLE = True
+    ref.tqdm = lambda it, **k: it
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            ds = ref.RealMetricsDataset(data_dir, textgrid_dir=tg_dir, cache_dir=cache_dir, force_rebuild=True)
+    finally:
+        for k, v in saved.items():
+            setattr(L, k, v) if v is not None else (hasattr(L, k) and delattr(L, k))
+        for k, v in saved_mod.items():
+            setattr(ref, k, v)
+    return ds
+
+
+def cache_build_golden(ref) -> None:
+    import tempfile
+    corpus = synth.tiny_corpus(seed=21)
+    with tempfile.TemporaryDirectory() as tmp:
+        ds = run_reference_cache_build(ref, corpus, tmp)
+        assert len(ds) >= 8, len(ds)
+        gold = {"stats_keys": np.array(sorted(ds.stats)), "stats": np.array([ds.stats[k] for k in sorted(ds.stats)]),
+                "vocab": np.array(ds.vocab), "n_records": np.array(len(ds))}
+        idx = []
+        for k, path in enumerate(ds.metadata):
+            u = torch.load(path, weights_only=False)
+            i = int(os.path.basename(path)[2:7])
+            idx.append(i)
+            gold[f"r{k}_phs"] = np.array(u["phs"])
+            gold[f"r{k}_durs"] = np.array(u["durs"], dtype=np.int64)
+            gold[f"r{k}_mel_shape"] = np.array(u["mel"].shape)
+            gold[f"r{k}_mel_dec"] = u["mel"].numpy()[::16, ::8].copy()
+            for c in ("pitch", "energy", "breath", "rough", "bright"):
+                gold[f"r{k}_{c}"] = np.asarray(u[c])
+        gold["index"] = np.array(idx)
+    np.savez_compressed(os.path.join(OUT, "cache_build.npz"), **gold)
+
+
 def main() -> None:
     os.makedirs(OUT, exist_ok=True)
     ref = reference_import.load()
@@ -169,6 +245,7 @@ def main() -> None:
                         conv_b=np.stack([e.bias.detach().numpy() for e in embs]),
                         dec_input=dec_input.numpy(), mel_len=mel_len.numpy(),
                         curves_expanded=np.stack([t[:, 0].numpy() for t in (pitch, energy, breath, rough, bright)]))
+    cache_build_golden(ref)
     print("golden fixtures written to", OUT)
     for f in sorted(os.listdir(OUT)):
         print(f"  {f:28s} {os.path.getsize(os.path.join(OUT, f)):>9d} B")

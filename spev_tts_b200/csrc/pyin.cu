@@ -37,6 +37,7 @@ struct spev_pyin {
     double* d_boltz_fact;     // [kMaxTroughs+1] (1-exp(-lambda)) / (1-exp(-lambda N))
     double* d_ltrans;         // [2][2][n_classes][trans_width] log(t_switch * t_local + tiny)
     double* d_freqs;          // [n_bins]
+    double* d_logf;           // [n_bins] log(freqs + 1e-8): the reference's f0_log on voiced frames (:399)
     int n_classes;
     std::vector<double> h_freqs, h_ltrans, h_beta;
 };
@@ -299,7 +300,7 @@ k_pyin_observe(const float* __restrict__ yin, int64_t n_frames, ObsParams p, flo
 // P3: Viterbi
 // ----------------------------------------------------------------------------------------------
 struct VitParams {
-    int n_bins, width, n_classes;
+    int n_bins, width, n_classes, lt_smem;    // lt_smem: the transition table fits shared memory
     const double* ltrans;     // [2][2][n_classes][width]
 };
 
@@ -333,7 +334,8 @@ k_pyin_viterbi(const float* __restrict__ logobs, const float* __restrict__ log_u
     __shared__ int s_item;
     const int nb = p.n_bins, S = 2 * nb, W = p.width, half = W / 2;
     const int lt_n = 4 * p.n_classes * W;
-    for (int i = threadIdx.x; i < lt_n; i += blockDim.x) s_lt[i] = p.ltrans[i];
+    if (p.lt_smem) for (int i = threadIdx.x; i < lt_n; i += blockDim.x) s_lt[i] = p.ltrans[i];
+    const double* lt_base = p.lt_smem ? s_lt : p.ltrans;     // wide bands (hop 512) stay in global memory / L1
     const int b = threadIdx.x;
     const bool act = b < nb;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -385,7 +387,7 @@ k_pyin_viterbi(const float* __restrict__ logobs, const float* __restrict__ log_u
                 int a00 = 0, a01 = 0, a10 = 0, a11 = 0;
                 const double* pv0 = prev;
                 const double* pv1 = prev + nb;
-                const double* l00 = s_lt;                       // [vp=0][v=0]
+                const double* l00 = lt_base;                    // [vp=0][v=0]
                 const double* l01 = l00 + cstride;              // [vp=0][v=1]
                 const double* l10 = l00 + 2 * cstride;          // [vp=1][v=0]
                 const double* l11 = l00 + 3 * cstride;          // [vp=1][v=1]
@@ -458,6 +460,54 @@ __global__ void k_pyin_finish(const int* __restrict__ states, int64_t n, int n_b
     }
 }
 
+// ---- per-phoneme pitch statistics (spev_real_metrics.py:399-414) -----------------------------------
+// f0_log = log(f0 + 1e-8) on voiced frames (unvoiced ones are log(2e-8) < -5 and masked out there):
+//   pitch = clip((mean(voiced f0_log) - p_mean) / p_std, lo, hi)   or clip(0) when the phone has no voiced frame
+//   rough = clip(std(voiced f0_log), 0, rough_hi)                  (np.std: population), 0 without voiced frames
+// One warp per utterance (warp scan of the durations), one lane per phoneme, float64 like numpy.
+__global__ void k_pitch_pool(const int* __restrict__ states, const int64_t* __restrict__ frame_off,
+                             const long long* __restrict__ durs, const int64_t* __restrict__ phone_off, int U, int n_bins,
+                             const double* __restrict__ logf, double p_mean, double p_std, float lo, float hi,
+                             float rough_hi, float* __restrict__ pitch, float* __restrict__ rough) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    for (int u = blockIdx.x * wpb + (threadIdx.x >> 5); u < U; u += gridDim.x * wpb) {
+        const int64_t p0 = phone_off[u], p1 = phone_off[u + 1];
+        const int* st = states + frame_off[u];
+        const int64_t T = frame_off[u + 1] - frame_off[u];
+        long long carry = 0;
+        for (int64_t pb = p0; pb < p1; pb += 32) {
+            const int64_t p = pb + lane;
+            long long dd = p < p1 ? durs[p] : 0;
+            if (dd < 0) dd = 0;
+            long long incl = dd;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const long long t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const long long start = carry + incl - dd;
+            if (p < p1) {
+                const long long end = min(static_cast<long long>(T), start + dd);
+                double sum = 0.0;
+                int n = 0;
+                for (long long t = start; t < end; ++t) { const int s = st[t]; if (s < n_bins) { sum += logf[s]; ++n; } }
+                double pv = 0.0, rv = 0.0;
+                if (n > 0) {
+                    const double mean = sum / n;
+                    double ss = 0.0;
+                    for (long long t = start; t < end; ++t) { const int s = st[t]; if (s < n_bins) { const double dlt = logf[s] - mean; ss += dlt * dlt; } }
+                    pv = (mean - p_mean) / p_std;
+                    rv = sqrt(ss / n);
+                }
+                pitch[p] = static_cast<float>(fmin(fmax(pv, static_cast<double>(lo)), static_cast<double>(hi)));
+                rough[p] = static_cast<float>(fmin(fmax(rv, 0.0), static_cast<double>(rough_hi)));
+            }
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+    }
+}
+
 }  // namespace spev
 
 using namespace spev;
@@ -487,10 +537,13 @@ static int up(T** dst, const std::vector<T>& src) {
 
 extern "C" {
 
-int spev_pyin_create(spev_pyin** out, int device, int sr, float fmin, float fmax, const double* beta_probs_host) {
+int spev_pyin_create(spev_pyin** out, int device, int sr, int hop_length, float fmin, float fmax,
+                     const double* beta_probs_host) {
     SPEV_REQUIRE(out, SPEV_E_INVALID, "spev_pyin_create: out is null");
     *out = nullptr;
     SPEV_REQUIRE(sr > 0 && fmin > 0.f && fmax > fmin, SPEV_E_INVALID, "spev_pyin_create: need sr > 0, 0 < fmin < fmax");
+    SPEV_REQUIRE(hop_length > 0 && hop_length % kHop == 0, SPEV_E_UNSUPPORTED,
+                 "spev_pyin_create: hop_length must be a multiple of 256 (frames are taken from the hop-256 grid)");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();
@@ -501,7 +554,7 @@ int spev_pyin_create(spev_pyin** out, int device, int sr, float fmin, float fmax
     SPEV_CUDA(cudaSetDevice(device));
     spev_pyin* c = new spev_pyin();
     c->device = device; c->sr = sr; c->fmin = fmin; c->fmax = fmax;
-    c->frame_length = 2048; c->win_length = 1024; c->hop = kHop;
+    c->frame_length = 2048; c->win_length = 1024; c->hop = hop_length;
     c->min_period = static_cast<int>(std::floor(static_cast<double>(sr) / fmax));
     c->max_period = std::min(static_cast<int>(std::ceil(static_cast<double>(sr) / fmin)), c->frame_length - c->win_length - 1);
     c->n_lags = c->max_period - c->min_period + 1;
@@ -510,7 +563,7 @@ int spev_pyin_create(spev_pyin** out, int device, int sr, float fmin, float fmax
     c->n_bins = static_cast<int>(std::floor(12.0 * c->bins_per_semitone * std::log2(static_cast<double>(fmax) / fmin))) + 1;
     const int max_semitones = static_cast<int>(std::nearbyint(35.92 * 12.0 * c->hop / sr));
     c->trans_width = max_semitones * c->bins_per_semitone + 1;
-    c->d_thresholds = c->d_beta_probs = c->d_beta_cum = c->d_boltz_exp = c->d_boltz_fact = c->d_ltrans = c->d_freqs = nullptr;
+    c->d_thresholds = c->d_beta_probs = c->d_beta_cum = c->d_boltz_exp = c->d_boltz_fact = c->d_ltrans = c->d_freqs = c->d_logf = nullptr;
     if (!(c->n_lags > 2 && c->n_lags <= 512 && c->max_period < 384 && c->n_bins >= 2 * c->trans_width && c->n_bins <= 384 &&
           c->trans_width >= 3 && (c->trans_width & 1))) {
         delete c;
@@ -554,10 +607,12 @@ int spev_pyin_create(spev_pyin** out, int device, int sr, float fmin, float fmax
     c->h_beta = bp;
     c->h_freqs.resize(nb);
     for (int i = 0; i < nb; ++i) c->h_freqs[i] = fmin * std::pow(2.0, static_cast<double>(i) / (12.0 * c->bins_per_semitone));
+    std::vector<double> logf(nb);
+    for (int i = 0; i < nb; ++i) logf[i] = std::log(c->h_freqs[i] + 1e-8);
     int rc;
     if ((rc = up(&c->d_thresholds, thr)) || (rc = up(&c->d_beta_probs, bp)) || (rc = up(&c->d_beta_cum, bc)) ||
         (rc = up(&c->d_boltz_exp, bexp)) || (rc = up(&c->d_boltz_fact, bfact)) || (rc = up(&c->d_ltrans, lt)) ||
-        (rc = up(&c->d_freqs, c->h_freqs))) {
+        (rc = up(&c->d_freqs, c->h_freqs)) || (rc = up(&c->d_logf, logf))) {
         spev_pyin_destroy(c);
         return rc;
     }
@@ -569,7 +624,7 @@ void spev_pyin_destroy(spev_pyin* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaFree(c->d_thresholds); cudaFree(c->d_beta_probs); cudaFree(c->d_beta_cum); cudaFree(c->d_boltz_exp);
-    cudaFree(c->d_boltz_fact); cudaFree(c->d_ltrans); cudaFree(c->d_freqs);
+    cudaFree(c->d_boltz_fact); cudaFree(c->d_ltrans); cudaFree(c->d_freqs); cudaFree(c->d_logf);
     delete c;
 }
 
@@ -649,8 +704,10 @@ int spev_pyin_decode(spev_pyin* c, const float* logobs, const float* log_unvoice
     unsigned* counter = reinterpret_cast<unsigned*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
     unsigned short* ptr = reinterpret_cast<unsigned short*>(counter + 64);
     SPEV_REQUIRE(c->n_bins <= kVitThreads, SPEV_E_UNSUPPORTED, "spev_pyin_decode: too many pitch bins");
-    VitParams p{c->n_bins, c->trans_width, c->n_classes, c->d_ltrans};
-    const size_t smem = sizeof(double) * (static_cast<size_t>(4) * c->n_bins + static_cast<size_t>(4) * c->n_classes * c->trans_width);
+    const size_t lt_bytes = sizeof(double) * static_cast<size_t>(4) * c->n_classes * c->trans_width;
+    const int lt_smem = lt_bytes <= 96 * 1024 ? 1 : 0;          // two CTAs per SM
+    VitParams p{c->n_bins, c->trans_width, c->n_classes, lt_smem, c->d_ltrans};
+    const size_t smem = sizeof(double) * static_cast<size_t>(4) * c->n_bins + (lt_smem ? lt_bytes : 0);
     SPEV_CUDA(cudaFuncSetAttribute(k_pyin_viterbi, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     SPEV_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned), st));
     const int grid = std::min(n_items, 148 * 2);
@@ -664,4 +721,23 @@ int spev_pyin_decode(spev_pyin* c, const float* logobs, const float* log_unvoice
     return SPEV_OK;
 }
 
+int spev_pitch_pool(const spev_pyin* c, const int32_t* states, const int64_t* frame_off, const int64_t* durs,
+                    const int64_t* phone_off, int n_items, double p_mean, double p_std, float lo, float hi, float rough_hi,
+                    float* pitch, float* rough, void* stream) {
+    SPEV_REQUIRE(c, SPEV_E_INVALID, "spev_pitch_pool: null ctx");
+    SPEV_CUDA(cudaSetDevice(c->device));
+    SPEV_REQUIRE(n_items >= 0, SPEV_E_INVALID, "spev_pitch_pool: n_items < 0");
+    if (n_items == 0) return SPEV_OK;
+    SPEV_REQUIRE(states && frame_off && durs && phone_off && pitch && rough, SPEV_E_INVALID, "spev_pitch_pool: null buffer");
+    SPEV_REQUIRE(p_std != 0.0, SPEV_E_INVALID, "spev_pitch_pool: p_std == 0");
+    const int wpb = 4;
+    const int grid = std::min((n_items + wpb - 1) / wpb, 148 * 16);
+    k_pitch_pool<<<grid, wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+        states, frame_off, reinterpret_cast<const long long*>(durs), phone_off, n_items, c->n_bins, c->d_logf, p_mean, p_std,
+        lo, hi, rough_hi, pitch, rough);
+    SPEV_CUDA(cudaGetLastError());
+    return SPEV_OK;
+}
+
 }  // extern "C"
+

@@ -30,7 +30,7 @@ def write_reference_cache(cache_dir: str, records: Sequence[dict], stats: dict, 
     os.makedirs(cache_dir, exist_ok=True)
     files = []
     for i, r in enumerate(records):
-        path = os.path.join(cache_dir, f"u_{i:05d}.pt")
+        path = os.path.join(cache_dir, f"u_{int(r.get('index', i)):05d}.pt")     # the reference numbers by wav index
         torch.save({"phs": list(r["phs"]), "durs": [int(d) for d in r["durs"]],
                     "mel": torch.as_tensor(r["mel"], dtype=torch.float32).cpu().clone(),
                     **{k: np.asarray(r[k]) for k in CURVES}}, path)

@@ -25,7 +25,7 @@ class PyinContext:
     _cache: dict = {}
     _lock = threading.Lock()
 
-    def __init__(self, device: int, sr: int, fmin: float, fmax: float):
+    def __init__(self, device: int, sr: int, fmin: float, fmax: float, hop: int = HOP):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise RuntimeError("spev_tts_b200 needs a CUDA (sm_100) device; there is no CPU path")
@@ -36,24 +36,24 @@ class PyinContext:
             beta_ptr = beta.ctypes.data
         except ImportError:                      # built-in closed form (same to ~1e-16 absolute)
             beta_ptr = None
-        _lib.check(self.lib.spev_pyin_create(C.byref(h), int(device), int(sr), float(fmin), float(fmax), beta_ptr),
+        _lib.check(self.lib.spev_pyin_create(C.byref(h), int(device), int(sr), int(hop), float(fmin), float(fmax), beta_ptr),
                    "spev_pyin_create")
-        self.handle, self.device, self.sr = h, int(device), int(sr)
+        self.handle, self.device, self.sr, self.hop = h, int(device), int(sr), int(hop)
         v = [C.c_int() for _ in range(4)]
         _lib.check(self.lib.spev_pyin_info(h, *[C.byref(x) for x in v]), "spev_pyin_info")
         self.n_bins, self.min_period, self.max_period, self.n_lags = (x.value for x in v)
 
     @classmethod
-    def get(cls, device, *, sr=22050, fmin=60.0, fmax=500.0) -> "PyinContext":
+    def get(cls, device, *, sr=22050, fmin=60.0, fmax=500.0, hop=HOP) -> "PyinContext":
         dev = torch.device(device)
         if dev.type != "cuda":
             raise RuntimeError(f"spev_tts_b200 runs on CUDA devices only (got {dev})")
         idx = dev.index if dev.index is not None else torch.cuda.current_device()
-        key = (idx, int(sr), float(fmin), float(fmax))
+        key = (idx, int(sr), float(fmin), float(fmax), int(hop))
         with cls._lock:
             ctx = cls._cache.get(key)
             if ctx is None:
-                ctx = cls._cache[key] = cls(idx, sr, fmin, fmax)
+                ctx = cls._cache[key] = cls(idx, sr, fmin, fmax, hop)
         return ctx
 
     def host_tables(self):
@@ -113,23 +113,35 @@ def decode(logobs: torch.Tensor, log_unvoiced: torch.Tensor, frame_off, pctx: Py
     return states, f0, flag.bool()
 
 
-def pyin_flat(samples: torch.Tensor, n_samples: Sequence[int], *, sr=22050, fmin=60.0, fmax=500.0,
+def pyin_flat(samples: torch.Tensor, n_samples: Sequence[int], *, sr=22050, fmin=60.0, fmax=500.0, hop_length=HOP,
               sample_off: Optional[np.ndarray] = None, batch: Optional[FlatBatch] = None, return_states=False):
-    """Ragged batch -> (f0 ``[F]``, voiced_flag ``[F]``, voiced_prob ``[F]``, batch)."""
+    """Ragged batch -> (f0 ``[F]``, voiced_flag ``[F]``, voiced_prob ``[F]``, frame_off ``[U+1]``).
+    ``hop_length`` 256 (item i has ``1 + len_i // 256`` frames) or a multiple of it (``1 + len_i // hop_length``
+    frames: the curves are computed on the hop-256 grid and every k-th frame is decoded, with the wider
+    transition band that hop implies)."""
     if not (samples.is_cuda and samples.dtype == torch.float32 and samples.is_contiguous()):
         raise ValueError("samples must be a contiguous float32 CUDA tensor")
     ctx = Context.get(samples.device, sr=sr)
-    pctx = PyinContext.get(samples.device, sr=sr, fmin=fmin, fmax=fmax)
+    pctx = PyinContext.get(samples.device, sr=sr, fmin=fmin, fmax=fmax, hop=hop_length)
     if batch is None:
         batch = make_batch(ctx, n_samples=n_samples, sample_off=sample_off)
+    frame_off = batch.frame_off
     with torch.cuda.device(samples.device):
         yin = cmnd_flat(samples, batch, pctx)
+        if hop_length != HOP:
+            k = hop_length // HOP
+            ns = np.asarray(n_samples, dtype=np.int64).reshape(-1)
+            frames = 1 + ns // hop_length
+            keep = np.concatenate([batch.frame_off[i] + k * np.arange(frames[i]) for i in range(len(ns))]) \
+                if len(ns) else np.zeros(0, np.int64)
+            yin = yin[torch.from_numpy(keep).to(samples.device)].contiguous()
+            frame_off = np.concatenate([[0], np.cumsum(frames)]).astype(np.int64)
         logobs, lunv, vp = observe(yin, pctx)
         del yin
-        states, f0, flag = decode(logobs, lunv, batch.frame_off, pctx)
+        states, f0, flag = decode(logobs, lunv, frame_off, pctx)
     if return_states:
-        return f0, flag, vp, batch, states
-    return f0, flag, vp, batch
+        return f0, flag, vp, frame_off, states
+    return f0, flag, vp, frame_off
 
 
 def pyin(y, *, fmin, fmax, sr=22050, frame_length=2048, win_length=None, hop_length=None, n_thresholds=100,
@@ -139,16 +151,16 @@ def pyin(y, *, fmin, fmax, sr=22050, frame_length=2048, win_length=None, hop_len
     shape ``[..., T]``.  f0 is float32 here (librosa: float64); unvoiced frames hold ``fill_na``."""
     hop_length = frame_length // 4 if hop_length is None else hop_length
     win_length = frame_length // 2 if win_length is None else win_length
-    if (frame_length, win_length, hop_length, n_thresholds, tuple(beta_parameters), boltzmann_parameter, resolution,
+    if (frame_length, win_length, n_thresholds, tuple(beta_parameters), boltzmann_parameter, resolution,
             max_transition_rate, switch_prob, no_trough_prob, center, pad_mode) != \
-            (2048, 1024, HOP, 100, (2, 18), 2, 0.1, 35.92, 0.01, 0.01, True, "constant"):
-        raise NotImplementedError("spev_tts_b200.pyin implements the reference's call only: frame_length=2048, "
-                                  "hop_length=256 and librosa's default pYIN parameters")
+            (2048, 1024, 100, (2, 18), 2, 0.1, 35.92, 0.01, 0.01, True, "constant") or hop_length not in (HOP, 2 * HOP):
+        raise NotImplementedError("spev_tts_b200.pyin implements the reference's calls only: frame_length=2048, "
+                                  "hop_length=256 (:369) or 512 (:311) and librosa's default pYIN parameters")
     t, was_numpy = _to_device(y, device)
     lead, n = t.shape[:-1], t.shape[-1]
     b = int(np.prod(lead)) if lead else 1
-    f0, flag, vp, _ = pyin_flat(t.reshape(-1), [n] * b, sr=sr, fmin=fmin, fmax=fmax)
-    T = 1 + n // HOP
+    f0, flag, vp, _ = pyin_flat(t.reshape(-1), [n] * b, sr=sr, fmin=fmin, fmax=fmax, hop_length=hop_length)
+    T = 1 + n // hop_length
     if fill_na is None:
         raise NotImplementedError("fill_na=None (best-guess f0 on unvoiced frames) is not implemented")
     if not (isinstance(fill_na, float) and np.isnan(fill_na)):

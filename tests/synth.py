@@ -156,3 +156,57 @@ def voiced_unvoiced(seed: int = 0, n: int = 3 * SR, sr: int = SR):
         kind = int((kind + r.integers(1, 3)) % 3)
     y += 1e-4 * r.standard_normal(n)
     return y.astype(np.float32), f_true
+
+
+def tiny_corpus(seed: int = 21, n: int = 14):
+    """A miniature LJSpeech-like corpus for the cache-build tests (spev_real_metrics.py:300-430):
+    list of {'name', 'y', 'text', 'intervals'}.  ``text`` drives the uniform-alignment path (:353-357),
+    ``intervals`` [(t0, t1, mark)] the TextGrid path (:337-351; marks may be empty -> '<SIL>', intervals may be
+    too short to get a frame).  Item 3 is shorter than 4000 samples (skipped at :333), item 5 has neither
+    text nor intervals (skipped at :359), item 7 has more phones than frames (uniform duration 0 -> :378)."""
+    r = np.random.default_rng(seed)
+    items = []
+    letters = "abcdefghijklmnop rstuv"
+    for i in range(n):
+        n_s = int(r.uniform(0.5, 1.8) * SR)
+        if i == 3:
+            n_s = 3500
+        y = voiced_unvoiced(seed=100 + seed + i, n=n_s)[0]
+        text = "".join(r.choice(list(letters), int(r.integers(4, 28))))
+        intervals = None
+        if i == 5:
+            text = None
+        if i == 7:
+            text = "".join(r.choice(list(letters), 1 + n_s // HOP + 9))
+        if i % 3 == 1 and i != 7:                            # TextGrid-aligned items: ragged durations
+            t, intervals = 0.0, []
+            dur_s = n_s / SR
+            stretch = 3.0 if i == 10 else float(r.uniform(0.8, 1.3))   # alignments rarely match the audio length;
+            while t < dur_s * stretch:                       # item 10: 3x too long, 1-2 frame phones -> tail trimming
+                d = float(r.choice([0.013, 0.02, 0.03] if i == 10 else [0.004, 0.02, 0.05, 0.11, 0.3]))
+                mark = "" if r.random() < 0.2 else str(r.choice(list("aeioukstn")))
+                intervals.append((t, t + d, mark))
+                t += d
+        items.append({"name": f"utt_{i:03d}", "y": y, "text": text, "intervals": intervals})
+    return items
+
+
+def corpus_alignments(corpus, sr: int = SR):
+    """What the reference holds in (phs, durs) at spev_real_metrics.py:359 for each item of ``tiny_corpus``:
+    TextGrid intervals -> frames = int(dur * sr / 256) if > 0 (:345-349), else the text split into characters
+    between two '<SIL>' with uniform durations (:353-357); (None, None) when neither exists."""
+    phones, durs = [], []
+    for it in corpus:
+        ph, du = [], []
+        if it["intervals"] is not None:
+            for a, b, mark in it["intervals"]:
+                frames = int((b - a) * sr / 256)
+                if frames > 0:
+                    ph.append(mark if mark else "<SIL>")
+                    du.append(frames)
+        if not ph and it["text"] is not None:
+            ph = ["<SIL>"] + list(it["text"]) + ["<SIL>"]
+            du = [int((len(it["y"]) / 256) / len(ph))] * len(ph)
+        phones.append(ph or None)
+        durs.append(du or None)
+    return phones, durs

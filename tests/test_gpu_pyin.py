@@ -42,7 +42,7 @@ def test_model_tables(cuda):
     import ctypes as C
     from spev_tts_b200 import _lib
     lib, h = _lib.load(), C.c_void_p()
-    _lib.check(lib.spev_pyin_create(C.byref(h), cuda.index or 0, SR, 60.0, 500.0, None))
+    _lib.check(lib.spev_pyin_create(C.byref(h), cuda.index or 0, SR, 256, 60.0, 500.0, None))
     bp2 = np.empty(100)
     _lib.check(lib.spev_pyin_host_tables(h, None, None, bp2.ctypes.data))
     lib.spev_pyin_destroy(h)
@@ -182,11 +182,11 @@ def test_ragged_batch_equals_single_calls(cuda):
     lens = [0, 100, 2048, 256 * 33 + 1, 30000, 255]
     ys = [synth.voiced_unvoiced(seed=10 + i, n=max(n, 1))[0][:n] for i, n in enumerate(lens)]
     flat = torch.from_numpy(np.concatenate(ys)).to(cuda)
-    f0, flag, vp, fb, st = gp.pyin_flat(flat, lens, return_states=True)
-    assert fb.n_frames == sum(1 + n // 256 for n in lens)
+    f0, flag, vp, fo, st = gp.pyin_flat(flat, lens, return_states=True)
+    assert fo[-1] == sum(1 + n // 256 for n in lens)
     st = st.cpu().numpy()
     for i, y in enumerate(ys):
-        sl = slice(fb.frame_off[i], fb.frame_off[i + 1])
+        sl = slice(fo[i], fo[i + 1])
         if len(y) == 0:
             assert st[sl].tolist() and (st[sl] >= CFG.n_pitch_bins).all()        # one frame of silence: unvoiced
             continue
@@ -199,8 +199,45 @@ def test_unsupported_parameters_raise(cuda):
     import spev_tts_b200 as sp
     y = np.zeros(4096, np.float32)
     with pytest.raises(NotImplementedError):
-        sp.pyin(y, fmin=60, fmax=500, sr=SR, hop_length=512)
+        sp.pyin(y, fmin=60, fmax=500, sr=SR, hop_length=128)
     with pytest.raises(NotImplementedError):
         sp.pyin(y, fmin=60, fmax=500, sr=SR, hop_length=256, frame_length=1024)
     with pytest.raises(RuntimeError):
         sp.pyin(y, fmin=20, fmax=500, sr=SR, hop_length=256)      # max_period beyond what the kernels hold
+
+
+def test_default_hop_512_of_the_statistics_pass(cuda):
+    """spev_real_metrics.py:311 calls librosa.pyin WITHOUT hop_length (-> frame_length // 4 = 512): frames every
+    512 samples and a 101-bin transition band."""
+    import spev_tts_b200 as sp
+    from spev_tts_b200 import pitch as gp
+    cfg = po.PyinConfig(hop_length=512)
+    assert cfg.transition_width == 101
+    p = gp.PyinContext.get(cuda, hop=512)
+    lt, _, _ = p.host_tables()
+    np.testing.assert_allclose(lt, np.log(cfg.transition() + po.TINY64), rtol=0, atol=1e-12)
+    tot = agree = 0
+    for seed in (4, 5):
+        y, _ = synth.voiced_unvoiced(seed=seed, n=2 * SR + 300)
+        f, flag, vp = sp.pyin(y, fmin=60, fmax=500, sr=SR)                  # hop_length=None -> 512
+        fo, flago, vpo = po.pyin(y, hop_length=512)
+        assert f.shape == fo.shape == (1 + len(y) // 512,)
+        both = flag & flago
+        same = np.zeros(len(f), bool)
+        same[both] = np.abs(1200 * np.log2(f[both] / fo[both])) <= 10.0 + 1e-6
+        agree += int(np.sum((flag == flago) & (same | ~flago)))
+        tot += len(f)
+        assert np.abs(vp - vpo).mean() <= 2e-3
+    assert agree / tot >= 0.98, agree / tot
+    # identical paths on identical log-observations (the wide table lives in global memory: separate code path)
+    y, _ = synth.voiced_unvoiced(seed=6, n=SR)
+    t = torch.from_numpy(y).to(cuda)
+    from spev_tts_b200.batch import Context, make_batch
+    fb = make_batch(Context.get(cuda), n_samples=[len(y)])
+    yin = gp.cmnd_flat(t, fb, p)[::2].contiguous()
+    logobs, lunv, _ = gp.observe(yin, p)
+    states, _, _ = gp.decode(logobs, lunv, np.array([0, yin.shape[0]]), p)
+    lo, lu = logobs.double().cpu().numpy(), lunv.double().cpu().numpy()
+    log_prob = np.concatenate([lo, np.repeat(lu[:, None], cfg.n_pitch_bins, 1)], axis=1)
+    want = po.viterbi_log(log_prob, lt, np.log(cfg.p_init() + po.TINY64))
+    np.testing.assert_array_equal(states.cpu().numpy(), want)
