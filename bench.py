@@ -152,6 +152,33 @@ def cpu_logmel_throughput(n_utts: int, procs: int, seed: int = 4):
     return frames / busy, frames, wall
 
 
+def _cpu_pyin_job(args):
+    seed, n = args
+    from oracle import pyin_restated as po
+    from tests import synth
+    y = synth.voiced_unvoiced(seed=seed, n=n)[0]
+    t = time.perf_counter()
+    f0, _, _ = po.pyin(y)
+    return len(f0), n / SR, time.perf_counter() - t
+
+
+def cpu_pyin_throughput(n_utts: int, procs: int, seed: int = 4):
+    """frames/s and audio-s/s of the restated librosa.pyin on cfg4-shaped utterances."""
+    import multiprocessing as mp
+    from tests import synth
+    lens = synth.utterance_lengths(seed=seed, n_utts=N_UTTS)[:n_utts]
+    jobs = [(i % 16, int(n)) for i, n in enumerate(lens)]
+    t = time.perf_counter()
+    if procs > 1:
+        with mp.get_context("fork").Pool(min(procs, n_utts), initializer=_cpu_worker_init) as pool:
+            res = pool.map(_cpu_pyin_job, jobs)
+    else:
+        res = [_cpu_pyin_job(j) for j in jobs]
+    wall = time.perf_counter() - t
+    busy = sum(r[2] for r in res) / max(1, min(procs, n_utts))
+    return sum(r[0] for r in res) / busy, sum(r[1] for r in res) / busy, wall
+
+
 def cpu_gl_throughput(n_items: int, T: int, n_iter: int, procs: int):
     import multiprocessing as mp
     jobs = [(300 + i, T, n_iter) for i in range(n_items)]
@@ -350,8 +377,10 @@ def run_ours(args):
         del parts
 
     # ---------------- second half of the metric: Griffin-Lim on cfg3 (rank 0 reports) ------------
-    gl = lr_res = tc = cfg5 = feat = coll = None
+    gl = lr_res = tc = cfg5 = feat = coll = pyin_res = None
     if not args.no_gl:
+        if rank == 0:
+            pyin_res = bench_pyin(sp, dev, hbm_peak, args, world == 1 and not args.no_cpu)
         cfg5 = bench_logmel_cfg5(sp, dev, hbm_peak, spcache)
         tc = bench_mel_gemm_tc(sp, dev, samples, lens, starts, hbm_peak, out)
         feat = bench_frame_features(sp, dev, samples, lens, starts, hbm_peak)
@@ -396,7 +425,7 @@ def run_ours(args):
                                          "note": "co-limited by issue slots and the shared-memory pipe, not HBM"},
                          "note": "fp32-pipe/shared-memory bound by design (SURVEY 0.7): ~25 kFLOP FFT per 1,344 B"},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks, "parity": parity,
-            "gather": gather, "logmel_cfg5": cfg5, "mel_gemm_tc": tc, "frame_features": feat, "collate": coll, "griffinlim": gl, "length_regulator": lr_res,
+            "gather": gather, "logmel_cfg5": cfg5, "mel_gemm_tc": tc, "frame_features": feat, "pyin": pyin_res, "collate": coll, "griffinlim": gl, "length_regulator": lr_res,
         }
         print(json.dumps(line))
     if world > 1:
@@ -495,6 +524,75 @@ def bench_frame_features(sp, dev, samples, lens, starts, hbm_peak):
                          "peak": hbm_peak, "unit": "GB/s", "frac": 1032.0 * F / (ms * 1e-3) / 1e9 / hbm_peak,
                          "alg_bytes_per_frame": 1032,
                          "note": "one full 1024-complex warp FFT per frame (2x the STFT kernel's FFT work): issue-bound"}}
+
+
+def bench_pyin(sp, dev, hbm_peak, args, with_cpu):
+    """librosa.pyin (:369) on a cfg4-shaped shard of speech-like signals (the decoder's
+    work depends on the voicing pattern, so white noise would flatter it) + whole cache records."""
+    import torch
+    from spev_tts_b200 import pitch as gp
+    from tests import synth
+    n_utts = min(2048, args.utts)
+    lens = synth.utterance_lengths(seed=4, n_utts=N_UTTS)[:n_utts]
+    base = [synth.voiced_unvoiced(seed=i, n=int(lens.max()))[0] for i in range(16)]
+    waves = [base[i % 16][: lens[i]] for i in range(n_utts)]
+    starts = sp.cache.aligned_offsets(lens)
+    host = np.zeros(int(starts[-1]) + 4, dtype=np.float32)
+    for w, st in zip(waves, starts[:-1]):
+        host[st: st + len(w)] = w
+    x = torch.from_numpy(host).to(dev)
+    ctx = sp.Context.get(dev, sr=SR, n_mels=N_MELS)
+    batch = sp.make_batch(ctx, n_samples=lens, sample_off=starts[:-1])
+    pctx = gp.PyinContext.get(dev, sr=SR)
+    F = batch.n_frames
+
+    def timed(fn, reps=2):
+        r = fn(); torch.cuda.synchronize(dev)
+        a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            r = fn()
+        b.record(); torch.cuda.synchronize(dev)
+        return a.elapsed_time(b) / reps, r
+    ms1, yin = timed(lambda: gp.cmnd_flat(x, batch, pctx))
+    ms2, (logobs, lunv, vp) = timed(lambda: gp.observe(yin, pctx))
+    del yin
+    ms3, (states, f0, flag) = timed(lambda: gp.decode(logobs, lunv, batch.frame_off, pctx))
+    del logobs, lunv
+    ms = ms1 + ms2 + ms3
+    audio_s = float(lens.sum()) / SR
+    res = {"config": {"workload": f"{n_utts} cfg4-length speech-like utterances ({F} frames, {audio_s:.0f} s of audio): "
+                                  "librosa.pyin(fmin=60, fmax=500, hop_length=256) = CMND + observation + Viterbi"},
+           "value": F / (ms * 1e-3), "unit": "frames/s", "audio_s_per_s": audio_s / (ms * 1e-3), "ms_per_step": ms,
+           "voiced_fraction": float(flag.float().mean()),
+           "stages_ms": {"k_yin_cmnd": ms1, "k_pyin_observe": ms2, "k_pyin_viterbi(+finish)": ms3},
+           "roofline": {"bound": "hbm", "kernel": "k_pyin_viterbi", "achieved": 2952.0 * F / (ms3 * 1e-3) / 1e9, "peak": hbm_peak,
+                        "unit": "GB/s", "frac": 2952.0 * F / (ms3 * 1e-3) / 1e9 / hbm_peak, "alg_bytes_per_frame": 2952,
+                        "note": "latency-bound sequential recursion: 736 states x 102 float64 candidates per frame, "
+                                "<= 296 utterances in flight; k_yin_cmnd runs at "
+                                f"{2 * 1024 * 384 * F / (ms1 * 1e-3) / 1e12:.1f} TFLOP/s fp32 (direct autocorrelation)"}}
+    # whole cache records (log-mel + rms/centroid + pYIN + per-phoneme pooling + host duration logic) on a subset
+    n_rec = min(512, n_utts)
+    phones = [["<SIL>"] + list("abcdefghijklmnopqrstuvwxyz"[: 5 + i % 20]) + ["<SIL>"] for i in range(n_rec)]
+    durs = [sp.uniform_durations(int(lens[i]), len(phones[i])) for i in range(n_rec)]
+    stats = {"p_mean": 5.2, "p_std": 0.35, "e_mean": -4.0, "e_std": 2.0, "c_mean": 7.5, "c_std": 0.8}
+    sp.build_records(waves[:8], phones[:8], durs[:8], stats, device=dev)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    recs, _ = sp.build_records(waves[:n_rec], phones[:n_rec], durs[:n_rec], stats, device=dev)
+    torch.cuda.synchronize(dev)
+    wall = time.perf_counter() - t0
+    res["cache_records"] = {"utterances": len(recs), "wall_s": wall, "utterances_per_s": len(recs) / wall,
+                            "audio_s_per_s": float(lens[:n_rec].sum()) / SR / wall,
+                            "note": "host wave list in -> per-utterance record dicts out (incl. H2D, D2H, Python record assembly)"}
+    if with_cpu:
+        cores = os.cpu_count() or 1
+        n_cpu = min(2 * cores, 32)
+        fps, aps, cwall = cpu_pyin_throughput(n_cpu, cores)
+        res["cpu_baseline"] = {"value": fps, "unit": "frames/s", "audio_s_per_s": aps, "cores": cores, "kind": "port",
+                               "sample": f"{n_cpu} cfg4-length utterances in {cwall:.1f}s, oracle/pyin_restated.py over "
+                                         f"{min(cores, n_cpu)} processes"}
+    return res
 
 
 def bench_collate(sp, dev, mel, batch, hbm_peak):

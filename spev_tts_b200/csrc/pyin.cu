@@ -35,7 +35,7 @@ struct spev_pyin {
     double* d_beta_cum;       // [n_thresholds+1] prefix sums of beta_probs (sequential, like np.sum of a slice... see note)
     double* d_boltz_exp;      // [kMaxTroughs] exp(-lambda k)
     double* d_boltz_fact;     // [kMaxTroughs+1] (1-exp(-lambda)) / (1-exp(-lambda N))
-    double* d_ltrans;         // [2][2][n_classes][trans_width] log(t_switch * t_local + tiny)
+    double* d_ltrans;         // [n_classes][trans_width] x (stay, switch): log(t_switch * t_local + tiny)
     double* d_freqs;          // [n_bins]
     double* d_logf;           // [n_bins] log(freqs + 1e-8): the reference's f0_log on voiced frames (:399)
     int n_classes;
@@ -300,8 +300,8 @@ k_pyin_observe(const float* __restrict__ yin, int64_t n_frames, ObsParams p, flo
 // P3: Viterbi
 // ----------------------------------------------------------------------------------------------
 struct VitParams {
-    int n_bins, width, n_classes, lt_smem;    // lt_smem: the transition table fits shared memory
-    const double* ltrans;     // [2][2][n_classes][width]
+    int n_bins, width, n_classes;
+    const double2* tab;       // [n_classes][width] (stay, switch) log transition probabilities
 };
 
 __device__ __forceinline__ int row_class(int b, int n_bins, int half) {
@@ -320,28 +320,38 @@ __device__ __forceinline__ ArgMax warp_argmax(ArgMax a) {
     return a;
 }
 
+// (ptxas turns this into DSETP + 2 FSEL + SEL whether it is written as a branch, a select or predicated PTX moves:
+// 12 of the ~23 instructions per candidate sit on the ALU pipe, which is what bounds the kernel.)
+__device__ __forceinline__ void upd_max(double& m, int& a, double s, int i) {
+    if (s > m) { m = s; a = i; }
+}
+
+// Transition table as the kernel reads it: tab[cls][d] = (log P(stay in the voicing half), log P(switch half)) for a
+// predecessor of row class cls and bin offset d - half.  kron(switch, local) gives the same value for
+// voiced->voiced and unvoiced->unvoiced (and for the two switches), so two numbers serve all four (vp, v) pairs.
+template <bool LT_SMEM>
 __global__ void __launch_bounds__(kVitThreads, 2)
 k_pyin_viterbi(const float* __restrict__ logobs, const float* __restrict__ log_unvoiced,
                const int64_t* __restrict__ frame_off, int n_items, VitParams p, unsigned short* __restrict__ ptr,
                int* __restrict__ states, unsigned* __restrict__ work_counter) {
-    extern __shared__ double smd[];
-    double* s_val = smd;                                   // [2][S]
-    double* s_lt = smd + 2 * 2 * p.n_bins;                 // [2][2][n_classes][width]
+    extern __shared__ __align__(16) double smd[];
+    double2* s_val = reinterpret_cast<double2*>(smd);      // [2][n_bins]: (voiced, unvoiced) value of each bin
+    double2* s_tab = s_val + 2 * p.n_bins;                 // [n_classes][width] when LT_SMEM
     __shared__ double s_red_v[kVitThreads / 32];
     __shared__ int s_red_i[kVitThreads / 32];
     __shared__ double s_gmax;
     __shared__ int s_garg;
     __shared__ int s_item;
     const int nb = p.n_bins, S = 2 * nb, W = p.width, half = W / 2;
-    const int lt_n = 4 * p.n_classes * W;
-    if (p.lt_smem) for (int i = threadIdx.x; i < lt_n; i += blockDim.x) s_lt[i] = p.ltrans[i];
-    const double* lt_base = p.lt_smem ? s_lt : p.ltrans;     // wide bands (hop 512) stay in global memory / L1
+    if (LT_SMEM) for (int i = threadIdx.x; i < p.n_classes * W; i += blockDim.x) s_tab[i] = p.tab[i];
+    const double2* tab = LT_SMEM ? s_tab : p.tab;          // wide bands (hop 512) stay in global memory / L1
     const int b = threadIdx.x;
     const bool act = b < nb;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int blo = max(0, b - half), bhi = min(nb - 1, b + half);
+    // predecessor rows by class: [blo, e1) left edge (class = row), [e1, e2) interior (class = half), [e2, bhi] right edge
+    const int e1 = min(bhi + 1, max(blo, half)), e2 = max(e1, min(bhi + 1, nb - half));
     const double log_init_unv = log(1.0 / nb + kTiny64);
-    const int cstride = p.n_classes * W;                   // s_lt stride between the four (vp, v) tables
 
     for (;;) {
         __syncthreads();
@@ -357,15 +367,14 @@ k_pyin_viterbi(const float* __restrict__ logobs, const float* __restrict__ log_u
         if (act) {
             cur0 = static_cast<double>(logobs[f0 * nb + b]) + kLogTiny64;
             cur1 = static_cast<double>(log_unvoiced[f0]) + log_init_unv;
-            s_val[b] = cur0;
-            s_val[nb + b] = cur1;
+            s_val[b] = make_double2(cur0, cur1);
         }
         for (int t = 1; t < T; ++t) {
             const int64_t ft = f0 + t;
             // this step's observations (issued early: the loads overlap the arg-max reduction)
             const float lp0f = act ? logobs[ft * nb + b] : 0.f;
             const float lp1f = log_unvoiced[ft];
-            // block arg-max of the previous values (lowest index on ties)
+            // block arg-max of the previous values (lowest state index on ties)
             ArgMax m;
             if (act) { if (cur1 > cur0) { m.v = cur1; m.i = nb + b; } else { m.v = cur0; m.i = b; } }
             else { m.v = -INFINITY; m.i = 0x7fffffff; }
@@ -379,30 +388,27 @@ k_pyin_viterbi(const float* __restrict__ logobs, const float* __restrict__ log_u
                 if (lane == 0) { s_gmax = m.v; s_garg = m.i; }
             }
             __syncthreads();
-            const double* prev = s_val + ((t - 1) & 1) * S;
-            double* next = s_val + (t & 1) * S;
+            const double2* prev = s_val + ((t - 1) & 1) * nb;
+            double2* next = s_val + (t & 1) * nb;
             if (act) {
                 // four independent running maxima: (from voiced | unvoiced) x (to voiced | unvoiced), ascending bin
                 double m00 = -INFINITY, m01 = -INFINITY, m10 = -INFINITY, m11 = -INFINITY;
                 int a00 = 0, a01 = 0, a10 = 0, a11 = 0;
-                const double* pv0 = prev;
-                const double* pv1 = prev + nb;
-                const double* l00 = lt_base;                    // [vp=0][v=0]
-                const double* l01 = l00 + cstride;              // [vp=0][v=1]
-                const double* l10 = l00 + 2 * cstride;          // [vp=1][v=0]
-                const double* l11 = l00 + 3 * cstride;          // [vp=1][v=1]
+                auto cand = [&](int bp, const double2 ab) {
+                    const double2 x = prev[bp];
+                    const double s00 = x.x + ab.x, s01 = x.x + ab.y, s10 = x.y + ab.y, s11 = x.y + ab.x;
+                    upd_max(m00, a00, s00, bp);
+                    upd_max(m01, a01, s01, bp);
+                    upd_max(m10, a10, s10, bp);
+                    upd_max(m11, a11, s11, bp);
+                };
+                for (int bp = blo; bp < e1; ++bp) cand(bp, tab[bp * W + (b - bp + half)]);
+                {
+                    const double2* q = tab + half * W + (b - e1 + half);
 #pragma unroll 2
-                for (int bp = blo; bp <= bhi; ++bp) {
-                    // row class of the predecessor: its own index near the edges, `half` in the interior
-                    const int cls = min(bp, half) + max(0, bp - nb + half + 1);
-                    const int off = cls * W + (b - bp + half);
-                    const double x0 = pv0[bp], x1 = pv1[bp];
-                    const double s00 = x0 + l00[off], s01 = x0 + l01[off], s10 = x1 + l10[off], s11 = x1 + l11[off];
-                    if (s00 > m00) { m00 = s00; a00 = bp; }
-                    if (s01 > m01) { m01 = s01; a01 = bp; }
-                    if (s10 > m10) { m10 = s10; a10 = bp; }
-                    if (s11 > m11) { m11 = s11; a11 = bp; }
+                    for (int bp = e1; bp < e2; ++bp, --q) cand(bp, *q);
                 }
+                for (int bp = e2; bp <= bhi; ++bp) cand(bp, tab[(half + 1 + bp - (nb - half)) * W + (b - bp + half)]);
                 // merge the two source halves; the voiced half holds the lower state indices and wins ties
                 double best0 = m00, best1 = m01;
                 int arg0 = a00, arg1 = a01;
@@ -419,8 +425,7 @@ k_pyin_viterbi(const float* __restrict__ logobs, const float* __restrict__ log_u
                 }
                 cur0 = static_cast<double>(lp0f) + best0;
                 cur1 = static_cast<double>(lp1f) + best1;
-                next[b] = cur0;
-                next[nb + b] = cur1;
+                next[b] = make_double2(cur0, cur1);
                 ptr[ft * S + b] = static_cast<unsigned short>(arg0);
                 ptr[ft * S + nb + b] = static_cast<unsigned short>(arg1);
             }
@@ -607,11 +612,23 @@ int spev_pyin_create(spev_pyin** out, int device, int sr, int hop_length, float 
     c->h_beta = bp;
     c->h_freqs.resize(nb);
     for (int i = 0; i < nb; ++i) c->h_freqs[i] = fmin * std::pow(2.0, static_cast<double>(i) / (12.0 * c->bins_per_semitone));
+    // device layout: (stay, switch) pairs; kron(switch, local) makes [0][0] == [1][1] and [0][1] == [1][0] bit for bit
+    std::vector<double> ab(static_cast<size_t>(2) * c->n_classes * W);
+    for (int i = 0; i < c->n_classes * W; ++i) {
+        const size_t n1 = static_cast<size_t>(c->n_classes) * W;
+        ab[2 * i] = lt[i];                 // [vp=0][v=0]
+        ab[2 * i + 1] = lt[n1 + i];        // [vp=0][v=1]
+        if (lt[3 * n1 + i] != lt[i] || lt[2 * n1 + i] != lt[n1 + i]) {
+            delete c;
+            set_error("spev_pyin_create: internal error, switch matrix not symmetric");
+            return SPEV_E_INVALID;
+        }
+    }
     std::vector<double> logf(nb);
     for (int i = 0; i < nb; ++i) logf[i] = std::log(c->h_freqs[i] + 1e-8);
     int rc;
     if ((rc = up(&c->d_thresholds, thr)) || (rc = up(&c->d_beta_probs, bp)) || (rc = up(&c->d_beta_cum, bc)) ||
-        (rc = up(&c->d_boltz_exp, bexp)) || (rc = up(&c->d_boltz_fact, bfact)) || (rc = up(&c->d_ltrans, lt)) ||
+        (rc = up(&c->d_boltz_exp, bexp)) || (rc = up(&c->d_boltz_fact, bfact)) || (rc = up(&c->d_ltrans, ab)) ||
         (rc = up(&c->d_freqs, c->h_freqs)) || (rc = up(&c->d_logf, logf))) {
         spev_pyin_destroy(c);
         return rc;
@@ -704,14 +721,15 @@ int spev_pyin_decode(spev_pyin* c, const float* logobs, const float* log_unvoice
     unsigned* counter = reinterpret_cast<unsigned*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
     unsigned short* ptr = reinterpret_cast<unsigned short*>(counter + 64);
     SPEV_REQUIRE(c->n_bins <= kVitThreads, SPEV_E_UNSUPPORTED, "spev_pyin_decode: too many pitch bins");
-    const size_t lt_bytes = sizeof(double) * static_cast<size_t>(4) * c->n_classes * c->trans_width;
-    const int lt_smem = lt_bytes <= 96 * 1024 ? 1 : 0;          // two CTAs per SM
-    VitParams p{c->n_bins, c->trans_width, c->n_classes, lt_smem, c->d_ltrans};
-    const size_t smem = sizeof(double) * static_cast<size_t>(4) * c->n_bins + (lt_smem ? lt_bytes : 0);
-    SPEV_CUDA(cudaFuncSetAttribute(k_pyin_viterbi, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    const size_t tab_bytes = sizeof(double2) * static_cast<size_t>(c->n_classes) * c->trans_width;
+    const bool tab_smem = tab_bytes <= 96 * 1024;              // two CTAs per SM
+    VitParams p{c->n_bins, c->trans_width, c->n_classes, reinterpret_cast<const double2*>(c->d_ltrans)};
+    const size_t smem = sizeof(double2) * static_cast<size_t>(2) * c->n_bins + (tab_smem ? tab_bytes : 0);
+    auto kern = tab_smem ? k_pyin_viterbi<true> : k_pyin_viterbi<false>;
+    SPEV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     SPEV_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned), st));
     const int grid = std::min(n_items, 148 * 2);
-    k_pyin_viterbi<<<grid, kVitThreads, smem, st>>>(logobs, log_unvoiced, frame_off, n_items, p, ptr, states, counter);
+    kern<<<grid, kVitThreads, smem, st>>>(logobs, log_unvoiced, frame_off, n_items, p, ptr, states, counter);
     SPEV_CUDA(cudaGetLastError());
     if (f0 || voiced_flag) {
         const int g2 = static_cast<int>(std::min<int64_t>((n_frames + 255) / 256, 148 * 8));
