@@ -52,20 +52,18 @@ constexpr double kLogTiny64 = -708.3964185322641;   // log(DBL_MIN)
 // ----------------------------------------------------------------------------------------------
 // P1: cumulative mean normalised difference
 // ----------------------------------------------------------------------------------------------
-constexpr int kCmndThreads = 384;
-constexpr int kQuads = 96;                 // lag quads per frame (lags 0..383), x 4 segments of the window
-
+// Block = 4 * Q threads, Q = lag quads (lags 0 .. 4Q-1 >= max_period), rounded so that the block is whole warps.
 __device__ __forceinline__ float block_incl_scan(float v, float* s_w) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const float t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
     if (lane == 31) s_w[wid] = v;
     __syncthreads();
     if (wid == 0) {
-        float w = lane < (kCmndThreads / 32) ? s_w[lane] : 0.f;
+        float w = lane < nw ? s_w[lane] : 0.f;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const float t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
-        if (lane < (kCmndThreads / 32)) s_w[lane] = w;
+        if (lane < nw) s_w[lane] = w;
     }
     __syncthreads();
     if (wid > 0) v += s_w[wid - 1];
@@ -73,15 +71,16 @@ __device__ __forceinline__ float block_incl_scan(float v, float* s_w) {
     return v;
 }
 
-__global__ void __launch_bounds__(kCmndThreads)
+__global__ void __launch_bounds__(1024)
 k_yin_cmnd(BatchView bv, const float* __restrict__ samples, float* __restrict__ yin, int frame_length, int win,
            int min_period, int max_period) {
     extern __shared__ __align__(16) float sm[];
+    const int nthr = blockDim.x, Q = nthr >> 2;        // lag quads
     float* s_x = sm + 3;                               // s_x[1] is 16-byte aligned (the window starts at sample 1)
     float* s_e = sm + 2056;                            // inclusive prefix sums of x^2
-    float* s_part = s_e + 2048;                        // [4][384] partial autocorrelations
-    float* s_w = s_part + 4 * kCmndThreads;            // [16]
-    const int need = win + 4 * kQuads + 4;             // samples the lag quads touch (<= frame_length)
+    float* s_part = s_e + 2048;                        // [4][nthr] partial autocorrelations
+    float* s_w = s_part + 4 * nthr;                    // [32]
+    const int need = win + 4 * Q + 4;                  // samples the lag quads touch (<= frame_length)
     const int n_lags = max_period - min_period + 1;
     const int64_t slots = static_cast<int64_t>(bv.n_ftiles) * kTileFrames;
     for (int64_t fidx = blockIdx.x; fidx < slots; fidx += gridDim.x) {
@@ -92,13 +91,13 @@ k_yin_cmnd(BatchView bv, const float* __restrict__ samples, float* __restrict__ 
         // the frame_length window starts frame_length/2 before the frame centre; src0 is n_fft/2 before it
         const int64_t first = d.src0 - (frame_length / 2 - kNfft / 2) + static_cast<int64_t>(fl) * kHop;
         __syncthreads();
-        for (int i = threadIdx.x; i < need; i += blockDim.x) {
+        for (int i = threadIdx.x; i < need; i += nthr) {
             const int64_t g = first + i;
             s_x[i] = (g >= d.lo && g < d.hi) ? __ldg(samples + g) : 0.f;
         }
         __syncthreads();
         {   // inclusive prefix sums of x^2 (numpy: cumsum in the input dtype)
-            const int per = (need + kCmndThreads - 1) / kCmndThreads;
+            const int per = (need + nthr - 1) / nthr;
             const int b0 = threadIdx.x * per, b1 = min(need, b0 + per);
             float loc = 0.f;
             for (int i = b0; i < b1; ++i) loc = fmaf(s_x[i], s_x[i], loc);
@@ -106,7 +105,7 @@ k_yin_cmnd(BatchView bv, const float* __restrict__ samples, float* __restrict__ 
             for (int i = b0; i < b1; ++i) { run = fmaf(s_x[i], s_x[i], run); s_e[i] = run; }
         }
         {   // acf(tau) = sum_{j=1..W} x_j x_{j+tau}: thread = (lag quad q, window segment g), 4x4 register tile
-            const int q = threadIdx.x % kQuads, g = threadIdx.x / kQuads;
+            const int q = threadIdx.x % Q, g = threadIdx.x / Q;
             const float4* x4 = reinterpret_cast<const float4*>(s_x + 1);
             const int seg = win / 16;                   // float4 per segment
             float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
@@ -118,14 +117,14 @@ k_yin_cmnd(BatchView bv, const float* __restrict__ samples, float* __restrict__ 
                 c2 = fmaf(a.x, b0.z, c2); c2 = fmaf(a.y, b0.w, c2); c2 = fmaf(a.z, b1.x, c2); c2 = fmaf(a.w, b1.y, c2);
                 c3 = fmaf(a.x, b0.w, c3); c3 = fmaf(a.y, b1.x, c3); c3 = fmaf(a.z, b1.y, c3); c3 = fmaf(a.w, b1.z, c3);
             }
-            float* o = s_part + g * kCmndThreads + 4 * q;
+            float* o = s_part + g * nthr + 4 * q;
             o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
         }
         __syncthreads();
         const int tau = threadIdx.x;                    // one lag per thread from here on
         float dval = 0.f;
         if (tau >= 1 && tau <= max_period) {
-            float acf = (s_part[tau] + s_part[kCmndThreads + tau]) + (s_part[2 * kCmndThreads + tau] + s_part[3 * kCmndThreads + tau]);
+            float acf = (s_part[tau] + s_part[nthr + tau]) + (s_part[2 * nthr + tau] + s_part[3 * nthr + tau]);
             float e_tau = s_e[tau + win] - s_e[tau];    // samples tau+1 .. tau+W
             float e_0 = s_e[win] - s_e[0];
             if (fabsf(acf) < 1e-6f) acf = 0.f;          // the reference's clean-ups
@@ -569,7 +568,7 @@ int spev_pyin_create(spev_pyin** out, int device, int sr, int hop_length, float 
     const int max_semitones = static_cast<int>(std::nearbyint(35.92 * 12.0 * c->hop / sr));
     c->trans_width = max_semitones * c->bins_per_semitone + 1;
     c->d_thresholds = c->d_beta_probs = c->d_beta_cum = c->d_boltz_exp = c->d_boltz_fact = c->d_ltrans = c->d_freqs = c->d_logf = nullptr;
-    if (!(c->n_lags > 2 && c->n_lags <= 512 && c->max_period < 384 && c->n_bins >= 2 * c->trans_width && c->n_bins <= 384 &&
+    if (!(c->n_lags > 2 && c->n_lags < 2 * kMaxTroughs && c->max_period <= 991 && c->n_bins >= 2 * c->trans_width && c->n_bins <= 384 &&
           c->trans_width >= 3 && (c->trans_width & 1))) {
         delete c;
         set_error("spev_pyin_create: (sr, fmin, fmax) outside what the kernels support");
@@ -681,7 +680,9 @@ int spev_pyin_cmnd(spev_pyin* c, const spev_batch* b, const float* samples, floa
     SPEV_REQUIRE(samples && yin && b->ftiles, SPEV_E_INVALID, "spev_pyin_cmnd: null buffer");
     const int64_t slots = static_cast<int64_t>(b->n_ftiles) * kTileFrames;
     const int grid = static_cast<int>(std::min<int64_t>(slots, 148 * 64));
-    k_yin_cmnd<<<grid, kCmndThreads, sizeof(float) * (2056 + 2048 + 4 * kCmndThreads + 16), static_cast<cudaStream_t>(stream)>>>(
+    const int quads = ((c->max_period + 1 + 3) / 4 + 7) / 8 * 8;      // whole warps: 4 * quads threads
+    const int threads = 4 * quads;
+    k_yin_cmnd<<<grid, threads, sizeof(float) * (2056 + 2048 + 4 * threads + 32), static_cast<cudaStream_t>(stream)>>>(
         view_of(b), samples, yin, c->frame_length, c->win_length, c->min_period, c->max_period);
     SPEV_CUDA(cudaGetLastError());
     return SPEV_OK;

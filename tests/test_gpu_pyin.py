@@ -241,3 +241,20 @@ def test_default_hop_512_of_the_statistics_pass(cuda):
     log_prob = np.concatenate([lo, np.repeat(lu[:, None], cfg.n_pitch_bins, 1)], axis=1)
     want = po.viterbi_log(log_prob, lt, np.log(cfg.p_init() + po.TINY64))
     np.testing.assert_array_equal(states.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("sr", [16000, 24000])
+def test_other_sample_rates(cuda, sr):
+    """cfg5 runs at 24 kHz (LibriTTS-R): max_period = 400 lags -> a wider CMND block; 16 kHz -> a narrower one."""
+    import spev_tts_b200 as sp
+    cfg = po.PyinConfig(sr=sr)
+    y, _ = synth.voiced_unvoiced(seed=7, n=int(1.5 * sr), sr=sr)
+    f, flag, vp = sp.pyin(y, fmin=60, fmax=500, sr=sr, hop_length=256)
+    fo, flago, vpo = po.pyin(y, sr=sr)
+    assert f.shape == fo.shape
+    both = flag & flago
+    same = np.zeros(len(f), bool)
+    same[both] = np.abs(1200 * np.log2(f[both] / fo[both])) <= 10.0 + 1e-6
+    agree = np.mean((flag == flago) & (same | ~flago))
+    assert agree >= 0.97, agree
+    assert np.abs(vp - vpo).mean() <= 3e-3
