@@ -159,10 +159,13 @@ def pyin(y, *, fmin, fmax, sr=22050, frame_length=2048, win_length=None, hop_len
     t, was_numpy = _to_device(y, device)
     lead, n = t.shape[:-1], t.shape[-1]
     b = int(np.prod(lead)) if lead else 1
-    f0, flag, vp, _ = pyin_flat(t.reshape(-1), [n] * b, sr=sr, fmin=fmin, fmax=fmax, hop_length=hop_length)
+    f0, flag, vp, _, states = pyin_flat(t.reshape(-1), [n] * b, sr=sr, fmin=fmin, fmax=fmax, hop_length=hop_length,
+                                        return_states=True)
     T = 1 + n // hop_length
-    if fill_na is None:
-        raise NotImplementedError("fill_na=None (best-guess f0 on unvoiced frames) is not implemented")
-    if not (isinstance(fill_na, float) and np.isnan(fill_na)):
+    if fill_na is None:                              # librosa: best-guess f0 of the decoded bin on unvoiced frames too
+        pctx = PyinContext.get(t.device, sr=sr, fmin=fmin, fmax=fmax, hop=hop_length)
+        freqs = torch.from_numpy(pctx.host_tables()[1].astype(np.float32)).to(t.device)
+        f0 = freqs[states.long() % pctx.n_bins]
+    elif not (isinstance(fill_na, float) and np.isnan(fill_na)):
         f0 = torch.where(flag, f0, torch.full_like(f0, float(fill_na)))
     return _ret(f0.view(*lead, T), was_numpy), _ret(flag.view(*lead, T), was_numpy), _ret(vp.view(*lead, T), was_numpy)

@@ -258,3 +258,22 @@ def test_other_sample_rates(cuda, sr):
     agree = np.mean((flag == flago) & (same | ~flago))
     assert agree >= 0.97, agree
     assert np.abs(vp - vpo).mean() <= 3e-3
+
+
+def test_fill_na_variants_and_batched_input(cuda):
+    import spev_tts_b200 as sp
+    y, _ = synth.voiced_unvoiced(seed=9, n=SR)
+    f_nan, flag, _ = sp.pyin(y, fmin=60, fmax=500, sr=SR, hop_length=256)
+    f_zero, flag2, _ = sp.pyin(y, fmin=60, fmax=500, sr=SR, hop_length=256, fill_na=0.0)
+    f_best, flag3, _ = sp.pyin(y, fmin=60, fmax=500, sr=SR, hop_length=256, fill_na=None)
+    assert np.array_equal(flag, flag2) and np.array_equal(flag, flag3) and (~flag).any() and flag.any()
+    assert np.isnan(f_nan[~flag]).all() and np.all(f_zero[~flag] == 0.0)
+    assert np.array_equal(f_nan[flag], f_zero[flag]) and np.array_equal(f_nan[flag], f_best[flag])
+    assert np.all((f_best[~flag] >= 60.0) & (f_best[~flag] <= 500.0))          # the decoded bin of the unvoiced state
+    fo, _, _ = po.pyin(y, fill_na=None)
+    assert np.mean(np.abs(1200 * np.log2(f_best / fo)) <= 10.0 + 1e-6) >= 0.97
+    # leading batch dimensions, torch in -> torch out on the same device
+    yy = torch.from_numpy(np.stack([y, y[::-1].copy()])).to(cuda)
+    fb, flb, vpb = sp.pyin(yy, fmin=60, fmax=500, sr=SR, hop_length=256)
+    assert fb.shape == (2, 1 + SR // 256) and fb.is_cuda and flb.dtype == torch.bool
+    assert np.array_equal(flb[0].cpu().numpy(), flag)
