@@ -52,7 +52,6 @@ constexpr double kLogTiny64 = -708.3964185322641;   // log(DBL_MIN)
 // ----------------------------------------------------------------------------------------------
 // P1: cumulative mean normalised difference
 // ----------------------------------------------------------------------------------------------
-// Block = 4 * Q threads, Q = lag quads (lags 0 .. 4Q-1 >= max_period), rounded so that the block is whole warps.
 __device__ __forceinline__ float block_incl_scan(float v, float* s_w) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
 #pragma unroll
@@ -71,16 +70,24 @@ __device__ __forceinline__ float block_incl_scan(float v, float* s_w) {
     return v;
 }
 
-__global__ void __launch_bounds__(1024)
+// Block = 8 * O threads: O lag octets (lags 0 .. 8*O-1 >= max_period) x 8 segments of the 1024-sample window.
+// The frame is staged twice: linearly (prefix sums) and split into even / odd float4 planes, so that the 8-lag x
+// 16-sample register tile reads its 23 shifted samples with conflict-free LDS.128 (lane o needs float4 2*o + k of
+// the linear order: stride 2 would be a 2-way bank conflict, planes make it stride 1).  128 FFMA per 10 LDS.128:
+// 0.22 shared-memory wavefronts per FFMA -- the 4-lag tile of the first version (0.56) was shared-memory bound.
+constexpr int kCmndSeg = 8;
+__global__ void __launch_bounds__(512)
 k_yin_cmnd(BatchView bv, const float* __restrict__ samples, float* __restrict__ yin, int frame_length, int win,
            int min_period, int max_period) {
     extern __shared__ __align__(16) float sm[];
-    const int nthr = blockDim.x, Q = nthr >> 2;        // lag quads
-    float* s_x = sm + 3;                               // s_x[1] is 16-byte aligned (the window starts at sample 1)
-    float* s_e = sm + 2056;                            // inclusive prefix sums of x^2
-    float* s_part = s_e + 2048;                        // [4][nthr] partial autocorrelations
-    float* s_w = s_part + 4 * nthr;                    // [32]
-    const int need = win + 4 * Q + 4;                  // samples the lag quads touch (<= frame_length)
+    const int nthr = blockDim.x, O = nthr >> 3;
+    float* s_z = sm;                                   // [2048] z[m] = frame sample m + 1 (sample 0 never contributes)
+    float4* s_ev = reinterpret_cast<float4*>(sm + 2048);   // [256] float4 2n   of z
+    float4* s_od = s_ev + 256;                             // [256] float4 2n+1 of z
+    float* s_e = sm + 4096;                            // [2048] P[k] = sum_{m<k} z[m]^2
+    float* s_part = s_e + 2048;                        // [8][nthr] partial autocorrelations
+    float* s_w = s_part + kCmndSeg * nthr;             // [32]
+    const int need = win + 8 * O;                      // z samples the tiles touch (<= frame_length - 1)
     const int n_lags = max_period - min_period + 1;
     const int64_t slots = static_cast<int64_t>(bv.n_ftiles) * kTileFrames;
     for (int64_t fidx = blockIdx.x; fidx < slots; fidx += gridDim.x) {
@@ -88,44 +95,66 @@ k_yin_cmnd(BatchView bv, const float* __restrict__ samples, float* __restrict__ 
         const spev_tile d = bv.ftiles[tile];
         const int fl = static_cast<int>(fidx - tile * kTileFrames);
         if (fl >= d.n) continue;                       // (uniform per CTA)
-        // the frame_length window starts frame_length/2 before the frame centre; src0 is n_fft/2 before it
-        const int64_t first = d.src0 - (frame_length / 2 - kNfft / 2) + static_cast<int64_t>(fl) * kHop;
+        // the frame_length window starts frame_length/2 before the frame centre; src0 is n_fft/2 before it; z skips sample 0
+        const int64_t first = d.src0 - (frame_length / 2 - kNfft / 2) + static_cast<int64_t>(fl) * kHop + 1;
         __syncthreads();
-        for (int i = threadIdx.x; i < need; i += nthr) {
-            const int64_t g = first + i;
-            s_x[i] = (g >= d.lo && g < d.hi) ? __ldg(samples + g) : 0.f;
-        }
-        __syncthreads();
-        {   // inclusive prefix sums of x^2 (numpy: cumsum in the input dtype)
-            const int per = (need + nthr - 1) / nthr;
-            const int b0 = threadIdx.x * per, b1 = min(need, b0 + per);
-            float loc = 0.f;
-            for (int i = b0; i < b1; ++i) loc = fmaf(s_x[i], s_x[i], loc);
-            float run = block_incl_scan(loc, s_w) - loc;
-            for (int i = b0; i < b1; ++i) { run = fmaf(s_x[i], s_x[i], run); s_e[i] = run; }
-        }
-        {   // acf(tau) = sum_{j=1..W} x_j x_{j+tau}: thread = (lag quad q, window segment g), 4x4 register tile
-            const int q = threadIdx.x % Q, g = threadIdx.x / Q;
-            const float4* x4 = reinterpret_cast<const float4*>(s_x + 1);
-            const int seg = win / 16;                   // float4 per segment
-            float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
-#pragma unroll 4
-            for (int i = g * seg; i < (g + 1) * seg; ++i) {
-                const float4 a = x4[i], b0 = x4[i + q], b1 = x4[i + q + 1];
-                c0 = fmaf(a.x, b0.x, c0); c0 = fmaf(a.y, b0.y, c0); c0 = fmaf(a.z, b0.z, c0); c0 = fmaf(a.w, b0.w, c0);
-                c1 = fmaf(a.x, b0.y, c1); c1 = fmaf(a.y, b0.z, c1); c1 = fmaf(a.z, b0.w, c1); c1 = fmaf(a.w, b1.x, c1);
-                c2 = fmaf(a.x, b0.z, c2); c2 = fmaf(a.y, b0.w, c2); c2 = fmaf(a.z, b1.x, c2); c2 = fmaf(a.w, b1.y, c2);
-                c3 = fmaf(a.x, b0.w, c3); c3 = fmaf(a.y, b1.x, c3); c3 = fmaf(a.z, b1.y, c3); c3 = fmaf(a.w, b1.z, c3);
+        {
+            const int i_lo = static_cast<int>(max(static_cast<int64_t>(0), min(static_cast<int64_t>(need), d.lo - first)));
+            const int i_hi = static_cast<int>(max(static_cast<int64_t>(0), min(static_cast<int64_t>(need), d.hi - first)));
+            const float* src = samples + first;
+            float* ev = reinterpret_cast<float*>(s_ev);
+            float* od = reinterpret_cast<float*>(s_od);
+            for (int m = threadIdx.x; m < need; m += nthr) {
+                const float v = (m >= i_lo && m < i_hi) ? __ldg(src + m) : 0.f;
+                s_z[m] = v;
+                ((m & 4) ? od : ev)[((m >> 3) << 2) | (m & 3)] = v;
             }
-            float* o = s_part + g * nthr + 4 * q;
-            o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
+        }
+        __syncthreads();
+        {   // exclusive prefix sums of z^2 (numpy: cumsum in the input dtype): P[k], k = 0 .. need
+            const int per = (need + nthr - 1) / nthr;
+            const int b0 = min(need, threadIdx.x * per), b1 = min(need, b0 + per);
+            float loc = 0.f;
+            for (int i = b0; i < b1; ++i) loc = fmaf(s_z[i], s_z[i], loc);
+            float run = block_incl_scan(loc, s_w) - loc;
+            for (int i = b0; i < b1; ++i) { s_e[i] = run; run = fmaf(s_z[i], s_z[i], run); }
+            if (b1 == need && b0 < need) s_e[need] = run;
+        }
+        {   // acf(tau) = sum_{m<W} z[m] z[m+tau]: thread = (lag octet o, window segment g), 8-lag x 16-sample register tile
+            const int o = threadIdx.x % O, g = threadIdx.x / O;
+            float c[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) c[r] = 0.f;
+            const int n_begin = g * (win / 8 / kCmndSeg);          // float4-pair index: z index / 8
+#pragma unroll 1
+            for (int it = 0; it < win / 16 / kCmndSeg; ++it) {
+                const int n = n_begin + 2 * it;
+                float A[16], B[24];
+                *reinterpret_cast<float4*>(A) = s_ev[n];       *reinterpret_cast<float4*>(A + 4) = s_od[n];
+                *reinterpret_cast<float4*>(A + 8) = s_ev[n + 1]; *reinterpret_cast<float4*>(A + 12) = s_od[n + 1];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    *reinterpret_cast<float4*>(B + 8 * k) = s_ev[n + o + k];
+                    *reinterpret_cast<float4*>(B + 8 * k + 4) = s_od[n + o + k];
+                }
+#pragma unroll
+                for (int m = 0; m < 16; ++m)
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) c[r] = fmaf(A[m], B[m + r], c[r]);
+            }
+            float* dst = s_part + g * nthr + 8 * o;
+            *reinterpret_cast<float4*>(dst) = make_float4(c[0], c[1], c[2], c[3]);
+            *reinterpret_cast<float4*>(dst + 4) = make_float4(c[4], c[5], c[6], c[7]);
         }
         __syncthreads();
         const int tau = threadIdx.x;                    // one lag per thread from here on
         float dval = 0.f;
         if (tau >= 1 && tau <= max_period) {
-            float acf = (s_part[tau] + s_part[nthr + tau]) + (s_part[2 * nthr + tau] + s_part[3 * nthr + tau]);
-            float e_tau = s_e[tau + win] - s_e[tau];    // samples tau+1 .. tau+W
+            float p[kCmndSeg];
+#pragma unroll
+            for (int k = 0; k < kCmndSeg; ++k) p[k] = s_part[k * nthr + tau];
+            float acf = ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
+            float e_tau = s_e[tau + win] - s_e[tau];    // samples tau+1 .. tau+W of the frame
             float e_0 = s_e[win] - s_e[0];
             if (fabsf(acf) < 1e-6f) acf = 0.f;          // the reference's clean-ups
             if (fabsf(e_tau) < 1e-6f) e_tau = 0.f;
@@ -568,7 +597,7 @@ int spev_pyin_create(spev_pyin** out, int device, int sr, int hop_length, float 
     const int max_semitones = static_cast<int>(std::nearbyint(35.92 * 12.0 * c->hop / sr));
     c->trans_width = max_semitones * c->bins_per_semitone + 1;
     c->d_thresholds = c->d_beta_probs = c->d_beta_cum = c->d_boltz_exp = c->d_boltz_fact = c->d_ltrans = c->d_freqs = c->d_logf = nullptr;
-    if (!(c->n_lags > 2 && c->n_lags < 2 * kMaxTroughs && c->max_period <= 991 && c->n_bins >= 2 * c->trans_width && c->n_bins <= 384 &&
+    if (!(c->n_lags > 2 && c->n_lags < 2 * kMaxTroughs && c->max_period <= 503 && c->n_bins >= 2 * c->trans_width && c->n_bins <= 384 &&
           c->trans_width >= 3 && (c->trans_width & 1))) {
         delete c;
         set_error("spev_pyin_create: (sr, fmin, fmax) outside what the kernels support");
@@ -680,9 +709,9 @@ int spev_pyin_cmnd(spev_pyin* c, const spev_batch* b, const float* samples, floa
     SPEV_REQUIRE(samples && yin && b->ftiles, SPEV_E_INVALID, "spev_pyin_cmnd: null buffer");
     const int64_t slots = static_cast<int64_t>(b->n_ftiles) * kTileFrames;
     const int grid = static_cast<int>(std::min<int64_t>(slots, 148 * 64));
-    const int quads = ((c->max_period + 1 + 3) / 4 + 7) / 8 * 8;      // whole warps: 4 * quads threads
-    const int threads = 4 * quads;
-    k_yin_cmnd<<<grid, threads, sizeof(float) * (2056 + 2048 + 4 * threads + 32), static_cast<cudaStream_t>(stream)>>>(
+    const int octets = ((c->max_period + 1 + 7) / 8 + 3) / 4 * 4;     // whole warps: 8 * octets threads
+    const int threads = 8 * octets;
+    k_yin_cmnd<<<grid, threads, sizeof(float) * (4096 + 2048 + 8 + kCmndSeg * threads + 32), static_cast<cudaStream_t>(stream)>>>(
         view_of(b), samples, yin, c->frame_length, c->win_length, c->min_period, c->max_period);
     SPEV_CUDA(cudaGetLastError());
     return SPEV_OK;
