@@ -68,7 +68,9 @@ def plan_chunk_tiles(frames, tile_chunks: int = 29) -> np.ndarray:
     out["row0"] = fo[item] + c0 - 1
     out["n"] = np.minimum(tile_chunks, nc[item] - c0)
     out["t0"], out["T"], out["item"] = c0, frames[item], item
-    return out
+    # full tiles first, partial tiles last (same order as the C planner): tile j runs on CTA j mod grid, so the
+    # cheap tiles fall into the last, incomplete round
+    return out[np.argsort(out["n"] < tile_chunks, kind="stable")]
 
 
 class Context:

@@ -361,17 +361,26 @@ int64_t spev_plan_frame_tiles(const int64_t* frames, const int64_t* sample_lo, c
 
 int64_t spev_plan_chunk_tiles(const int64_t* frames, int n_items, spev_tile* out) {
     if (!frames || n_items < 0) return SPEV_E_INVALID;
-    int64_t nt = 0, fo = 0;
-    for (int i = 0; i < n_items; ++i) {
-        const int64_t T = frames[i], nc = T - 1;
-        for (int64_t c0 = 0; c0 < nc; c0 += kTileChunks, ++nt) {
-            if (!out) continue;
-            spev_tile& d = out[nt];
-            d.src0 = kHop * (fo - i) + kHop * c0; d.lo = 0; d.hi = 0; d.row0 = fo + c0 - 1;
-            d.n = static_cast<int32_t>(std::min<int64_t>(kTileChunks, nc - c0));
-            d.t0 = static_cast<int32_t>(c0); d.T = static_cast<int32_t>(T); d.item = i;
+    // Full tiles first, then the (at most one per item) partial tiles: the persistent kernels hand tile j to CTA
+    // j mod grid, so the cheap tiles land in the last, incomplete round (cfg3: 448 tiles on 148 SMs).
+    int64_t nt = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        int64_t fo = 0;
+        for (int i = 0; i < n_items; ++i) {
+            const int64_t T = frames[i], nc = T - 1;
+            for (int64_t c0 = 0; c0 < nc; c0 += kTileChunks) {
+                const int64_t n = std::min<int64_t>(kTileChunks, nc - c0);
+                if ((n == kTileChunks) != (pass == 0)) continue;
+                if (out) {
+                    spev_tile& d = out[nt];
+                    d.src0 = kHop * (fo - i) + kHop * c0; d.lo = 0; d.hi = 0; d.row0 = fo + c0 - 1;
+                    d.n = static_cast<int32_t>(n);
+                    d.t0 = static_cast<int32_t>(c0); d.T = static_cast<int32_t>(T); d.item = i;
+                }
+                ++nt;
+            }
+            fo += T;
         }
-        fo += T;
     }
     return nt;
 }
