@@ -6,18 +6,20 @@
 //
 //   P1 k_yin_cmnd     frame -> cumulative-mean-normalised difference for lags min_period..max_period.
 //                     d(tau) = e(0) + e(tau) - 2 acf(tau) with the autocorrelation summed directly
-//                     (one lag per thread, four accumulators), energies from a block prefix sum, the
-//                     reference's |.| < 1e-6 -> 0 clean-ups, block scan for the cumulative mean.
+//                     (8-lag x 16-sample register tiles over even/odd float4 planes), energies from a
+//                     block prefix sum, the reference's |.| < 1e-6 -> 0 clean-ups, block scan for the
+//                     cumulative mean.
 //   P2 k_pyin_observe frame -> troughs, parabolic refinement, for each of the 100 thresholds the
 //                     Boltzmann prior over the troughs below it (bitmask + popcount ranks, float64),
 //                     beta-weighted sum, global-minimum bonus, mapping to 10-cent pitch bins ->
 //                     float32 log observation probabilities [F, n_bins] + voiced probability [F].
-//   P3 k_pyin_viterbi utterance -> state path.  One CTA per utterance, one thread per state
-//                     (2 x n_bins), float64 log-domain recursion over the banded transition
-//                     (kron(switch 2x2, triangular local band)); predecessors outside the band carry
-//                     log(tiny) exactly as in the dense reference, so the best of them is the previous
-//                     step's global maximum, found by a block arg-max.  Backpointers go to a
+//   P3 k_pyin_viterbi utterance -> state path.  One CTA per utterance (dynamic work counter), one thread
+//                     per pitch bin owning its voiced and unvoiced state, float64 log-domain recursion over
+//                     the banded transition (kron(switch 2x2, triangular local band)); predecessors outside
+//                     the band carry log(tiny) exactly as in the dense reference, so the best of them is the
+//                     previous step's global maximum, found by a block arg-max.  Backpointers go to a
 //                     caller-provided workspace; ties resolve to the lowest state index like np.argmax.
+//   k_pitch_pool      per-phoneme masked mean / std of log-f0 from the decoded states (:399-414).
 #include <algorithm>
 #include <cmath>
 #include <vector>
@@ -331,10 +333,6 @@ struct VitParams {
     int n_bins, width, n_classes;
     const double2* tab;       // [n_classes][width] (stay, switch) log transition probabilities
 };
-
-__device__ __forceinline__ int row_class(int b, int n_bins, int half) {
-    return b < half ? b : (b >= n_bins - half ? half + 1 + (b - (n_bins - half)) : half);
-}
 
 constexpr int kVitThreads = 384;                 // one thread per pitch bin: it owns the voiced AND the unvoiced state of that bin
 struct ArgMax { double v; int i; };
