@@ -572,7 +572,7 @@ def bench_pyin(sp, dev, hbm_peak, args, with_cpu):
                                 "<= 296 utterances in flight; k_yin_cmnd runs at "
                                 f"{2 * 1024 * 384 * F / (ms1 * 1e-3) / 1e12:.1f} TFLOP/s fp32 (direct autocorrelation)"}}
     # whole cache records (log-mel + rms/centroid + pYIN + per-phoneme pooling + host duration logic) on a subset
-    n_rec = min(512, n_utts)
+    n_rec = n_utts
     phones = [["<SIL>"] + list("abcdefghijklmnopqrstuvwxyz"[: 5 + i % 20]) + ["<SIL>"] for i in range(n_rec)]
     durs = [sp.uniform_durations(int(lens[i]), len(phones[i])) for i in range(n_rec)]
     stats = {"p_mean": 5.2, "p_std": 0.35, "e_mean": -4.0, "e_std": 2.0, "c_mean": 7.5, "c_std": 0.8}

@@ -81,7 +81,7 @@ def plan_records(n_samples: Sequence[int], phones: Sequence[Optional[Sequence[st
 def _upload(waves: Sequence[np.ndarray], device) -> Tuple[torch.Tensor, np.ndarray, np.ndarray]:
     lens = np.array([len(w) for w in waves], dtype=np.int64)
     starts = aligned_offsets(lens)                           # [U+1], last entry = buffer size
-    host = torch.zeros(int(starts[-1]) + 4, dtype=torch.float32).pin_memory()
+    host = torch.zeros(int(starts[-1]) + 4, dtype=torch.float32, pin_memory=True)
     hv = host.numpy()
     for w, s in zip(waves, starts[:-1]):
         hv[s: s + len(w)] = np.asarray(w, dtype=np.float32)
@@ -120,7 +120,8 @@ def corpus_stats(waves: Sequence[np.ndarray], *, sr: int = 22050, device=None) -
 def build_records(waves: Sequence[np.ndarray], phones: Sequence[Optional[Sequence[str]]],
                   durs: Sequence[Optional[Sequence[int]]], stats: dict, *, sr: int = 22050, device=None):
     """Processing pass (``:328-417``).  -> (records, vocab); ``records[k]['index']`` is the position of the
-    utterance in ``waves`` (the reference numbers its files ``u_{index:05d}.pt``, gaps included)."""
+    utterance in ``waves`` (the reference numbers its files ``u_{index:05d}.pt``, gaps included).  The arrays of
+    a record are views into corpus-wide host buffers (``write_reference_cache`` copies them out per file)."""
     dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
     kept, k_phs, k_durs, vocab = plan_records([len(w) for w in waves], phones, durs)
     records: List[dict] = []
@@ -148,11 +149,12 @@ def build_records(waves: Sequence[np.ndarray], phones: Sequence[Optional[Sequenc
                                                 d_po.data_ptr(), len(kept), float(stats["p_mean"]), float(stats["p_std"]),
                                                 -2.5, 2.5, 1.5, pitch.data_ptr(), rough.data_ptr(), stream_ptr(dev)),
                        "spev_pitch_pool")
-            mel_h = mel.cpu()
+            mel_h = torch.empty(mel.shape, dtype=mel.dtype, pin_memory=True)
+            mel_h.copy_(mel)                                  # pinned D2H; records below are views of this buffer
             curves = {k: v.cpu().numpy() for k, v in (("pitch", pitch), ("energy", energy), ("breath", breath),
                                                       ("rough", rough), ("bright", bright))}
         for k, i in enumerate(kept):
-            rec = {"index": i, "phs": k_phs[k], "durs": k_durs[k], "mel": mel_h[fo[k]: fo[k + 1]].clone()}
-            rec.update({name: v[po[k]: po[k + 1]].copy() for name, v in curves.items()})
+            rec = {"index": i, "phs": k_phs[k], "durs": k_durs[k], "mel": mel_h[fo[k]: fo[k + 1]]}
+            rec.update({name: v[po[k]: po[k + 1]] for name, v in curves.items()})
             records.append(rec)
     return records, vocab
