@@ -106,3 +106,45 @@ def test_lr_and_bucketize_stay_in_bounds(cuda):
     emb = Guarded(n * Hh, cuda)
     _lib.check(lib.spev_bucketize_embed(v.data_ptr(), n, bnd.data_ptr(), 255, 0, tab.data_ptr(), Hh, None, emb.ptr(), 0, st))
     assert bool(torch.isfinite(emb.check("bucketize")).all())
+
+
+@pytest.mark.parametrize("lens", [[1], [255, 256, 257], [8191, 8192, 8193, 5], [33 * 256 + 5, 0, 70001]])
+def test_pyin_kernels_stay_in_bounds(cuda, lens):
+    """Every pYIN stage writes all of its output and nothing else (guarded buffers, ragged sizes)."""
+    import spev_tts_b200 as sp
+    from spev_tts_b200 import _lib
+    from spev_tts_b200.pitch import PyinContext
+    from tests import synth
+    ys = [synth.voiced_unvoiced(seed=3 + i, n=max(n, 1))[0][:n] for i, n in enumerate(lens)]
+    flat = torch.from_numpy(np.concatenate(ys)).to(cuda) if sum(lens) else torch.zeros(1, device=cuda)
+    ctx = sp.Context.get(cuda)
+    p = PyinContext.get(cuda)
+    fb = sp.make_batch(ctx, n_samples=lens)
+    st = torch.cuda.current_stream(cuda).cuda_stream
+    F = fb.n_frames
+    yin = Guarded(F * p.n_lags, cuda)
+    _lib.check(p.lib.spev_pyin_cmnd(p.handle, fb.desc, flat.data_ptr(), yin.ptr(), st))
+    assert bool(torch.isfinite(yin.check("spev_pyin_cmnd")).all())
+    lo, lu, vp = Guarded(F * p.n_bins, cuda), Guarded(F, cuda), Guarded(F, cuda)
+    _lib.check(p.lib.spev_pyin_observe(p.handle, yin.ptr(), F, lo.ptr(), lu.ptr(), vp.ptr(), st))
+    for g, name in ((lo, "logobs"), (lu, "log_unvoiced"), (vp, "voiced_prob")):
+        assert bool(torch.isfinite(g.check(name)).all())
+    nbytes = p.lib.spev_pyin_decode_workspace_bytes(p.handle, F)
+    ws = Guarded((nbytes + 3) // 4, cuda)
+    states, f0, flag = Guarded(F, cuda), Guarded(F, cuda), Guarded((F + 3) // 4, cuda)
+    fo = torch.from_numpy(fb.frame_off).to(cuda)
+    _lib.check(p.lib.spev_pyin_decode(p.handle, lo.ptr(), lu.ptr(), fo.data_ptr(), len(lens), F, states.ptr(), f0.ptr(),
+                                      flag.ptr(), ws.ptr(), nbytes, st))
+    ws.check("viterbi workspace")
+    s = states.check("states").view(torch.int32)
+    assert bool(((s >= 0) & (s < 2 * p.n_bins)).all())
+    f0v = f0.check("f0")
+    voiced = flag.check("voiced_flag").view(torch.uint8)[:F]
+    assert bool(((voiced == 1) == (s < p.n_bins)).all()) and bool((torch.isnan(f0v) == (voiced == 0)).all())
+    # pooling over arbitrary phone cuts
+    durs = torch.tensor([max(1, int(t) // 2) for t in fb.frames for _ in range(2)], dtype=torch.int64, device=cuda)
+    po = torch.arange(0, 2 * len(lens) + 1, 2, dtype=torch.int64, device=cuda)
+    pitch, rough = Guarded(2 * len(lens), cuda), Guarded(2 * len(lens), cuda)
+    _lib.check(p.lib.spev_pitch_pool(p.handle, states.ptr(), fo.data_ptr(), durs.data_ptr(), po.data_ptr(), len(lens),
+                                     5.2, 0.3, -2.5, 2.5, 1.5, pitch.ptr(), rough.ptr(), st))
+    assert bool(torch.isfinite(pitch.check("pitch")).all()) and bool(torch.isfinite(rough.check("rough")).all())
