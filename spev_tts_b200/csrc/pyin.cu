@@ -194,6 +194,9 @@ k_pyin_observe(const float* __restrict__ yin, int64_t n_frames, ObsParams p, flo
     __shared__ double s_prob[kMaxTroughs];
     __shared__ unsigned s_mask[128][kMaskWords];     // [threshold][word]: troughs below that threshold
     __shared__ int s_count[128];
+    __shared__ unsigned s_cmask[128][kMaskWords];    // the same at the change points only, prefix-ORed
+    __shared__ int s_cp[128], s_cpidx[128];
+    __shared__ double s_cw[128];
     __shared__ int s_wcnt[kObsThreads / 32];
     __shared__ double s_wsum[kObsThreads / 32];
     __shared__ double s_obs[512];
@@ -248,30 +251,57 @@ k_pyin_observe(const float* __restrict__ yin, int64_t n_frames, ObsParams p, flo
             if (lo < NT) atomicOr(&s_mask[lo][k >> 5], 1u << (k & 31));
         }
         __syncthreads();
-        if (threadIdx.x < kMaskWords) {                 // prefix-OR over thresholds
-            unsigned run = 0u;
-            for (int i = 0; i < NT; ++i) { run |= s_mask[i][threadIdx.x]; s_mask[i][threadIdx.x] = run; }
+        // The set of troughs below threshold i only changes at the thresholds some trough starts at ("change
+        // points", at most min(K, 100) of them): compact them, so that the sums below run over runs of equal
+        // Boltzmann terms weighted by the beta mass of the run instead of over all 100 thresholds.
+        int J = 0;
+        {
+            const int i = threadIdx.x;                   // NT <= blockDim.x
+            bool cp = false;
+            if (i < NT) {
+#pragma unroll
+                for (int w = 0; w < kMaskWords; ++w) cp |= s_mask[i][w] != 0u;
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, cp);
+            if (lane == 0) s_wcnt[wid] = __popc(bal);
+            __syncthreads();
+            int off = 0;
+            for (int w = 0; w < wid; ++w) off += s_wcnt[w];
+            for (int w = 0; w < kObsThreads / 32; ++w) J += s_wcnt[w];
+            if (cp) {
+                const int j = off + __popc(bal & ((1u << lane) - 1u));
+                s_cp[j] = i;
+                s_cpidx[i] = j;
+#pragma unroll
+                for (int w = 0; w < kMaskWords; ++w) s_cmask[j][w] = s_mask[i][w];
+            }
         }
         __syncthreads();
-        for (int i = threadIdx.x; i < NT; i += blockDim.x) {
+        if (threadIdx.x < kMaskWords) {                 // prefix-OR over the change points
+            unsigned run = 0u;
+            for (int j = 0; j < J; ++j) { run |= s_cmask[j][threadIdx.x]; s_cmask[j][threadIdx.x] = run; }
+        }
+        __syncthreads();
+        for (int j = threadIdx.x; j < J; j += blockDim.x) {
             int c = 0;
 #pragma unroll
-            for (int w = 0; w < kMaskWords; ++w) c += __popc(s_mask[i][w]);
-            s_count[i] = c;
+            for (int w = 0; w < kMaskWords; ++w) c += __popc(s_cmask[j][w]);
+            s_count[j] = c;
+            s_cw[j] = s_bcum[j + 1 < J ? s_cp[j + 1] : NT] - s_bcum[s_cp[j]];   // beta mass of thresholds [cp_j, cp_j+1)
         }
         __syncthreads();
         // probs[k] = sum_i boltzmann.pmf(rank_{k,i}, lambda, n_i) * beta_probs[i]   (i >= ithr[k]);
-        // four threads per trough (thresholds interleaved), partials combined in a fixed order
+        // four threads per trough (change points interleaved), partials combined in a fixed order
         for (int kb = 0; kb < K; kb += kObsThreads / 4) {
             const int k = kb + (threadIdx.x >> 2), sub = threadIdx.x & 3;
             double acc = 0.0;
-            if (k < K) {
+            if (k < K && s_ithr[k] < NT) {
                 const int w0 = k >> 5;
                 const unsigned below = (1u << (k & 31)) - 1u;
-                for (int i = s_ithr[k] + sub; i < NT; i += 4) {
-                    int rank = __popc(s_mask[i][w0] & below);
-                    for (int w = 0; w < w0; ++w) rank += __popc(s_mask[i][w]);
-                    acc += (s_bfact[s_count[i]] * s_bexp[rank]) * s_beta[i];
+                for (int j = s_cpidx[s_ithr[k]] + sub; j < J; j += 4) {
+                    int rank = __popc(s_cmask[j][w0] & below);
+                    for (int w = 0; w < w0; ++w) rank += __popc(s_cmask[j][w]);
+                    acc += (s_bfact[s_count[j]] * s_bexp[rank]) * s_cw[j];
                 }
             }
             acc += __shfl_xor_sync(0xffffffffu, acc, 1);
@@ -279,18 +309,29 @@ k_pyin_observe(const float* __restrict__ yin, int64_t n_frames, ObsParams p, flo
             if (k < K && sub == 0) s_prob[k] = acc;
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            // global minimum bonus (np.argmin: first minimum)
-            int gm = 0;
-            float hmin = s_y[s_tidx[0]];
-            for (int k = 1; k < K; ++k) { const float h = s_y[s_tidx[k]]; if (h < hmin) { hmin = h; gm = k; } }
-            s_prob[gm] += p.no_trough_prob * s_bcum[s_ithr[gm]];
-            // candidates -> pitch bins, ascending lag (later entries overwrite earlier ones in the same bin)
-            for (int k = 0; k < K; ++k) {
-                const float prf = static_cast<float>(s_prob[k]);   // yin_probs takes the curve's dtype (float32)
-                if (prf == 0.f) continue;                // np.nonzero
+        {   // global minimum bonus (np.argmin: first minimum) -- warp 0 arg-min over the trough heights
+            if (wid == 0) {
+                float hmin = INFINITY;
+                int gm = 0x7fffffff;
+                for (int k = lane; k < K; k += 32) { const float h = s_y[s_tidx[k]]; if (h < hmin) { hmin = h; gm = k; } }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float oh = __shfl_xor_sync(0xffffffffu, hmin, o);
+                    const int og = __shfl_xor_sync(0xffffffffu, gm, o);
+                    if (oh < hmin || (oh == hmin && og < gm)) { hmin = oh; gm = og; }
+                }
+                if (lane == 0) s_prob[gm] += p.no_trough_prob * s_bcum[s_ithr[gm]];
+            }
+        }
+        __syncthreads();
+        // candidates -> pitch bins, one thread per trough.  numpy assigns in ascending lag order, so of several
+        // troughs landing in one bin the LAST non-zero one stays: a trough writes unless a later one claims its bin.
+        for (int k = threadIdx.x; k < K; k += blockDim.x) {
+            const float prf = static_cast<float>(s_prob[k]);   // yin_probs takes the curve's dtype (float32)
+            int bin = -1;
+            if (prf != 0.f) {                                   // np.nonzero
                 const int i = s_tidx[k];
-                double shift = 0.0;                      // parabolic interpolation on the float32 curve
+                double shift = 0.0;                             // parabolic interpolation on the float32 curve
                 if (i >= 1 && i + 1 < L) {
                     const float a = s_y[i + 1] + s_y[i - 1] - 2.f * s_y[i];
                     const float b = (s_y[i + 1] - s_y[i - 1]) / 2.f;
@@ -300,9 +341,18 @@ k_pyin_observe(const float* __restrict__ yin, int64_t n_frames, ObsParams p, flo
                 const double f0 = static_cast<double>(p.sr) / period;
                 double bi = rint(12.0 * p.bins_per_semitone * log2(f0 / p.fmin));
                 bi = fmin(fmax(bi, 0.0), static_cast<double>(p.n_bins));
-                const int bin = static_cast<int>(bi);
-                if (bin < p.n_bins) s_obs[bin] = static_cast<double>(prf);   // bin == n_bins falls in the unvoiced half, overwritten there
+                bin = static_cast<int>(bi);
+                if (bin >= p.n_bins) bin = -1;                  // bin == n_bins falls in the unvoiced half, overwritten there
             }
+            s_ithr[k] = bin;                                    // (the threshold indices are dead from here on)
+        }
+        __syncthreads();
+        for (int k = threadIdx.x; k < K; k += blockDim.x) {
+            const int bin = s_ithr[k];
+            if (bin < 0) continue;
+            bool last = true;
+            for (int k2 = k + 1; k2 < K; ++k2) if (s_ithr[k2] == bin) { last = false; break; }
+            if (last) s_obs[bin] = static_cast<double>(static_cast<float>(s_prob[k]));
         }
         __syncthreads();
         {   // voiced probability = clip(sum of the voiced bins, 0, 1)
