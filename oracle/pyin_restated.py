@@ -42,7 +42,9 @@ def frame_signal(y, frame_length=2048, hop_length=256, center=True):
 
 def cmnd(y_frames, frame_length, win_length, min_period, max_period):
     """Cumulative mean normalised difference, FFT-based exactly like librosa (incl. the
-    ``|.| < 1e-6 -> 0`` clean-ups).  y_frames ``[frame_length, T]`` -> ``[max_period-min_period+1, T]``."""
+    ``|.| < 1e-6 -> 0`` clean-ups).  y_frames ``[frame_length, T]`` -> ``[max_period-min_period+1, T]``.
+    Note the dtype: for float32 audio the FFTs and energies are float32 (numpy >= 2), but the cumulative mean
+    divides by an int64 lag vector, so the returned curve -- and everything downstream -- is float64."""
     a = np.fft.rfft(y_frames, frame_length, axis=-2)
     b = np.fft.rfft(y_frames[..., win_length:0:-1, :], frame_length, axis=-2)
     acf_frames = np.fft.irfft(a * b, frame_length, axis=-2)[..., win_length:, :]

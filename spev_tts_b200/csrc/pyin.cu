@@ -327,15 +327,18 @@ k_pyin_observe(const float* __restrict__ yin, int64_t n_frames, ObsParams p, flo
         // candidates -> pitch bins, one thread per trough.  numpy assigns in ascending lag order, so of several
         // troughs landing in one bin the LAST non-zero one stays: a trough writes unless a later one claims its bin.
         for (int k = threadIdx.x; k < K; k += blockDim.x) {
-            const float prf = static_cast<float>(s_prob[k]);   // yin_probs takes the curve's dtype (float32)
+            // librosa's CMND array is float64 even for float32 audio (the cumulative mean divides by an int64 lag
+            // vector), so the probabilities and the parabolic refinement below are float64 on the stored values
+            const double pr = s_prob[k];
             int bin = -1;
-            if (prf != 0.f) {                                   // np.nonzero
+            if (pr != 0.0) {                                    // np.nonzero
                 const int i = s_tidx[k];
-                double shift = 0.0;                             // parabolic interpolation on the float32 curve
+                double shift = 0.0;
                 if (i >= 1 && i + 1 < L) {
-                    const float a = s_y[i + 1] + s_y[i - 1] - 2.f * s_y[i];
-                    const float b = (s_y[i + 1] - s_y[i - 1]) / 2.f;
-                    if (fabsf(b) < fabsf(a)) shift = static_cast<double>(-b / a);
+                    const double y0 = s_y[i - 1], y1 = s_y[i], y2 = s_y[i + 1];
+                    const double a = y2 + y0 - 2.0 * y1;
+                    const double b = (y2 - y0) / 2.0;
+                    if (fabs(b) < fabs(a)) shift = -b / a;
                 }
                 const double period = static_cast<double>(p.min_period + i) + shift;
                 const double f0 = static_cast<double>(p.sr) / period;
@@ -352,7 +355,7 @@ k_pyin_observe(const float* __restrict__ yin, int64_t n_frames, ObsParams p, flo
             if (bin < 0) continue;
             bool last = true;
             for (int k2 = k + 1; k2 < K; ++k2) if (s_ithr[k2] == bin) { last = false; break; }
-            if (last) s_obs[bin] = static_cast<double>(static_cast<float>(s_prob[k]));
+            if (last) s_obs[bin] = s_prob[k];
         }
         __syncthreads();
         {   // voiced probability = clip(sum of the voiced bins, 0, 1)

@@ -38,7 +38,7 @@ class PyinContext:
             beta_ptr = None
         _lib.check(self.lib.spev_pyin_create(C.byref(h), int(device), int(sr), int(hop), float(fmin), float(fmax), beta_ptr),
                    "spev_pyin_create")
-        self.handle, self.device, self.sr, self.hop = h, int(device), int(sr), int(hop)
+        self.handle, self.device, self.sr, self.hop, self.fmin = h, int(device), int(sr), int(hop), float(fmin)
         v = [C.c_int() for _ in range(4)]
         _lib.check(self.lib.spev_pyin_info(h, *[C.byref(x) for x in v]), "spev_pyin_info")
         self.n_bins, self.min_period, self.max_period, self.n_lags = (x.value for x in v)
@@ -55,6 +55,12 @@ class PyinContext:
             if ctx is None:
                 ctx = cls._cache[key] = cls(idx, sr, fmin, fmax, hop)
         return ctx
+
+    @property
+    def freqs64(self) -> np.ndarray:
+        """Bin frequencies computed the way librosa computes them (numpy ``fmin * 2 ** (arange / (12 * bps))``):
+        ``std::pow`` in the library differs from numpy's power in the last bit on ~6 % of the bins."""
+        return self.fmin * 2.0 ** (np.arange(self.n_bins) / 120.0)
 
     def host_tables(self):
         """-> (dense log-transition ``[2n, 2n]``, bin frequencies ``[n]``, beta threshold weights ``[100]``)."""
@@ -148,7 +154,8 @@ def pyin(y, *, fmin, fmax, sr=22050, frame_length=2048, win_length=None, hop_len
          beta_parameters=(2, 18), boltzmann_parameter=2, resolution=0.1, max_transition_rate=35.92, switch_prob=0.01,
          no_trough_prob=0.01, fill_na=np.nan, center=True, pad_mode="constant", device=None):
     """Drop-in for ``librosa.pyin`` in the reference's configuration -> ``(f0, voiced_flag, voiced_prob)`` with
-    shape ``[..., T]``.  f0 is float32 here (librosa: float64); unvoiced frames hold ``fill_na``."""
+    shape ``[..., T]``; unvoiced frames hold ``fill_na``.  numpy input -> numpy float64 / bool / float64 like
+    librosa; CUDA tensor input -> float32 / bool / float32 tensors on the same device (no host round trip)."""
     hop_length = frame_length // 4 if hop_length is None else hop_length
     win_length = frame_length // 2 if win_length is None else win_length
     if (frame_length, win_length, n_thresholds, tuple(beta_parameters), boltzmann_parameter, resolution,
@@ -162,10 +169,21 @@ def pyin(y, *, fmin, fmax, sr=22050, frame_length=2048, win_length=None, hop_len
     f0, flag, vp, _, states = pyin_flat(t.reshape(-1), [n] * b, sr=sr, fmin=fmin, fmax=fmax, hop_length=hop_length,
                                         return_states=True)
     T = 1 + n // hop_length
+    if was_numpy:
+        # numpy in -> float64 out like librosa: f0 is read from the float64 bin table, so it is bit-identical to
+        # librosa's wherever the decoded state is
+        pctx = PyinContext.get(t.device, sr=sr, fmin=fmin, fmax=fmax, hop=hop_length)
+        st = states.cpu().numpy().astype(np.int64)
+        voiced = st < pctx.n_bins
+        f0_h = pctx.freqs64[st % pctx.n_bins]
+        if fill_na is not None:
+            f0_h[~voiced] = fill_na
+        return (f0_h.reshape(*lead, T), voiced.reshape(*lead, T),
+                vp.cpu().numpy().astype(np.float64).reshape(*lead, T))
     if fill_na is None:                              # librosa: best-guess f0 of the decoded bin on unvoiced frames too
         pctx = PyinContext.get(t.device, sr=sr, fmin=fmin, fmax=fmax, hop=hop_length)
         freqs = torch.from_numpy(pctx.host_tables()[1].astype(np.float32)).to(t.device)
         f0 = freqs[states.long() % pctx.n_bins]
     elif not (isinstance(fill_na, float) and np.isnan(fill_na)):
         f0 = torch.where(flag, f0, torch.full_like(f0, float(fill_na)))
-    return _ret(f0.view(*lead, T), was_numpy), _ret(flag.view(*lead, T), was_numpy), _ret(vp.view(*lead, T), was_numpy)
+    return f0.view(*lead, T), flag.view(*lead, T), vp.view(*lead, T)

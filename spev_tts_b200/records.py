@@ -102,7 +102,7 @@ def corpus_stats(waves: Sequence[np.ndarray], *, sr: int = 22050, device=None) -
     with torch.cuda.device(dev):
         # voiced log-f0 from the exact float64 bin table (f0 itself is only stored as float32)
         _, _, _, _, states = pyin_flat(x, lens, sr=sr, hop_length=2 * HOP, batch=batch, return_states=True)
-        logf = torch.from_numpy(np.log(PyinContext.get(dev, sr=sr, hop=2 * HOP).host_tables()[1] + 1e-8)).to(dev)
+        logf = torch.from_numpy(np.log(PyinContext.get(dev, sr=sr, hop=2 * HOP).freqs64 + 1e-8)).to(dev)
         st = states.long()
         p = logf[st[st < logf.numel()]]
         rms, cent, _ = frame_features_flat(x, lens, sr=sr, batch=batch)

@@ -37,6 +37,7 @@ def test_model_tables(cuda):
     want = np.log(CFG.transition() + po.TINY64)
     np.testing.assert_allclose(lt, want, rtol=0, atol=1e-12)
     np.testing.assert_allclose(fr, CFG.freqs, rtol=1e-14)
+    np.testing.assert_array_equal(p.freqs64, CFG.freqs)          # what numpy callers get: librosa's exact doubles
     np.testing.assert_array_equal(bp, CFG.beta_probs)            # the shim hands scipy's (= librosa's) table down
     # the library's built-in closed form (C callers without scipy): equal to double rounding of the CDF
     import ctypes as C
@@ -77,13 +78,16 @@ def test_stage2_observation_vs_oracle(cuda):
     p = _pctx(cuda)
     for y in _signals()[:3]:
         yin, _ = _gpu_cmnd(cuda, y)
-        y32 = yin.cpu().numpy().T.copy()                 # the oracle consumes the very same float32 curve
-        obs, vp = po.observation_probs(y32, po.parabolic_interpolation(y32), CFG)
+        # the oracle consumes the very same curve, as float64 like librosa's own CMND array (its cumulative mean
+        # divides by an int64 lag vector, so the array is float64 even for float32 audio)
+        y64 = yin.cpu().numpy().T.astype(np.float64)
+        obs, vp = po.observation_probs(y64, po.parabolic_interpolation(y64), CFG)
         logobs, lunv, vprob = gp.observe(yin, p)
         got = np.exp(logobs.double().cpu().numpy()).T    # [n_bins, T]
         np.testing.assert_allclose(got, obs[: CFG.n_pitch_bins], rtol=1e-4, atol=1e-7)
         np.testing.assert_allclose(vprob.cpu().numpy(), vp, atol=2e-6)
-        np.testing.assert_allclose(np.exp(lunv.double().cpu().numpy()), obs[CFG.n_pitch_bins], rtol=1e-4, atol=1e-300)
+        # (1 - voiced_prob) cancels to a few ulps when the voiced mass sums to 1: absolute tolerance on the probability
+        np.testing.assert_allclose(np.exp(lunv.double().cpu().numpy()), obs[CFG.n_pitch_bins], rtol=1e-4, atol=1e-15)
         # the sparsity pattern (which bins carry mass) must be identical
         assert np.array_equal(got > 1e-300, obs[: CFG.n_pitch_bins] > 0)
 
@@ -168,6 +172,10 @@ def test_end_to_end_agreement_with_oracle(cuda):
         same_f0[both] = np.abs(1200 * np.log2(f[both] / fo[both])) <= 10.0 + 1e-6       # within one bin
         agree += int(np.sum((flag == flago) & (same_f0 | ~flago)))
         assert np.abs(vp - vpo).mean() <= 2e-3
+        # numpy in -> float64 out, read from the same float64 bin table as librosa: bit-identical where the state is
+        assert f.dtype == np.float64 and vp.dtype == np.float64 and flag.dtype == np.bool_
+        assert np.mean(f[both] == fo[both]) >= 0.98
+        assert np.array_equal(flag, flago) or np.mean(flag == flago) >= 0.98
         # and against the ground truth of the synthetic signal (frames well inside voiced segments)
         idx = np.clip(np.arange(len(f)) * 256 - 500, 0, len(y) - 1)     # centre of the analysed span (see test_oracle_pyin)
         inner = np.array([f_true[max(0, i - 1500): i + 1500].min() > 0 for i in idx]) & (f_true[idx] < 480) & (f_true[idx] > 64)
