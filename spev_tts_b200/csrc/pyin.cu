@@ -416,10 +416,8 @@ k_pyin_viterbi(const float* __restrict__ logobs, const float* __restrict__ log_u
     extern __shared__ __align__(16) double smd[];
     double2* s_val = reinterpret_cast<double2*>(smd);      // [2][n_bins]: (voiced, unvoiced) value of each bin
     double2* s_tab = s_val + 2 * p.n_bins;                 // [n_classes][width] when LT_SMEM
-    __shared__ double s_red_v[kVitThreads / 32];
-    __shared__ int s_red_i[kVitThreads / 32];
-    __shared__ double s_gmax;
-    __shared__ int s_garg;
+    __shared__ double s_red_v[2 * (kVitThreads / 32)];
+    __shared__ int s_red_i[2 * (kVitThreads / 32)];
     __shared__ int s_item;
     const int nb = p.n_bins, S = 2 * nb, W = p.width, half = W / 2;
     if (LT_SMEM) for (int i = threadIdx.x; i < p.n_classes * W; i += blockDim.x) s_tab[i] = p.tab[i];
@@ -458,15 +456,16 @@ k_pyin_viterbi(const float* __restrict__ logobs, const float* __restrict__ log_u
             if (act) { if (cur1 > cur0) { m.v = cur1; m.i = nb + b; } else { m.v = cur0; m.i = b; } }
             else { m.v = -INFINITY; m.i = 0x7fffffff; }
             m = warp_argmax(m);
-            if (lane == 0) { s_red_v[wid] = m.v; s_red_i[wid] = m.i; }
+            double* red_v = s_red_v + (t & 1) * (kVitThreads / 32);     // double-buffered: one barrier per step
+            int* red_i = s_red_i + (t & 1) * (kVitThreads / 32);
+            if (lane == 0) { red_v[wid] = m.v; red_i[wid] = m.i; }
             __syncthreads();                               // also publishes s_val[prev]
-            if (wid == 0) {
-                if (lane < kVitThreads / 32) { m.v = s_red_v[lane]; m.i = s_red_i[lane]; }
-                else { m.v = -INFINITY; m.i = 0x7fffffff; }
-                m = warp_argmax(m);
-                if (lane == 0) { s_gmax = m.v; s_garg = m.i; }
-            }
-            __syncthreads();
+            // every warp finishes the reduction for itself (no second barrier, no serial section)
+            if (lane < kVitThreads / 32) { m.v = red_v[lane]; m.i = red_i[lane]; }
+            else { m.v = -INFINITY; m.i = 0x7fffffff; }
+            m = warp_argmax(m);
+            const double gmax = m.v;
+            const int garg = m.i;
             const double2* prev = s_val + ((t - 1) & 1) * nb;
             double2* next = s_val + (t & 1) * nb;
             if (act) {
@@ -495,10 +494,10 @@ k_pyin_viterbi(const float* __restrict__ logobs, const float* __restrict__ log_u
                 if (m11 > best1) { best1 = m11; arg1 = nb + a11; }
                 // predecessors outside the band have transition probability 0 -> log(0 + tiny); the best
                 // of them is the global maximum when that state is itself outside the band
-                const int ga = s_garg;
+                const int ga = garg;
                 const int gb = ga >= nb ? ga - nb : ga;
                 if (gb < blo || gb > bhi) {
-                    const double sc = s_gmax + kLogTiny64;
+                    const double sc = gmax + kLogTiny64;
                     if (sc > best0 || (sc == best0 && ga < arg0)) { best0 = sc; arg0 = ga; }
                     if (sc > best1 || (sc == best1 && ga < arg1)) { best1 = sc; arg1 = ga; }
                 }
@@ -511,6 +510,7 @@ k_pyin_viterbi(const float* __restrict__ logobs, const float* __restrict__ log_u
             // (the __syncthreads at the top of the next iteration orders next[] before it is read)
         }
         // final arg-max and backtrace
+        __syncthreads();                                   // the last step's reduction buffers are no longer read
         {
             ArgMax m;
             if (act) { if (cur1 > cur0) { m.v = cur1; m.i = nb + b; } else { m.v = cur0; m.i = b; } }
