@@ -85,8 +85,9 @@ k_yin_cmnd(BatchView bv, const float* __restrict__ samples, float* __restrict__ 
     const int nthr = blockDim.x, O = nthr >> 3;
     float* s_z = sm;                                   // [2048] z[m] = frame sample m + 1 (sample 0 never contributes)
     float4* s_ev = reinterpret_cast<float4*>(sm + 2048);   // [256] float4 2n   of z
-    float4* s_od = s_ev + 256;                             // [256] float4 2n+1 of z
-    float* s_e = sm + 4096;                            // [2048] P[k] = sum_{m<k} z[m]^2
+    float4* s_od = s_ev + 256 + 4;                         // [256] float4 2n+1 of z (+16 floats: the staging scatter of one
+                                                           //       warp then covers all 32 banks instead of 16 twice)
+    float* s_e = sm + 4096 + 16;                       // [2048] P[k] = sum_{m<k} z[m]^2
     float* s_part = s_e + 2048;                        // [8][nthr] partial autocorrelations
     float* s_w = s_part + kCmndSeg * nthr;             // [32]
     const int need = win + 8 * O;                      // z samples the tiles touch (<= frame_length - 1)
@@ -762,7 +763,7 @@ int spev_pyin_cmnd(spev_pyin* c, const spev_batch* b, const float* samples, floa
     const int grid = static_cast<int>(std::min<int64_t>(slots, 148 * 64));
     const int octets = ((c->max_period + 1 + 7) / 8 + 3) / 4 * 4;     // whole warps: 8 * octets threads
     const int threads = 8 * octets;
-    k_yin_cmnd<<<grid, threads, sizeof(float) * (4096 + 2048 + 8 + kCmndSeg * threads + 32), static_cast<cudaStream_t>(stream)>>>(
+    k_yin_cmnd<<<grid, threads, sizeof(float) * (4096 + 16 + 2048 + 8 + kCmndSeg * threads + 32), static_cast<cudaStream_t>(stream)>>>(
         view_of(b), samples, yin, c->frame_length, c->win_length, c->min_period, c->max_period);
     SPEV_CUDA(cudaGetLastError());
     return SPEV_OK;

@@ -15,8 +15,9 @@ flat = np.concatenate([ys[i % 16][: lens[i]] for i in range(n_utts)])
 x = torch.from_numpy(flat).to(dev)
 fb = make_batch(Context.get(dev), n_samples=lens)
 p = gp.PyinContext.get(dev)
-def t(fn, n=3):
-    fn(); torch.cuda.synchronize()
+def t(fn, n=5):
+    for _ in range(3): fn()
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
     e0.record()
     for _ in range(n): r = fn()
