@@ -285,3 +285,18 @@ def test_fill_na_variants_and_batched_input(cuda):
     fb, flb, vpb = sp.pyin(yy, fmin=60, fmax=500, sr=SR, hop_length=256)
     assert fb.shape == (2, 1 + SR // 256) and fb.is_cuda and flb.dtype == torch.bool
     assert np.array_equal(flb[0].cpu().numpy(), flag)
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13, 14, 15])
+def test_randomised_agreement_sweep(cuda, seed):
+    """More signals (different voicing patterns, glide ranges, harmonic counts, levels): flags and bins vs the oracle."""
+    import spev_tts_b200 as sp
+    rng = np.random.default_rng(seed)
+    y, _ = synth.voiced_unvoiced(seed=seed, n=int(rng.uniform(1.0, 2.0) * SR))
+    y = (y * rng.uniform(0.05, 1.5)).astype(np.float32)            # level must not matter (CMND is scale-invariant)
+    f, flag, vp = sp.pyin(y, fmin=60, fmax=500, sr=SR, hop_length=256)
+    fo, flago, vpo = po.pyin(y)
+    both = flag & flago
+    assert np.mean(flag == flago) >= 0.97
+    assert both.sum() == 0 or np.mean(np.abs(1200 * np.log2(f[both] / fo[both])) <= 10.0 + 1e-6) >= 0.97
+    assert np.abs(vp - vpo).mean() <= 3e-3
