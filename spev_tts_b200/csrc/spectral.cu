@@ -55,9 +55,15 @@ __device__ __forceinline__ void stage_async(float* s_stage, const float* __restr
     const float* xs = x + first;
     const bool vec_ok = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((d.lo & 3) == 0);
     if (vec_ok) {   // lo % 4 == 0 and first == lo (mod 4): a float4 never straddles `lo`
-        for (int i = threadIdx.x * 4; i < count; i += blockDim.x * 4) {
-            int nb = i >= i_lo ? (i_hi - i) * 4 : 0;
-            nb = max(0, min(16, nb));
+        // [0, a4) lies before the item (zero fill), [a4, b4) are whole 16-byte chunks inside it -- the only
+        // non-empty range for interior tiles, copied by a loop without any bounds arithmetic --, [b4, count)
+        // holds the chunk that straddles `hi` and the zero fill after it.
+        const int a4 = min(count, i_lo), b4 = max(a4, min(count, i_hi) & ~3);
+        const int step = blockDim.x * 4;
+        for (int i = threadIdx.x * 4; i < a4; i += step) cp_async16(s_stage + i, x, 0);
+        for (int i = a4 + threadIdx.x * 4; i < b4; i += step) cp_async16(s_stage + i, xs + i, 16);
+        for (int i = b4 + threadIdx.x * 4; i < count; i += step) {
+            const int nb = max(0, min(16, (i_hi - i) * 4));
             cp_async16(s_stage + i, nb > 0 ? xs + i : x, nb);
         }
     } else {
