@@ -13,11 +13,13 @@ raise ``RuntimeError``.
 """
 from ._lib import EXPORTED_SYMBOLS, LIB_PATH, load  # noqa: F401
 from .batch import Context, FlatBatch, make_batch, plan_chunk_tiles, plan_frame_tiles  # noqa: F401
-from .dataset import ResidentCache, read_reference_cache, write_reference_cache  # noqa: F401
+from .dataset import (ResidentCache, read_reference_cache, write_metadata, write_records,  # noqa: F401
+                      write_reference_cache)
 from .features import frame_features_flat, rms, segment_pool, spectral_centroid  # noqa: F401
 from .install import install, patch_model, uninstall  # noqa: F401
 from .pitch import PyinContext, pyin, pyin_flat  # noqa: F401
-from .records import build_records, corpus_stats, plan_records, scale_durations, uniform_durations  # noqa: F401
+from .records import (build_cache_sharded, build_records, corpus_stats, plan_records, scale_durations,  # noqa: F401
+                      uniform_durations)  # noqa: F401
 from .length_regulator import (LengthRegulator, VARIANCE_CLAMPS, expand, mel_mask, plan,  # noqa: F401
                                regulate_variances, variance_adaptor)
 from .spectral import (griffinlim, griffinlim_flat, istft, logmel, logmel_flat, mel_project,  # noqa: F401

@@ -25,18 +25,30 @@ from .batch import stream_ptr
 CURVES = ("pitch", "energy", "breath", "rough", "bright")
 
 
-def write_reference_cache(cache_dir: str, records: Sequence[dict], stats: dict, vocab: Sequence[str]) -> List[str]:
-    """records[i] = {'phs': list[str], 'durs': list[int], 'mel': Tensor[T,80], 'pitch': ndarray[P], ...}."""
+def write_records(cache_dir: str, records: Sequence[dict]) -> List[str]:
+    """One ``u_%05d.pt`` per record (``spev_real_metrics.py:419-425``), numbered by ``record['index']`` when present
+    (the reference numbers by wav index, gaps included) else by position."""
     os.makedirs(cache_dir, exist_ok=True)
     files = []
     for i, r in enumerate(records):
-        path = os.path.join(cache_dir, f"u_{int(r.get('index', i)):05d}.pt")     # the reference numbers by wav index
+        path = os.path.join(cache_dir, f"u_{int(r.get('index', i)):05d}.pt")
         torch.save({"phs": list(r["phs"]), "durs": [int(d) for d in r["durs"]],
                     "mel": torch.as_tensor(r["mel"], dtype=torch.float32).cpu().clone(),
                     **{k: np.asarray(r[k]) for k in CURVES}}, path)
         files.append(path)
+    return files
+
+
+def write_metadata(cache_dir: str, files: Sequence[str], stats: dict, vocab: Sequence[str]) -> None:
+    """``metadata.json`` = ``{'files', 'stats', 'vocab'}`` (``:428-430``; reloaded at ``:291-298``)."""
     with open(os.path.join(cache_dir, "metadata.json"), "w") as f:
-        json.dump({"files": files, "stats": stats, "vocab": list(vocab)}, f)
+        json.dump({"files": list(files), "stats": stats, "vocab": list(vocab)}, f)
+
+
+def write_reference_cache(cache_dir: str, records: Sequence[dict], stats: dict, vocab: Sequence[str]) -> List[str]:
+    """records[i] = {'phs': list[str], 'durs': list[int], 'mel': Tensor[T,80], 'pitch': ndarray[P], ...}."""
+    files = write_records(cache_dir, records)
+    write_metadata(cache_dir, files, stats, vocab)
     return files
 
 

@@ -158,3 +158,41 @@ def build_records(waves: Sequence[np.ndarray], phones: Sequence[Optional[Sequenc
             rec.update({name: v[po[k]: po[k + 1]] for name, v in curves.items()})
             records.append(rec)
     return records, vocab
+
+
+def build_cache_sharded(cache_dir: str, waves: Sequence[np.ndarray], phones, durs, stats: Optional[dict] = None, *,
+                        sr: int = 22050, device=None, builder=None):
+    """The whole cache build over one process per GPU (``torch.distributed`` initialised; works unsharded without
+    it).  The path shards by utterance with no data-path collective: every rank builds and writes the records of
+    its own shard (``cache.shard_utterances``: balanced by frames); the only exchange is an object all-gather of
+    file names and vocabularies, after which rank 0 writes ``metadata.json``.
+    ``stats=None``: every rank computes the statistics pass over the same utterances (deterministic, no exchange)
+    -- pass the reference's <= 500-file sample result instead for large corpora.
+    -> (files in wav order, stats, vocab) on every rank.  ``builder`` (tests): replaces ``build_records``."""
+    import torch.distributed as dist
+    from .cache import shard_utterances
+    from .dataset import write_metadata, write_records
+    on = dist.is_available() and dist.is_initialized()
+    rank, world = (dist.get_rank(), dist.get_world_size()) if on else (0, 1)
+    build = builder if builder is not None else build_records
+    if stats is None:
+        stats = corpus_stats(waves, sr=sr, device=device)
+    lens = np.array([len(w) for w in waves], dtype=np.int64)
+    mine = shard_utterances(lens, world)[rank]
+    recs, vocab = build([waves[i] for i in mine], [phones[i] for i in mine], [durs[i] for i in mine], stats,
+                        sr=sr, device=device)
+    for r in recs:
+        r["index"] = int(mine[r["index"]])                      # position in the whole corpus
+    files = write_records(cache_dir, recs)
+    local = ([(r["index"], f) for r, f in zip(recs, files)], list(vocab))
+    gathered = [local]
+    if on and world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, local)
+    all_files = [f for _, f in sorted(p for part, _ in gathered for p in part)]
+    all_vocab = sorted(set().union(*[set(v) for _, v in gathered]))
+    if rank == 0:
+        write_metadata(cache_dir, all_files, stats, all_vocab)
+    if on and world > 1:
+        dist.barrier()
+    return all_files, stats, all_vocab

@@ -90,3 +90,55 @@ def test_cpulist_parser():
     from spev_tts_b200 import cache
     assert cache._parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
     assert cache._parse_cpulist("") == []
+
+
+def _fake_builder(waves, phones, durs, stats, *, sr=22050, device=None):
+    """CPU stand-in for build_records (which needs a GPU): drops items shorter than 4000 samples like the real one,
+    returns records whose content encodes the waveform so that the merge can be checked."""
+    recs, vocab = [], {"<PAD>", "<UNK>", "<SIL>"}
+    for i, (w, ph, du) in enumerate(zip(waves, phones, durs)):
+        if len(w) < 4000:
+            continue
+        vocab.update(ph)
+        T = 1 + len(w) // 256
+        recs.append({"index": i, "phs": list(ph), "durs": [T], "mel": torch.full((T, 80), float(w[0])),
+                     **{k: np.array([float(w[0])]) for k in ("pitch", "energy", "breath", "rough", "bright")}})
+    return recs, sorted(vocab)
+
+
+def _sharded_build_worker(rank, world, port, tmp, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import spev_tts_b200 as sp
+    lens = [5000, 3000, 9000, 4100, 12000, 4000, 2000, 7000, 8000]
+    waves = [np.full(n, float(i), np.float32) for i, n in enumerate(lens)]
+    phones = [["<SIL>", chr(97 + i)] for i in range(len(lens))]
+    durs = [[1, 1]] * len(lens)
+    stats = {"p_mean": 5.0, "p_std": 0.3, "e_mean": -3.0, "e_std": 1.0, "c_mean": 7.0, "c_std": 0.5}
+    files, st, vocab = sp.build_cache_sharded(tmp, waves, phones, durs, stats, builder=_fake_builder)
+    q.put((rank, [os.path.basename(f) for f in files], vocab))
+    dist.destroy_process_group()
+
+
+def test_sharded_cache_build_merges_ranks(tmp_path):
+    """world_size 2 over gloo: every rank writes its shard's files, rank 0 the merged metadata (wav order, gaps)."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sharded_build_worker, args=(r, world, port, str(tmp_path), q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = [f"u_{i:05d}.pt" for i in (0, 2, 3, 4, 5, 7, 8)]            # items 1 and 6 are shorter than 4000 samples
+    want_vocab = sorted({"<PAD>", "<UNK>", "<SIL>"} | {chr(97 + i) for i in (0, 2, 3, 4, 5, 7, 8)})
+    for _, files, vocab in res:
+        assert files == want and vocab == want_vocab
+    import spev_tts_b200 as sp
+    recs, stats, vocab = sp.read_reference_cache(str(tmp_path))
+    assert len(recs) == 7 and vocab == want_vocab and stats["p_mean"] == 5.0
+    for r, i in zip(recs, (0, 2, 3, 4, 5, 7, 8)):
+        assert float(r["mel"][0, 0]) == float(i) and r["phs"] == ["<SIL>", chr(97 + i)]   # file i holds utterance i

@@ -62,3 +62,45 @@ def test_sharded_build_gather_assemble_equals_single_gpu():
         p.join(timeout=120)
         assert p.exitcode == 0
     assert res == {0: True, 1: True}
+
+
+def _records_worker(rank, world, port, tmp, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    import spev_tts_b200 as sp
+    corpus = synth.tiny_corpus(seed=21)
+    waves = [it["y"] for it in corpus]
+    phones, durs = synth.corpus_alignments(corpus)
+    stats = {"p_mean": 5.4, "p_std": 0.35, "e_mean": -4.6, "e_std": 2.9, "c_mean": 8.0, "c_std": 0.88}
+    files, _, vocab = sp.build_cache_sharded(os.path.join(tmp, "sharded"), waves, phones, durs, stats, device=dev)
+    ok = True
+    if rank == 0:
+        recs, vocab1 = sp.build_records(waves, phones, durs, stats, device=dev)          # one process, one GPU
+        got, _, vocab2 = sp.read_reference_cache(os.path.join(tmp, "sharded"))
+        ok = vocab == vocab1 == vocab2 and len(got) == len(recs)
+        ok = ok and [os.path.basename(f) for f in files] == [f"u_{r['index']:05d}.pt" for r in recs]
+        for a, b in zip(got, recs):
+            ok = ok and a["phs"] == b["phs"] and a["durs"] == b["durs"] and torch.equal(a["mel"], b["mel"])
+            ok = ok and all(np.array_equal(a[k], b[k]) for k in ("pitch", "energy", "breath", "rough", "bright"))
+    q.put((rank, ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_sharded_record_build_equals_single_gpu(tmp_path):
+    """Whole cache records (log-mel, pYIN, pooling) built by two ranks == built by one, bit for bit."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_records_worker, args=(r, world, port, str(tmp_path), q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert res == {0: True, 1: True}
