@@ -202,6 +202,11 @@ SPEV_API int spev_frame_features(spev_ctx* ctx, const spev_batch* batch, const f
 SPEV_API int spev_segment_pool(const float* curve, const int64_t* frame_off, const int64_t* durs,
                                const int64_t* phone_off, int n_items, float mu, float sigma, float lo, float hi,
                                float* out, void* stream);
+/* Same, pooling log(curve + log_eps): the reference takes np.log(rms + 1e-6) / np.log(cent + 1e-8) per frame
+ * (spev_real_metrics.py:370, :397) before the per-phone mean. */
+SPEV_API int spev_segment_pool_log(const float* curve, float log_eps, const int64_t* frame_off, const int64_t* durs,
+                                   const int64_t* phone_off, int n_items, float mu, float sigma, float lo, float hi,
+                                   float* out, void* stream);
 
 /* GPU-side batching of a resident cache: ragged -> zero-padded copies, i.e. the
  * pad_sequence(..., batch_first=True) calls of the reference's collate_fn (spev_real_metrics.py:449-462)

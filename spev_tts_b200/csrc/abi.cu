@@ -44,7 +44,8 @@ int launch_pcm16_to_f32(const int16_t*, int64_t, float*, cudaStream_t);
 int launch_collate(const spev_pad_array*, int, const int64_t*, const int64_t*, const int64_t*, int, int64_t, int64_t, cudaStream_t);
 int launch_bucketize_embed(const float*, int64_t, const float*, int, int, const float*, int, int64_t*, float*, int, cudaStream_t);
 int launch_frame_features(spev_ctx*, const spev_batch*, const float*, float*, float*, cudaStream_t);
-int launch_segment_pool(const float*, const int64_t*, const int64_t*, const int64_t*, int, float, float, float, float, float*, cudaStream_t);
+int launch_segment_pool(const float*, const int64_t*, const int64_t*, const int64_t*, int, float, float, float, float, int, float,
+                        float*, cudaStream_t);
 int launch_mel_project_tc(spev_ctx*, const float*, int64_t, float*, int, float, float, float, cudaStream_t);
 int launch_mel_to_mag_tc(spev_ctx*, const float*, int64_t, int, float*, int64_t, cudaStream_t);
 int gemm_tc_init(spev_ctx*);
@@ -485,7 +486,14 @@ int spev_frame_features(spev_ctx* c, const spev_batch* b, const float* samples, 
 
 int spev_segment_pool(const float* curve, const int64_t* frame_off, const int64_t* durs, const int64_t* phone_off,
                       int n_items, float mu, float sigma, float lo, float hi, float* out, void* stream) {
-    return launch_segment_pool(curve, frame_off, durs, phone_off, n_items, mu, sigma, lo, hi, out,
+    return launch_segment_pool(curve, frame_off, durs, phone_off, n_items, mu, sigma, lo, hi, 0, 0.f, out,
+                               static_cast<cudaStream_t>(stream));
+}
+
+int spev_segment_pool_log(const float* curve, float log_eps, const int64_t* frame_off, const int64_t* durs,
+                          const int64_t* phone_off, int n_items, float mu, float sigma, float lo, float hi, float* out,
+                          void* stream) {
+    return launch_segment_pool(curve, frame_off, durs, phone_off, n_items, mu, sigma, lo, hi, 1, log_eps, out,
                                static_cast<cudaStream_t>(stream));
 }
 

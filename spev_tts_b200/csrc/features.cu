@@ -124,9 +124,12 @@ k_frame_features(BatchView bv, const float* __restrict__ samples, float* __restr
 }
 
 // ---- per-phoneme pooling -----------------------------------------------------------------------
+// LOG: pool log(curve + log_eps) instead of the curve itself (the reference takes the log of rms / centroid per
+// frame before the per-phone mean, spev_real_metrics.py:370, :397)
+template <bool LOG>
 __global__ void k_segment_pool(const float* __restrict__ curve, const int64_t* __restrict__ frame_off,
                                const long long* __restrict__ durs, const int64_t* __restrict__ phone_off, int U,
-                               float mu, float sigma, float lo, float hi, float* __restrict__ out) {
+                               float mu, float sigma, float lo, float hi, float log_eps, float* __restrict__ out) {
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     for (int u = blockIdx.x * wpb + (threadIdx.x >> 5); u < U; u += gridDim.x * wpb) {
@@ -148,10 +151,11 @@ __global__ void k_segment_pool(const float* __restrict__ curve, const int64_t* _
             if (p < p1) {
                 float acc = 0.f;
                 const long long end = min(static_cast<long long>(T), start + dd);
-                for (long long t = start; t < end; ++t) acc += c[t];
+                for (long long t = start; t < end; ++t) acc += LOG ? logf(c[t] + log_eps) : c[t];
                 // numpy: mean of an empty slice is NaN
                 const float m = dd > 0 ? acc / static_cast<float>(dd) : __int_as_float(0x7fc00000);
-                out[p] = fminf(fmaxf((m - mu) / sigma, lo), hi);
+                // np.clip propagates the NaN of an empty phone; fminf/fmaxf would swallow it
+                out[p] = dd > 0 ? fminf(fmaxf((m - mu) / sigma, lo), hi) : m;
             }
             carry += __shfl_sync(0xffffffffu, incl, 31);
         }
@@ -176,15 +180,20 @@ int launch_frame_features(spev_ctx* ctx, const spev_batch* b, const float* sampl
 }
 
 int launch_segment_pool(const float* curve, const int64_t* frame_off, const int64_t* durs, const int64_t* phone_off,
-                        int U, float mu, float sigma, float lo, float hi, float* out, cudaStream_t st) {
+                        int U, float mu, float sigma, float lo, float hi, int take_log, float log_eps, float* out,
+                        cudaStream_t st) {
     SPEV_REQUIRE(U >= 0, SPEV_E_INVALID, "segment_pool: U < 0");
     if (U == 0) return SPEV_OK;
     SPEV_REQUIRE(curve && frame_off && durs && phone_off && out, SPEV_E_INVALID, "segment_pool: null buffer");
     SPEV_REQUIRE(sigma != 0.f, SPEV_E_INVALID, "segment_pool: sigma == 0");
     const int wpb = 4;
     const int grid = std::min((U + wpb - 1) / wpb, 148 * 16);
-    k_segment_pool<<<grid, wpb * 32, 0, st>>>(curve, frame_off, reinterpret_cast<const long long*>(durs), phone_off, U, mu,
-                                              sigma, lo, hi, out);
+    if (take_log)
+        k_segment_pool<true><<<grid, wpb * 32, 0, st>>>(curve, frame_off, reinterpret_cast<const long long*>(durs), phone_off,
+                                                        U, mu, sigma, lo, hi, log_eps, out);
+    else
+        k_segment_pool<false><<<grid, wpb * 32, 0, st>>>(curve, frame_off, reinterpret_cast<const long long*>(durs), phone_off,
+                                                         U, mu, sigma, lo, hi, 0.f, out);
     SPEV_CUDA(cudaGetLastError());
     return SPEV_OK;
 }

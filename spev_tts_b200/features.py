@@ -61,7 +61,7 @@ def spectral_centroid(*, y, sr=22050, n_fft=2048, hop_length=512, center=True, p
 
 
 def segment_pool(curve: torch.Tensor, frame_off, durs: torch.Tensor, phone_off, *, mu=0.0, sigma=1.0,
-                 lo=-float("inf"), hi=float("inf")) -> torch.Tensor:
+                 lo=-float("inf"), hi=float("inf"), log_eps: Optional[float] = None) -> torch.Tensor:
     """``clip((mean(curve[seg]) - mu) / sigma, lo, hi)`` per phoneme (``spev_real_metrics.py:400-417``).
     ``curve``: ``[F]`` float32 CUDA; ``durs``: flat int64 durations; ``frame_off`` / ``phone_off``: ``[U+1]``
     prefix offsets (array-likes or CUDA int64 tensors)."""
@@ -74,7 +74,12 @@ def segment_pool(curve: torch.Tensor, frame_off, durs: torch.Tensor, phone_off, 
     curve = curve.to(torch.float32).contiguous()
     out = torch.empty(du.numel(), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        _lib.check(_lib.load().spev_segment_pool(curve.data_ptr(), fo.data_ptr(), du.data_ptr(), po.data_ptr(),
-                                                 fo.numel() - 1, float(mu), float(sigma), float(lo), float(hi),
-                                                 out.data_ptr(), stream_ptr(dev)), "spev_segment_pool")
+        if log_eps is None:
+            _lib.check(_lib.load().spev_segment_pool(curve.data_ptr(), fo.data_ptr(), du.data_ptr(), po.data_ptr(),
+                                                     fo.numel() - 1, float(mu), float(sigma), float(lo), float(hi),
+                                                     out.data_ptr(), stream_ptr(dev)), "spev_segment_pool")
+        else:                                    # pool log(curve + log_eps) (``:370`` / ``:397`` take the log per frame)
+            _lib.check(_lib.load().spev_segment_pool_log(curve.data_ptr(), float(log_eps), fo.data_ptr(), du.data_ptr(),
+                                                         po.data_ptr(), fo.numel() - 1, float(mu), float(sigma), float(lo),
+                                                         float(hi), out.data_ptr(), stream_ptr(dev)), "spev_segment_pool_log")
     return out

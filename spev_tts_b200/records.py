@@ -137,10 +137,10 @@ def build_records(waves: Sequence[np.ndarray], phones: Sequence[Optional[Sequenc
             mel, _ = logmel_flat(x, lens, sr=sr, batch=batch)
             rms, cent, _ = frame_features_flat(x, lens, sr=sr, batch=batch)
             _, _, vp, _, states = pyin_flat(x, lens, sr=sr, batch=batch, return_states=True)
-            energy = segment_pool(torch.log(rms + 1e-6), d_fo, d_durs, d_po, mu=stats["e_mean"], sigma=stats["e_std"],
-                                  lo=-2.5, hi=2.5)
-            bright = segment_pool(torch.log(cent + 1e-8), d_fo, d_durs, d_po, mu=stats["c_mean"], sigma=stats["c_std"],
-                                  lo=-2.5, hi=2.5)
+            energy = segment_pool(rms, d_fo, d_durs, d_po, mu=stats["e_mean"], sigma=stats["e_std"], lo=-2.5, hi=2.5,
+                                  log_eps=1e-6)
+            bright = segment_pool(cent, d_fo, d_durs, d_po, mu=stats["c_mean"], sigma=stats["c_std"], lo=-2.5, hi=2.5,
+                                  log_eps=1e-8)
             breath = segment_pool(vp, d_fo, d_durs, d_po, mu=1.0, sigma=-1.0, lo=0.0, hi=0.8)
             pitch = torch.empty_like(energy)
             rough = torch.empty_like(energy)

@@ -12,7 +12,7 @@ int spev_c99_probe(void) {
     USE(spev_logmel); USE(spev_stft_power); USE(spev_mel_project); USE(spev_mel_to_mag); USE(spev_set_tensor_core);
     USE(spev_istft); USE(spev_stft); USE(spev_gl_phase_update); USE(spev_griffinlim_workspace_bytes);
     USE(spev_griffinlim); USE(spev_lr_plan); USE(spev_lr_expand); USE(spev_lr_expand_fused);
-    USE(spev_duration_rule); USE(spev_bucketize_embed); USE(spev_frame_features); USE(spev_segment_pool); USE(spev_pcm16_to_f32); USE(spev_collate); USE(spev_variance_fuse);
+    USE(spev_duration_rule); USE(spev_bucketize_embed); USE(spev_frame_features); USE(spev_segment_pool); USE(spev_segment_pool_log); USE(spev_pcm16_to_f32); USE(spev_collate); USE(spev_variance_fuse);
     USE(spev_pyin_create); USE(spev_pyin_destroy); USE(spev_pyin_info); USE(spev_pyin_host_tables);
     USE(spev_pyin_cmnd); USE(spev_pyin_observe); USE(spev_pyin_decode_workspace_bytes); USE(spev_pyin_decode); USE(spev_pitch_pool);
     t.n = 0; b.n_items = 0;

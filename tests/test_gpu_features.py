@@ -73,3 +73,28 @@ def test_segment_pool_vs_reference_lines(cuda):
                           zip(np.cumsum(dd) - dd, dd)]), 0.0, 0.8) for u, dd in
                           enumerate(np.split(durs, po[1:-1]))]).astype(np.float32)
     assert np.abs(got - ref).max() <= 2e-6
+
+
+def test_segment_pool_log_mode(cuda):
+    """spev_segment_pool_log == pooling the per-frame log, the way :370 / :397 / :404 / :408 do it in numpy."""
+    import spev_tts_b200 as sp
+    rng = np.random.default_rng(9)
+    frames = np.array([40, 7, 123])
+    fo = np.concatenate([[0], np.cumsum(frames)])
+    curve = (rng.random(fo[-1]) * 0.2).astype(np.float32)
+    durs = [np.array([10, 0, 30]), np.array([7]), np.array([100, 20, 3])]
+    po = np.concatenate([[0], np.cumsum([len(d) for d in durs])])
+    want = []
+    for u, d in enumerate(durs):
+        logc = np.log(curve[fo[u]: fo[u + 1]] + 1e-6)                       # float32, like np.log(rms + 1e-6)
+        cur = 0
+        for dd in d:
+            m = np.mean(logc[cur: cur + dd]) if dd else np.float32(np.nan)     # numpy: mean of an empty slice is NaN
+            want.append(np.clip((m - (-3.0)) / 1.5, -2.5, 2.5))
+            cur += dd
+    got = sp.segment_pool(torch.from_numpy(curve).to(cuda), fo, torch.from_numpy(np.concatenate(durs)).to(cuda), po,
+                          mu=-3.0, sigma=1.5, lo=-2.5, hi=2.5, log_eps=1e-6).cpu().numpy()
+    want = np.array(want, dtype=np.float64)
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    ok = ~np.isnan(want)
+    assert np.abs(got[ok] - want[ok]).max() <= 2e-6          # float32 sums of up to 100 logs, sequential vs pairwise
