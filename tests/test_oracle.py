@@ -139,3 +139,25 @@ def test_rms_and_centroid_vs_torch():
     assert lr.spectral_centroid(y=np.zeros(4096, np.float32), sr=22050)[0].max() == 0.0    # silent columns
     pooled = lr.phoneme_pool(np.arange(10, dtype=np.float32), [2, 3, 5], 1.0, 2.0, -1.0, 1.5)
     assert np.allclose(pooled, np.clip((np.array([0.5, 3.0, 7.0]) - 1) / 2, -1, 1.5))
+
+
+def test_logmel_chain_against_transformers_audio_utils(monkeypatch):
+    """Independent end-to-end pin of the STFT -> |X|^2 -> Slaney mel -> log chain: Hugging Face's
+    ``transformers.audio_utils`` (written to reproduce librosa's spectrogram / mel filter bank) on the same
+    signals, with the reference's parameters (n_fft=1024, hop=256, periodic Hann, centre zero padding, 80 mels)."""
+    import sys
+    for name, mod in list(sys.modules.items()):          # reference_import's stand-ins (librosa, ...) confuse
+        if getattr(mod, "__stub__", False):              # transformers' optional-dependency probing
+            monkeypatch.delitem(sys.modules, name)
+    au = pytest.importorskip("transformers.audio_utils")
+    win = au.window_function(1024, "hann", periodic=True)
+    fb = au.mel_filter_bank(513, 80, 0.0, 11025.0, 22050, norm="slaney", mel_scale="slaney")        # [513, 80]
+    assert np.abs(fb.T - lr.mel_filter(sr=22050, n_fft=1024, n_mels=80)).max() <= 1e-8
+    for y in (synth.white(seed=0), synth.speechy(seed=1)):
+        S = au.spectrogram(y, win, frame_length=1024, hop_length=256, fft_length=1024, power=2.0, center=True,
+                           pad_mode="constant", mel_filters=fb, mel_floor=0.0, dtype=np.float64)    # [80, T]
+        M = lr.melspectrogram(y=y, sr=22050, n_fft=1024, hop_length=256, n_mels=80)
+        assert S.shape == M.shape == (80, 1 + len(y) // 256)
+        assert np.abs(S - M).max() <= 1e-6 * np.abs(M).max()
+        lm = np.clip(np.log(np.clip(S, 1e-5, None)), -10.0, 2.0).T
+        assert np.abs(lm - lr.reference_logmel(y)).max() <= 5e-6
