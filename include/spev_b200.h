@@ -264,6 +264,31 @@ SPEV_API int spev_variance_fuse(const float* x, const float* feats, int n_feat, 
                                 const int32_t* cumsum, int B, int T, int H, float* out, float* feats_out,
                                 int64_t max_len, void* stream);
 
+/* Backward of spev_lr_expand / spev_lr_expand_fused: the autograd of the reference's repeat / cat / pad / stack
+ * (spev_real_metrics.py:135-146), which its Trainer differentiates through (loss.backward(), :574).
+ *   grad_x[b,t,:]     = sum over the frames f of segment t (cumsum[t-1] <= f < cumsum[t]) of grad_out[b,f,:]
+ *   grad_feats[j,b,t] = pass_j(feats[j,b,t]) * sum over segment t of grad_feats_out[j,b,f]
+ * pass_j = (lo_j <= v <= hi_j), torch.clamp's backward mask, when clamp_lo/hi are given (then `feats`, the
+ * forward's curves, is required); padding frames belong to no segment.  Every output element has one owner
+ * thread that adds its frames in ascending order: no atomics, bit-reproducible.
+ *   grad_out [B,max_len,H] / grad_x [B,T,H] of dtype 0=float32 1=float64 2=float16 3=bfloat16 (NULL,NULL: skip)
+ *   grad_feats_out [n_feat,B,max_len] / grad_feats [n_feat,B,T] float32 (n_feat = 0: skip) */
+SPEV_API int spev_lr_expand_backward(const void* grad_out, int dtype, int H, const float* grad_feats_out, int n_feat,
+                                     const float* feats, const float* clamp_lo_host, const float* clamp_hi_host,
+                                     const int32_t* cumsum, int B, int T, int64_t max_len, void* grad_x,
+                                     float* grad_feats, void* stream);
+
+/* Backward of spev_variance_fuse (the autograd of spev_real_metrics.py:226-252: six LengthRegulator calls, five
+ * clamps, five Conv1d(1,H,3,padding=1) embeddings, their sum).  Any of the four outputs may be NULL.
+ *   grad_out [B,max_len,H];  grad_x [B,T,H];  grad_feats [n_feat,B,T];  grad_w [n_feat,H,3];  grad_b [n_feat,H]
+ * n_feat <= 5, H <= 1024.  Deterministic (per-CTA partial sums added in CTA order).  Workspace: caller-owned device
+ * memory of spev_variance_fuse_backward_workspace_bytes(). */
+SPEV_API size_t spev_variance_fuse_backward_workspace_bytes(int n_feat, int B, int H, int64_t max_len);
+SPEV_API int spev_variance_fuse_backward(const float* grad_out, const float* feats, int n_feat, const float* clamp_lo_host,
+                                         const float* clamp_hi_host, const float* conv_w, const int32_t* cumsum, int B,
+                                         int T, int H, int64_t max_len, float* grad_x, float* grad_feats, float* grad_w,
+                                         float* grad_b, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Inference duration rule, spev_real_metrics.py:215:
  *   dur = (int64) rint(clamp((exp(log_dur) - 1) * d_control, 0, 500))   (round-half-even) */
 SPEV_API int spev_duration_rule(const float* log_dur, int64_t n, float d_control, int64_t* dur,

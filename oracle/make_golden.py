@@ -245,6 +245,52 @@ def main() -> None:
                         conv_b=np.stack([e.bias.detach().numpy() for e in embs]),
                         dec_input=dec_input.numpy(), mel_len=mel_len.numpy(),
                         curves_expanded=np.stack([t[:, 0].numpy() for t in (pitch, energy, breath, rough, bright)]))
+    # ---- backward of the variance adaptor block: the reference model's own modules under autograd -------
+    xg = xv.clone().requires_grad_(True)
+    cg = [c.clone().requires_grad_(True) for c in curves]
+    for e in embs:
+        e.zero_grad()
+    x_expanded, _ = model.length_regulator(xg, dv)
+    ex = [model.length_regulator(c.unsqueeze(-1), dv)[0].transpose(1, 2) for c in cg]
+    ex = [torch.clamp(e, lo, hi) for e, (lo, hi) in zip(ex, ((-3.0, 3.0), (-3.0, 3.0), (0.0, 1.0), (0.0, 2.0), (-3.0, 3.0)))]
+    di = x_expanded.transpose(1, 2)
+    di = di + model.pitch_embedding(ex[0]) + model.energy_embedding(ex[1]) + model.breath_embedding(ex[2]) + \
+        model.rough_embedding(ex[3]) + model.bright_embedding(ex[4])
+    di = di.transpose(1, 2)
+    gup = torch.from_numpy(synth.upstream_grad(di.shape, seed=12))
+    (di * gup).sum().backward()
+    np.savez_compressed(os.path.join(OUT, "variance_adaptor_bwd.npz"),
+                        grad_x=xg.grad.numpy(), grad_curves=np.stack([c.grad.numpy() for c in cg]),
+                        grad_w=np.stack([e.weight.grad.numpy() for e in embs]),
+                        grad_b=np.stack([e.bias.grad.numpy() for e in embs]))
+
+    # ---- LengthRegulator backward: the REFERENCE'S OWN class under torch autograd (:122-146, used under
+    #      loss.backward() at :574) -------------------------------------------------------------------------
+    bw = {}
+    x, dur, _ = synth.cfg2_batch(seed=2)
+    xt = torch.from_numpy(x).requires_grad_(True)
+    o, _ = LR(xt, torch.from_numpy(dur))
+    (o * torch.from_numpy(synth.upstream_grad(o.shape, seed=13))).sum().backward()
+    bw["cfg2_grad_x_dec"] = xt.grad.numpy()[::3, ::7, ::5].copy()
+    bw["cfg2_grad_x_sha256_f32"] = np.array(sha(xt.grad.numpy()))
+    ft = torch.from_numpy(synth.cfg2_features(seed=2)[0]).requires_grad_(True)          # expand_feat, H = 1 (:228-230)
+    o1, _ = LR(ft.unsqueeze(-1), torch.from_numpy(dur))
+    (o1 * torch.from_numpy(synth.upstream_grad(o1.shape, seed=14))).sum().backward()
+    bw["cfg2_grad_feat0"] = ft.grad.numpy()
+    small = np.load(os.path.join(OUT, "lr_small.npz"))
+    for dt, tag in ((torch.float32, "f32"), (torch.float64, "f64")):
+        xs_t = torch.from_numpy(small["x"]).to(dt).requires_grad_(True)
+        o, _ = LR(xs_t, torch.from_numpy(small["dur"]))
+        (o * torch.from_numpy(synth.upstream_grad(o.shape, seed=15)).to(dt)).sum().backward()
+        bw[f"small_grad_x_{tag}"] = xs_t.grad.numpy()
+    for name, (xe, de) in synth.lr_edge_cases().items():
+        xe_t = torch.from_numpy(xe).requires_grad_(True)
+        o, _ = LR(xe_t, torch.from_numpy(de))
+        if o.requires_grad:      # an all-empty batch yields constant zeros in the reference (no grad_fn)
+            (o * torch.from_numpy(synth.upstream_grad(o.shape, seed=16))).sum().backward()
+        bw[f"edge_{name}_grad_x"] = xe_t.grad.numpy() if xe_t.grad is not None else np.zeros_like(xe)
+    np.savez_compressed(os.path.join(OUT, "lr_backward.npz"), **bw)
+
     cache_build_golden(ref)
     print("golden fixtures written to", OUT)
     for f in sorted(os.listdir(OUT)):

@@ -135,6 +135,10 @@ class LogMelCacheBuilder:
         self._pcm: List[Optional[torch.Tensor]] = [None] * n_buffers
         self._in: List[Optional[torch.Tensor]] = [None] * n_buffers
         self._out: List[Optional[torch.Tensor]] = [None] * n_buffers
+        # per-buffer "free again" events live across build() calls: a second build() enqueued without a host
+        # synchronise must not start copying into a staging buffer the previous build's kernels still read
+        self._in_free: List[Optional[torch.cuda.Event]] = [None] * n_buffers    # compute finished reading buffer i
+        self._out_free: List[Optional[torch.cuda.Event]] = [None] * n_buffers   # D2H finished reading buffer i
         self.launches = 0
 
     def _buf(self, pool, i, n, dtype=torch.float32):
@@ -159,8 +163,7 @@ class LogMelCacheBuilder:
         if out_host is None:
             out_host = torch.empty((F, self.n_mels), dtype=torch.float32).pin_memory()
         nb = self.n_buffers
-        in_free = [torch.cuda.Event() for _ in range(nb)]    # compute finished reading buffer i
-        out_free = [torch.cuda.Event() for _ in range(nb)]   # D2H finished reading buffer i
+        in_free, out_free = self._in_free, self._out_free
         max_in = max(int(plan.sample_off[b] - plan.sample_off[a]) for a, b in plan.chunks)
         max_out = max(int(plan.frame_off[b] - plan.frame_off[a]) for a, b in plan.chunks) * self.n_mels
         for i in range(nb):
@@ -172,8 +175,10 @@ class LogMelCacheBuilder:
         batches = [make_batch(self.ctx, n_samples=plan.n_samples[a:b],
                               sample_off=plan.sample_off[a:b] - plan.sample_off[a]) for a, b in plan.chunks]
         tables_up = torch.cuda.Event()
-        tables_up.record(torch.cuda.current_stream(self.device))   # descriptor uploads ran here
+        tables_up.record(torch.cuda.current_stream(self.device))   # descriptor uploads and staging allocations ran here
         self.compute.wait_event(tables_up)
+        self.copy_in.wait_event(tables_up)                         # (a re-used allocation may still be in use upstream)
+        self.copy_out.wait_event(tables_up)
         for ci, (a, b) in enumerate(plan.chunks):
             i = ci % nb
             s0, s1 = int(plan.sample_off[a]), int(plan.sample_off[b])
@@ -181,14 +186,14 @@ class LogMelCacheBuilder:
             d_in = self._in[i][: s1 - s0]
             d_out = self._out[i][: (f1 - f0) * self.n_mels].view(f1 - f0, self.n_mels)
             with torch.cuda.stream(self.copy_in):
-                if ci >= nb:
+                if in_free[i] is not None:          # also set by a previous build()
                     self.copy_in.wait_event(in_free[i])
                 (self._pcm[i][: s1 - s0] if pcm else d_in).copy_(samples_host[s0:s1], non_blocking=True)
                 ready = torch.cuda.Event()
                 ready.record(self.copy_in)
             with torch.cuda.stream(self.compute):
                 self.compute.wait_event(ready)
-                if ci >= nb:
+                if out_free[i] is not None:
                     self.compute.wait_event(out_free[i])
                 if pcm:
                     _lib.check(self.ctx.lib.spev_pcm16_to_f32(self._pcm[i].data_ptr(), s1 - s0, d_in.data_ptr(),
@@ -197,12 +202,14 @@ class LogMelCacheBuilder:
                 spectral.logmel_flat(d_in, plan.n_samples[a:b], sr=self.sr, n_mels=self.n_mels,
                                      out=d_out, batch=batches[ci])
                 self.launches += 1
+                in_free[i] = torch.cuda.Event()
                 in_free[i].record(self.compute)
                 done = torch.cuda.Event()
                 done.record(self.compute)
             with torch.cuda.stream(self.copy_out):
                 self.copy_out.wait_event(done)
                 out_host[f0:f1].copy_(d_out, non_blocking=True)
+                out_free[i] = torch.cuda.Event()
                 out_free[i].record(self.copy_out)
         fin = torch.cuda.Event()
         fin.record(self.copy_out)

@@ -39,6 +39,11 @@ int launch_mel_to_mag(spev_ctx*, const spev_batch*, const float*, int, int, floa
 int launch_lr_plan(const void*, int, int, int, int32_t*, int64_t*, int64_t*, int64_t*, cudaStream_t);
 int launch_lr_expand(const void*, int64_t, const float*, int, const float*, const float*, const int32_t*, int, int, void*, float*, int64_t, cudaStream_t);
 int launch_duration_rule(const float*, int64_t, float, int64_t*, cudaStream_t);
+int launch_lr_expand_backward(const void*, int, int, const float*, int, const float*, const float*, const float*, const int32_t*,
+                              int, int, int64_t, void*, float*, cudaStream_t);
+size_t variance_fuse_backward_workspace_bytes(int, int, int, int64_t);
+int launch_variance_fuse_backward(const float*, const float*, int, const float*, const float*, const float*, const int32_t*, int,
+                                  int, int, int64_t, float*, float*, float*, float*, void*, size_t, cudaStream_t);
 int launch_variance_fuse(const float*, const float*, int, const float*, const float*, const float*, const float*, const int32_t*, int, int, int, float*, float*, int64_t, cudaStream_t);
 int launch_pcm16_to_f32(const int16_t*, int64_t, float*, cudaStream_t);
 int launch_collate(const spev_pad_array*, int, const int64_t*, const int64_t*, const int64_t*, int, int64_t, int64_t, cudaStream_t);
@@ -158,6 +163,23 @@ static float tf32_trunc(float x) {
     return x;
 }
 
+// Entry points that take a ctx run on the ctx's device and leave the caller's current device as they found it.
+struct DeviceGuard {
+    int prev = -1, rc = SPEV_OK;
+    explicit DeviceGuard(const spev_ctx* c) {
+        if (!c) { set_error("ctx is null"); rc = SPEV_E_INVALID; return; }
+        cudaError_t e = cudaGetDevice(&prev);
+        if (e == cudaSuccess && prev != c->device) e = cudaSetDevice(c->device); else if (e == cudaSuccess) prev = -1;
+        if (e != cudaSuccess) { rc = cuda_fail(e, "cudaSetDevice(ctx->device)"); prev = -1; }
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define SPEV_ON_CTX_DEVICE(c)      \
+    DeviceGuard _guard(c);         \
+    if (_guard.rc) return _guard.rc
+
 }  // namespace spev
 
 using namespace spev;
@@ -185,8 +207,11 @@ int spev_create(spev_ctx** out, int device, int sr, int n_fft, int hop, int win,
     SPEV_REQUIRE(device >= 0 && device < ndev, SPEV_E_DEVICE, "spev_create: device %d out of range", device);
     cudaDeviceProp prop;
     SPEV_CUDA(cudaGetDeviceProperties(&prop, device));
-    SPEV_REQUIRE(prop.major == 10, SPEV_E_DEVICE, "spev_create: device %d is sm_%d%d; this build is sm_100a only",
-                 device, prop.major, prop.minor);
+    SPEV_REQUIRE(prop.major == 10 && prop.minor == 0, SPEV_E_DEVICE,
+                 "spev_create: device %d is sm_%d%d; this build carries sm_100a code only", device, prop.major, prop.minor);
+    int prev_device = -1;
+    SPEV_CUDA(cudaGetDevice(&prev_device));
+    struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prev_device != device ? prev_device : -1};
     SPEV_CUDA(cudaSetDevice(device));
 
     spev_ctx* c = new spev_ctx();
@@ -289,7 +314,7 @@ int spev_create(spev_ctx** out, int device, int sr, int n_fft, int hop, int win,
 
 void spev_destroy(spev_ctx* c) {
     if (!c) return;
-    cudaSetDevice(c->device);
+    DeviceGuard guard(c);
     gemm_tc_destroy(c);
     cudaFree(c->d_tw); cudaFree(c->d_window); cudaFree(c->d_win2048); cudaFree(c->d_tw2048); cudaFree(c->d_basis_pad); cudaFree(c->d_basis_hi);
     cudaFree(c->d_basis_lo); cudaFree(c->d_pinv_t); cudaFree(c->d_pinv_hi); cudaFree(c->d_pinv_lo);
@@ -386,38 +411,29 @@ int64_t spev_plan_chunk_tiles(const int64_t* frames, int n_items, spev_tile* out
     return nt;
 }
 
-static int with_device(spev_ctx* c) {
-    SPEV_REQUIRE(c, SPEV_E_INVALID, "ctx is null");
-    SPEV_CUDA(cudaSetDevice(c->device));
-    return SPEV_OK;
-}
 
 int spev_logmel(spev_ctx* c, const spev_batch* b, const float* samples, float* out, int mode,
                 float floor_v, float lo, float hi, void* stream) {
-    int rc = with_device(c);
-    if (rc) return rc;
+    SPEV_ON_CTX_DEVICE(c);
     SPEV_REQUIRE(mode == 0 || mode == 1, SPEV_E_INVALID, "spev_logmel: mode must be 0 or 1");
     return launch_stft_mel(c, b, samples, out, false, mode, floor_v, lo, hi, static_cast<cudaStream_t>(stream));
 }
 
 int spev_stft_power(spev_ctx* c, const spev_batch* b, const float* samples, float* power, void* stream) {
-    int rc = with_device(c);
-    if (rc) return rc;
+    SPEV_ON_CTX_DEVICE(c);
     return launch_stft_mel(c, b, samples, power, true, 0, 0.f, 0.f, 0.f, static_cast<cudaStream_t>(stream));
 }
 
 int spev_mel_project(spev_ctx* c, const float* power, int64_t n_frames, float* out, int mode,
                      float floor_v, float lo, float hi, void* stream) {
-    int rc = with_device(c);
-    if (rc) return rc;
+    SPEV_ON_CTX_DEVICE(c);
     SPEV_REQUIRE(mode == 0 || mode == 1, SPEV_E_INVALID, "spev_mel_project: mode must be 0 or 1");
     return launch_mel_project_tc(c, power, n_frames, out, mode, floor_v, lo, hi, static_cast<cudaStream_t>(stream));
 }
 
 int spev_mel_to_mag(spev_ctx* c, const spev_batch* b, const float* mel, int layout, int is_log,
                     float* S, int64_t ld_s, void* stream) {
-    int rc = with_device(c);
-    if (rc) return rc;
+    SPEV_ON_CTX_DEVICE(c);
     SPEV_REQUIRE(b, SPEV_E_INVALID, "spev_mel_to_mag: batch is null");
     // frame-major input: TMA-staged tcgen05 (3xTF32) GEMM; [n_mels, T] items: FFMA kernel
     const bool tc_ok = c->use_tc && layout == 0 && c->n_mels % 4 == 0 && ld_s % 4 == 0 && b->n_frames > 0 &&
@@ -428,21 +444,18 @@ int spev_mel_to_mag(spev_ctx* c, const spev_batch* b, const float* mel, int layo
 }
 
 int spev_istft(spev_ctx* c, const spev_batch* b, const void* spec, int64_t ld, float* y, void* stream) {
-    int rc = with_device(c);
-    if (rc) return rc;
+    SPEV_ON_CTX_DEVICE(c);
     return launch_istft(c, b, spec, ld, y, static_cast<cudaStream_t>(stream));
 }
 
 int spev_stft(spev_ctx* c, const spev_batch* b, const float* y, void* spec, int64_t ld, void* stream) {
-    int rc = with_device(c);
-    if (rc) return rc;
+    SPEV_ON_CTX_DEVICE(c);
     return launch_stft_phase(c, b, y, nullptr, 0, spec, nullptr, ld, 0.f, 0, false, static_cast<cudaStream_t>(stream));
 }
 
 int spev_gl_phase_update(spev_ctx* c, const spev_batch* b, const float* y, const float* S, int64_t ld_s,
                          void* ang, void* tprev, int64_t ld, float alpha, int has_prev, void* stream) {
-    int rc = with_device(c);
-    if (rc) return rc;
+    SPEV_ON_CTX_DEVICE(c);
     return launch_stft_phase(c, b, y, S, ld_s, ang, tprev, ld, alpha, has_prev, true, static_cast<cudaStream_t>(stream));
 }
 
@@ -454,8 +467,7 @@ size_t spev_griffinlim_workspace_bytes(int64_t n_frames) {
 int spev_griffinlim(spev_ctx* c, const spev_batch* b, const float* S, int64_t ld_s, const float* init_phase,
                     uint64_t seed, int n_iter, float momentum, float* y, void* workspace,
                     size_t workspace_bytes, void* stream) {
-    int rc = with_device(c);
-    if (rc) return rc;
+    SPEV_ON_CTX_DEVICE(c);
     SPEV_REQUIRE(b, SPEV_E_INVALID, "spev_griffinlim: batch is null");
     SPEV_REQUIRE(n_iter >= 0 && momentum >= 0.f, SPEV_E_INVALID, "spev_griffinlim: need n_iter >= 0, momentum >= 0");
     if (b->n_frames == 0) return SPEV_OK;
@@ -470,6 +482,7 @@ int spev_griffinlim(spev_ctx* c, const spev_batch* b, const float* S, int64_t ld
     float2* tprev = ang + b->n_frames * kSpecLd;
     // librosa: (momentum / (1 + momentum)) is a Python float applied to a complex64 array
     const float alpha = static_cast<float>(static_cast<double>(momentum) / (1.0 + static_cast<double>(momentum)));
+    int rc = SPEV_OK;
     if ((rc = launch_gl_init(c, S, ld_s, init_phase, seed, ang, kSpecLd, b->n_frames, st))) return rc;
     for (int it = 0; it < n_iter; ++it) {
         if ((rc = launch_istft(c, b, ang, kSpecLd, y, st))) return rc;
@@ -479,8 +492,7 @@ int spev_griffinlim(spev_ctx* c, const spev_batch* b, const float* S, int64_t ld
 }
 
 int spev_frame_features(spev_ctx* c, const spev_batch* b, const float* samples, float* rms, float* centroid, void* stream) {
-    int rc = with_device(c);
-    if (rc) return rc;
+    SPEV_ON_CTX_DEVICE(c);
     return launch_frame_features(c, b, samples, rms, centroid, static_cast<cudaStream_t>(stream));
 }
 
@@ -531,6 +543,27 @@ int spev_variance_fuse(const float* x, const float* feats, int n_feat, const flo
                        float* feats_out, int64_t max_len, void* stream) {
     return launch_variance_fuse(x, feats, n_feat, clamp_lo_host, clamp_hi_host, conv_w, conv_b, cumsum, B, T, H, out,
                                 feats_out, max_len, static_cast<cudaStream_t>(stream));
+}
+
+int spev_lr_expand_backward(const void* grad_out, int dtype, int H, const float* grad_feats_out, int n_feat,
+                            const float* feats, const float* clamp_lo_host, const float* clamp_hi_host,
+                            const int32_t* cumsum, int B, int T, int64_t max_len, void* grad_x, float* grad_feats,
+                            void* stream) {
+    return launch_lr_expand_backward(grad_out, dtype, H, grad_feats_out, n_feat, feats, clamp_lo_host, clamp_hi_host, cumsum,
+                                     B, T, max_len, grad_x, grad_feats, static_cast<cudaStream_t>(stream));
+}
+
+size_t spev_variance_fuse_backward_workspace_bytes(int n_feat, int B, int H, int64_t max_len) {
+    return variance_fuse_backward_workspace_bytes(n_feat, B, H, max_len);
+}
+
+int spev_variance_fuse_backward(const float* grad_out, const float* feats, int n_feat, const float* clamp_lo_host,
+                                const float* clamp_hi_host, const float* conv_w, const int32_t* cumsum, int B, int T,
+                                int H, int64_t max_len, float* grad_x, float* grad_feats, float* grad_w, float* grad_b,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+    return launch_variance_fuse_backward(grad_out, feats, n_feat, clamp_lo_host, clamp_hi_host, conv_w, cumsum, B, T, H,
+                                         max_len, grad_x, grad_feats, grad_w, grad_b, workspace, workspace_bytes,
+                                         static_cast<cudaStream_t>(stream));
 }
 
 int spev_duration_rule(const float* log_dur, int64_t n, float d_control, int64_t* dur, void* stream) {

@@ -54,6 +54,9 @@ def bucketize_embed(values: torch.Tensor, boundaries: torch.Tensor, table: torch
     v = _cuda_f32(values, "values")
     b = _cuda_f32(boundaries, "boundaries")
     tb = _cuda_f32(table, "table")
+    if tb.dim() != 2 or tb.shape[0] < b.numel() + 1:
+        # bucket len(boundaries) is reachable (NaN, +inf, values above the last boundary): F.embedding would raise
+        raise IndexError(f"table must have at least len(boundaries)+1 = {b.numel() + 1} rows (got {tuple(tb.shape)})")
     H = tb.shape[1]
     idx = torch.empty(v.shape, dtype=torch.int64, device=v.device) if return_index else None
     if accumulate_into is not None:

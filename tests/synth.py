@@ -78,6 +78,11 @@ def lr_edge_cases():
     return cases
 
 
+def upstream_grad(shape, seed: int) -> np.ndarray:
+    """N(0,1) upstream gradient (``dL/d out``) shared between the golden generator and the GPU backward tests."""
+    return np.random.default_rng(seed).standard_normal(tuple(int(s) for s in shape)).astype(np.float32)
+
+
 def log_durations(seed: int = 7, B: int = 32, T: int = 200) -> np.ndarray:
     r = np.random.default_rng(seed)
     return np.clip(r.standard_normal((B, T)), -4, 4).astype(np.float32)

@@ -74,3 +74,37 @@ def test_patch_model_swaps_length_regulator():
     finally:
         sp.uninstall()
     assert ref.LengthRegulator is orig
+
+
+def test_passthrough_binds_through_librosa_signatures():
+    """Legitimate librosa calls the shims do not implement exactly reach the original function instead of raising
+    TypeError: feature input S=, htk/norm/dtype variations, unknown keywords; spelled-out defaults and a positional
+    signal are accepted."""
+    import importlib
+    inst = importlib.import_module("spev_tts_b200.install")
+    from spev_tts_b200 import features, pitch, spectral
+    seen = []
+
+    def melspectrogram(*, y=None, sr=22050, S=None, n_fft=2048, hop_length=512, win_length=None, window="hann",
+                       center=True, pad_mode="constant", power=2.0, **kwargs):
+        seen.append("mel")
+        return "orig"
+
+    def rms(*, y=None, S=None, frame_length=2048, hop_length=512, center=True, pad_mode="constant", dtype=np.float32):
+        seen.append("rms")
+        return "orig"
+
+    def pyin(y, *, fmin, fmax, sr=22050, frame_length=2048, hop_length=None, fill_na=np.nan):
+        return "orig"
+    y = np.zeros(4096, np.float32)
+    w = inst._passthrough(spectral.melspectrogram, melspectrogram)
+    assert w(S=np.ones((513, 4), np.float32), sr=22050) == "orig"                    # spectrogram input
+    assert w(y=y, sr=22050, n_fft=1024, hop_length=256, n_mels=80, htk=True) == "orig"
+    assert w(y=y, sr=22050, n_fft=1024, hop_length=256, n_mels=80, dtype=np.float64) == "orig"
+    assert w(y=y, sr=22050, n_fft=1024, hop_length=256, n_mels=80, some_future_kwarg=1) == "orig"
+    assert inst._passthrough(features.rms, rms)(S=np.ones((1025, 4), np.float32)) == "orig"
+    assert seen == ["mel"] * 4 + ["rms"]
+    b = inst._bind(spectral.melspectrogram, melspectrogram, (), dict(y=y, S=None, htk=False, norm="slaney", n_fft=1024))
+    assert set(b) == {"y", "n_fft"}
+    assert set(inst._bind(pitch.pyin, pyin, (y,), dict(fmin=60, fmax=500))) == {"y", "fmin", "fmax"}
+    assert inst._as_float64(np.zeros(3, np.float32)).dtype == np.float64
