@@ -4,21 +4,25 @@
     python bench.py --gpus N --steps K --warmup W            (our arm: sm_100a kernels)
     python bench.py --impl reference --gpus N --steps K ...  (reference arm: CPU path)
 
-Metric (BASELINE.json): mel frames/s (STFT -> 80-mel log-spectrogram) on the LJSpeech-shaped
-cache build (configs[3]: 13,100 synthetic utterances of 1-10 s at 22.05 kHz, 6.35 GB of float32
-samples, ~6.2 M frames per GPU -- far larger than the 126 MB L2, so no L2 flush is needed
-between steps).  One "step" = one pass of the fused kernel over the rank's whole shard.
-Scaling is weak: every rank builds the cache of its own 13,100-utterance shard (seed + rank);
-the path has no data-path collective, the NCCL gather of shards is timed separately and
-reported under "gather".
+Metric (BASELINE.json): mel frames/s (STFT -> 80-mel log-spectrogram) on the LJSpeech-shaped cache build
+(configs[3]: 13,100 synthetic utterances of 1-10 s at 22.05 kHz = 6.35 GB of float32 samples, ~6.2 M frames -- far
+larger than the 126 MB L2, so no L2 flush is needed between steps).
 
-The same JSON line also carries the second half of the metric, Griffin-Lim audio-seconds/s on
-configs[2] (16 x [80,800] log-mels, 60 iterations), with its own roofline, under "griffinlim",
-and the LengthRegulator/bucketize timing on configs[1] under "length_regulator".
+STRONG scaling, as configs[3] says: the corpus is FIXED (seed 4, the same 13,100 utterances for every N) and is
+sharded by utterance across the N ranks (greedy length balancing); one "step" is the whole multi-GPU job -- every
+rank's fused kernel over its shard AND the NCCL gather of the shards into rank 0's cache (chunked, overlapped with the
+kernel).  `value` = corpus frames / that time; `kernel_only` (no gather: every data-parallel rank keeps its shard
+resident), `gather_serial` (kernel, then gather) and the gather's own bandwidth are reported beside it.  At N = 1
+there is nothing to gather and a step is one launch over the whole corpus.
 
-The reference arm times the reference's own CPU implementation of the path: the oracle
-restatement of librosa 0.11 (``oracle/librosa_restated.py``; librosa itself is not installable
-here) fanned over all host cores, on a bounded sample of the same workload.
+The same JSON line also carries the second half of the metric, Griffin-Lim audio-seconds/s on configs[2] (16 x
+[80,800] log-mels, 60 iterations), with its own roofline, under "griffinlim", and the LengthRegulator / bucketize
+timing on configs[1] under "length_regulator".
+
+The reference arm times the reference's own CPU implementation of the path: real librosa when it is importable on the
+box, else the oracle restatement of librosa 0.11 (``oracle/librosa_restated.py``), fanned over all host
+cores, on a bounded sample of the same workload.  Its `value` and `ms_per_step` share one basis: wall time of the
+pooled map over the sample.
 """
 from __future__ import annotations
 
@@ -38,6 +42,9 @@ sys.path.insert(0, ROOT)
 SR, HOP, N_MELS = 22050, 256, 80
 ALG_BYTES_PER_FRAME = 1344          # 256 new samples * 4 B read + 80 * 4 B written
 NCU_DRAM_BYTES_PER_FRAME = 1339.6   # dram__bytes_read+write of k_stft_mel<0> / frames, profiles/r01e_ncu_forward_kernels.txt
+NCU_TRAFFIC_SOURCE = "ncu --set full, profiles/r01e_ncu_forward_kernels.txt (1,339.6 B/frame measured)"
+NCU_ISSUE_NOTE = {"warp_instr_per_frame": 1090, "issue_active_pct": 65.0, "lsu_wavefront_pct": 61.3,
+                  "note": "co-limited by issue slots and the shared-memory pipe, not HBM"}
 GL_BYTES_PER_FRAME_ITER = 20516
 N_UTTS = 13100
 
@@ -114,13 +121,30 @@ def _cpu_worker_init():
         pass
 
 
-def _cpu_logmel_job(args):
-    seed, n = args
-    from oracle import librosa_restated as lr
-    y = (0.05 * np.random.default_rng(seed).standard_normal(n)).astype(np.float32)
-    t = time.perf_counter()
-    m = lr.reference_logmel(y)
-    return m.shape[0], time.perf_counter() - t
+_CPU_WAVES = None          # the bounded sample, generated in the parent before the pool forks
+_USE_LIBROSA = False
+
+
+def have_librosa() -> bool:
+    try:
+        import librosa  # noqa: F401
+        import librosa.feature  # noqa: F401
+        return hasattr(librosa.feature, "melspectrogram")
+    except Exception:
+        return False
+
+
+def _cpu_logmel_job(i):
+    y = _CPU_WAVES[i]
+    if _USE_LIBROSA:       # the reference's own statements, spev_real_metrics.py:363-367 + :421
+        import librosa
+        mel = librosa.feature.melspectrogram(y=y, sr=SR, n_fft=1024, hop_length=HOP, n_mels=N_MELS)
+        mel = np.clip(np.log(np.clip(mel, 1e-5, None)), -10, 2)
+        m = np.ascontiguousarray(mel.T, dtype=np.float32)
+    else:
+        from oracle import librosa_restated as lr
+        m = lr.reference_logmel(y)
+    return m.shape[0]
 
 
 def _cpu_gl_job(args):
@@ -133,23 +157,40 @@ def _cpu_gl_job(args):
     return (T - 1) * HOP / SR, time.perf_counter() - t
 
 
-def cpu_logmel_throughput(n_utts: int, procs: int, seed: int = 4):
-    """frames/s of the restated reference path on `n_utts` cfg4-shaped utterances."""
-    import multiprocessing as mp
-    from tests import synth
-    lens = synth.utterance_lengths(seed=seed, n_utts=N_UTTS)[:n_utts]
-    jobs = [(seed * 100000 + i, int(n)) for i, n in enumerate(lens)]
-    os.environ.setdefault("OMP_NUM_THREADS", "1")
-    t = time.perf_counter()
-    if procs > 1:
-        with mp.get_context("fork").Pool(procs, initializer=_cpu_worker_init) as pool:
-            res = pool.map(_cpu_logmel_job, jobs, chunksize=4)
-    else:
-        res = [_cpu_logmel_job(j) for j in jobs]
-    wall = time.perf_counter() - t
-    frames = sum(r[0] for r in res)
-    busy = sum(r[1] for r in res) / max(1, procs)    # per-worker compute time (data generation excluded)
-    return frames / busy, frames, wall
+class CpuLogmel:
+    """The reference's CPU log-mel path on a bounded sample of the cfg4 corpus, one utterance per task over a pool of
+    `procs` single-threaded workers.  One time basis everywhere: WALL time of the pooled map (pool start-up and data
+    generation happen once, before the first step)."""
+
+    def __init__(self, n_utts: int, procs: int, seed: int = 4):
+        import multiprocessing as mp
+        from tests import synth
+        global _CPU_WAVES, _USE_LIBROSA
+        lens = synth.utterance_lengths(seed=seed, n_utts=N_UTTS)[:n_utts]
+        rng = np.random.default_rng(seed)
+        _CPU_WAVES = [(0.05 * rng.standard_normal(int(n))).astype(np.float32) for n in lens]
+        _USE_LIBROSA = have_librosa()
+        self.kind = "reference" if _USE_LIBROSA else "port"
+        self.impl = "librosa.feature.melspectrogram + log/clip" if _USE_LIBROSA else "oracle/librosa_restated.py"
+        self.n, self.procs = len(lens), procs
+        os.environ.setdefault("OMP_NUM_THREADS", "1")
+        self.pool = mp.get_context("fork").Pool(procs, initializer=_cpu_worker_init) if procs > 1 else None
+
+    def step(self):
+        """-> (frames/s, frames, wall seconds)"""
+        t = time.perf_counter()
+        if self.pool is not None:
+            res = self.pool.map(_cpu_logmel_job, range(self.n), chunksize=4)
+        else:
+            res = [_cpu_logmel_job(i) for i in range(self.n)]
+        wall = time.perf_counter() - t
+        frames = int(sum(res))
+        return frames / wall, frames, wall
+
+    def close(self):
+        if self.pool is not None:
+            self.pool.close()
+            self.pool.join()
 
 
 def _cpu_pyin_job(args):
@@ -189,8 +230,7 @@ def cpu_gl_throughput(n_items: int, T: int, n_iter: int, procs: int):
     else:
         res = [_cpu_gl_job(j) for j in jobs]
     wall = time.perf_counter() - t
-    busy = sum(r[1] for r in res) / max(1, min(procs, n_items))
-    return sum(r[0] for r in res) / busy, wall
+    return sum(r[0] for r in res) / wall, wall
 
 
 def run_reference(args):
@@ -199,28 +239,31 @@ def run_reference(args):
         return 0
     cores = os.cpu_count() or 1
     n_utts = args.ref_utts
-    vals = []
+    cpu = CpuLogmel(n_utts, cores)
     for _ in range(args.warmup):
-        cpu_logmel_throughput(max(8, n_utts // 8), cores)
-    t_all = time.perf_counter()
+        cpu.step()
+    walls, frames = [], 0
     for _ in range(args.steps):
-        v, frames, wall = cpu_logmel_throughput(n_utts, cores)
-        vals.append(v)
-    ms = (time.perf_counter() - t_all) * 1e3 / max(1, args.steps)
-    value = float(np.mean(vals))
+        _, frames, wall = cpu.step()
+        walls.append(wall)
+    cpu.close()
+    ms = float(np.mean(walls)) * 1e3
+    value = frames / (ms * 1e-3)                      # same basis as ms_per_step: wall time of one pooled pass
     gl_v, gl_wall = cpu_gl_throughput(min(cores, 16), 800, 60, cores)
-    sample = f"{n_utts} of {N_UTTS} cfg4 utterances per step ({frames} frames), {cores} processes"
+    sample = f"{n_utts} of {N_UTTS} cfg4 utterances per step ({frames} frames), {cores} processes, {cpu.impl}"
     line = {
         "impl": "reference", "metric": "mel frames/s (STFT->80-mel log, cache build)", "value": value,
         "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64 FFT / f32 mel (librosa semantics)", "data": "synthetic",
         "config": {"workload": "cfg4: 13,100 synthetic utterances 1-10 s @22.05 kHz (bounded sample)",
                    "n_fft": 1024, "hop": 256, "n_mels": 80},
-        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": cpu.kind, "sample": sample,
+                         "time_basis": "wall time of the pooled map"},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "griffinlim": {"value": gl_v, "unit": "audio-s/s", "n_iter": 60, "cores": cores,
-                       "sample": f"{min(cores, 16)} x [80,800], wall {gl_wall:.1f}s, NNLS L-BFGS-B on"},
+                       "sample": f"{min(cores, 16)} x [80,800], wall {gl_wall:.1f}s, NNLS L-BFGS-B on",
+                       "time_basis": "wall time of the pooled map"},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
@@ -268,57 +311,98 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    # ---------------- cfg4 shard of this rank (weak scaling: a full 13,100-utterance set) --------
-    lens = synth.utterance_lengths(seed=4 + rank, n_utts=args.utts)
-    starts = spcache.aligned_offsets(lens)      # item starts are multiples of 4 samples (16-B cp.async path)
+    # ---------------- cfg4: the FIXED 13,100-utterance corpus, sharded by utterance over the ranks --------
+    lens = synth.utterance_lengths(seed=4, n_utts=args.utts)
+    plan = spcache.plan_shards(lens, world, n_chunks=args.chunks)
+    bld = spcache.ShardedCacheBuilder(plan, rank, dev, dst=0, sr=SR, n_mels=N_MELS, reserve_sms=args.reserve_sms)
+    ctx = bld.ctx
+    mine = plan.shards[rank]
+    starts = bld.sample_off                     # item starts are multiples of 4 samples (16-B cp.async path)
     total = int(starts[-1])
-    g = torch.Generator(device=dev).manual_seed(4 + rank)
-    samples = torch.empty(total, dtype=torch.float32, device=dev)
+    # every rank derives the same corpus from seed 4 and keeps its shard's utterances (setup, untimed)
+    full_starts = spcache.aligned_offsets(lens)
+    g = torch.Generator(device=dev).manual_seed(4)
+    full = torch.empty(int(full_starts[-1]), dtype=torch.float32, device=dev)
     blk = 1 << 27
-    for s in range(0, total, blk):       # generate in blocks to bound the temporary
-        e = min(total, s + blk)
-        samples[s:e] = torch.randn(e - s, generator=g, device=dev) * 0.05
-    ctx = sp.Context.get(dev, sr=SR, n_mels=N_MELS)
-    batch = sp.make_batch(ctx, n_samples=lens, sample_off=starts)
-    F = batch.n_frames
-    out = torch.empty((F, N_MELS), dtype=torch.float32, device=dev)
+    for s0 in range(0, full.numel(), blk):       # generate in blocks to bound the temporary
+        e0 = min(full.numel(), s0 + blk)
+        full[s0:e0] = torch.randn(e0 - s0, generator=g, device=dev) * 0.05
+    if world == 1:
+        samples = full
+    else:
+        samples = torch.zeros(total, dtype=torch.float32, device=dev)
+        spcache.copy_segments(full.view(-1, 1), samples.view(-1, 1), full_starts[mine], starts[:-1], lens[mine])
+        torch.cuda.synchronize(dev)
+    del full
+    torch.cuda.empty_cache()
+    batch = bld.batch_all
+    F = batch.n_frames                           # this rank's frames
+    F_total = plan.n_rows                        # corpus frames (the same for every N)
+    out = bld.alloc_out()                        # rank 0: the gathered cache [F_total, 80]; others: their shard
+    out_local = bld.local_rows(out)
 
-    def step():
-        sp.logmel_flat(samples, lens, out=out, batch=batch)
+    def timed(fn, n, warm):
+        """n steps back to back, bracketed by barrier + synchronize; -> (max-over-ranks ms per step, this rank's
+        mean per-step ms from CUDA events around each step)"""
+        for _ in range(warm):
+            fn()
+        barrier()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+        a0 = torch.cuda.Event(enable_timing=True); a1 = torch.cuda.Event(enable_timing=True)
+        barrier()
+        a0.record()
+        for ea, eb in evs:
+            ea.record(); fn(); eb.record()
+        a1.record()
+        barrier()
+        return max_over_ranks(a0.elapsed_time(a1)) / n, float(np.mean([ea.elapsed_time(eb) for ea, eb in evs]))
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
+    W = max(args.warmup, 3)
     sampler = ClockSampler(local).start() if rank == 0 else None
     time.sleep(0.3)
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
     t0 = time.perf_counter()
-    e_all0 = torch.cuda.Event(enable_timing=True); e_all1 = torch.cuda.Event(enable_timing=True)
-    e_all0.record()
-    for a, b in evs:
-        a.record(); step(); b.record()
-    e_all1.record()
-    barrier()
-    t1 = time.perf_counter()
-    total_ms = e_all0.elapsed_time(e_all1)
-    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
-    total_ms = max_over_ranks(total_ms)
+    # (1) kernels only: every rank builds its shard and keeps it (the sharded-resident alternative)
+    ko_ms, kern_ms = timed(lambda: bld.build(samples, out, gather=False), args.steps, W)
     kern_ms_max = max_over_ranks(kern_ms)
-    frames_all = sum_over_ranks(float(F))
-    ms_per_step = total_ms / args.steps
-    value = frames_all / (ms_per_step * 1e-3)
+    launches_per_step = 1
+    gather = None
+    if world == 1:
+        ms_per_step = ko_ms
+    else:
+        # (2) the whole job: kernels + gather into rank 0, chunked and overlapped  -> the headline value
+        l0 = bld.launches
+        ov_ms, _ = timed(lambda: bld.build(samples, out, gather=True, overlap=True), args.steps, W)
+        launches_per_step = (bld.launches - l0) // (args.steps + W)
+        # (3) for comparison: kernel, then one grouped gather (no overlap), and the gather alone
+        se_ms, _ = timed(lambda: bld.build(samples, out, gather=True, overlap=False), max(3, args.steps // 2), 1)
+        peers_rows = F_total - int(plan.row_off[1] - plan.row_off[0])
+        nbytes = peers_rows * N_MELS * 4
+        ms_per_step = ov_ms
+        gather = {"bytes_into_root": nbytes, "backend": "nccl send/recv (batch_isend_irecv), receives land in their final rows",
+                  "overlapped_ms_per_step": ov_ms, "serial_ms_per_step": se_ms, "kernel_only_ms_per_step": ko_ms,
+                  "gather_alone_ms": se_ms - ko_ms, "gather_alone_GBps": nbytes / max(1e-9, (se_ms - ko_ms) * 1e-3) / 1e9,
+                  "chunks_per_rank": args.chunks, "reserved_sms": args.reserve_sms,
+                  "limiter": "root NVLink ingress: (N-1)/N of the 1.99 GB cache must enter rank 0; lower bound = bytes / "
+                             "measured peer-copy bandwidth (770 GB/s per direction, B200_PROFILING.md)",
+                  "ingress_floor_ms": nbytes / 770e9 * 1e3}
+    t1 = time.perf_counter()
+    value = F_total / (ms_per_step * 1e-3)
+    kernel_only = {"value": F_total / (ko_ms * 1e-3), "unit": "frames/s", "ms_per_step": ko_ms,
+                   "note": "no gather: each data-parallel rank keeps its shard resident (ResidentCache)"}
     achieved = ALG_BYTES_PER_FRAME * F / (kern_ms * 1e-3) / 1e9      # GB/s, this rank's kernel
+    if world > 1 and rank == 0:
+        gc = spcache.GatheredCache(out, plan)    # spot check below reads utterances through the gathered layout
 
-    # ---------------- e2e: pinned host samples -> public API -> pinned host cache --------------
+    # ---------------- e2e: pinned host samples -> public API -> pinned host cache (this rank's shard) -------
     e2e = None
     if not args.no_e2e:
         host = torch.empty(total, dtype=torch.float32).pin_memory()
         host.copy_(samples)
         out_host = torch.empty((F, N_MELS), dtype=torch.float32).pin_memory()
+        pcie = measure_pcie(dev, host, out_host)
         builder = spcache.LogMelCacheBuilder(dev, sr=SR, n_mels=N_MELS)
-        plan = spcache.plan_chunks(lens, builder.chunk_samples, starts)
-        builder.build(host, lens, out_host=out_host, plan=plan)        # warm-up (allocs, descriptors)
+        cplan = spcache.plan_chunks(lens[mine], builder.chunk_samples, starts)
+        builder.build(host, lens[mine], out_host=out_host, plan=cplan)        # warm-up (allocs, descriptors)
         torch.cuda.synchronize(dev)
         n_e2e = max(1, min(args.steps, args.e2e_steps))
         barrier()
@@ -326,16 +410,22 @@ def run_ours(args):
         l0 = builder.launches
         e0.record()
         for _ in range(n_e2e):
-            builder.build(host, lens, out_host=out_host, plan=plan)
+            builder.build(host, lens[mine], out_host=out_host, plan=cplan)
         e1.record()
         barrier()
         e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / n_e2e
         e2e_launches = (builder.launches - l0) // n_e2e
-        ok = bool(torch.equal(out_host[: 4096].to(dev), out[: 4096]))
-        e2e = {"value": frames_all / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": total * 4,
-               "d2h_bytes_per_step": F * N_MELS * 4, "ms_per_step": e2e_ms, "steps": n_e2e,
+        ok = bool(torch.equal(out_host[: 4096].to(dev), out_local[: 4096]))
+        h2d_b, d2h_b = total * 4, F * N_MELS * 4
+        floor_ms = max(h2d_b / pcie["h2d_GBps"], d2h_b / pcie["d2h_GBps"]) / 1e6
+        e2e = {"value": F_total / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d_b,
+               "d2h_bytes_per_step": d2h_b, "ms_per_step": e2e_ms, "steps": n_e2e,
                "launches_per_step": e2e_launches, "matches_device_result": ok,
                "api": "spev_tts_b200.cache.LogMelCacheBuilder.build (pinned host in/out, 3-stream pipeline)",
+               "bytes_note": "per rank (its shard); all ranks copy concurrently",
+               "roofline": {"bound": "pcie", "peak": pcie, "floor_ms": floor_ms, "frac": floor_ms / e2e_ms,
+                            "note": "floor = max(H2D bytes / measured pinned H2D GB/s, D2H bytes / measured D2H GB/s) "
+                                    "of this rank measured alone in this run (PCIe is full duplex)"},
                "host_numa_binding_rank0": numa}
         # extra: the same corpus as 16-bit PCM on the host (the on-disk format of LJSpeech-style
         # corpora; pcm/32768 is exactly what the reference's loader produces) -> half the H2D bytes
@@ -344,120 +434,197 @@ def run_ours(args):
         host16 = torch.empty(total, dtype=torch.int16).pin_memory()
         host16.copy_(pcm)
         del pcm
-        builder.build(host16, lens, out_host=out_host, plan=plan)
+        builder.build(host16, lens[mine], out_host=out_host, plan=cplan)
         torch.cuda.synchronize(dev)
         barrier()
         p0 = torch.cuda.Event(enable_timing=True); p1 = torch.cuda.Event(enable_timing=True)
         p0.record()
         for _ in range(n_e2e):
-            builder.build(host16, lens, out_host=out_host, plan=plan)
+            builder.build(host16, lens[mine], out_host=out_host, plan=cplan)
         p1.record()
         barrier()
         pcm_ms = max_over_ranks(p0.elapsed_time(p1)) / n_e2e
-        e2e["pcm16_host_input"] = {"value": frames_all / (pcm_ms * 1e-3), "unit": "frames/s", "ms_per_step": pcm_ms,
-                                   "h2d_bytes_per_step": total * 2, "d2h_bytes_per_step": F * N_MELS * 4,
+        pfloor = max(total * 2 / pcie["h2d_GBps"], d2h_b / pcie["d2h_GBps"]) / 1e6
+        e2e["pcm16_host_input"] = {"value": F_total / (pcm_ms * 1e-3), "unit": "frames/s", "ms_per_step": pcm_ms,
+                                   "h2d_bytes_per_step": total * 2, "d2h_bytes_per_step": d2h_b,
+                                   "roofline_frac_of_pcie_floor": pfloor / pcm_ms,
                                    "note": "input quantised to int16 (not the float32 arm's exact values)"}
         del host16, out_host, builder
     clocks = sampler.stop(t0, t1) if sampler else None
 
-    # ---------------- gather of shards (the one collective; timed separately) -------------------
-    gather = None
+    # ---------------- gather integrity: every rank's rows arrived where the plan says (exact checksums) ---------
+    gather_ok = None
     if world > 1:
-        spcache.gather_shards(out[:1024], dst=0)     # warm-up: NCCL P2P connections are set up lazily
-        barrier()
-        g0 = torch.cuda.Event(enable_timing=True); g1 = torch.cuda.Event(enable_timing=True)
-        g0.record()
-        parts, counts = spcache.gather_shards(out, dst=0)
-        g1.record()
-        barrier()
-        gms = max_over_ranks(g0.elapsed_time(g1))
-        nbytes = sum(counts[1:]) * N_MELS * 4
-        gather = {"ms": gms, "bytes_into_root": nbytes, "GBps": nbytes / (gms * 1e-3) / 1e9,
-                  "backend": "nccl send/recv (no gatherv)"}
-        del parts
+        bld.build(samples, out, gather=True, overlap=True)
+        mysum = out_local.double().sum().reshape(1)
+        sums = [torch.zeros_like(mysum) for _ in range(world)]
+        dist.all_gather(sums, mysum)
+        if rank == 0:
+            gather_ok = all(bool(out[int(plan.row_off[r]): int(plan.row_off[r + 1])].double().sum() == sums[r][0])
+                            for r in range(world))
+            gather["rows_checksum_matches_every_rank"] = gather_ok
 
-    # ---------------- second half of the metric: Griffin-Lim on cfg3 (rank 0 reports) ------------
+    # ---------------- second half of the metric and the other configs ------------------------------------------
     gl = lr_res = tc = cfg5 = feat = coll = pyin_res = None
+    lens_mine = lens[mine]
     if not args.no_gl:
+        cfg5 = bench_cfg5(sp, dev, hbm_peak, spcache, world, max_over_ranks, sum_over_ranks)     # all ranks (aggregated)
         if rank == 0:
             pyin_res = bench_pyin(sp, dev, hbm_peak, args, world == 1 and not args.no_cpu)
-        cfg5 = bench_logmel_cfg5(sp, dev, hbm_peak, spcache)
-        tc = bench_mel_gemm_tc(sp, dev, samples, lens, starts, hbm_peak, out)
-        feat = bench_frame_features(sp, dev, samples, lens, starts, hbm_peak)
-        coll = bench_collate(sp, dev, out, batch, hbm_peak)
-        gl = bench_griffinlim(sp, dev, hbm_peak, args)
-        lr_res = bench_length_regulator(sp, dev, args)
+            tc = bench_mel_gemm_tc(sp, dev, samples, lens_mine, starts, hbm_peak, out_local)
+            feat = bench_frame_features(sp, dev, samples, lens_mine, starts, hbm_peak)
+            coll = bench_collate(sp, dev, out_local, batch, hbm_peak)
+            gl = bench_griffinlim(sp, dev, hbm_peak, args)
+            lr_res = bench_length_regulator(sp, dev, args)
     parity = None
     if rank == 0 and not args.no_cpu:
         # spot-check of the measured result against the CPU oracle on the same inputs (checker only)
         from oracle import librosa_restated as lr_oracle
         errs = []
-        for u in (0, 1, args.utts // 2, args.utts - 1):
-            yy = samples[int(starts[u]): int(starts[u]) + int(lens[u])].cpu().numpy()
+        nl = len(mine)
+        for i in (0, 1, nl // 2, nl - 1):
+            yy = samples[int(starts[i]): int(starts[i]) + int(lens_mine[i])].cpu().numpy()
             ref_lm = lr_oracle.reference_logmel(yy)
-            got_lm = out[int(batch.frame_off[u]): int(batch.frame_off[u + 1])].cpu().numpy()
+            got_lm = out_local[int(batch.frame_off[i]): int(batch.frame_off[i + 1])].cpu().numpy()
             errs.append(float(np.abs(ref_lm - got_lm).max()))
         parity = {"logmel_max_abs_err_vs_oracle": max(errs), "tolerance": 1e-4, "utterances_checked": 4}
-    del samples, out
+        if not args.no_gl:
+            parity.update(parity_griffinlim(sp, dev, lr_oracle))
+    del samples, out, out_local
     torch.cuda.empty_cache()
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
-            v, frames, wall = cpu_logmel_throughput(args.ref_utts, cores)
-            cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
-                   "sample": f"{args.ref_utts} of {N_UTTS} cfg4 utterances ({frames} frames) in {wall:.1f}s, "
-                             f"oracle/librosa_restated.py over {cores} processes"}
+            c = CpuLogmel(args.ref_utts, cores)
+            c.step()                                                  # warm-up: worker imports, page faults
+            v, frames, wall = c.step()
+            c.close()
+            cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": c.kind,
+                   "sample": f"{args.ref_utts} of {N_UTTS} cfg4 utterances ({frames} frames) in {wall:.1f}s wall, "
+                             f"{c.impl} over {cores} processes", "time_basis": "wall time of the pooled map"}
         line = {
             "metric": "mel frames/s (STFT->80-mel log, cache build)", "value": value, "unit": "frames/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"cfg4: {args.utts} synthetic utterances 1-10 s @22.05 kHz per GPU "
-                                   f"({total * 4 / 1e9:.2f} GB samples, {F} frames); inputs >> L2 (126 MB), no flush needed",
-                       "n_fft": 1024, "hop": 256, "n_mels": 80, "utterances_per_gpu": args.utts,
-                       "frames_per_gpu": F, "parallelism": f"utterance-sharded x{world}, no data-path collective"},
+            "n_gpus": world, "steps": args.steps, "warmup": W, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"cfg4: the fixed corpus of {args.utts} synthetic utterances 1-10 s @22.05 kHz "
+                                   f"({int(full_starts[-1]) * 4 / 1e9:.2f} GB samples, {F_total} frames), sharded by utterance over "
+                                   f"{world} GPU(s); step = every rank's fused kernel"
+                                   + (" + NCCL gather of the shards into rank 0 (chunked, overlapped)" if world > 1 else "")
+                                   + "; inputs >> L2 (126 MB), no flush needed",
+                       "n_fft": 1024, "hop": 256, "n_mels": 80, "utterances": args.utts, "frames": F_total,
+                       "frames_this_rank": F, "parallelism": f"utterance-sharded x{world}; one exchange: gather of shards"},
+            "kernel_only": kernel_only,
             "roofline": {"bound": "hbm", "kernel": "k_stft_mel<0>", "achieved": achieved, "peak": hbm_peak,
                          "unit": "GB/s", "frac": achieved / hbm_peak, "peak_source": peak_src,
                          "alg_bytes_per_frame": ALG_BYTES_PER_FRAME, "kernel_ms": kern_ms,
                          "kernel_ms_max_over_ranks": kern_ms_max, "traffic": NCU_DRAM_BYTES_PER_FRAME * F,
-                         "traffic_source": "ncu --set full, profiles/r01e_ncu_forward_kernels.txt (1,339.6 B/frame measured)",
-                         "issue_slots": {"warp_instr_per_frame": 1090, "issue_active_pct": 65.0, "lsu_wavefront_pct": 61.3,
-                                         "note": "co-limited by issue slots and the shared-memory pipe, not HBM"},
+                         "traffic_source": NCU_TRAFFIC_SOURCE,
+                         "issue_slots": NCU_ISSUE_NOTE,
                          "note": "fp32-pipe/shared-memory bound by design (SURVEY 0.7): ~25 kFLOP FFT per 1,344 B"},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks, "parity": parity,
-            "gather": gather, "logmel_cfg5": cfg5, "mel_gemm_tc": tc, "frame_features": feat, "pyin": pyin_res, "collate": coll, "griffinlim": gl, "length_regulator": lr_res,
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps * launches_per_step, "clocks": clocks,
+            "parity": parity, "gather": gather, "cfg5": cfg5, "mel_gemm_tc": tc, "frame_features": feat,
+            "pyin": pyin_res, "collate": coll, "griffinlim": gl, "length_regulator": lr_res,
         }
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 
 
-def bench_logmel_cfg5(sp, dev, hbm_peak, spcache):
-    """cfg5-shaped cache build: 24 kHz (mel basis fmax 12 kHz), LibriTTS-R-like log-normal lengths
-    1-20 s, 4,096 utterances per GPU in one ragged launch."""
+def measure_pcie(dev, host_in, host_out):
+    """Pinned host <-> device copy bandwidth of THIS rank, measured alone and in both directions at once (the e2e
+    pipeline overlaps them): the denominator of e2e.roofline."""
+    import torch
+    n_in = min(host_in.numel(), 1 << 28)           # <= 1 GiB of float32
+    n_out = min(host_out.numel(), 1 << 27)
+    d_in = torch.empty(n_in, dtype=host_in.dtype, device=dev)
+    d_out = torch.empty(n_out, dtype=host_out.dtype, device=dev)
+    hi, ho = host_in.view(-1)[:n_in], host_out.view(-1)[:n_out]
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def run(do_in, do_out):
+        torch.cuda.synchronize(dev)
+        a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+        a.record()
+        s1.wait_event(a); s2.wait_event(a)
+        if do_in:
+            with torch.cuda.stream(s1):
+                d_in.copy_(hi, non_blocking=True)
+        if do_out:
+            with torch.cuda.stream(s2):
+                ho.copy_(d_out, non_blocking=True)
+        torch.cuda.current_stream(dev).wait_stream(s1); torch.cuda.current_stream(dev).wait_stream(s2)
+        b.record(); torch.cuda.synchronize(dev)
+        return a.elapsed_time(b) * 1e-3
+    run(True, True)
+    t_in = min(run(True, False) for _ in range(2))
+    t_out = min(run(False, True) for _ in range(2))
+    t_both = min(run(True, True) for _ in range(2))
+    bi, bo = n_in * hi.element_size(), n_out * ho.element_size()
+    return {"h2d_GBps": bi / t_in / 1e9, "d2h_GBps": bo / t_out / 1e9,
+            "duplex_GBps": (bi + bo) / t_both / 1e9, "unit": "GB/s", "how": "cudaMemcpyAsync from/to pinned memory, "
+            f"{bi >> 20} MiB in / {bo >> 20} MiB out, best of 2, this rank alone"}
+
+
+def parity_griffinlim(sp, dev, lr_oracle):
+    """Spectral-convergence delta of one cfg3 item (80 x 800, 60 iterations, shared initial phase) against the CPU
+    oracle -- the north-star's Griffin-Lim tolerance (<= 1e-3), checked inside the measured run."""
+    from tests import synth
+    y = synth.speechy(seed=300, n=799 * HOP)
+    lm = lr_oracle.reference_logmel(y).T.copy()                    # [80, 800]
+    ph = synth.init_phase((513, 800), seed=3)
+    S = lr_oracle.mel_to_stft(np.exp(lm), sr=SR, n_fft=1024, fmin=0, fmax=8000, lbfgs=True)
+    w_ref = lr_oracle.griffinlim(S, n_iter=60, hop_length=HOP, n_fft=1024, init_phase=ph)
+    w = sp.Vocoder(n_iter=60, device=dev).infer(lm, init_phase=ph)
+    sc_ref, sc = lr_oracle.spectral_convergence(w_ref, S), lr_oracle.spectral_convergence(w, S)
+    return {"griffinlim_sc_gpu": sc, "griffinlim_sc_oracle": sc_ref, "griffinlim_sc_delta": abs(sc - sc_ref),
+            "griffinlim_sc_tolerance": 1e-3, "griffinlim_case": "1 x [80,800], 60 iterations, shared init phase, NNLS L-BFGS-B on in the oracle"}
+
+
+def bench_cfg5(sp, dev, hbm_peak, spcache, world, max_over_ranks, sum_over_ranks):
+    """configs[4]: LibriTTS-R-shaped multi-speaker 24 kHz variable-length batches across the GPUs of the box.  Every
+    rank takes its own set of buckets (seed 5 + rank; weak: more GPUs = more speakers' data): STFT->log-mel on 4,096
+    utterances of 1-20 s (mel basis fmax 12 kHz) in one ragged launch, and Griffin-Lim (60 iterations) on a
+    256-utterance subset.  Aggregate = sum over ranks / slowest rank's time."""
+    import torch
+    import torch.distributed as dist
+    rank = dist.get_rank() if world > 1 else 0
+    res = {"n_gpus": world, "scaling": "weak (per-GPU buckets fixed)"}
+    res["logmel"] = _cfg5_logmel(sp, dev, hbm_peak, spcache, rank, world, max_over_ranks, sum_over_ranks)
+    res["griffinlim"] = bench_griffinlim_cfg5(sp, dev, hbm_peak, rank, world, max_over_ranks, sum_over_ranks)
+    torch.cuda.empty_cache()
+    return res
+
+
+def _cfg5_logmel(sp, dev, hbm_peak, spcache, rank, world, max_over_ranks, sum_over_ranks):
     import torch
     from tests import synth
-    lens = synth.lognormal_lengths(seed=5, n_utts=4096, sr=24000)
+    lens = synth.lognormal_lengths(seed=5 + rank, n_utts=4096, sr=24000)
     starts = spcache.aligned_offsets(lens)
-    g = torch.Generator(device=dev).manual_seed(5)
+    g = torch.Generator(device=dev).manual_seed(5 + rank)
     x = torch.randn(int(starts[-1]), generator=g, device=dev) * 0.05
     ctx = sp.Context.get(dev, sr=24000, n_mels=N_MELS)
     batch = sp.make_batch(ctx, n_samples=lens, sample_off=starts)
     out = torch.empty((batch.n_frames, N_MELS), dtype=torch.float32, device=dev)
     for _ in range(3):
         sp.logmel_flat(x, lens, sr=24000, out=out, batch=batch)
+    torch.cuda.synchronize(dev)
     a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(5):
         sp.logmel_flat(x, lens, sr=24000, out=out, batch=batch)
     b.record(); torch.cuda.synchronize(dev)
-    ms = a.elapsed_time(b) / 5
+    ms_local = a.elapsed_time(b) / 5
+    ms = max_over_ranks(ms_local)
     F = batch.n_frames
-    return {"config": {"workload": f"cfg5: 4096 utterances 1-20 s @24 kHz per GPU ({x.numel() * 4 / 1e9:.2f} GB, {F} frames)"},
-            "value": F / (ms * 1e-3), "unit": "frames/s", "ms_per_step": ms,
-            "roofline": {"bound": "hbm", "achieved": ALG_BYTES_PER_FRAME * F / (ms * 1e-3) / 1e9, "peak": hbm_peak,
-                         "unit": "GB/s", "frac": ALG_BYTES_PER_FRAME * F / (ms * 1e-3) / 1e9 / hbm_peak}}
+    F_all = sum_over_ranks(float(F))
+    return {"config": {"workload": f"cfg5: 4096 utterances 1-20 s @24 kHz per GPU ({x.numel() * 4 / 1e9:.2f} GB, {F} frames on rank 0)"},
+            "value": F_all / (ms * 1e-3), "unit": "frames/s", "ms_per_step": ms,
+            "roofline": {"bound": "hbm", "achieved": ALG_BYTES_PER_FRAME * F / (ms_local * 1e-3) / 1e9, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": ALG_BYTES_PER_FRAME * F / (ms_local * 1e-3) / 1e9 / hbm_peak,
+                         "note": "rank 0's kernel"}}
 
 
 def bench_mel_gemm_tc(sp, dev, samples, lens, starts, hbm_peak, fused_out):
@@ -669,8 +836,7 @@ def bench_griffinlim(sp, dev, hbm_peak, args):
     for _ in range(n_e):
         w = voc.infer(lm_host)
     e2e_ms = (time.perf_counter() - t) * 1e3 / n_e
-    scale = bench_griffinlim_cfg5(sp, dev, hbm_peak)
-    return {"metric": "Griffin-Lim audio-s/s", "value": audio_s / (ms * 1e-3), "unit": "audio-s/s", "cfg5_subset": scale,
+    return {"metric": "Griffin-Lim audio-s/s", "value": audio_s / (ms * 1e-3), "unit": "audio-s/s",
             "config": {"workload": "cfg3: 16 x [80,800] log-mel, 60 iterations, momentum 0.99; L2 flushed between steps"},
             "ms_per_step": ms, "launches_per_step": 2 * n_iter + 3,
             "roofline": {"bound": "hbm", "kernels": "k_istft + k_stft_phase<1>", "achieved": alg / (ms * 1e-3) / 1e9,
@@ -681,18 +847,18 @@ def bench_griffinlim(sp, dev, hbm_peak, args):
                     "h2d_bytes_per_step": int(lm.numel() * 4), "d2h_bytes_per_step": int(w.size * 4)}}
 
 
-def bench_griffinlim_cfg5(sp, dev, hbm_peak):
+def bench_griffinlim_cfg5(sp, dev, hbm_peak, rank, world, max_over_ranks, sum_over_ranks):
     """cfg5-shaped Griffin-Lim: 256 variable-length utterances per GPU (LibriTTS-R-like log-normal
     lengths 1-20 s at 24 kHz), 60 iterations, one ragged flat batch."""
     import torch
     from spev_tts_b200 import _lib
     from tests import synth
     sr, n_iter = 24000, 60
-    lens = synth.lognormal_lengths(seed=5, n_utts=256, sr=sr)
+    lens = synth.lognormal_lengths(seed=5 + rank, n_utts=256, sr=sr)
     frames = 1 + lens // HOP
     ctx = sp.Context.get(dev, sr=sr, n_mels=N_MELS, fmin=0.0, fmax=8000.0)
     fb = sp.make_batch(ctx, n_frames=frames, with_chunks=True)
-    g = torch.Generator(device=dev).manual_seed(5)
+    g = torch.Generator(device=dev).manual_seed(5 + rank)
     lm = (-4 + 2 * torch.randn(fb.n_frames, N_MELS, generator=g, device=dev)).clamp(-10, 2)   # frame-major
     S = torch.empty((fb.n_frames, _lib.SPEC_LD), dtype=torch.float32, device=dev)
     y = torch.empty(fb.n_out_samples, dtype=torch.float32, device=dev)
@@ -710,13 +876,15 @@ def bench_griffinlim_cfg5(sp, dev, hbm_peak):
     for _ in range(3):
         step()
     b.record(); torch.cuda.synchronize(dev)
-    ms = a.elapsed_time(b) / 3
+    ms_local = a.elapsed_time(b) / 3
+    ms = max_over_ranks(ms_local)
+    audio_all = sum_over_ranks(float(fb.n_out_samples) / sr)
     alg = GL_BYTES_PER_FRAME_ITER * fb.n_frames * n_iter + (2372 + 5128) * fb.n_frames
-    return {"config": {"workload": f"cfg5 subset: 256 utterances 1-20 s @24 kHz ({fb.n_frames} frames, state "
+    return {"config": {"workload": f"cfg5 subset: 256 utterances 1-20 s @24 kHz per GPU ({fb.n_frames} frames on rank 0, state "
                                    f"{fb.n_frames * 10400 / 1e6:.0f} MB >> L2), 60 iterations, ragged flat batch"},
-            "value": float(fb.n_out_samples) / sr / (ms * 1e-3), "unit": "audio-s/s", "ms_per_step": ms,
-            "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": alg / (ms * 1e-3) / 1e9 / hbm_peak}}
+            "value": audio_all / (ms * 1e-3), "unit": "audio-s/s", "ms_per_step": ms,
+            "roofline": {"bound": "hbm", "achieved": alg / (ms_local * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": alg / (ms_local * 1e-3) / 1e9 / hbm_peak, "note": "rank 0's kernels"}}
 
 
 def bench_length_regulator(sp, dev, args):
@@ -792,10 +960,99 @@ def bench_length_regulator(sp, dev, args):
     big_bytes = ob.shape[0] * ob.shape[1] * (256 + 5) * 4
     big = {"B": 512, "frames": int(ob.shape[1]), "expand_kernel_ms": kb_ms, "expand_GBps": big_bytes / (kb_ms * 1e-3) / 1e9,
            "output_GB": big_bytes / 1e9}
-    return {"B512": big, "variance_adaptor_fused_ms": fused_ms, "variance_adaptor_expand_plus_cudnn_ms": unfused_ms,"config": {"workload": "cfg2: B=32, T<=200, H=256 + 5 curves (the 6 LengthRegulator calls of one forward)"},
-            "forward_ms_wall_incl_one_sync": wall_ms, "expand_kernel_ms": k_ms,
-            "expand_GBps": out_bytes / (k_ms * 1e-3) / 1e9, "frames": int(o.shape[1]),
-            "reference_cpu_s_per_forward": "6 x 1.42 s (SURVEY App. B)"}
+    # the same forward when the caller knows max_len (training: b['mel'].size(1)): no host sync at all
+    maxF = int(o.shape[1])
+    for _ in range(3):
+        sp.regulate_variances(xd, dd, fd, max_len=maxF)
+    torch.cuda.synchronize(dev)
+    t = time.perf_counter()
+    for _ in range(n):
+        sp.regulate_variances(xd, dd, fd, max_len=maxF)
+    torch.cuda.synchronize(dev)
+    nosync_ms = (time.perf_counter() - t) * 1e3 / n
+    # training step: forward + backward of the six LengthRegulator calls (segment-sum kernels)
+    xg = xd.clone().requires_grad_(True)
+    fg = [f.clone().requires_grad_(True) for f in fd]
+
+    def fwd_bwd():
+        oe, _, ce = sp.regulate_variances(xg, dd, fg, max_len=maxF)
+        (oe.sum() + sum(c.sum() for c in ce)).backward()
+        xg.grad = None
+        for f in fg:
+            f.grad = None
+    for _ in range(3):
+        fwd_bwd()
+    torch.cuda.synchronize(dev)
+    t = time.perf_counter()
+    for _ in range(n):
+        fwd_bwd()
+    torch.cuda.synchronize(dev)
+    train_ms = (time.perf_counter() - t) * 1e3 / n
+    go = torch.ones_like(o)
+    gf = torch.ones((5, o.shape[0], maxF), device=dev)
+    ab = torch.cuda.Event(enable_timing=True); bb = torch.cuda.Event(enable_timing=True)
+    gx = torch.empty_like(xd); gfe = torch.empty((5,) + tuple(dd.shape), device=dev)
+    from spev_tts_b200 import _lib
+    from spev_tts_b200.length_regulator import _clamp_arrays
+    lo, hi = _clamp_arrays(sp.VARIANCE_CLAMPS, 5)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    ab.record()
+    for _ in range(n):
+        _lib.check(_lib.load().spev_lr_expand_backward(go.data_ptr(), 0, 256, gf.data_ptr(), 5, ft.data_ptr(), lo, hi,
+                                                       p.cumsum.data_ptr(), p.B, p.T, maxF, gx.data_ptr(), gfe.data_ptr(), st))
+    bb.record()
+    torch.cuda.synchronize(dev)
+    bwd_ms = ab.elapsed_time(bb) / n
+    # bucketize + embedding lookup (configs[1] second half): v [32,200] -> [32,200,256], and frame-level [32,maxF]
+    v, bins, table = synth.bucketize_case(seed=2)
+    vt, bt, tt = (torch.from_numpy(a_).to(dev) for a_ in (v, bins, table))
+    vfr = torch.randn(32, maxF, device=dev)
+
+    def t_buck(vv):
+        for _ in range(3):
+            sp.bucketize_embed(vv, bt, tt)
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            sp.bucketize_embed(vv, bt, tt)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / n
+    bk_ms, bk_fr_ms = t_buck(vt), t_buck(vfr)
+    buck = {"phone_level": {"elements": int(vt.numel()), "kernel_ms": bk_ms,
+                            "GBps": vt.numel() * 1028 / (bk_ms * 1e-3) / 1e9},
+            "frame_level": {"elements": int(vfr.numel()), "kernel_ms": bk_fr_ms,
+                            "GBps": vfr.numel() * 1028 / (bk_fr_ms * 1e-3) / 1e9},
+            "alg_bytes_per_element": 1028, "note": "4 B read + 1,024 B written per element; table (256 KB) stays in L2"}
+    cpu = None
+    if not args.no_cpu:
+        # same-run CPU legs on this box's host cores: the literal-loop restatement of the reference class
+        # (oracle/torch_reference.py, pinned against the class itself) and torch's own bucketize + embedding
+        from oracle import torch_reference as tr
+        xc, dc = torch.from_numpy(x), torch.from_numpy(dur)
+        lr_cpu = tr.LengthRegulator()
+        t = time.perf_counter()
+        lr_cpu(xc, dc)
+        t_h = time.perf_counter() - t
+        t = time.perf_counter()
+        lr_cpu(torch.from_numpy(feats[0]).unsqueeze(-1), dc)
+        t_1 = time.perf_counter() - t
+        vc, bc, tc_ = torch.from_numpy(v), torch.from_numpy(bins), torch.from_numpy(table)
+        torch.nn.functional.embedding(torch.bucketize(vc, bc), tc_)
+        t = time.perf_counter()
+        for _ in range(10):
+            torch.nn.functional.embedding(torch.bucketize(vc, bc), tc_)
+        t_b = (time.perf_counter() - t) / 10
+        cpu = {"length_regulator_forward_s": t_h + 5 * t_1, "cores": 1, "kind": "port",
+               "sample": f"one H=256 call ({t_h:.2f} s) + 5 x one H=1 call ({t_1:.2f} s each measured once), "
+                         "oracle/torch_reference.LengthRegulator (the reference's per-(b,t) .item() loop) on CPU tensors",
+               "bucketize_embed_ms": t_b * 1e3, "bucketize_threads": torch.get_num_threads()}
+    return {"B512": big, "variance_adaptor_fused_ms": fused_ms, "variance_adaptor_expand_plus_cudnn_ms": unfused_ms,
+            "config": {"workload": "cfg2: B=32, T<=200, H=256 + 5 curves (the 6 LengthRegulator calls of one forward)"},
+            "forward_ms_wall_incl_one_sync": wall_ms, "forward_ms_wall_max_len_known_no_sync": nosync_ms,
+            "expand_kernel_ms": k_ms, "expand_GBps": out_bytes / (k_ms * 1e-3) / 1e9, "frames": int(o.shape[1]),
+            "train_fwd_bwd_ms_wall_no_sync": train_ms, "backward_kernels_ms": bwd_ms, "backward_GBps": out_bytes / (bwd_ms * 1e-3) / 1e9,
+            "bucketize_embed": buck, "cpu_baseline": cpu}
 
 
 def main():
@@ -807,6 +1064,8 @@ def main():
     ap.add_argument("--utts", type=int, default=N_UTTS, help="utterances per GPU (cfg4: 13100)")
     ap.add_argument("--ref-utts", type=int, default=2048, help="bounded CPU sample (utterances per step)")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--chunks", type=int, default=4, help="chunks per shard for the compute/gather overlap (N > 1)")
+    ap.add_argument("--reserve-sms", type=int, default=16, help="SMs left to NCCL's kernels while a gather is in flight")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-gl", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

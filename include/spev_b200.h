@@ -226,6 +226,21 @@ SPEV_API int spev_collate(const spev_pad_array* arrays_host, int n_arrays, const
                           const int64_t* phone_off, const int64_t* sel, int B, int64_t t_max, int64_t p_max,
                           void* stream);
 
+/* Segmented device copy: dst[dst_off[i] .. +nbytes[i]) = src[src_off[i] .. +nbytes[i]) for n_segments runs of bytes
+ * (all tables on the device; piece_off[i] = first 16 KB piece of segment i, piece_off is the exclusive prefix sum of
+ * ceil(nbytes[i] / spev_copy_segments_piece_bytes()), n_pieces its total).  Used to put gathered cache shards
+ * (rank-major rows) into corpus order and to pack utterances into shards: the GPU form of the per-utterance
+ * `'mel': mel.T.clone()` stores of spev_real_metrics.py:419-425. */
+SPEV_API int spev_copy_segments_piece_bytes(void);
+SPEV_API int spev_copy_segments(const void* src, void* dst, const int64_t* src_off, const int64_t* dst_off,
+                                const int64_t* nbytes, const int64_t* piece_off, int n_segments, int64_t n_pieces,
+                                void* stream);
+
+/* Cap the number of CTAs the persistent FFT kernels launch (default: one per SM).  A multi-GPU cache build that
+ * overlaps the NCCL gather of finished chunks with the kernel of the next chunk leaves a few SMs to NCCL's
+ * send/recv kernels this way (the FFT CTAs each fill a whole SM).  max_ctas = 0 restores the default. */
+SPEV_API int spev_set_sm_limit(spev_ctx* ctx, int max_ctas);
+
 /* LengthRegulator, phase 1: sanitise durations (non-finite / <0 / >1000 -> 0, truncate),
  * inclusive row cumsum, mel_lens = max(total, 1), max_len = max(mel_lens).
  *   dur       : dev [B,T], dur_dtype 0=int64 1=int32 2=float32 3=float64 4=float16 5=bfloat16

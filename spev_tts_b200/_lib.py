@@ -85,6 +85,10 @@ _SIGS = {
                                         C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
     "spev_collate": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64,
                                C.c_void_p]),
+    "spev_copy_segments_piece_bytes": (C.c_int, []),
+    "spev_copy_segments": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                     C.c_int64, C.c_void_p]),
+    "spev_set_sm_limit": (C.c_int, [C.c_void_p, C.c_int]),
     "spev_lr_plan": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                C.c_void_p, C.c_void_p, C.c_void_p]),
     "spev_lr_expand": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_void_p,

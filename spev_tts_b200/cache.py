@@ -256,6 +256,33 @@ def gather_shards(local: torch.Tensor, dst: int = 0, group=None):
     return None, counts
 
 
+def copy_segments(src: torch.Tensor, dst: torch.Tensor, src_row, dst_row, n_rows) -> None:
+    """``dst[dst_row[i] : dst_row[i] + n_rows[i]] = src[src_row[i] : src_row[i] + n_rows[i]]`` for runs of rows of two
+    row-major 2-D CUDA tensors with equal row size, in one launch (``spev_copy_segments``)."""
+    if not (src.is_cuda and dst.is_cuda and src.is_contiguous() and dst.is_contiguous()):
+        raise RuntimeError("copy_segments needs contiguous CUDA tensors (no CPU path)")
+    rb = src.shape[1] * src.element_size()
+    if rb != dst.shape[1] * dst.element_size():
+        raise ValueError("row sizes differ")
+    n_rows = np.asarray(n_rows, dtype=np.int64)
+    keep = n_rows > 0
+    nb = n_rows[keep] * rb
+    if nb.size == 0:
+        return
+    lib = _lib.load()
+    piece = lib.spev_copy_segments_piece_bytes()
+    npieces = (nb + piece - 1) // piece
+    poff = np.cumsum(npieces) - npieces
+    table = np.stack([np.asarray(src_row, dtype=np.int64)[keep] * rb, np.asarray(dst_row, dtype=np.int64)[keep] * rb, nb, poff])
+    t = torch.from_numpy(np.ascontiguousarray(table)).pin_memory().to(src.device, non_blocking=True)
+    n = int(nb.size)
+    with torch.cuda.device(src.device):
+        _lib.check(lib.spev_copy_segments(src.data_ptr(), dst.data_ptr(), t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(),
+                                          t[3].data_ptr(), n, int(npieces.sum()),
+                                          torch.cuda.current_stream(src.device).cuda_stream), "spev_copy_segments")
+    t.record_stream(torch.cuda.current_stream(src.device))
+
+
 def assemble(parts: Sequence[torch.Tensor], shards: Sequence[np.ndarray], n_samples: Sequence[int]):
     """Re-order gathered shards into corpus order.  Returns ``(cache [F, n_mels], frame_off)``
     such that utterance ``u`` is ``cache[frame_off[u]:frame_off[u+1]]`` -- i.e. the tensor each
@@ -267,6 +294,189 @@ def assemble(parts: Sequence[torch.Tensor], shards: Sequence[np.ndarray], n_samp
         if len(idx) == 0:
             continue
         loc = np.concatenate([[0], np.cumsum(fr[idx])])
-        dest = np.repeat(fo[idx] - loc[:-1], fr[idx]) + np.arange(loc[-1])
-        out[torch.from_numpy(dest).to(out.device)] = part
+        if out.is_cuda:      # one row-run copy per utterance, all in one launch
+            copy_segments(part.contiguous(), out, loc[:-1], fo[idx], fr[idx])
+        else:                # host tensors (the gloo tests of the host logic): plain slice copies
+            for k, u in enumerate(idx):
+                out[fo[u]: fo[u + 1]] = part[loc[k]: loc[k + 1]]
     return out, fo
+
+
+# ---------------------------------------------------------------------------------------------
+# the multi-GPU cache build as one pipelined step: shard -> fused kernel per chunk -> gather
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class ShardPlan:
+    """Everything every rank can compute on its own from the corpus' utterance lengths: who owns which utterance,
+    where each rank's rows land in the gathered (rank-major) cache, and how each shard is cut into chunks for the
+    compute/gather overlap.  No metadata exchange is needed at run time."""
+    world: int
+    n_samples: np.ndarray            # [U]
+    frames: np.ndarray               # [U]
+    shards: List[np.ndarray]         # per rank: sorted utterance indices
+    row_off: np.ndarray              # [world+1] first row of each rank's block in the gathered cache
+    utt_row: np.ndarray              # [U] first row of utterance u in the gathered cache
+    chunks: List[List[Tuple[int, int]]]   # per rank: (first, last-exclusive) LOCAL utterance positions per chunk
+
+    def chunk_rows(self, rank: int, k: int) -> Tuple[int, int]:
+        """absolute rows [lo, hi) of chunk k of `rank` in the gathered cache"""
+        a, b = self.chunks[rank][k]
+        idx = self.shards[rank]
+        lo = int(self.row_off[rank] + self.frames[idx[:a]].sum())
+        return lo, lo + int(self.frames[idx[a:b]].sum())
+
+    @property
+    def n_rows(self) -> int:
+        return int(self.row_off[-1])
+
+
+def plan_shards(n_samples: Sequence[int], world: int, n_chunks: int = 4) -> ShardPlan:
+    ns = np.asarray(n_samples, dtype=np.int64)
+    fr = frames_of(ns)
+    shards = shard_utterances(ns, world)
+    per_rank = np.array([int(fr[s].sum()) for s in shards], dtype=np.int64)
+    row_off = np.concatenate([[0], np.cumsum(per_rank)]).astype(np.int64)
+    utt_row = np.empty(len(ns), dtype=np.int64)
+    chunks = []
+    for r, idx in enumerate(shards):
+        loc = np.concatenate([[0], np.cumsum(fr[idx])])
+        utt_row[idx] = row_off[r] + loc[:-1]
+        k = max(1, min(n_chunks, len(idx)))
+        cuts = [int(np.searchsorted(loc, loc[-1] * j / k, side="left")) for j in range(k + 1)]
+        cuts[0], cuts[-1] = 0, len(idx)
+        chunks.append([(a, b) for a, b in zip(cuts[:-1], cuts[1:]) if b > a] or [(0, len(idx))])
+    return ShardPlan(world, ns, fr, shards, row_off, utt_row, chunks)
+
+
+class GatheredCache:
+    """The gathered log-mel cache on the root: one ``[F, n_mels]`` buffer in rank-major row order plus the row of
+    every utterance.  ``utterance(u)`` is the tensor ``cache_stable/u_%05d.pt`` holds under ``'mel'``
+    (``spev_real_metrics.py:419-425``) as a zero-copy view; ``corpus_order()`` re-packs once (one launch)."""
+
+    def __init__(self, buf: torch.Tensor, plan: ShardPlan):
+        self.buf, self.plan = buf, plan
+
+    def utterance(self, u: int) -> torch.Tensor:
+        r0 = int(self.plan.utt_row[u])
+        return self.buf[r0: r0 + int(self.plan.frames[u])]
+
+    def corpus_order(self):
+        fr = self.plan.frames
+        fo = np.concatenate([[0], np.cumsum(fr)])
+        out = torch.empty_like(self.buf)
+        copy_segments(self.buf, out, self.plan.utt_row, fo[:-1], fr)
+        return out, fo
+
+
+class ShardedCacheBuilder:
+    """One rank of the utterance-sharded cache build (one process per GPU).  ``build()`` is the whole multi-GPU step:
+    this rank's fused STFT->log-mel kernel over its shard, and the gather of all shards into the root's cache --
+    the only cross-GPU exchange of the path (NCCL send/recv over NVLink; gloo in the CPU tests).
+
+    ``overlap=True`` cuts every shard into ``plan``'s chunks: the root posts all receives up front (they land
+    directly in their final rows -- no staging, no re-ordering pass) and every rank sends chunk k while its kernel
+    works on chunk k+1.  The FFT kernels fill whole SMs, so ``reserve_sms`` CTAs are left to NCCL's kernels while a
+    transfer is in flight (``spev_set_sm_limit``)."""
+
+    def __init__(self, plan: ShardPlan, rank: int, device, *, dst: int = 0, group=None, sr=22050, n_mels=80,
+                 reserve_sms: int = 16, kernel=None):
+        """``kernel(samples, out_rows, a, b)``: test hook replacing the CUDA kernel for the local utterances [a, b)
+        (the gloo tests of the host logic); the product always runs ``spev_logmel``."""
+        self.plan, self.rank, self.dst, self.group = plan, rank, dst, group
+        self.device = torch.device(device)
+        self.sr, self.n_mels = sr, n_mels
+        self.reserve_sms = reserve_sms
+        idx = plan.shards[rank]
+        self.lens = plan.n_samples[idx]
+        self.sample_off = aligned_offsets(self.lens)
+        self.n_rows_local = int(plan.frames[idx].sum())
+        self._kernel_hook = kernel
+        self.launches = 0
+        if kernel is not None:
+            self.ctx = None
+            return
+        self.ctx = Context.get(self.device, sr=sr, n_mels=n_mels)
+        self.batch_all = make_batch(self.ctx, n_samples=self.lens, sample_off=self.sample_off)
+        self.batch_chunk = [make_batch(self.ctx, n_samples=self.lens[a:b], sample_off=self.sample_off[a:b])
+                            for a, b in plan.chunks[rank]]
+
+    # -- layout helpers -------------------------------------------------------------------------
+    def alloc_out(self) -> torch.Tensor:
+        """root: the gathered cache ``[F_total, n_mels]``; other ranks: their shard ``[F_r, n_mels]``"""
+        rows = self.plan.n_rows if self.rank == self.dst else self.n_rows_local
+        return torch.empty((rows, self.n_mels), dtype=torch.float32, device=self.device)
+
+    def local_rows(self, out: torch.Tensor, k: Optional[int] = None) -> torch.Tensor:
+        base = int(self.plan.row_off[self.rank]) if self.rank == self.dst else 0
+        if k is None:
+            return out[base: base + self.n_rows_local]
+        lo, hi = self.plan.chunk_rows(self.rank, k)
+        off = int(self.plan.row_off[self.rank]) - base
+        return out[lo - off: hi - off]
+
+    def _kernel(self, samples: torch.Tensor, out_rows: torch.Tensor, k: Optional[int]) -> None:
+        self.launches += 1
+        if self._kernel_hook is not None:
+            a, b = (0, len(self.lens)) if k is None else self.plan.chunks[self.rank][k]
+            self._kernel_hook(samples, out_rows, a, b)
+            return
+        spectral.logmel_flat(samples, None, sr=self.sr, n_mels=self.n_mels, out=out_rows,
+                             batch=self.batch_all if k is None else self.batch_chunk[k])
+
+    def _limit(self, on: bool) -> None:
+        if self.ctx is None:
+            return
+        _lib.check(self.ctx.lib.spev_set_sm_limit(self.ctx.handle, max(1, self._sms() - self.reserve_sms) if on else 0),
+                   "spev_set_sm_limit")
+
+    def _sms(self) -> int:
+        return torch.cuda.get_device_properties(self.device).multi_processor_count
+
+    # -- the step ---------------------------------------------------------------------------------
+    def build(self, samples: torch.Tensor, out: torch.Tensor, *, gather: bool = True, overlap: bool = True):
+        """``samples``: this rank's shard, utterances at ``self.sample_off`` (device float32).  Enqueues everything on
+        the current stream (plus NCCL's own stream) and returns without a host synchronisation; afterwards the root's
+        ``out`` holds every rank's rows (``GatheredCache(out, plan)``)."""
+        import torch.distributed as dist
+        plan, rank, dst = self.plan, self.rank, self.dst
+        if not gather or plan.world == 1:
+            self._kernel(samples, self.local_rows(out), None)
+            return out
+        peers = [r for r in range(plan.world) if r != dst]
+        if not overlap:
+            self._kernel(samples, self.local_rows(out), None)
+            if rank == dst:
+                ops = [dist.P2POp(dist.irecv, out[int(plan.row_off[r]): int(plan.row_off[r + 1])], r, self.group)
+                       for r in peers if plan.row_off[r + 1] > plan.row_off[r]]
+            else:
+                ops = [dist.P2POp(dist.isend, self.local_rows(out), dst, self.group)] if self.n_rows_local else []
+            for w in (dist.batch_isend_irecv(ops) if ops else []):
+                w.wait()
+            return out
+        works = []
+        self._limit(True)
+        try:
+            if rank == dst:
+                kmax = max(len(plan.chunks[r]) for r in peers)
+                for k in range(kmax):             # all receives first: chunk k of every peer is one grouped launch
+                    ops = []
+                    for r in peers:
+                        if k < len(plan.chunks[r]):
+                            lo, hi = plan.chunk_rows(r, k)
+                            if hi > lo:
+                                ops.append(dist.P2POp(dist.irecv, out[lo:hi], r, self.group))
+                    if ops:
+                        works += dist.batch_isend_irecv(ops)
+                for k in range(len(plan.chunks[rank])):
+                    self._kernel(samples, self.local_rows(out, k), k)
+            else:
+                for k in range(len(plan.chunks[rank])):
+                    rows = self.local_rows(out, k)
+                    self._kernel(samples, rows, k)
+                    if rows.shape[0]:
+                        works += dist.batch_isend_irecv([dist.P2POp(dist.isend, rows, dst, self.group)])
+        finally:
+            self._limit(False)
+        for w in works:
+            w.wait()                              # stream-level join (non-blocking on the host for NCCL)
+        return out

@@ -47,6 +47,7 @@ int launch_variance_fuse_backward(const float*, const float*, int, const float*,
 int launch_variance_fuse(const float*, const float*, int, const float*, const float*, const float*, const float*, const int32_t*, int, int, int, float*, float*, int64_t, cudaStream_t);
 int launch_pcm16_to_f32(const int16_t*, int64_t, float*, cudaStream_t);
 int launch_collate(const spev_pad_array*, int, const int64_t*, const int64_t*, const int64_t*, int, int64_t, int64_t, cudaStream_t);
+int launch_copy_segments(const void*, void*, const int64_t*, const int64_t*, const int64_t*, const int64_t*, int, int64_t, cudaStream_t);
 int launch_bucketize_embed(const float*, int64_t, const float*, int, int, const float*, int, int64_t*, float*, int, cudaStream_t);
 int launch_frame_features(spev_ctx*, const spev_batch*, const float*, float*, float*, cudaStream_t);
 int launch_segment_pool(const float*, const int64_t*, const int64_t*, const int64_t*, int, float, float, float, float, int, float,
@@ -216,7 +217,7 @@ int spev_create(spev_ctx** out, int device, int sr, int n_fft, int hop, int win,
 
     spev_ctx* c = new spev_ctx();
     c->device = device; c->sr = sr; c->n_fft = n_fft; c->hop = hop; c->win = kNfft; c->n_mels = n_mels;
-    c->fmin = fmin; c->fmax = fmax; c->num_sms = prop.multiProcessorCount; c->tma = nullptr; c->use_tc = 1;
+    c->fmin = fmin; c->fmax = fmax; c->num_sms = c->num_sms_device = prop.multiProcessorCount; c->tma = nullptr; c->use_tc = 1;
     c->d_tw = nullptr; c->d_window = nullptr; c->d_win2048 = nullptr; c->d_tw2048 = nullptr; c->d_basis_pad = c->d_basis_hi = c->d_basis_lo = nullptr;
     c->d_pinv_t = c->d_pinv_hi = c->d_pinv_lo = nullptr;
     c->d_prog_w = nullptr; c->d_prog_i = nullptr;
@@ -512,6 +513,21 @@ int spev_segment_pool_log(const float* curve, float log_eps, const int64_t* fram
 int spev_collate(const spev_pad_array* arrays, int n_arrays, const int64_t* frame_off, const int64_t* phone_off,
                  const int64_t* sel, int B, int64_t t_max, int64_t p_max, void* stream) {
     return launch_collate(arrays, n_arrays, frame_off, phone_off, sel, B, t_max, p_max, static_cast<cudaStream_t>(stream));
+}
+
+int spev_copy_segments_piece_bytes(void) { return 256 * 16 * 4; }
+
+int spev_copy_segments(const void* src, void* dst, const int64_t* src_off, const int64_t* dst_off, const int64_t* nbytes,
+                       const int64_t* piece_off, int n_segments, int64_t n_pieces, void* stream) {
+    return launch_copy_segments(src, dst, src_off, dst_off, nbytes, piece_off, n_segments, n_pieces,
+                                static_cast<cudaStream_t>(stream));
+}
+
+int spev_set_sm_limit(spev_ctx* c, int max_ctas) {
+    SPEV_REQUIRE(c, SPEV_E_INVALID, "ctx is null");
+    SPEV_REQUIRE(max_ctas >= 0, SPEV_E_INVALID, "spev_set_sm_limit: negative limit");
+    c->num_sms = (max_ctas == 0 || max_ctas > c->num_sms_device) ? c->num_sms_device : max_ctas;
+    return SPEV_OK;
 }
 
 int spev_lr_plan(const void* dur, int dur_dtype, int B, int T, int32_t* cumsum, int64_t* mel_lens,

@@ -78,4 +78,47 @@ int launch_collate(const spev_pad_array* arrays, int n_arrays, const int64_t* fr
     return SPEV_OK;
 }
 
+// ---- segmented copy: dst[dst_off[i] .. +nbytes[i]) = src[src_off[i] .. +nbytes[i]) -------------------------------
+// Re-orders a gathered cache (rank-major rows) into corpus order, or packs scattered utterances into a shard: each
+// segment is a contiguous run of rows.  CTA <-> 16 KB piece of one segment (binary search in the piece prefix table).
+__global__ void __launch_bounds__(kPadThreads)
+k_copy_segments(const unsigned char* __restrict__ src, unsigned char* __restrict__ dst, const int64_t* __restrict__ src_off,
+                const int64_t* __restrict__ dst_off, const int64_t* __restrict__ nbytes, const int64_t* __restrict__ piece_off,
+                int n_seg, int64_t n_pieces) {
+    for (int64_t piece = blockIdx.x; piece < n_pieces; piece += gridDim.x) {
+        int lo = 0, hi = n_seg;                       // last segment whose first piece is <= piece
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (piece_off[mid] <= piece) lo = mid; else hi = mid;
+        }
+        const int64_t b0 = (piece - piece_off[lo]) * kPadBytesPerCta;
+        const int64_t b1 = min(nbytes[lo], b0 + kPadBytesPerCta);
+        const unsigned char* s = src + src_off[lo];
+        unsigned char* d = dst + dst_off[lo];
+        if (((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(d)) & 15) == 0) {
+            const int64_t v1 = b0 + ((b1 - b0) & ~static_cast<int64_t>(15));
+            for (int64_t i = b0 + threadIdx.x * 16; i < v1; i += kPadThreads * 16)
+                *reinterpret_cast<uint4*>(d + i) = __ldg(reinterpret_cast<const uint4*>(s + i));
+            for (int64_t i = v1 + threadIdx.x; i < b1; i += kPadThreads) d[i] = s[i];
+        } else if (((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(d) | static_cast<uintptr_t>(b1 - b0)) & 3) == 0) {
+            for (int64_t i = b0 + threadIdx.x * 4; i < b1; i += kPadThreads * 4)
+                *reinterpret_cast<uint32_t*>(d + i) = __ldg(reinterpret_cast<const uint32_t*>(s + i));
+        } else {
+            for (int64_t i = b0 + threadIdx.x; i < b1; i += kPadThreads) d[i] = s[i];
+        }
+    }
+}
+
+int launch_copy_segments(const void* src, void* dst, const int64_t* src_off, const int64_t* dst_off, const int64_t* nbytes,
+                         const int64_t* piece_off, int n_seg, int64_t n_pieces, cudaStream_t st) {
+    SPEV_REQUIRE(n_seg >= 0 && n_pieces >= 0, SPEV_E_INVALID, "copy_segments: negative sizes");
+    if (n_seg == 0 || n_pieces == 0) return SPEV_OK;
+    SPEV_REQUIRE(src && dst && src_off && dst_off && nbytes && piece_off, SPEV_E_INVALID, "copy_segments: null buffer");
+    const int grid = static_cast<int>(std::min<int64_t>(n_pieces, 148 * 32));
+    k_copy_segments<<<grid, kPadThreads, 0, st>>>(static_cast<const unsigned char*>(src), static_cast<unsigned char*>(dst),
+                                                  src_off, dst_off, nbytes, piece_off, n_seg, n_pieces);
+    SPEV_CUDA(cudaGetLastError());
+    return SPEV_OK;
+}
+
 }  // namespace spev

@@ -50,7 +50,9 @@ struct MelProgram {
 }  // namespace spev
 
 struct spev_ctx {
-    int device, sr, n_fft, hop, win, n_mels, num_sms;
+    int device, sr, n_fft, hop, win, n_mels;
+    int num_sms;          // CTAs the persistent kernels launch (<= num_sms_device; spev_set_sm_limit)
+    int num_sms_device;
     float fmin, fmax;
     // host copies
     std::vector<float> h_basis;      // [n_mels*513]

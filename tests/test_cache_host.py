@@ -86,6 +86,69 @@ def test_gather_shards_world2_gloo():
     assert res == {0: True, 1: True}
 
 
+def test_plan_shards_layout():
+    from spev_tts_b200 import cache
+    lens = synth.utterance_lengths(seed=4, n_utts=1310)
+    for world in (1, 2, 8):
+        p = cache.plan_shards(lens, world, n_chunks=4)
+        cover = np.zeros(p.n_rows, dtype=np.int64)
+        for u in range(len(lens)):
+            cover[p.utt_row[u]: p.utt_row[u] + p.frames[u]] += 1
+        assert (cover == 1).all() and p.n_rows == cache.frames_of(lens).sum()
+        for r in range(world):                       # chunks tile the rank's block of rows, in order
+            rows = [p.chunk_rows(r, k) for k in range(len(p.chunks[r]))]
+            assert rows[0][0] == p.row_off[r] and rows[-1][1] == p.row_off[r + 1]
+            assert all(a[1] == b[0] for a, b in zip(rows[:-1], rows[1:]))
+            sizes = np.array([hi - lo for lo, hi in rows])
+            assert sizes.max() - sizes.min() <= 2 * cache.frames_of(lens).max()
+    one = cache.plan_shards([3000], 4, n_chunks=4)   # more ranks than utterances: empty shards are fine
+    assert one.n_rows == 12 and [len(s) for s in one.shards].count(0) == 3
+
+
+def _pipeline_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from spev_tts_b200 import cache
+    lens = synth.utterance_lengths(seed=7, n_utts=41)
+    plan = cache.plan_shards(lens, world, n_chunks=3)
+    fr = plan.frames
+
+    def kernel(samples, out_rows, a, b):             # stand-in rows: (utterance, frame) so placement can be verified
+        idx = plan.shards[rank][a:b]
+        rows = [torch.tensor([[float(u), float(t), 0.0, 0.0] for t in range(fr[u])]) for u in idx]
+        out_rows.copy_(torch.cat(rows) if rows else torch.zeros((0, 4)))
+    ok = True
+    for overlap in (False, True):
+        bld = cache.ShardedCacheBuilder(plan, rank, "cpu", n_mels=4, kernel=kernel)
+        out = torch.full((plan.n_rows if rank == 0 else bld.n_rows_local, 4), -1.0)
+        bld.build(None, out, gather=True, overlap=overlap)
+        if rank == 0:
+            g = cache.GatheredCache(out, plan)
+            for u in range(len(lens)):
+                seg = g.utterance(u)
+                ok &= seg.shape[0] == fr[u] and bool((seg[:, 0] == u).all()) and bool((seg[:, 1] == torch.arange(float(fr[u]))).all())
+        ok &= bld.launches == (len(plan.chunks[rank]) if overlap else 1)
+    q.put((rank, bool(ok)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_builder_pipeline_world2_gloo():
+    """ShardedCacheBuilder.build over gloo (host logic of the chunked compute/gather overlap): every utterance's rows
+    land where the plan says, serial and overlapped."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_pipeline_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == {0: True, 1: True}
+
+
 def test_cpulist_parser():
     from spev_tts_b200 import cache
     assert cache._parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
