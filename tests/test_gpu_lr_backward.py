@@ -45,7 +45,8 @@ def test_backward_vs_reference_class_goldens(cuda, golden):
     assert np.abs(_ours_grad(s["x"], s["dur"], 15, torch.float64, cuda) - g["small_grad_x_f64"]).max() <= 1e-12
     for name, (xe, de) in synth.lr_edge_cases().items():       # zero rows, >1000, negatives, NaN/inf durations
         got = _ours_grad(xe, de, 16, cuda=cuda)
-        assert np.abs(got - g[f"edge_{name}_grad_x"]).max() <= 2e-6, name
+        ref = g[f"edge_{name}_grad_x"]              # "gt1000" holds a 1000-frame segment: float32 sum order matters
+        assert np.abs(got - ref).max() <= 1e-6 * max(1.0, np.abs(ref).max()), name
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
