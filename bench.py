@@ -366,6 +366,7 @@ def run_ours(args):
     kern_ms_max = max_over_ranks(kern_ms)
     launches_per_step = 1
     gather = None
+    bld_p = out_p = None
     if world == 1:
         ms_per_step = ko_ms
     else:
@@ -377,22 +378,44 @@ def run_ours(args):
         se_ms, _ = timed(lambda: bld.build(samples, out, gather=True, overlap=False), max(3, args.steps // 2), 1)
         peers_rows = F_total - int(plan.row_off[1] - plan.row_off[0])
         nbytes = peers_rows * N_MELS * 4
-        ms_per_step = ov_ms
-        gather = {"bytes_into_root": nbytes, "backend": "nccl send/recv (batch_isend_irecv), receives land in their final rows",
-                  "overlapped_ms_per_step": ov_ms, "serial_ms_per_step": se_ms, "kernel_only_ms_per_step": ko_ms,
-                  "gather_alone_ms": se_ms - ko_ms, "gather_alone_GBps": nbytes / max(1e-9, (se_ms - ko_ms) * 1e-3) / 1e9,
-                  "chunks_per_rank": args.chunks, "reserved_sms": args.reserve_sms,
+        gather = {"bytes_into_root": nbytes,
+                  "nccl": {"backend": "ncclSend/ncclRecv (batch_isend_irecv), receives land in their final rows",
+                           "overlapped_ms_per_step": ov_ms, "serial_ms_per_step": se_ms,
+                           "gather_alone_ms": se_ms - ko_ms,
+                           "gather_alone_GBps": nbytes / max(1e-9, (se_ms - ko_ms) * 1e-3) / 1e9,
+                           "reserved_sms": args.reserve_sms,
+                           "note": "NCCL's send/recv kernels need SMs; the FFT CTAs each fill one, so the kernels run "
+                                   "on 148 - reserved SMs while a transfer is in flight"},
+                  "kernel_only_ms_per_step": ko_ms, "chunks_per_rank": args.chunks,
                   "limiter": "root NVLink ingress: (N-1)/N of the 1.99 GB cache must enter rank 0; lower bound = bytes / "
                              "measured peer-copy bandwidth (770 GB/s per direction, B200_PROFILING.md)",
                   "ingress_floor_ms": nbytes / 770e9 * 1e3}
+        ms_per_step, transport = ov_ms, "nccl"
+        bld_p = out_p = None
+        if args.transport in ("best", "p2p"):
+            try:
+                bld_p = spcache.ShardedCacheBuilder(plan, rank, dev, dst=0, sr=SR, n_mels=N_MELS, transport="p2p")
+                out_p = bld_p.alloc_out()
+                l0 = bld_p.launches
+                pv_ms, _ = timed(lambda: bld_p.build(samples, out_p, gather=True, overlap=True), args.steps, W)
+                p_launches = (bld_p.launches - l0) // (args.steps + W)
+                ps_ms, _ = timed(lambda: bld_p.build(samples, out_p, gather=True, overlap=False), max(3, args.steps // 2), 1)
+                gather["p2p"] = {"backend": "copy-engine pushes into the root's symmetric-memory window (cudaMemcpyAsync over "
+                                            "NVLink, no SMs), signal-pad barrier",
+                                 "overlapped_ms_per_step": pv_ms, "serial_ms_per_step": ps_ms,
+                                 "gather_alone_ms": ps_ms - ko_ms,
+                                 "gather_alone_GBps": nbytes / max(1e-9, (ps_ms - ko_ms) * 1e-3) / 1e9}
+                if pv_ms < ms_per_step or args.transport == "p2p":
+                    ms_per_step, transport, launches_per_step = pv_ms, "p2p", p_launches
+            except RuntimeError as e:
+                gather["p2p"] = {"unavailable": str(e)[:300]}
+                bld_p = out_p = None
+        gather["headline_transport"] = transport
     t1 = time.perf_counter()
     value = F_total / (ms_per_step * 1e-3)
     kernel_only = {"value": F_total / (ko_ms * 1e-3), "unit": "frames/s", "ms_per_step": ko_ms,
                    "note": "no gather: each data-parallel rank keeps its shard resident (ResidentCache)"}
     achieved = ALG_BYTES_PER_FRAME * F / (kern_ms * 1e-3) / 1e9      # GB/s, this rank's kernel
-    if world > 1 and rank == 0:
-        gc = spcache.GatheredCache(out, plan)    # spot check below reads utterances through the gathered layout
-
     # ---------------- e2e: pinned host samples -> public API -> pinned host cache (this rank's shard) -------
     e2e = None
     if not args.no_e2e:
@@ -453,16 +476,20 @@ def run_ours(args):
     clocks = sampler.stop(t0, t1) if sampler else None
 
     # ---------------- gather integrity: every rank's rows arrived where the plan says (exact checksums) ---------
-    gather_ok = None
     if world > 1:
-        bld.build(samples, out, gather=True, overlap=True)
-        mysum = out_local.double().sum().reshape(1)
-        sums = [torch.zeros_like(mysum) for _ in range(world)]
-        dist.all_gather(sums, mysum)
-        if rank == 0:
-            gather_ok = all(bool(out[int(plan.row_off[r]): int(plan.row_off[r + 1])].double().sum() == sums[r][0])
-                            for r in range(world))
-            gather["rows_checksum_matches_every_rank"] = gather_ok
+        for name, b_, o_ in (("nccl", bld, out), ("p2p", bld_p, out_p)):
+            if b_ is None:
+                continue
+            if rank == 0:
+                o_.fill_(-1.0)
+            b_.build(samples, o_, gather=True, overlap=True)
+            mysum = b_.local_rows(o_).double().sum().reshape(1)
+            sums = [torch.zeros_like(mysum) for _ in range(world)]
+            dist.all_gather(sums, mysum)
+            if rank == 0:
+                gather[name]["rows_checksum_matches_every_rank"] = all(
+                    bool(o_[int(plan.row_off[r]): int(plan.row_off[r + 1])].double().sum() == sums[r][0]) for r in range(world))
+        del out_p, bld_p
 
     # ---------------- second half of the metric and the other configs ------------------------------------------
     gl = lr_res = tc = cfg5 = feat = coll = pyin_res = None
@@ -510,7 +537,7 @@ def run_ours(args):
             "config": {"workload": f"cfg4: the fixed corpus of {args.utts} synthetic utterances 1-10 s @22.05 kHz "
                                    f"({int(full_starts[-1]) * 4 / 1e9:.2f} GB samples, {F_total} frames), sharded by utterance over "
                                    f"{world} GPU(s); step = every rank's fused kernel"
-                                   + (" + NCCL gather of the shards into rank 0 (chunked, overlapped)" if world > 1 else "")
+                                   + (f" + gather of the shards into rank 0 over NVLink (chunked, overlapped; transport: {gather['headline_transport']})" if world > 1 else "")
                                    + "; inputs >> L2 (126 MB), no flush needed",
                        "n_fft": 1024, "hop": 256, "n_mels": 80, "utterances": args.utts, "frames": F_total,
                        "frames_this_rank": F, "parallelism": f"utterance-sharded x{world}; one exchange: gather of shards"},
@@ -1065,6 +1092,8 @@ def main():
     ap.add_argument("--ref-utts", type=int, default=2048, help="bounded CPU sample (utterances per step)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--chunks", type=int, default=4, help="chunks per shard for the compute/gather overlap (N > 1)")
+    ap.add_argument("--transport", default="best", choices=["best", "nccl", "p2p"],
+                    help="gather transport of the headline value at N > 1 (best: the faster of the two, named in the line)")
     ap.add_argument("--reserve-sms", type=int, default=16, help="SMs left to NCCL's kernels while a gather is in flight")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-gl", action="store_true")

@@ -379,9 +379,18 @@ class ShardedCacheBuilder:
     transfer is in flight (``spev_set_sm_limit``)."""
 
     def __init__(self, plan: ShardPlan, rank: int, device, *, dst: int = 0, group=None, sr=22050, n_mels=80,
-                 reserve_sms: int = 16, kernel=None):
-        """``kernel(samples, out_rows, a, b)``: test hook replacing the CUDA kernel for the local utterances [a, b)
+                 reserve_sms: int = 16, kernel=None, transport: str = "nccl"):
+        """``transport``: ``"nccl"`` -- grouped ncclSend/ncclRecv (the default; NCCL's kernels need SMs, see
+        ``reserve_sms``) -- or ``"p2p"`` -- the root's cache is a symmetric-memory window mapped into every rank
+        (``torch.distributed._symmetric_memory``) and each rank pushes its finished chunks into their final rows with
+        copy-engine ``cudaMemcpyAsync`` over NVLink: no SM is taken from the FFT kernels, and a stream-ordered
+        signal-pad barrier closes the step.
+        ``kernel(samples, out_rows, a, b)``: test hook replacing the CUDA kernel for the local utterances [a, b)
         (the gloo tests of the host logic); the product always runs ``spev_logmel``."""
+        if transport not in ("nccl", "p2p"):
+            raise ValueError("transport must be 'nccl' or 'p2p'")
+        self.transport = transport
+        self._window = self._root_view = self._copy_stream = None
         self.plan, self.rank, self.dst, self.group = plan, rank, dst, group
         self.device = torch.device(device)
         self.sr, self.n_mels = sr, n_mels
@@ -402,12 +411,25 @@ class ShardedCacheBuilder:
 
     # -- layout helpers -------------------------------------------------------------------------
     def alloc_out(self) -> torch.Tensor:
-        """root: the gathered cache ``[F_total, n_mels]``; other ranks: their shard ``[F_r, n_mels]``"""
+        """root: the gathered cache ``[F_total, n_mels]``; other ranks: their shard ``[F_r, n_mels]``.  With the p2p
+        transport every rank holds a full-size symmetric window (rows outside its shard stay unused off the root)."""
+        if self.transport == "p2p" and self.plan.world > 1:
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm
+            try:
+                buf = symm.empty((self.plan.n_rows, self.n_mels), dtype=torch.float32, device=self.device)
+                self._window = symm.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
+                self._root_view = self._window.get_buffer(self.dst, (self.plan.n_rows, self.n_mels), torch.float32)
+            except Exception as e:     # no silent change of transport: the caller decides
+                raise RuntimeError(f"p2p transport unavailable (symmetric-memory rendezvous failed: {e!r})") from e
+            self._copy_stream = torch.cuda.Stream(self.device)
+            return buf
         rows = self.plan.n_rows if self.rank == self.dst else self.n_rows_local
         return torch.empty((rows, self.n_mels), dtype=torch.float32, device=self.device)
 
     def local_rows(self, out: torch.Tensor, k: Optional[int] = None) -> torch.Tensor:
-        base = int(self.plan.row_off[self.rank]) if self.rank == self.dst else 0
+        full = self.rank == self.dst or self._window is not None
+        base = int(self.plan.row_off[self.rank]) if full else 0
         if k is None:
             return out[base: base + self.n_rows_local]
         lo, hi = self.plan.chunk_rows(self.rank, k)
@@ -443,6 +465,8 @@ class ShardedCacheBuilder:
             self._kernel(samples, self.local_rows(out), None)
             return out
         peers = [r for r in range(plan.world) if r != dst]
+        if self._window is not None:
+            return self._build_p2p(samples, out, overlap)
         if not overlap:
             self._kernel(samples, self.local_rows(out), None)
             if rank == dst:
@@ -479,4 +503,27 @@ class ShardedCacheBuilder:
             self._limit(False)
         for w in works:
             w.wait()                              # stream-level join (non-blocking on the host for NCCL)
+        return out
+
+    def _build_p2p(self, samples: torch.Tensor, out: torch.Tensor, overlap: bool):
+        """Copy-engine transport: chunk k is pushed into the root's window (its final rows) on a side stream while the
+        kernel of chunk k+1 runs on all SMs; a signal-pad barrier (stream-ordered, no host sync) ends the step."""
+        plan, rank = self.plan, self.rank
+        cur = torch.cuda.current_stream(self.device)
+        ks = range(len(plan.chunks[rank])) if overlap else [None]
+        for k in ks:
+            rows = self.local_rows(out, k)
+            self._kernel(samples, rows, k)
+            if rank != self.dst and rows.shape[0]:
+                if k is None:
+                    lo, hi = int(plan.row_off[rank]), int(plan.row_off[rank + 1])
+                else:
+                    lo, hi = plan.chunk_rows(rank, k)
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                with torch.cuda.stream(self._copy_stream):
+                    self._copy_stream.wait_event(ev)
+                    self._root_view[lo:hi].copy_(rows, non_blocking=True)
+        cur.wait_stream(self._copy_stream)
+        self._window.barrier()                    # every rank's pushes are complete and visible on the root
         return out
