@@ -510,6 +510,15 @@ class ShardedCacheBuilder:
         kernel of chunk k+1 runs on all SMs; a signal-pad barrier (stream-ordered, no host sync) ends the step."""
         plan, rank = self.plan, self.rank
         cur = torch.cuda.current_stream(self.device)
+        # The window is one-sided: nothing may land in it before the root's earlier work on it (a consumer of the
+        # previous step's cache, a fill) has finished.  The root arrives at this barrier on ITS stream, i.e. after that
+        # work; the other ranks wait for it on their copy stream only, so their kernels start at once.
+        if rank == self.dst:
+            self._window.barrier(channel=1)
+        else:
+            with torch.cuda.stream(self._copy_stream):
+                self._copy_stream.wait_stream(cur)
+                self._window.barrier(channel=1)
         ks = range(len(plan.chunks[rank])) if overlap else [None]
         for k in ks:
             rows = self.local_rows(out, k)
@@ -525,5 +534,5 @@ class ShardedCacheBuilder:
                     self._copy_stream.wait_event(ev)
                     self._root_view[lo:hi].copy_(rows, non_blocking=True)
         cur.wait_stream(self._copy_stream)
-        self._window.barrier()                    # every rank's pushes are complete and visible on the root
+        self._window.barrier(channel=0)           # every rank's pushes are complete and visible on the root
         return out
