@@ -510,6 +510,10 @@ class ShardedCacheBuilder:
         kernel of chunk k+1 runs on all SMs; a signal-pad barrier (stream-ordered, no host sync) ends the step."""
         plan, rank = self.plan, self.rank
         cur = torch.cuda.current_stream(self.device)
+        # The FFT CTAs fill whole SMs; one SM is left free so that the (single-CTA) barrier kernels below can run
+        # beside them instead of queueing behind a whole shard.
+        _lib.check(self.ctx.lib.spev_set_sm_limit(self.ctx.handle, max(1, self._sms() - 1)), "spev_set_sm_limit") \
+            if self.ctx is not None else None
         # The window is one-sided: nothing may land in it before the root's earlier work on it (a consumer of the
         # previous step's cache, a fill) has finished.  The root arrives at this barrier on ITS stream, i.e. after that
         # work; the other ranks wait for it on their copy stream only, so their kernels start at once.
@@ -535,4 +539,5 @@ class ShardedCacheBuilder:
                     self._root_view[lo:hi].copy_(rows, non_blocking=True)
         cur.wait_stream(self._copy_stream)
         self._window.barrier(channel=0)           # every rank's pushes are complete and visible on the root
+        self._limit(False)
         return out
