@@ -1091,7 +1091,7 @@ def main():
     ap.add_argument("--utts", type=int, default=N_UTTS, help="utterances per GPU (cfg4: 13100)")
     ap.add_argument("--ref-utts", type=int, default=2048, help="bounded CPU sample (utterances per step)")
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--chunks", type=int, default=4, help="chunks per shard for the compute/gather overlap (N > 1)")
+    ap.add_argument("--chunks", type=int, default=8, help="chunks per shard for the compute/gather overlap (N > 1)")
     ap.add_argument("--transport", default="best", choices=["best", "nccl", "p2p"],
                     help="gather transport of the headline value at N > 1 (best: the faster of the two, named in the line)")
     ap.add_argument("--reserve-sms", type=int, default=16, help="SMs left to NCCL's kernels while a gather is in flight")
