@@ -236,6 +236,10 @@ SPEV_API int spev_copy_segments(const void* src, void* dst, const int64_t* src_o
                                 const int64_t* nbytes, const int64_t* piece_off, int n_segments, int64_t n_pieces,
                                 void* stream);
 
+/* A/B switch of the fused log-mel kernel: 1 (default) = decoupled warps with split-phase mbarrier synchronisation
+ * (k_stft_mel_ws), 0 = the tile kernel with three CTA barriers per tile (k_stft_mel<0>).  Results are bit-identical. */
+SPEV_API int spev_set_logmel_variant(spev_ctx* ctx, int variant);
+
 /* Cap the number of CTAs the persistent FFT kernels launch (default: one per SM).  A multi-GPU cache build that
  * overlaps the NCCL gather of finished chunks with the kernel of the next chunk leaves a few SMs to NCCL's
  * send/recv kernels this way (the FFT CTAs each fill a whole SM).  max_ctas = 0 restores the default. */

@@ -217,10 +217,10 @@ int spev_create(spev_ctx** out, int device, int sr, int n_fft, int hop, int win,
 
     spev_ctx* c = new spev_ctx();
     c->device = device; c->sr = sr; c->n_fft = n_fft; c->hop = hop; c->win = kNfft; c->n_mels = n_mels;
-    c->fmin = fmin; c->fmax = fmax; c->num_sms = c->num_sms_device = prop.multiProcessorCount; c->tma = nullptr; c->use_tc = 1;
+    c->fmin = fmin; c->fmax = fmax; c->num_sms = c->num_sms_device = prop.multiProcessorCount; c->tma = nullptr; c->use_tc = 1; c->k1_variant = 1;
     c->d_tw = nullptr; c->d_window = nullptr; c->d_win2048 = nullptr; c->d_tw2048 = nullptr; c->d_basis_pad = c->d_basis_hi = c->d_basis_lo = nullptr;
     c->d_pinv_t = c->d_pinv_hi = c->d_pinv_lo = nullptr;
-    c->d_prog_w = nullptr; c->d_prog_i = nullptr;
+    c->d_prog_w = nullptr; c->d_prog_i = nullptr; c->d_prog_p = nullptr;
 
     // periodic Hann, float64 -> float32
     c->h_window.resize(kNfft);
@@ -288,6 +288,8 @@ int spev_create(spev_ctx** out, int device, int sr, int n_fft, int hop, int win,
             }
     }
     c->prog_gmax = gmax;
+    std::vector<int> prog_p(prog_i.size());
+    for (size_t g = 0; g < prog_i.size(); ++g) prog_p[g] = prog_i[g].x | ((prog_i[g].y + 1) << 16);
 
     // padded / split operands for the tensor-core GEMMs
     std::vector<float> basis_pad(static_cast<size_t>(n_mels) * kSpecLd, 0.f), b_hi(basis_pad.size()), b_lo(basis_pad.size());
@@ -304,7 +306,7 @@ int spev_create(spev_ctx** out, int device, int sr, int n_fft, int hop, int win,
         (rc = upload(&c->d_win2048, win2048)) || (rc = upload(&c->d_tw2048, tw2048)) ||
         (rc = upload(&c->d_basis_pad, basis_pad)) || (rc = upload(&c->d_basis_hi, b_hi)) ||
         (rc = upload(&c->d_basis_lo, b_lo)) || (rc = upload(&c->d_pinv_t, pinv_t)) ||
-        (rc = upload(&c->d_prog_w, prog_w)) || (rc = upload(&c->d_prog_i, prog_i)) ||
+        (rc = upload(&c->d_prog_w, prog_w)) || (rc = upload(&c->d_prog_i, prog_i)) || (rc = upload(&c->d_prog_p, prog_p)) ||
         (rc = gemm_tc_init(c))) {
         spev_destroy(c);
         return rc;
@@ -319,7 +321,7 @@ void spev_destroy(spev_ctx* c) {
     gemm_tc_destroy(c);
     cudaFree(c->d_tw); cudaFree(c->d_window); cudaFree(c->d_win2048); cudaFree(c->d_tw2048); cudaFree(c->d_basis_pad); cudaFree(c->d_basis_hi);
     cudaFree(c->d_basis_lo); cudaFree(c->d_pinv_t); cudaFree(c->d_pinv_hi); cudaFree(c->d_pinv_lo);
-    cudaFree(c->d_prog_w); cudaFree(c->d_prog_i);
+    cudaFree(c->d_prog_w); cudaFree(c->d_prog_i); cudaFree(c->d_prog_p);
     delete c;
 }
 
@@ -359,6 +361,13 @@ int spev_host_pinv(const float* a, int m, int n, float* pinv) {
 int spev_set_tensor_core(spev_ctx* c, int enable) {
     SPEV_REQUIRE(c, SPEV_E_INVALID, "ctx is null");
     c->use_tc = enable ? 1 : 0;
+    return SPEV_OK;
+}
+
+int spev_set_logmel_variant(spev_ctx* c, int variant) {
+    SPEV_REQUIRE(c, SPEV_E_INVALID, "ctx is null");
+    SPEV_REQUIRE(variant == 0 || variant == 1, SPEV_E_INVALID, "spev_set_logmel_variant: 0 (tile lock-step) or 1 (decoupled warps)");
+    c->k1_variant = variant;
     return SPEV_OK;
 }
 

@@ -509,6 +509,170 @@ k_stft_phase_w(BatchView bv, const float* __restrict__ y, const float* __restric
 }
 
 // ---------------------------------------------------------------------------------------
+// K1 (default): fused STFT -> power -> mel -> log with DECOUPLED warps
+//
+// Same arithmetic as k_stft_mel<0> (bit-identical results), different schedule.  In the tile kernel above every
+// warp of the CTA walks through "stage / FFT / mel / copy-out" in lock-step, separated by three CTA barriers per
+// 32-frame tile: the four warps of a scheduler hit the shared-memory bursts, the latency-bound mel chains and the
+// barriers together (ncu: issue-active 65 %).  Here a warp owns one frame pair per tile end to end:
+//   * it stages its own 1280 samples with cp.async into its warp-private region (which is also its transpose
+//     tile), one pair ahead -- no CTA-wide staging buffer, no CTA barrier for the samples;
+//   * |X|^2 goes to a dedicated CTA buffer P (32 frames x 516 words) because the mel phase needs all 32 frames
+//     (lane <-> frame) -- the only cross-warp exchange;
+//   * all synchronisation is SPLIT-PHASE on four mbarriers (FULL: P written, EMPTY: P consumed, OUT: mel rows
+//     staged, COPIED: rows stored): a warp arrives as soon as its share is done and waits only where it needs the
+//     others', with the copy-out of the previous tile and the register-only first half of its next transform
+//     (frame loads, 32-point DFTs, twiddles) in between.  Warps drift apart by up to about a third of a tile, so
+//     the mel chains and exchanges of some overlap the FFT arithmetic of others.
+// Shared memory: twiddles 8 KB, window 4 KB, 16 regions x 8,480 B, P 66,048 B, staged rows 10,368 B, mel program.
+// ---------------------------------------------------------------------------------------
+constexpr int kPRow2 = 2 * kPSlot;               // words per frame PAIR in P: 1032 == 2 (mod 8) in 16-byte units
+constexpr int kPWords = kWarps * kPRow2;         // 16,512 words
+
+__global__ void __launch_bounds__(kThreads, 1)
+k_stft_mel_ws(BatchView bv, const float* __restrict__ samples, float* __restrict__ out,
+              const float2* __restrict__ g_tw, const float* __restrict__ g_win, MelProgram mb,
+              int log_mode, float floor_v, float lo, float hi) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* s_tw = reinterpret_cast<float2*>(smem_raw);
+    float* s_win = reinterpret_cast<float*>(s_tw + 1024);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_win + 1024);          // [4] FULL, EMPTY, OUT, COPIED (+4 pad)
+    float* s_x = reinterpret_cast<float*>(s_bar + 8);                     // 16 warp regions
+    float* s_p = s_x + kWarps * kXWords;                                  // |X|^2 of the tile
+    float* s_out = s_p + kPWords;                                         // [32][n_mels + 1]
+    float4* s_gw = reinterpret_cast<float4*>(s_out + kTileFrames * (mb.n_mels + 1) + ((4 - (kTileFrames * (mb.n_mels + 1)) % 4) % 4));
+    int* s_gi = reinterpret_cast<int*>(s_gw + kWarps * mb.gmax);          // first bin | (mel + 1) << 16
+    uint64_t* b_full = s_bar, *b_empty = s_bar + 1, *b_out = s_bar + 2, *b_copied = s_bar + 3;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    load_tables(s_tw, s_win, g_tw, g_win, 0.5f);
+    for (int i = threadIdx.x; i < kWarps * mb.gmax; i += blockDim.x) { s_gw[i] = mb.gw[i]; s_gi[i] = mb.gp[i]; }
+    if (threadIdx.x == 0) {
+        bar_init(b_full, kWarps); bar_init(b_empty, kWarps); bar_init(b_out, kWarps); bar_init(b_copied, kWarps);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();                                                      // the only CTA-wide barrier
+
+    float* region = s_x + warp * kXWords;
+    float2* xb = reinterpret_cast<float2*>(region);
+    const int n_mels = mb.n_mels, out_pitch = n_mels + 1;
+    const int rows_per_pass = kThreads / n_mels;
+    const int cp_m = threadIdx.x % n_mels, cp_f0 = threadIdx.x / n_mels;
+    const float* pf = s_p + (lane >> 1) * kPRow2 + (lane & 1) * kPSlot;   // mel phase: lane <-> frame
+    float* pw = s_p + warp * kPRow2;                                      // this warp's two rows of P
+    const float4* gw = s_gw + warp * mb.gmax;
+    const int* gi = s_gi + warp * mb.gmax;
+
+    const int first = blockIdx.x, stride = gridDim.x;
+    const int my_n = first < bv.n_ftiles ? (bv.n_ftiles - first + stride - 1) / stride : 0;
+    const int64_t n_pairs = static_cast<int64_t>(bv.n_ftiles) * kWarps;
+
+    // mel projection + log of tile j (all 32 frames, this warp's bands) into s_out
+    auto mel_phase = [&](int j) {
+        bar_wait(b_full, j & 1);                       // everybody's |X|^2 of tile j is in P
+        if (j >= 1) bar_wait(b_copied, (j - 1) & 1);   // tile j-1's rows have left s_out
+        float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll 4
+        for (int g = 0; g < mb.gmax; ++g) {
+            const float4 w = gw[g];                    // warp-uniform: broadcast
+            const int inf = gi[g];
+            const float4 x = *reinterpret_cast<const float4*>(pf + (inf & 0xffff));   // conflict-free LDS.128
+            acc0 = fmaf(w.x, x.x, acc0);
+            acc1 = fmaf(w.y, x.y, acc1);
+            acc0 = fmaf(w.z, x.z, acc0);
+            acc1 = fmaf(w.w, x.w, acc1);
+            if (inf >> 16) {                           // last group of band (inf >> 16) - 1: emit (warp-uniform)
+                float acc = acc0 + acc1;
+                if (log_mode) acc = fminf(fmaxf(__logf(fmaxf(acc, floor_v)), lo), hi);
+                s_out[lane * out_pitch + (inf >> 16) - 1] = acc;
+                acc0 = 0.f; acc1 = 0.f;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) { bar_arrive(b_out); bar_arrive(b_empty); }
+    };
+    // store the staged rows of tile j (this thread's share)
+    auto copy_out = [&](int j) {
+        const spev_tile* d = bv.ftiles + first + static_cast<int64_t>(j) * stride;
+        const int nf = __ldg(&d->n);
+        const int64_t row0 = __ldg(&d->row0);
+        bar_wait(b_out, j & 1);                        // everybody's bands of tile j are in s_out
+        float* o = out + row0 * n_mels;
+        if (cp_f0 < rows_per_pass)
+            for (int f = cp_f0; f < nf; f += rows_per_pass) o[f * n_mels + cp_m] = s_out[f * out_pitch + cp_m];
+        __syncwarp();
+        if (lane == 0) bar_arrive(b_copied);
+    };
+
+    PairInfo cur{0, 0, 0};
+    if (my_n > 0) cur = stage_pair(region, samples, bv.ftiles, static_cast<int64_t>(first) * kWarps + warp, n_pairs, lane);
+    cp_async_commit();
+
+    for (int i = 0; i < my_n; ++i) {
+        // ---- front half of tile i's transform: registers only ----
+        float2 v[32];
+        cp_async_wait_all();
+        __syncwarp();
+        if (cur.valid) {
+            load_frame_pair(v, region, s_win, 0, cur.b_valid != 0, lane);
+            dft32<-1>(v);
+            static_for<1, 32>([&](auto k1c) {
+                constexpr int k1 = decltype(k1c)::value;
+                v[k1] = cmul(v[k1], s_tw[k1 * 32 + lane]);
+            });
+        }
+        __syncwarp();                                  // staged samples consumed: the region may be overwritten
+        // ---- previous tile: mel phase (needs all warps' P; they had the whole front half above to get there) ----
+        if (i >= 1) mel_phase(i - 1);
+        // ---- back half: exchange, second DFT, Hermitian split, |X|^2 -> P ----
+        PairInfo nxt{0, 0, 0};
+        if (cur.valid) {
+            static_for<0, 32>([&](auto k1c) {
+                constexpr int k1 = decltype(k1c)::value;
+                xb[k1 * kXPitch + lane] = v[k1];
+            });
+            __syncwarp();
+            static_for<0, 32>([&](auto n2c) {
+                constexpr int n2 = decltype(n2c)::value;
+                v[n2] = xb[lane * kXPitch + n2];
+            });
+            __syncwarp();                              // tile read back: free for the next pair's samples
+        }
+        if (i + 1 < my_n)
+            nxt = stage_pair(region, samples, bv.ftiles, (static_cast<int64_t>(first) + static_cast<int64_t>(i + 1) * stride) * kWarps + warp,
+                             n_pairs, lane);
+        cp_async_commit();
+        if (cur.valid) {
+            dft32<-1>(v);
+            float2 p[16];
+            fetch_mirror(v, p, lane);
+            if (i >= 1) bar_wait(b_empty, (i - 1) & 1);   // everybody has finished reading P of tile i-1
+            const float pa512 = 4.f * v[16].x * v[16].x, pb512 = 4.f * v[16].y * v[16].y;
+            static_for<0, 16>([&](auto kc) {
+                constexpr int k2 = decltype(kc)::value;
+                float2 xa, xb2;
+                split_pair_prescaled(v[k2], p[k2], xa, xb2);
+                pw[lane + 32 * k2] = fmaf(xa.x, xa.x, xa.y * xa.y);
+                pw[kPSlot + lane + 32 * k2] = fmaf(xb2.x, xb2.x, xb2.y * xb2.y);
+            });
+            if (lane < 4) {   // bin 512 + three zero words so that padded float4 band reads stay clean
+                pw[512 + lane] = lane == 0 ? pa512 : 0.f;
+                pw[kPSlot + 512 + lane] = lane == 0 ? pb512 : 0.f;
+            }
+        } else if (i >= 1) {
+            bar_wait(b_empty, (i - 1) & 1);            // keep the phase bookkeeping uniform
+        }
+        __syncwarp();
+        if (lane == 0) bar_arrive(b_full);
+        // ---- the previous tile's staged rows (everybody's bands arrived before their own back half) ----
+        if (i >= 1) copy_out(i - 1);
+        cur = nxt;
+    }
+    // ---- drain: the last tile ----
+    if (my_n >= 1) { mel_phase(my_n - 1); copy_out(my_n - 1); }
+}
+
+// ---------------------------------------------------------------------------------------
 // K4: ISTFT with gather overlap-add and window-sum-square normalisation
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads, 1)
@@ -769,13 +933,25 @@ int launch_stft_mel(spev_ctx* ctx, const spev_batch* b, const float* samples, fl
     if (rc) return rc;
     if (b->n_ftiles == 0) return SPEV_OK;
     SPEV_REQUIRE(samples && out, SPEV_E_INVALID, "null samples/out");
-    MelProgram mb{ctx->n_mels, ctx->prog_gmax, ctx->d_prog_w, ctx->d_prog_i};
+    MelProgram mb{ctx->n_mels, ctx->prog_gmax, ctx->d_prog_w, ctx->d_prog_i, ctx->d_prog_p};
     const size_t smem = smem_stft(ctx->prog_gmax);
     SPEV_REQUIRE(smem <= 232448, SPEV_E_UNSUPPORTED,
                  "this mel basis (n_mels=%d: %d float4 groups per warp program) does not fit the fused kernel's shared memory "
                  "(%zu B > 232448); bands wider than ~128 bins (n_mels below ~24 at 22 kHz) are not supported",
                  ctx->n_mels, ctx->prog_gmax, smem);
     const int grid = std::min<int64_t>(b->n_ftiles, ctx->num_sms);
+    const size_t out_words = (static_cast<size_t>(kTileFrames) * (ctx->n_mels + 1) + 3) & ~static_cast<size_t>(3);
+    const size_t smem_ws = sizeof(float2) * 1024 + sizeof(float) * 1024 + sizeof(uint64_t) * 8 +
+                           sizeof(float) * kWarps * kXWords + sizeof(float) * kPWords + sizeof(float) * out_words +
+                           (sizeof(float4) + sizeof(int)) * kWarps * ctx->prog_gmax;
+    if (!power_only && ctx->k1_variant == 1 && smem_ws <= 232448) {
+        rc = set_smem(k_stft_mel_ws, smem_ws);
+        if (rc) return rc;
+        k_stft_mel_ws<<<grid, kThreads, smem_ws, st>>>(view_of(b), samples, out, ctx->d_tw, ctx->d_window, mb, log_mode,
+                                                       floor_v, lo, hi);
+        SPEV_CUDA(cudaGetLastError());
+        return SPEV_OK;
+    }
     if (power_only) {
         rc = set_smem(k_stft_mel<1>, smem);
         if (rc) return rc;

@@ -45,6 +45,7 @@ struct MelProgram {
     int gmax;            // groups per warp
     const float4* gw;    // dev [16*gmax]
     const int2* gi;      // dev [16*gmax]
+    const int* gp;       // dev [16*gmax] packed form: first bin | (mel index + 1) << 16 (0 in the high half: no emit)
 };
 
 }  // namespace spev
@@ -71,9 +72,11 @@ struct spev_ctx {
     float* d_pinv_lo;    //   residual
     float4* d_prog_w;    // mel program of the fused kernel (MelProgram)
     int2* d_prog_i;
+    int* d_prog_p;       // packed (bin | (mel+1) << 16) form of d_prog_i
     int prog_gmax;
     int band_nnz;        // nnz of the basis (diagnostics)
     int band_max_len;
     void* tma;           // opaque: tensor-map cache (gemm_tc.cu)
     int use_tc;          // mel->magnitude on frame-major input uses the tcgen05 GEMM
+    int k1_variant;      // fused log-mel kernel: 1 = decoupled warps (k_stft_mel_ws, default), 0 = tile lock-step (k_stft_mel<0>)
 };

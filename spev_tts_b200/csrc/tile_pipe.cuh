@@ -60,6 +60,31 @@ __device__ __forceinline__ void fetch_desc(spev_tile* slot, const spev_tile* g) 
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
 
+// ---------------------------------------------------------------------------------------
+// split-phase CTA synchronisation on shared-memory mbarriers: a warp ARRIVES when its part of a
+// phase is done and WAITS only where it needs everybody's part -- with useful work in between.
+// (one elected lane arrives after __syncwarp(); waits are bounded: a protocol bug traps instead of hanging)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void bar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];\n" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_addr(bar);
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (spin > (1u << 26)) asm volatile("trap;\n");
+    }
+}
+
 // Persistent-loop bookkeeping shared by the kernels: prologue of the descriptor ring.
 __device__ __forceinline__ int ring_prologue(spev_tile* s_ring, const spev_tile* tiles, int n_tiles) {
     const int first = blockIdx.x, stride = gridDim.x;
