@@ -220,7 +220,7 @@ int spev_create(spev_ctx** out, int device, int sr, int n_fft, int hop, int win,
     c->fmin = fmin; c->fmax = fmax; c->num_sms = c->num_sms_device = prop.multiProcessorCount; c->tma = nullptr; c->use_tc = 1; c->k1_variant = 1;
     c->d_tw = nullptr; c->d_window = nullptr; c->d_win2048 = nullptr; c->d_tw2048 = nullptr; c->d_basis_pad = c->d_basis_hi = c->d_basis_lo = nullptr;
     c->d_pinv_t = c->d_pinv_hi = c->d_pinv_lo = nullptr;
-    c->d_prog_w = nullptr; c->d_prog_i = nullptr; c->d_prog_p = nullptr;
+    c->d_prog_w = nullptr; c->d_prog_h = nullptr;
 
     // periodic Hann, float64 -> float32
     c->h_window.resize(kNfft);
@@ -254,42 +254,46 @@ int spev_create(spev_ctx** out, int device, int sr, int n_fft, int hop, int win,
         bn4[m] = hi >= lo ? (hi - bstart[m] + 4) / 4 : 1;   // an empty filter still emits (a zero)
         c->band_max_len = std::max(c->band_max_len, hi >= lo ? hi - lo + 1 : 0);
     }
+    // Bands are dealt to the 16 warps, at most nb = ceil(n_mels / 16) each, longest first onto the least-loaded warp
+    // (LPT).  A warp's weights are stored band after band as float4 groups of consecutive bins, so a band is fully
+    // described by one header: (first group, first bin, group count, mel index).
+    const int nb = (n_mels + kWarps - 1) / kWarps;
     std::vector<std::vector<int>> warp_bands(kWarps);
     {
         std::vector<int> by_len(n_mels), load(kWarps, 0);
         for (int m = 0; m < n_mels; ++m) by_len[m] = m;
         std::stable_sort(by_len.begin(), by_len.end(), [&](int a, int b) { return bn4[a] > bn4[b]; });
         for (int m : by_len) {
-            const int w = static_cast<int>(std::min_element(load.begin(), load.end()) - load.begin());
+            int w = -1;
+            for (int q = 0; q < kWarps; ++q)
+                if (static_cast<int>(warp_bands[q].size()) < nb && (w < 0 || load[q] < load[w])) w = q;
             warp_bands[w].push_back(m);
             load[w] += bn4[m] + 1;   // +1: emit cost
         }
     }
+    std::vector<float4> prog_w;
+    std::vector<int4> prog_h(static_cast<size_t>(kWarps) * nb, make_int4(0, 0, 0, -1));
     int gmax = 1;
     for (int w = 0; w < kWarps; ++w) {
-        int g = 0;
-        for (int m : warp_bands[w]) g += bn4[m];
-        gmax = std::max(gmax, g);
-    }
-    gmax = (gmax + 3) & ~3;   // unroll-friendly
-    std::vector<float4> prog_w(static_cast<size_t>(kWarps) * gmax, make_float4(0.f, 0.f, 0.f, 0.f));
-    std::vector<int2> prog_i(static_cast<size_t>(kWarps) * gmax, make_int2(0, -1));
-    for (int w = 0; w < kWarps; ++w) {
-        int g = w * gmax;
-        for (int m : warp_bands[w])
-            for (int j = 0; j < bn4[m]; ++j, ++g) {
+        int gw = 0;
+        for (size_t q = 0; q < warp_bands[w].size(); ++q) {
+            const int m = warp_bands[w][q];
+            prog_h[static_cast<size_t>(w) * nb + q] = make_int4(static_cast<int>(prog_w.size()), bstart[m], bn4[m], m);
+            for (int j = 0; j < bn4[m]; ++j) {
                 float wv[4];
-                for (int q = 0; q < 4; ++q) {
-                    const int bin = bstart[m] + 4 * j + q;   // bins 513..515 of a slot are kept at zero
-                    wv[q] = bin < kBins ? c->h_basis[static_cast<size_t>(m) * kBins + bin] : 0.f;
+                for (int t = 0; t < 4; ++t) {
+                    const int bin = bstart[m] + 4 * j + t;   // bins 513..515 of a slot are kept at zero
+                    wv[t] = bin < kBins ? c->h_basis[static_cast<size_t>(m) * kBins + bin] : 0.f;
                 }
-                prog_w[g] = make_float4(wv[0], wv[1], wv[2], wv[3]);
-                prog_i[g] = make_int2(bstart[m] + 4 * j, j == bn4[m] - 1 ? m : -1);
+                prog_w.push_back(make_float4(wv[0], wv[1], wv[2], wv[3]));
             }
+            gw += bn4[m];
+        }
+        gmax = std::max(gmax, gw);
     }
     c->prog_gmax = gmax;
-    std::vector<int> prog_p(prog_i.size());
-    for (size_t g = 0; g < prog_i.size(); ++g) prog_p[g] = prog_i[g].x | ((prog_i[g].y + 1) << 16);
+    c->prog_nb = nb;
+    c->prog_groups = static_cast<int>(prog_w.size());
 
     // padded / split operands for the tensor-core GEMMs
     std::vector<float> basis_pad(static_cast<size_t>(n_mels) * kSpecLd, 0.f), b_hi(basis_pad.size()), b_lo(basis_pad.size());
@@ -306,7 +310,7 @@ int spev_create(spev_ctx** out, int device, int sr, int n_fft, int hop, int win,
         (rc = upload(&c->d_win2048, win2048)) || (rc = upload(&c->d_tw2048, tw2048)) ||
         (rc = upload(&c->d_basis_pad, basis_pad)) || (rc = upload(&c->d_basis_hi, b_hi)) ||
         (rc = upload(&c->d_basis_lo, b_lo)) || (rc = upload(&c->d_pinv_t, pinv_t)) ||
-        (rc = upload(&c->d_prog_w, prog_w)) || (rc = upload(&c->d_prog_i, prog_i)) || (rc = upload(&c->d_prog_p, prog_p)) ||
+        (rc = upload(&c->d_prog_w, prog_w)) || (rc = upload(&c->d_prog_h, prog_h)) ||
         (rc = gemm_tc_init(c))) {
         spev_destroy(c);
         return rc;
@@ -321,7 +325,7 @@ void spev_destroy(spev_ctx* c) {
     gemm_tc_destroy(c);
     cudaFree(c->d_tw); cudaFree(c->d_window); cudaFree(c->d_win2048); cudaFree(c->d_tw2048); cudaFree(c->d_basis_pad); cudaFree(c->d_basis_hi);
     cudaFree(c->d_basis_lo); cudaFree(c->d_pinv_t); cudaFree(c->d_pinv_hi); cudaFree(c->d_pinv_lo);
-    cudaFree(c->d_prog_w); cudaFree(c->d_prog_i); cudaFree(c->d_prog_p);
+    cudaFree(c->d_prog_w); cudaFree(c->d_prog_h);
     delete c;
 }
 

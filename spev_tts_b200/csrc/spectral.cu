@@ -102,9 +102,60 @@ __device__ __forceinline__ void load_frame_pair(float2 (&v)[32], const float* s_
 }
 
 // ---------------------------------------------------------------------------------------
+// Mel phase shared by the fused kernels: lane <-> frame (pf = the lane's |X|^2 row, conflict-free LDS.128),
+// warp <-> its NB bands.  Per float4 group: one broadcast LDS.128 of weights, one LDS.128 of |X|^2, four FFMA --
+// no index loads, no per-group branch (a band is a run of consecutive bins); the NB results stay in registers
+// until all bands are done, so nothing orders the loads behind a store and they pipeline freely.
+// NB == 0: run-time band count (n_mels > 128).
+// ---------------------------------------------------------------------------------------
+template <int NB>
+__device__ __forceinline__ void mel_bands(const float* __restrict__ pf, const float4* __restrict__ s_gw,
+                                          const int4* __restrict__ hdr, int nb_rt, float* __restrict__ s_row,
+                                          int log_mode, float floor_v, float lo, float hi) {
+    auto band = [&](const int4 h) {
+        const float4* wv = s_gw + h.x;
+        const float* px = pf + h.y;
+        float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll 2
+        for (int g = 0; g < h.z; ++g) {
+            const float4 w = wv[g];
+            const float4 x = *reinterpret_cast<const float4*>(px + 4 * g);
+            acc0 = fmaf(w.x, x.x, acc0);
+            acc1 = fmaf(w.y, x.y, acc1);
+            acc0 = fmaf(w.z, x.z, acc0);
+            acc1 = fmaf(w.w, x.w, acc1);
+        }
+        float acc = acc0 + acc1;
+        // __logf: <= 3 ulp (2^-21.4 abs in [0.5,2]) -- far inside the 1e-4 tolerance
+        if (log_mode) acc = fminf(fmaxf(__logf(fmaxf(acc, floor_v)), lo), hi);
+        return acc;
+    };
+    if constexpr (NB > 0) {
+        float r[NB];
+        int mel[NB];
+        static_for<0, NB>([&](auto bc) {
+            constexpr int b = decltype(bc)::value;
+            const int4 h = hdr[b];
+            r[b] = band(h);
+            mel[b] = h.w;
+        });
+        static_for<0, NB>([&](auto bc) {
+            constexpr int b = decltype(bc)::value;
+            if (mel[b] >= 0) s_row[mel[b]] = r[b];
+        });
+    } else {
+        for (int b = 0; b < nb_rt; ++b) {
+            const int4 h = hdr[b];
+            const float r = band(h);
+            if (h.w >= 0) s_row[h.w] = r;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // K1: fused STFT -> power -> mel -> log
 // ---------------------------------------------------------------------------------------
-template <int MODE>   // 0: mel epilogue, 1: power-spectrum output
+template <int MODE, int NB>   // MODE 0: mel epilogue (NB bands per warp, 0 = run time), 1: power-spectrum output
 __global__ void __launch_bounds__(kThreads, 1)
 k_stft_mel(BatchView bv, const float* __restrict__ samples, float* __restrict__ out,
            const float2* __restrict__ g_tw, const float* __restrict__ g_win, MelProgram mb,
@@ -115,13 +166,14 @@ k_stft_mel(BatchView bv, const float* __restrict__ samples, float* __restrict__ 
     spev_tile* s_ring = reinterpret_cast<spev_tile*>(s_win + 1024);
     float* s_stage = reinterpret_cast<float*>(s_ring + kRing);
     float* s_x = s_stage + 2 * kStageSamples;
-    float4* s_gw = reinterpret_cast<float4*>(s_x + kWarps * kWarpRegionWords);   // [16*gmax], 16-B aligned
-    int2* s_gi = reinterpret_cast<int2*>(s_gw + kWarps * mb.gmax);
+    float4* s_gw = reinterpret_cast<float4*>(s_x + kWarps * kWarpRegionWords);   // [n_groups], 16-B aligned
+    int4* s_hdr = reinterpret_cast<int4*>(s_gw + mb.n_groups);                   // [16*nb]
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     load_tables(s_tw, s_win, g_tw, g_win, 0.5f);
     if (MODE == 0) {
-        for (int i = threadIdx.x; i < kWarps * mb.gmax; i += blockDim.x) { s_gw[i] = mb.gw[i]; s_gi[i] = mb.gi[i]; }
+        for (int i = threadIdx.x; i < mb.n_groups; i += blockDim.x) s_gw[i] = mb.gw[i];
+        for (int i = threadIdx.x; i < kWarps * mb.nb; i += blockDim.x) s_hdr[i] = mb.hdr[i];
     }
     float* xw = s_x + warp * kWarpRegionWords;
     const int n_mels = mb.n_mels;
@@ -192,29 +244,9 @@ k_stft_mel(BatchView bv, const float* __restrict__ samples, float* __restrict__ 
             // copied out as contiguous rows; storing 4-byte values straight from this loop was
             // measured slower (650 vs 702 M frames/s: 32 sectors per store instruction).
             float* s_out = stage;
-            {   // lanes >= nf run on stale slots; their rows are never copied out (no divergence)
-                const float* pf = s_x + (lane >> 1) * kWarpRegionWords + (lane & 1) * kPSlot;
-                const float4* gw = s_gw + warp * mb.gmax;
-                const int2* gi = s_gi + warp * mb.gmax;
-                float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll 4
-                for (int g = 0; g < mb.gmax; ++g) {
-                    const float4 w = gw[g];                 // warp-uniform: broadcast
-                    const int2 inf = gi[g];
-                    const float4 x = *reinterpret_cast<const float4*>(pf + inf.x);   // conflict-free LDS.128
-                    acc0 = fmaf(w.x, x.x, acc0);
-                    acc1 = fmaf(w.y, x.y, acc1);
-                    acc0 = fmaf(w.z, x.z, acc0);
-                    acc1 = fmaf(w.w, x.w, acc1);
-                    if (inf.y >= 0) {                       // last group of band inf.y: emit (warp-uniform)
-                        float acc = acc0 + acc1;
-                        // __logf: <= 3 ulp (2^-21.4 abs in [0.5,2]) -- far inside the 1e-4 tolerance
-                        if (log_mode) acc = fminf(fmaxf(__logf(fmaxf(acc, floor_v)), lo), hi);
-                        s_out[lane * out_pitch + inf.y] = acc;
-                        acc0 = 0.f; acc1 = 0.f;
-                    }
-                }
-            }
+            // lanes >= nf run on stale slots; their rows are never copied out (no divergence)
+            mel_bands<NB>(s_x + (lane >> 1) * kWarpRegionWords + (lane & 1) * kPSlot, s_gw, s_hdr + warp * mb.nb, mb.nb,
+                          s_out + lane * out_pitch, log_mode, floor_v, lo, hi);
             __syncthreads();   // B3
             float* o = out + row0 * n_mels;
             if (cp_f0 < rows_per_pass)
@@ -529,6 +561,7 @@ k_stft_phase_w(BatchView bv, const float* __restrict__ y, const float* __restric
 constexpr int kPRow2 = 2 * kPSlot;               // words per frame PAIR in P: 1032 == 2 (mod 8) in 16-byte units
 constexpr int kPWords = kWarps * kPRow2;         // 16,512 words
 
+template <int NB>
 __global__ void __launch_bounds__(kThreads, 1)
 k_stft_mel_ws(BatchView bv, const float* __restrict__ samples, float* __restrict__ out,
               const float2* __restrict__ g_tw, const float* __restrict__ g_win, MelProgram mb,
@@ -541,12 +574,13 @@ k_stft_mel_ws(BatchView bv, const float* __restrict__ samples, float* __restrict
     float* s_p = s_x + kWarps * kXWords;                                  // |X|^2 of the tile
     float* s_out = s_p + kPWords;                                         // [32][n_mels + 1]
     float4* s_gw = reinterpret_cast<float4*>(s_out + kTileFrames * (mb.n_mels + 1) + ((4 - (kTileFrames * (mb.n_mels + 1)) % 4) % 4));
-    int* s_gi = reinterpret_cast<int*>(s_gw + kWarps * mb.gmax);          // first bin | (mel + 1) << 16
+    int4* s_hdr = reinterpret_cast<int4*>(s_gw + mb.n_groups);
     uint64_t* b_full = s_bar, *b_empty = s_bar + 1, *b_out = s_bar + 2, *b_copied = s_bar + 3;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     load_tables(s_tw, s_win, g_tw, g_win, 0.5f);
-    for (int i = threadIdx.x; i < kWarps * mb.gmax; i += blockDim.x) { s_gw[i] = mb.gw[i]; s_gi[i] = mb.gp[i]; }
+    for (int i = threadIdx.x; i < mb.n_groups; i += blockDim.x) s_gw[i] = mb.gw[i];
+    for (int i = threadIdx.x; i < kWarps * mb.nb; i += blockDim.x) s_hdr[i] = mb.hdr[i];
     if (threadIdx.x == 0) {
         bar_init(b_full, kWarps); bar_init(b_empty, kWarps); bar_init(b_out, kWarps); bar_init(b_copied, kWarps);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -560,8 +594,7 @@ k_stft_mel_ws(BatchView bv, const float* __restrict__ samples, float* __restrict
     const int cp_m = threadIdx.x % n_mels, cp_f0 = threadIdx.x / n_mels;
     const float* pf = s_p + (lane >> 1) * kPRow2 + (lane & 1) * kPSlot;   // mel phase: lane <-> frame
     float* pw = s_p + warp * kPRow2;                                      // this warp's two rows of P
-    const float4* gw = s_gw + warp * mb.gmax;
-    const int* gi = s_gi + warp * mb.gmax;
+    const int4* hdr = s_hdr + warp * mb.nb;
 
     const int first = blockIdx.x, stride = gridDim.x;
     const int my_n = first < bv.n_ftiles ? (bv.n_ftiles - first + stride - 1) / stride : 0;
@@ -571,23 +604,7 @@ k_stft_mel_ws(BatchView bv, const float* __restrict__ samples, float* __restrict
     auto mel_phase = [&](int j) {
         bar_wait(b_full, j & 1);                       // everybody's |X|^2 of tile j is in P
         if (j >= 1) bar_wait(b_copied, (j - 1) & 1);   // tile j-1's rows have left s_out
-        float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll 4
-        for (int g = 0; g < mb.gmax; ++g) {
-            const float4 w = gw[g];                    // warp-uniform: broadcast
-            const int inf = gi[g];
-            const float4 x = *reinterpret_cast<const float4*>(pf + (inf & 0xffff));   // conflict-free LDS.128
-            acc0 = fmaf(w.x, x.x, acc0);
-            acc1 = fmaf(w.y, x.y, acc1);
-            acc0 = fmaf(w.z, x.z, acc0);
-            acc1 = fmaf(w.w, x.w, acc1);
-            if (inf >> 16) {                           // last group of band (inf >> 16) - 1: emit (warp-uniform)
-                float acc = acc0 + acc1;
-                if (log_mode) acc = fminf(fmaxf(__logf(fmaxf(acc, floor_v)), lo), hi);
-                s_out[lane * out_pitch + (inf >> 16) - 1] = acc;
-                acc0 = 0.f; acc1 = 0.f;
-            }
-        }
+        mel_bands<NB>(pf, s_gw, hdr, mb.nb, s_out + lane * out_pitch, log_mode, floor_v, lo, hi);
         __syncwarp();
         if (lane == 0) { bar_arrive(b_out); bar_arrive(b_empty); }
     };
@@ -885,9 +902,9 @@ k_mel_to_mag(BatchView bv, const float* __restrict__ mel, int layout, int is_log
 // host-side launchers
 // ---------------------------------------------------------------------------------------
 static size_t smem_common() { return sizeof(float2) * 1024 + sizeof(float) * 1024 + sizeof(spev_tile) * kRing; }
-static size_t smem_stft(int gmax) {
-    return smem_common() + sizeof(float) * 2 * kStageSamples + sizeof(float) * kWarps * kWarpRegionWords +
-           (sizeof(float4) + sizeof(int2)) * kWarps * gmax;
+static size_t smem_prog(const spev_ctx* c) { return sizeof(float4) * c->prog_groups + sizeof(int4) * kWarps * c->prog_nb; }
+static size_t smem_stft(size_t prog_bytes) {
+    return smem_common() + sizeof(float) * 2 * kStageSamples + sizeof(float) * kWarps * kWarpRegionWords + prog_bytes;
 }
 static size_t smem_istft() { return smem_common() + sizeof(float) * kHop + sizeof(float) * kWarps * kWarpRegionWords; }
 
@@ -933,38 +950,35 @@ int launch_stft_mel(spev_ctx* ctx, const spev_batch* b, const float* samples, fl
     if (rc) return rc;
     if (b->n_ftiles == 0) return SPEV_OK;
     SPEV_REQUIRE(samples && out, SPEV_E_INVALID, "null samples/out");
-    MelProgram mb{ctx->n_mels, ctx->prog_gmax, ctx->d_prog_w, ctx->d_prog_i, ctx->d_prog_p};
-    const size_t smem = smem_stft(ctx->prog_gmax);
+    MelProgram mb{ctx->n_mels, ctx->prog_nb, ctx->prog_groups, ctx->d_prog_w, ctx->d_prog_h};
+    const size_t smem = smem_stft(power_only ? 0 : smem_prog(ctx));
     SPEV_REQUIRE(smem <= 232448, SPEV_E_UNSUPPORTED,
-                 "this mel basis (n_mels=%d: %d float4 groups per warp program) does not fit the fused kernel's shared memory "
+                 "this mel basis (n_mels=%d: %d float4 weight groups) does not fit the fused kernel's shared memory "
                  "(%zu B > 232448); bands wider than ~128 bins (n_mels below ~24 at 22 kHz) are not supported",
-                 ctx->n_mels, ctx->prog_gmax, smem);
+                 ctx->n_mels, ctx->prog_groups, smem);
     const int grid = std::min<int64_t>(b->n_ftiles, ctx->num_sms);
     const size_t out_words = (static_cast<size_t>(kTileFrames) * (ctx->n_mels + 1) + 3) & ~static_cast<size_t>(3);
     const size_t smem_ws = sizeof(float2) * 1024 + sizeof(float) * 1024 + sizeof(uint64_t) * 8 +
                            sizeof(float) * kWarps * kXWords + sizeof(float) * kPWords + sizeof(float) * out_words +
-                           (sizeof(float4) + sizeof(int)) * kWarps * ctx->prog_gmax;
-    if (!power_only && ctx->k1_variant == 1 && smem_ws <= 232448) {
-        rc = set_smem(k_stft_mel_ws, smem_ws);
-        if (rc) return rc;
-        k_stft_mel_ws<<<grid, kThreads, smem_ws, st>>>(view_of(b), samples, out, ctx->d_tw, ctx->d_window, mb, log_mode,
-                                                       floor_v, lo, hi);
+                           smem_prog(ctx);
+    const bool ws = !power_only && ctx->k1_variant == 1 && smem_ws <= 232448;
+    const size_t bytes = ws ? smem_ws : smem;
+    auto go = [&](auto kernel, bool mel) -> int {
+        int rc2 = set_smem(kernel, bytes);
+        if (rc2) return rc2;
+        kernel<<<grid, kThreads, bytes, st>>>(view_of(b), samples, out, ctx->d_tw, ctx->d_window, mb, mel ? log_mode : 0,
+                                              mel ? floor_v : 0.f, mel ? lo : 0.f, mel ? hi : 0.f);
         SPEV_CUDA(cudaGetLastError());
         return SPEV_OK;
+    };
+    if (power_only) return go(k_stft_mel<1, 0>, false);
+#define SPEV_K1_CASE(NBV) case NBV: return ws ? go(k_stft_mel_ws<NBV>, true) : go(k_stft_mel<0, NBV>, true)
+    switch (mb.nb) {
+        SPEV_K1_CASE(1); SPEV_K1_CASE(2); SPEV_K1_CASE(3); SPEV_K1_CASE(4);
+        SPEV_K1_CASE(5); SPEV_K1_CASE(6); SPEV_K1_CASE(7); SPEV_K1_CASE(8);
+        default: return ws ? go(k_stft_mel_ws<0>, true) : go(k_stft_mel<0, 0>, true);
     }
-    if (power_only) {
-        rc = set_smem(k_stft_mel<1>, smem);
-        if (rc) return rc;
-        k_stft_mel<1><<<grid, kThreads, smem, st>>>(view_of(b), samples, out, ctx->d_tw,
-                                                    ctx->d_window, mb, 0, 0.f, 0.f, 0.f);
-    } else {
-        rc = set_smem(k_stft_mel<0>, smem);
-        if (rc) return rc;
-        k_stft_mel<0><<<grid, kThreads, smem, st>>>(view_of(b), samples, out, ctx->d_tw,
-                                                    ctx->d_window, mb, log_mode, floor_v, lo, hi);
-    }
-    SPEV_CUDA(cudaGetLastError());
-    return SPEV_OK;
+#undef SPEV_K1_CASE
 }
 
 int launch_stft_phase(spev_ctx* ctx, const spev_batch* b, const float* y, const float* S,

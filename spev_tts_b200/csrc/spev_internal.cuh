@@ -35,17 +35,15 @@ int cuda_fail(cudaError_t e, const char* what);
         }                                                                      \
     } while (0)
 
-// Mel projection of the fused kernel as a flat per-warp "program" built on the host: warp w runs
-// groups [w*gmax, (w+1)*gmax).  A group is four consecutive bins (start multiple of 4) of one
-// band: weights gw[g] (zero padded), first bin gi[g].x, and gi[g].y = mel index if this is the
-// band's last group (emit), else -1.  Bands are LPT-balanced over the 16 warps; short warps are
-// padded with zero-weight groups so that the trip count is uniform.
+// Mel projection of the fused kernels as a per-warp band list built on the host: warp w owns the nb bands
+// hdr[w*nb .. w*nb+nb) (LPT-balanced; unused slots have mel = -1).  A band is a run of float4 weight groups over
+// consecutive bins starting at a multiple of 4: hdr = (first group in gw, first bin, group count, mel index).
 struct MelProgram {
     int n_mels;
-    int gmax;            // groups per warp
-    const float4* gw;    // dev [16*gmax]
-    const int2* gi;      // dev [16*gmax]
-    const int* gp;       // dev [16*gmax] packed form: first bin | (mel index + 1) << 16 (0 in the high half: no emit)
+    int nb;              // bands per warp = ceil(n_mels / 16)
+    int n_groups;        // float4 groups in gw
+    const float4* gw;    // dev [n_groups]
+    const int4* hdr;     // dev [16*nb]
 };
 
 }  // namespace spev
@@ -71,9 +69,9 @@ struct spev_ctx {
     float* d_pinv_hi;    // [528, n_mels_pad]: pinv rows (K-major B operand), tf32 hi
     float* d_pinv_lo;    //   residual
     float4* d_prog_w;    // mel program of the fused kernel (MelProgram)
-    int2* d_prog_i;
-    int* d_prog_p;       // packed (bin | (mel+1) << 16) form of d_prog_i
-    int prog_gmax;
+    int4* d_prog_h;
+    int prog_gmax;       // most groups any warp runs (diagnostics)
+    int prog_nb, prog_groups;
     int band_nnz;        // nnz of the basis (diagnostics)
     int band_max_len;
     void* tma;           // opaque: tensor-map cache (gemm_tc.cu)

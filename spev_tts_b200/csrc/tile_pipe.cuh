@@ -78,10 +78,10 @@ __device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity) {
     for (uint32_t spin = 0; !done; ++spin) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}\n"
-            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-        if (spin > (1u << 26)) asm volatile("trap;\n");
+            : "=r"(done) : "r"(addr), "r"(parity), "r"(200000u) : "memory");   // sleep in hardware (<= 200 us) instead of polling
+        if (spin > (1u << 22)) asm volatile("trap;\n");
     }
 }
 
