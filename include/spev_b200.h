@@ -239,6 +239,9 @@ SPEV_API int spev_copy_segments(const void* src, void* dst, const int64_t* src_o
 /* A/B switch of the fused log-mel kernel: 1 (default) = decoupled warps with split-phase mbarrier synchronisation
  * (k_stft_mel_ws), 0 = the tile kernel with three CTA barriers per tile (k_stft_mel<0>).  Results are bit-identical. */
 SPEV_API int spev_set_logmel_variant(spev_ctx* ctx, int variant);
+/* A/B switch of the Griffin-Lim kernels: 1 (default) = dynamic tile tickets + bulk-staged tprev rows, 0 = the static
+ * round-robin tile kernels of round 1.  Same arithmetic, bit-identical results. */
+SPEV_API int spev_set_griffinlim_variant(spev_ctx* ctx, int variant);
 
 /* Cap the number of CTAs the persistent FFT kernels launch (default: one per SM).  A multi-GPU cache build that
  * overlaps the NCCL gather of finished chunks with the kernel of the next chunk leaves a few SMs to NCCL's

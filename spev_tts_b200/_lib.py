@@ -90,6 +90,7 @@ _SIGS = {
                                      C.c_int64, C.c_void_p]),
     "spev_set_sm_limit": (C.c_int, [C.c_void_p, C.c_int]),
     "spev_set_logmel_variant": (C.c_int, [C.c_void_p, C.c_int]),
+    "spev_set_griffinlim_variant": (C.c_int, [C.c_void_p, C.c_int]),
     "spev_lr_plan": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                C.c_void_p, C.c_void_p, C.c_void_p]),
     "spev_lr_expand": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_void_p,

@@ -32,8 +32,11 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 // launchers implemented in spectral.cu / lr.cu / gemm_tc.cu
 int launch_stft_mel(spev_ctx*, const spev_batch*, const float*, float*, bool, int, float, float, float, cudaStream_t);
-int launch_stft_phase(spev_ctx*, const spev_batch*, const float*, const float*, int64_t, void*, void*, int64_t, float, int, bool, cudaStream_t);
-int launch_istft(spev_ctx*, const spev_batch*, const void*, int64_t, float*, cudaStream_t);
+int launch_stft_phase(spev_ctx*, const spev_batch*, const float*, const float*, int64_t, void*, void*, int64_t, float, int, bool, cudaStream_t,
+                      unsigned* counter = nullptr, unsigned base = 0);
+int launch_istft(spev_ctx*, const spev_batch*, const void*, int64_t, float*, cudaStream_t, unsigned* counter = nullptr, unsigned base = 0);
+int fft_grid(const spev_ctx*, int64_t);
+int spectral_init(spev_ctx*);
 int launch_gl_init(spev_ctx*, const float*, int64_t, const float*, uint64_t, void*, int64_t, int64_t, cudaStream_t);
 int launch_mel_to_mag(spev_ctx*, const spev_batch*, const float*, int, int, float*, int64_t, cudaStream_t);
 int launch_lr_plan(const void*, int, int, int, int32_t*, int64_t*, int64_t*, int64_t*, cudaStream_t);
@@ -217,7 +220,7 @@ int spev_create(spev_ctx** out, int device, int sr, int n_fft, int hop, int win,
 
     spev_ctx* c = new spev_ctx();
     c->device = device; c->sr = sr; c->n_fft = n_fft; c->hop = hop; c->win = kNfft; c->n_mels = n_mels;
-    c->fmin = fmin; c->fmax = fmax; c->num_sms = c->num_sms_device = prop.multiProcessorCount; c->tma = nullptr; c->use_tc = 1; c->k1_variant = 1;
+    c->fmin = fmin; c->fmax = fmax; c->num_sms = c->num_sms_device = prop.multiProcessorCount; c->tma = nullptr; c->use_tc = 1; c->k1_variant = 1; c->gl_variant = 1;
     c->d_tw = nullptr; c->d_window = nullptr; c->d_win2048 = nullptr; c->d_tw2048 = nullptr; c->d_basis_pad = c->d_basis_hi = c->d_basis_lo = nullptr;
     c->d_pinv_t = c->d_pinv_hi = c->d_pinv_lo = nullptr;
     c->d_prog_w = nullptr; c->d_prog_h = nullptr;
@@ -311,7 +314,7 @@ int spev_create(spev_ctx** out, int device, int sr, int n_fft, int hop, int win,
         (rc = upload(&c->d_basis_pad, basis_pad)) || (rc = upload(&c->d_basis_hi, b_hi)) ||
         (rc = upload(&c->d_basis_lo, b_lo)) || (rc = upload(&c->d_pinv_t, pinv_t)) ||
         (rc = upload(&c->d_prog_w, prog_w)) || (rc = upload(&c->d_prog_h, prog_h)) ||
-        (rc = gemm_tc_init(c))) {
+        (rc = gemm_tc_init(c)) || (rc = spectral_init(c))) {
         spev_destroy(c);
         return rc;
     }
@@ -365,6 +368,13 @@ int spev_host_pinv(const float* a, int m, int n, float* pinv) {
 int spev_set_tensor_core(spev_ctx* c, int enable) {
     SPEV_REQUIRE(c, SPEV_E_INVALID, "ctx is null");
     c->use_tc = enable ? 1 : 0;
+    return SPEV_OK;
+}
+
+int spev_set_griffinlim_variant(spev_ctx* c, int variant) {
+    SPEV_REQUIRE(c, SPEV_E_INVALID, "ctx is null");
+    SPEV_REQUIRE(variant == 0 || variant == 1, SPEV_E_INVALID, "spev_set_griffinlim_variant: 0 (r01 static tile kernels) or 1");
+    c->gl_variant = variant;
     return SPEV_OK;
 }
 
@@ -475,7 +485,7 @@ int spev_gl_phase_update(spev_ctx* c, const spev_batch* b, const float* y, const
 
 size_t spev_griffinlim_workspace_bytes(int64_t n_frames) {
     if (n_frames < 0) return 0;
-    return static_cast<size_t>(n_frames) * kSpecLd * 2 * sizeof(float2) + 256;
+    return static_cast<size_t>(n_frames) * kSpecLd * 2 * sizeof(float2) + 256 /* alignment */ + 256 /* ticket counters */;
 }
 
 int spev_griffinlim(spev_ctx* c, const spev_batch* b, const float* S, int64_t ld_s, const float* init_phase,
@@ -494,15 +504,23 @@ int spev_griffinlim(spev_ctx* c, const spev_batch* b, const float* S, int64_t ld
     uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~static_cast<uintptr_t>(255);
     float2* ang = reinterpret_cast<float2*>(base);
     float2* tprev = ang + b->n_frames * kSpecLd;
+    // ticket counters of the dynamic tile scheduler: [0] ISTFT tiles, [32] phase-update pairs (separate cache lines);
+    // they only grow during a call -- launch j starts at base j * (work + workers), see draw_ticket()
+    unsigned* counters = reinterpret_cast<unsigned*>(tprev + b->n_frames * kSpecLd);
+    SPEV_CUDA(cudaMemsetAsync(counters, 0, 256, st));
+    const unsigned per_istft = static_cast<unsigned>(b->n_ctiles + fft_grid(c, b->n_ctiles));
+    const unsigned per_phase = static_cast<unsigned>(static_cast<int64_t>(b->n_ftiles) * kWarps +
+                                                     static_cast<int64_t>(fft_grid(c, b->n_ftiles)) * kWarps);
     // librosa: (momentum / (1 + momentum)) is a Python float applied to a complex64 array
     const float alpha = static_cast<float>(static_cast<double>(momentum) / (1.0 + static_cast<double>(momentum)));
     int rc = SPEV_OK;
     if ((rc = launch_gl_init(c, S, ld_s, init_phase, seed, ang, kSpecLd, b->n_frames, st))) return rc;
     for (int it = 0; it < n_iter; ++it) {
-        if ((rc = launch_istft(c, b, ang, kSpecLd, y, st))) return rc;
-        if ((rc = launch_stft_phase(c, b, y, S, ld_s, ang, tprev, kSpecLd, alpha, it > 0, true, st))) return rc;
+        if ((rc = launch_istft(c, b, ang, kSpecLd, y, st, counters, per_istft * static_cast<unsigned>(it)))) return rc;
+        if ((rc = launch_stft_phase(c, b, y, S, ld_s, ang, tprev, kSpecLd, alpha, it > 0, true, st, counters + 32,
+                                    per_phase * static_cast<unsigned>(it)))) return rc;
     }
-    return launch_istft(c, b, ang, kSpecLd, y, st);
+    return launch_istft(c, b, ang, kSpecLd, y, st, counters, per_istft * static_cast<unsigned>(n_iter));
 }
 
 int spev_frame_features(spev_ctx* c, const spev_batch* b, const float* samples, float* rms, float* centroid, void* stream) {

@@ -379,11 +379,11 @@ k_stft_phase(BatchView bv, const float* __restrict__ y, const float* __restrict_
 // K5w: warp-independent STFT (+ Griffin-Lim phase update)
 //
 // The phase update has no cross-warp data dependence, so here every warp is its own worker:
-// it walks the (tile, slot) pairs with a grid-wide stride, cp.async-stages the 1280 samples of
-// its NEXT pair into its own transpose tile as soon as the current transform has read the tile
-// back (the copy lands during the second 32-point DFT and the memory epilogue), and never meets
-// a CTA barrier.  Warps drift out of phase, so the FFTs of some overlap the L2/HBM epilogues of
-// others instead of the whole SM alternating between "compute only" and "memory only".
+// it takes (tile, slot) pairs one at a time, cp.async-stages the 1280 samples of its NEXT pair
+// into a warp-private buffer as soon as the current pair's samples are in registers (the copy has
+// the whole transform to land), and never meets a CTA barrier.  Warps drift out of phase, so the
+// FFTs of some overlap the L2/HBM epilogues of others instead of the whole SM alternating between
+// "compute only" and "memory only".
 // ---------------------------------------------------------------------------------------
 struct PairInfo {
     int64_t row;      // global row of frame a
@@ -425,36 +425,82 @@ __device__ __forceinline__ PairInfo stage_pair(float* region, const float* __res
     return pi;
 }
 
-template <int MODE>   // 0: plain STFT into `ang`; 1: Griffin-Lim phase update
+// Work distribution: with `counter` the warps draw (tile, slot) pairs dynamically (draw_ticket) -- cfg3 has 2.7 pairs
+// per warp, which a static stride pays as 3 --, else they stride statically.
+// STAGE_T (phase update only): the pair's `tprev` rows are pulled into the warp's transpose tile by ONE bulk
+// asynchronous copy (cp.async.bulk, 8,272 B) as soon as the exchange has been read back; it lands during the second
+// 32-point DFT, so the epilogue reads them from shared memory instead of waiting on 32 global loads per lane
+// (ncu before: long_scoreboard 2.5 warps per issue cycle on exactly those loads).
+constexpr int kWsRegionWords = kXWords + kNfft + kHop;   // transpose tile + 1280 staged samples of the NEXT pair
+
+template <int MODE, bool STAGE_T>   // MODE 0: plain STFT into `ang`; 1: Griffin-Lim phase update
 __global__ void __launch_bounds__(kThreads, 1)
 k_stft_phase_w(BatchView bv, const float* __restrict__ y, const float* __restrict__ S, int64_t ld_s,
                float2* __restrict__ ang, float2* tprev, int64_t ld, float alpha, int has_prev,
-               const float2* __restrict__ g_tw, const float* __restrict__ g_win) {
+               const float2* __restrict__ g_tw, const float* __restrict__ g_win, unsigned* counter, unsigned base) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* s_tw = reinterpret_cast<float2*>(smem_raw);
     float* s_win = reinterpret_cast<float*>(s_tw + 1024);
-    float* s_x = s_win + 1024;
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_win + 1024);        // one mbarrier per warp
+    float* s_x = reinterpret_cast<float*>(s_bar + kWarps);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     pdl_launch_dependents();
     load_tables(s_tw, s_win, g_tw, g_win, 0.5f);
+    if (STAGE_T && threadIdx.x < kWarps) bar_init(s_bar + threadIdx.x, 1);
+    if (STAGE_T && threadIdx.x == 0) asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     __syncthreads();                                     // the only CTA-wide barrier
-    pdl_wait();                                          // y / ang / tprev come from the previous kernel
-    float* region = s_x + warp * kWarpRegionWords;       // staging for 1280 samples, then transpose tile
-    float2* xb = reinterpret_cast<float2*>(region);
+    float* tile = s_x + warp * kWsRegionWords;           // exchange tile, then the staged tprev rows
+    float* xs = tile + kXWords;                          // samples of the pair being loaded / staged next
+    float2* xb = reinterpret_cast<float2*>(tile);
+    uint64_t* tbar = s_bar + warp;
+    unsigned tphase = 0;
 
     const int64_t n_pairs = static_cast<int64_t>(bv.n_ftiles) * kWarps;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * kWarps;
-    int64_t p = static_cast<int64_t>(blockIdx.x) * kWarps + warp;
-    PairInfo cur = stage_pair(region, y, bv.ftiles, p, n_pairs, lane);
-    while (!cur.valid && p < n_pairs) { p += stride; cur = stage_pair(region, y, bv.ftiles, p, n_pairs, lane); }
+    int64_t p_static = static_cast<int64_t>(blockIdx.x) * kWarps + warp;
+    bool drained = false;
+    // next (tile, slot) pair of this warp: >= n_pairs when the work is exhausted (a drained warp draws no more)
+    auto next_pair = [&]() -> int64_t {
+        if (counter == nullptr) { const int64_t p = p_static; p_static += stride; return p; }
+        if (drained) return n_pairs;
+        unsigned t = 0;
+        if (lane == 0) t = draw_ticket(counter, base);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= static_cast<unsigned>(n_pairs)) { drained = true; return n_pairs; }
+        return static_cast<int64_t>(t);
+    };
+    // stage the samples of this warp's next pair that has frames (slots past a partial tile's end have none)
+    auto stage_next = [&]() -> PairInfo {
+        PairInfo pi{0, 0, 0};
+        for (;;) {
+            const int64_t p = next_pair();
+            if (p >= n_pairs) return pi;
+            pi = stage_pair(xs, y, bv.ftiles, p, n_pairs, lane);
+            if (pi.valid) return pi;
+        }
+    };
+    pdl_wait();                                          // y / ang / tprev come from the previous kernel
+    PairInfo cur = stage_next();
     cp_async_commit();
 
     while (cur.valid) {
         cp_async_wait_all();
         __syncwarp();
         float2 v[32];
-        load_frame_pair(v, region, s_win, 0, cur.b_valid != 0, lane);
-        __syncwarp();                                    // staging fully consumed: tile may be overwritten
+        load_frame_pair(v, xs, s_win, 0, cur.b_valid != 0, lane);
+        __syncwarp();                                    // staged samples consumed
+        // ---- stage the next pair's samples now: they have this whole pair's time to arrive ----
+        const PairInfo nxt = stage_next();
+        cp_async_commit();
+        const bool b_valid = cur.b_valid != 0;
+        const int64_t ra = cur.row * ld, rb = ra + ld;
+        const float* sa = S + cur.row * ld_s;
+        const float* sb = sa + ld_s;
+        if (MODE == 1) {                                 // pull this pair's S rows (and tprev, unless staged) into L2
+            const int rows = b_valid ? 2 : 1;
+            warp_prefetch_l2(sa, static_cast<int>((rows - 1) * ld_s + kBins) * 4, lane);
+            if (!STAGE_T && has_prev) warp_prefetch_l2(tprev + ra, static_cast<int>((rows - 1) * ld + kBins) * 8, lane);
+        }
         // ---- first half of the transform: 32-point DFTs, inter-stage twiddles, transpose ----
         dft32<-1>(v);
         static_for<1, 32>([&](auto k1c) {
@@ -470,23 +516,21 @@ k_stft_phase_w(BatchView bv, const float* __restrict__ y, const float* __restric
             constexpr int n2 = decltype(n2c)::value;
             v[n2] = xb[lane * kXPitch + n2];
         });
-        __syncwarp();                                    // tile read back: free for the next pair's samples
-        // ---- stage the next pair (lands during the second DFT and the epilogue) ----
-        PairInfo nxt{0, 0, 0};
-        do { p += stride; nxt = stage_pair(region, y, bv.ftiles, p, n_pairs, lane); } while (!nxt.valid && p < n_pairs);
-        cp_async_commit();
-        if (MODE == 1 && nxt.valid) {                    // and pull its epilogue operands into L2
-            const int rows = nxt.b_valid ? 2 : 1;
-            warp_prefetch_l2(S + nxt.row * ld_s, static_cast<int>((rows - 1) * ld_s + kBins) * 4, lane);
-            if (has_prev) warp_prefetch_l2(tprev + nxt.row * ld, static_cast<int>((rows - 1) * ld + kBins) * 8, lane);
+        __syncwarp();                                    // tile read back: free for the tprev rows
+        const bool staged = STAGE_T && MODE == 1 && has_prev;
+        if (staged) {
+            const uint32_t bytes = b_valid ? static_cast<uint32_t>(ld * 8 + (kBins + 1) * 8) : static_cast<uint32_t>((kBins + 1) * 8);
+            if (lane == 0) {
+                fence_proxy_async();
+                bar_expect_tx(tbar, bytes);
+                bulk_g2s(tile, tprev + ra, bytes, tbar);
+            }
         }
         dft32<-1>(v);
         float2 pm[16];
         fetch_mirror(v, pm, lane);
-        const bool b_valid = cur.b_valid != 0;
-        const int64_t ra = cur.row * ld, rb = ra + ld;
-        const float* sa = S + cur.row * ld_s;
-        const float* sb = sa + ld_s;
+        const float2* tsm = reinterpret_cast<const float2*>(tile);   // staged rows: a at [0, 514), b at [ld, ld + 514)
+        if (staged) { bar_wait(tbar, tphase); tphase ^= 1; }
         static_for<0, 4>([&](auto gc) {
             constexpr int g = decltype(gc)::value;
             float2 tpa[4], tpb[4];
@@ -497,8 +541,13 @@ k_stft_phase_w(BatchView bv, const float* __restrict__ y, const float* __restric
                     const int k = lane + 32 * (4 * g + q);
                     s_a[q] = sa[k];
                     s_b[q] = b_valid ? sb[k] : 0.f;
-                    tpa[q] = has_prev ? tprev[ra + k] : make_float2(0.f, 0.f);
-                    tpb[q] = (has_prev && b_valid) ? tprev[rb + k] : make_float2(0.f, 0.f);
+                    if (staged) {
+                        tpa[q] = tsm[k];
+                        tpb[q] = b_valid ? tsm[ld + k] : make_float2(0.f, 0.f);
+                    } else {
+                        tpa[q] = has_prev ? tprev[ra + k] : make_float2(0.f, 0.f);
+                        tpb[q] = (has_prev && b_valid) ? tprev[rb + k] : make_float2(0.f, 0.f);
+                    }
                 });
             }
             static_for<0, 4>([&](auto qc) {
@@ -528,14 +577,17 @@ k_stft_phase_w(BatchView bv, const float* __restrict__ y, const float* __restric
                 if (b_valid) ang[rb + 512] = xbv;
             } else {
                 const float2 z = make_float2(0.f, 0.f);
-                ang[ra + 512] = phase_of(xa, sa[512], has_prev ? tprev[ra + 512] : z, alpha, has_prev);
+                const float2 ta = !has_prev ? z : (staged ? tsm[512] : tprev[ra + 512]);
+                ang[ra + 512] = phase_of(xa, sa[512], ta, alpha, has_prev);
                 tprev[ra + 512] = xa;
                 if (b_valid) {
-                    ang[rb + 512] = phase_of(xbv, sb[512], has_prev ? tprev[rb + 512] : z, alpha, has_prev);
+                    const float2 tb = !has_prev ? z : (staged ? tsm[ld + 512] : tprev[rb + 512]);
+                    ang[rb + 512] = phase_of(xbv, sb[512], tb, alpha, has_prev);
                     tprev[rb + 512] = xbv;
                 }
             }
         }
+        __syncwarp();                                    // staged rows consumed: the tile is free for the next exchange
         cur = nxt;
     }
 }
@@ -692,14 +744,17 @@ k_stft_mel_ws(BatchView bv, const float* __restrict__ samples, float* __restrict
 // ---------------------------------------------------------------------------------------
 // K4: ISTFT with gather overlap-add and window-sum-square normalisation
 // ---------------------------------------------------------------------------------------
+// With `counter` the CTAs draw their tiles dynamically (draw_ticket; thread 0 draws three tiles ahead, like the static
+// ring): cfg3's 448 chunk tiles are 3.03 rounds of work on 148 SMs, which the static round-robin pays as 4.
 __global__ void __launch_bounds__(kThreads, 1)
 k_istft(BatchView bv, const float2* __restrict__ spec, int64_t ld, float* __restrict__ y,
-        const float2* __restrict__ g_tw, const float* __restrict__ g_win) {
+        const float2* __restrict__ g_tw, const float* __restrict__ g_win, unsigned* counter, unsigned base) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* s_tw = reinterpret_cast<float2*>(smem_raw);
     float* s_win = reinterpret_cast<float*>(s_tw + 1024);
     spev_tile* s_ring = reinterpret_cast<spev_tile*>(s_win + 1024);
-    float* s_iw = reinterpret_cast<float*>(s_ring + kRing);   // [256] 1 / sum_q w^2 for interior chunks
+    int* s_tick = reinterpret_cast<int*>(s_ring + kRing);     // [kRing] tile index held by each ring slot, -1: none
+    float* s_iw = reinterpret_cast<float*>(s_tick + kRing);   // [256] 1 / sum_q w^2 for interior chunks
     float* s_x = s_iw + kHop;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     load_tables(s_tw, s_win, g_tw, g_win, 1.0f);
@@ -715,18 +770,36 @@ k_istft(BatchView bv, const float2* __restrict__ spec, int64_t ld, float* __rest
 
     const int stride = gridDim.x;
     pdl_launch_dependents();
-    const int my_n = ring_prologue(s_ring, bv.ctiles, bv.n_ctiles);
+    // slot j of the ring <- the CTA's j-th tile: static (blockIdx.x + j * grid) or the next ticket (thread 0 only;
+    // it stops drawing at its first ticket past the end, so a launch consumes exactly n_ctiles + grid tickets)
+    bool drained = false;
+    auto claim = [&](int j) {
+        if (threadIdx.x != 0) return;
+        int t = -1;
+        if (counter == nullptr) {
+            const int64_t q = blockIdx.x + static_cast<int64_t>(j) * stride;
+            if (q < bv.n_ctiles) t = static_cast<int>(q);
+        } else if (!drained) {
+            const unsigned q = draw_ticket(counter, base);
+            if (q < static_cast<unsigned>(bv.n_ctiles)) t = static_cast<int>(q); else drained = true;
+        }
+        s_tick[j & 3] = t;
+        if (t >= 0) fetch_desc(s_ring + (j & 3), bv.ctiles + t);
+    };
+    for (int j = 0; j < 3; ++j) claim(j);
+    cp_async_commit();
     pdl_wait();   // the spectra come from the previous kernel
 
-    for (int i = 0; i < my_n; ++i) {
+    for (int i = 0;; ++i) {
         cp_async_wait_all();
         __syncthreads();   // previous tile's gather finished; descriptor i visible
+        if (s_tick[i & 3] < 0) break;
         const spev_tile d = s_ring[i & 3];
-        if (i + 3 < my_n) fetch_desc(s_ring + ((i + 3) & 3), bv.ctiles + blockIdx.x + (i + 3) * stride);
+        claim(i + 3);
         cp_async_commit();
         const int c0 = d.t0, T = d.T, nchunks = d.n;
         const int lfa = 2 * warp;
-        if (i + 1 < my_n) {   // pull the next tile's spectra of this warp into L2 during this tile's FFT
+        if (s_tick[(i + 1) & 3] >= 0) {   // pull the next tile's spectra of this warp into L2 during this tile's FFT
             const spev_tile& nx = s_ring[(i + 1) & 3];
             const int nta = nx.t0 - 1 + lfa;
             int r0 = lfa, r1 = lfa + 2;                       // local rows [r0, r1) to prefetch
@@ -902,11 +975,12 @@ k_mel_to_mag(BatchView bv, const float* __restrict__ mel, int layout, int is_log
 // host-side launchers
 // ---------------------------------------------------------------------------------------
 static size_t smem_common() { return sizeof(float2) * 1024 + sizeof(float) * 1024 + sizeof(spev_tile) * kRing; }
+static size_t smem_ws_phase() { return sizeof(float2) * 1024 + sizeof(float) * 1024 + sizeof(uint64_t) * kWarps + sizeof(float) * kWarps * kWsRegionWords; }
 static size_t smem_prog(const spev_ctx* c) { return sizeof(float4) * c->prog_groups + sizeof(int4) * kWarps * c->prog_nb; }
 static size_t smem_stft(size_t prog_bytes) {
     return smem_common() + sizeof(float) * 2 * kStageSamples + sizeof(float) * kWarps * kWarpRegionWords + prog_bytes;
 }
-static size_t smem_istft() { return smem_common() + sizeof(float) * kHop + sizeof(float) * kWarps * kWarpRegionWords; }
+static size_t smem_istft() { return smem_common() + sizeof(int) * kRing + sizeof(float) * kHop + sizeof(float) * kWarps * kWarpRegionWords; }
 
 // Launch with the programmatic-stream-serialization attribute (PDL).
 template <class... KArgs, class... Args>
@@ -964,8 +1038,6 @@ int launch_stft_mel(spev_ctx* ctx, const spev_batch* b, const float* samples, fl
     const bool ws = !power_only && ctx->k1_variant == 1 && smem_ws <= 232448;
     const size_t bytes = ws ? smem_ws : smem;
     auto go = [&](auto kernel, bool mel) -> int {
-        int rc2 = set_smem(kernel, bytes);
-        if (rc2) return rc2;
         kernel<<<grid, kThreads, bytes, st>>>(view_of(b), samples, out, ctx->d_tw, ctx->d_window, mb, mel ? log_mode : 0,
                                               mel ? floor_v : 0.f, mel ? lo : 0.f, mel ? hi : 0.f);
         SPEV_CUDA(cudaGetLastError());
@@ -981,55 +1053,68 @@ int launch_stft_mel(spev_ctx* ctx, const spev_batch* b, const float* samples, fl
 #undef SPEV_K1_CASE
 }
 
+// Grid of the persistent FFT kernels for n work tiles (also used by the Griffin-Lim driver to compute ticket bases).
+int fft_grid(const spev_ctx* ctx, int64_t n_tiles) { return static_cast<int>(std::min<int64_t>(n_tiles, ctx->num_sms)); }
+
 int launch_stft_phase(spev_ctx* ctx, const spev_batch* b, const float* y, const float* S,
                       int64_t ld_s, void* ang, void* tprev, int64_t ld, float alpha, int has_prev,
-                      bool phase, cudaStream_t st) {
+                      bool phase, cudaStream_t st, unsigned* counter, unsigned base) {
     int rc = check_batch(ctx, b, false);
     if (rc) return rc;
     if (b->n_ftiles == 0) return SPEV_OK;
     SPEV_REQUIRE(ang && ld >= kBins, SPEV_E_INVALID, "stft: null buffer or ld < 513");
     SPEV_REQUIRE(y || b->n_frames == b->n_items, SPEV_E_INVALID, "stft: y is null");
     if (!y) y = reinterpret_cast<const float*>(ang);   // every item has T == 1 (empty signal): never dereferenced as signal
-    // Plain STFT: warp-independent kernel (measured 18.0 vs 19.9 us at cfg3, 128 vs 156 us on 120 k frames).
-    // Phase update: tile kernel (the warp-independent variant is not faster there -- 51.7 vs 50.6 us, and
-    // 444 vs 372 us at scale: that path is bound by bytes in flight against L2/HBM latency, not by lock-step).
-    const size_t smem_w = sizeof(float2) * 1024 + sizeof(float) * 1024 + sizeof(float) * kWarps * kWarpRegionWords;
-    const size_t smem = smem_stft(0);
-    const int grid = static_cast<int>(std::min<int64_t>(b->n_ftiles, ctx->num_sms));
-    if (phase) {
-        SPEV_REQUIRE(S && tprev && ld_s >= kBins, SPEV_E_INVALID, "phase update: null S/tprev");
-        rc = set_smem(k_stft_phase<1>, smem);
-        if (rc) return rc;
-        rc = launch_pdl(k_stft_phase<1>, grid, kThreads, smem, st, view_of(b), y, S, ld_s, static_cast<float2*>(ang),
-                        static_cast<float2*>(tprev), ld, alpha, has_prev, static_cast<const float2*>(ctx->d_tw),
-                        static_cast<const float*>(ctx->d_window));
-        if (rc) return rc;
-    } else {
-        rc = set_smem(k_stft_phase_w<0>, smem_w);
-        if (rc) return rc;
-        rc = launch_pdl(k_stft_phase_w<0>, grid, kThreads, smem_w, st, view_of(b), y, static_cast<const float*>(nullptr),
-                        static_cast<int64_t>(0), static_cast<float2*>(ang), static_cast<float2*>(nullptr), ld, 0.f, 0,
-                        static_cast<const float2*>(ctx->d_tw), static_cast<const float*>(ctx->d_window));
-        if (rc) return rc;
+    const int grid = fft_grid(ctx, b->n_ftiles);
+    const float2* tw = ctx->d_tw;
+    const float* win = ctx->d_window;
+    if (!phase) {
+        // plain STFT: warp-independent kernel (r01: 18.0 vs 19.9 us at cfg3, 128 vs 156 us on 120 k frames)
+        return launch_pdl(k_stft_phase_w<0, false>, grid, kThreads, smem_ws_phase(), st, view_of(b), y, static_cast<const float*>(nullptr),
+                          static_cast<int64_t>(0), static_cast<float2*>(ang), static_cast<float2*>(nullptr), ld, 0.f, 0, tw, win,
+                          counter, base);
     }
-    SPEV_CUDA(cudaGetLastError());
-    return SPEV_OK;
+    SPEV_REQUIRE(S && tprev && ld_s >= kBins, SPEV_E_INVALID, "phase update: null S/tprev");
+    if (ctx->gl_variant == 0)   // r01 tile kernel: CTA-staged samples, direct tprev loads, static round-robin
+        return launch_pdl(k_stft_phase<1>, grid, kThreads, smem_stft(0), st, view_of(b), y, S, ld_s, static_cast<float2*>(ang),
+                          static_cast<float2*>(tprev), ld, alpha, has_prev, tw, win);
+    // bulk staging of the tprev rows needs 16-byte aligned rows with one readable pad column, and both rows of a pair
+    // must fit the warp's transpose tile
+    const bool stage_t = (reinterpret_cast<uintptr_t>(tprev) & 15) == 0 && ld % 2 == 0 && ld > kBins &&
+                         static_cast<size_t>(ld) * 8 + (kBins + 1) * 8 <= sizeof(float) * kXWords;
+    if (stage_t)
+        return launch_pdl(k_stft_phase_w<1, true>, grid, kThreads, smem_ws_phase(), st, view_of(b), y, S, ld_s, static_cast<float2*>(ang),
+                          static_cast<float2*>(tprev), ld, alpha, has_prev, tw, win, counter, base);
+    return launch_pdl(k_stft_phase_w<1, false>, grid, kThreads, smem_ws_phase(), st, view_of(b), y, S, ld_s, static_cast<float2*>(ang),
+                      static_cast<float2*>(tprev), ld, alpha, has_prev, tw, win, counter, base);
 }
 
 int launch_istft(spev_ctx* ctx, const spev_batch* b, const void* spec, int64_t ld, float* y,
-                 cudaStream_t st) {
+                 cudaStream_t st, unsigned* counter, unsigned base) {
     int rc = check_batch(ctx, b, true);
     if (rc) return rc;
     if (b->n_ctiles == 0) return SPEV_OK;
     SPEV_REQUIRE(spec && y && ld >= kBins, SPEV_E_INVALID, "istft: null buffer or ld < 513");
-    const size_t smem = smem_istft();
-    rc = set_smem(k_istft, smem);
-    if (rc) return rc;
-    const int grid = std::min<int64_t>(b->n_ctiles, ctx->num_sms);
-    rc = launch_pdl(k_istft, grid, kThreads, smem, st, view_of(b), static_cast<const float2*>(spec), ld, y,
-                    static_cast<const float2*>(ctx->d_tw), static_cast<const float*>(ctx->d_window));
-    if (rc) return rc;
-    return SPEV_OK;
+    return launch_pdl(k_istft, fft_grid(ctx, b->n_ctiles), kThreads, smem_istft(), st, view_of(b), static_cast<const float2*>(spec), ld, y,
+                      static_cast<const float2*>(ctx->d_tw), static_cast<const float*>(ctx->d_window),
+                      ctx->gl_variant == 0 ? static_cast<unsigned*>(nullptr) : counter, base);
+}
+
+// Opt every FFT kernel into the full shared-memory carve-out ONCE per ctx (per device) -- r01 re-issued
+// cudaFuncSetAttribute before each of the 121 launches of a Griffin-Lim call.
+int spectral_init(spev_ctx*) {
+    const int kMax = 232448;
+    int rc = SPEV_OK;
+    auto opt = [&](auto kernel) { if (!rc) rc = set_smem(kernel, kMax); };
+    opt(k_stft_mel<1, 0>); opt(k_stft_mel<0, 0>); opt(k_stft_mel_ws<0>);
+    opt(k_stft_mel<0, 1>); opt(k_stft_mel<0, 2>); opt(k_stft_mel<0, 3>); opt(k_stft_mel<0, 4>);
+    opt(k_stft_mel<0, 5>); opt(k_stft_mel<0, 6>); opt(k_stft_mel<0, 7>); opt(k_stft_mel<0, 8>);
+    opt(k_stft_mel_ws<1>); opt(k_stft_mel_ws<2>); opt(k_stft_mel_ws<3>); opt(k_stft_mel_ws<4>);
+    opt(k_stft_mel_ws<5>); opt(k_stft_mel_ws<6>); opt(k_stft_mel_ws<7>); opt(k_stft_mel_ws<8>);
+    opt(k_stft_phase<0>); opt(k_stft_phase<1>);
+    opt(k_stft_phase_w<0, false>); opt(k_stft_phase_w<1, false>); opt(k_stft_phase_w<1, true>);
+    opt(k_istft);
+    return rc;
 }
 
 int launch_gl_init(spev_ctx* ctx, const float* S, int64_t ld_s, const float* phase, uint64_t seed,

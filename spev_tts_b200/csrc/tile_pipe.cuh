@@ -85,6 +85,24 @@ __device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// Bulk asynchronous copy global -> shared (the TMA unit's 1-D path): one instruction moves up to a whole row,
+// needs no registers and no LSU issue slots, and signals an mbarrier with the byte count.  Addresses and size must
+// be multiples of 16 bytes.
+__device__ __forceinline__ void bar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(smem_addr(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+// generic-proxy accesses (LDS/STS) before this point are ordered before later async-proxy (bulk copy) accesses
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+// Dynamic work distribution without a reset between launches: the counter only ever grows; launch number j of a
+// kernel draws tickets base_j, base_j + 1, ... where base_j is computed on the host.  Every worker (warp or CTA)
+// stops at its first ticket >= n_work, so a launch consumes exactly n_work + n_workers tickets.
+__device__ __forceinline__ unsigned draw_ticket(unsigned* counter, unsigned base) { return atomicAdd(counter, 1u) - base; }
+
 // Persistent-loop bookkeeping shared by the kernels: prologue of the descriptor ring.
 __device__ __forceinline__ int ring_prologue(spev_tile* s_ring, const spev_tile* tiles, int n_tiles) {
     const int first = blockIdx.x, stride = gridDim.x;

@@ -16,6 +16,9 @@ S = torch.rand(F, 520, generator=g, device=dev)
 y = torch.zeros(fb.n_out_samples, device=dev)
 st = torch.cuda.current_stream(dev).cuda_stream
 lib = ctx.lib
+variant = int(os.environ.get("GL_VARIANT", "1"))
+_lib.check(lib.spev_set_griffinlim_variant(ctx.handle, variant))
+print("griffinlim variant", variant)
 def t_loop(fn, n=60, reps=5):
     for _ in range(2): 
         for _ in range(n): fn()
@@ -36,7 +39,13 @@ def both():
     lib.spev_istft(ctx.handle, fb.desc, ang.data_ptr(), 520, y.data_ptr(), st)
     lib.spev_gl_phase_update(ctx.handle, fb.desc, y.data_ptr(), S.data_ptr(), 520, ang.data_ptr(), tprev.data_ptr(), 520, 0.4975, 1, st)
 kb = t_loop(both)
+# the real thing: spev_griffinlim (tickets + PDL chain), 60 iterations
+ws = torch.empty(lib.spev_griffinlim_workspace_bytes(F), dtype=torch.uint8, device=dev)
+def full():
+    _lib.check(lib.spev_griffinlim(ctx.handle, fb.desc, S.data_ptr(), 520, None, 7, 60, 0.99, y.data_ptr(), ws.data_ptr(), ws.numel(), st))
+kf = t_loop(full, n=1, reps=8)
 print(f"B={B} T={T} frames={F} ftiles={fb.n_ftiles} ctiles={fb.n_ctiles}")
+print(f"spev_griffinlim 60 it: {kf/1e3:8.3f} ms  -> {kf/60:6.2f} us/iter  roofline {F*(20516*60+5128)/kf/1e3/6542.1:.3f}")
 print(f"istft          {k4:8.2f} us/launch   {F*(4104+1024)/k4/1e3:8.1f} GB/s")
 print(f"phase_update   {k5:8.2f} us/launch   {F*15388/k5/1e3:8.1f} GB/s")
 print(f"phase no-prev   {k5n:8.2f} us/launch   (no tprev loads: S 2 KB read, ang+tprev 8 KB written per frame)")
