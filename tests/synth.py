@@ -215,3 +215,25 @@ def corpus_alignments(corpus, sr: int = SR):
         phones.append(ph or None)
         durs.append(du or None)
     return phones, durs
+
+
+def _cfg3_oracle_job(args):
+    """(worker for a spawn pool) oracle Griffin-Lim of one cfg3 item -> its spectral convergences at the n_iter list."""
+    b, n_iters, sr, T = args
+    from oracle import librosa_restated as lr
+    lm = lr.reference_logmel(speechy(seed=300 + b, n=(T - 1) * HOP, sr=sr), sr=sr).T.copy()
+    S = lr.mel_to_stft(np.exp(lm), sr=sr, n_fft=1024, fmin=0, fmax=8000, lbfgs=False)
+    ph = init_phase((513, T), seed=3000 + b)
+    return b, [lr.spectral_convergence(lr.griffinlim(S, n_iter=n, hop_length=HOP, n_fft=1024, init_phase=ph), S)
+               for n in n_iters]
+
+
+def cfg3_oracle_sc(items, n_iters, sr=SR, T=800, procs=None):
+    """Oracle spectral convergences of cfg3 items (configs[2]: [80,800] log-mels of `speechy` signals, shared initial
+    phases seed 3000+b), fanned over a spawn pool (the caller may already hold a CUDA context)."""
+    import multiprocessing as mp
+    import os
+    procs = procs or min(len(items), os.cpu_count() or 1)
+    with mp.get_context("spawn").Pool(procs) as pool:
+        res = dict(pool.map(_cfg3_oracle_job, [(b, tuple(n_iters), sr, T) for b in items]))
+    return res

@@ -182,3 +182,60 @@ def test_cfg3_batch16_properties(cuda):
     S3 = sp.mel_to_stft(torch.exp(lm[3]), sr=22050, n_fft=1024, fmin=0, fmax=8000).cpu().numpy()
     sc = lr.spectral_convergence(y3.cpu().numpy(), S3)
     assert sc < 0.6, sc
+
+
+def test_cfg3_full_size_sc_delta_vs_oracle(cuda):
+    """configs[2] at its REAL size: 16 x [80,800], 60 iterations (BASELINE) and 32 (the reference's librosa default),
+    initial phases shared with the oracle: per item |SC_gpu - SC_oracle| <= 1e-3 (north-star tolerance; expected 1e-6).
+    The 16 oracle runs (numpy, float64 FFTs) are fanned over the host cores."""
+    import spev_tts_b200 as sp
+    T, B, n_iters = 800, 16, (60, 32)
+    ref = synth.cfg3_oracle_sc(range(B), n_iters)
+    lms = np.stack([lr.reference_logmel(synth.speechy(seed=300 + b, n=(T - 1) * 256)).T for b in range(B)])
+    phs = np.stack([synth.init_phase((513, T), seed=3000 + b) for b in range(B)])
+    S = sp.mel_to_stft(np.exp(lms), sr=22050, n_fft=1024, fmin=0, fmax=8000)
+    worst = 0.0
+    for j, n_iter in enumerate(n_iters):
+        y = sp.mel_to_audio(torch.from_numpy(lms).to(cuda), sr=22050, n_fft=1024, hop_length=256, fmin=0, fmax=8000,
+                            n_iter=n_iter, is_log=True, init_phase=torch.from_numpy(phs).to(cuda)).cpu().numpy()
+        assert y.shape == (B, (T - 1) * 256)
+        for b in range(B):
+            sc = lr.spectral_convergence(y[b], S[b])
+            worst = max(worst, abs(sc - ref[b][j]))
+            assert abs(sc - ref[b][j]) <= 1e-3, (n_iter, b, sc, ref[b][j])
+    print(f"cfg3 full size: worst |SC_gpu - SC_oracle| over 16 items x {n_iters} iterations = {worst:.2e}")
+
+
+def test_griffinlim_24khz_cfg5(cuda):
+    """configs[4] geometry: sr = 24 kHz (mel basis / pseudo-inverse rebuilt for that rate), 60 iterations."""
+    import spev_tts_b200 as sp
+    T, sr = 300, 24000
+    ref = synth.cfg3_oracle_sc([0, 1], (60,), sr=sr, T=T)
+    for b in (0, 1):
+        lm = lr.reference_logmel(synth.speechy(seed=300 + b, n=(T - 1) * 256, sr=sr), sr=sr).T.copy()
+        ph = synth.init_phase((513, T), seed=3000 + b)
+        y = sp.mel_to_audio(lm, sr=sr, n_fft=1024, hop_length=256, fmin=0, fmax=8000, n_iter=60, is_log=True, init_phase=ph)
+        S = lr.mel_to_stft(np.exp(lm), sr=sr, n_fft=1024, fmin=0, fmax=8000, lbfgs=False)
+        assert rel_l2(sp.mel_to_stft(np.exp(lm), sr=sr, n_fft=1024, fmin=0, fmax=8000), S) <= 1e-5
+        assert abs(lr.spectral_convergence(y, S) - ref[b][0]) <= 1e-3
+
+
+def test_griffinlim_kernel_variants_agree(cuda):
+    """The r02 Griffin-Lim kernels (dynamic tile tickets, bulk-staged tprev rows) and the r01 static tile kernels
+    perform the same arithmetic: bit-identical waveforms, ragged batch included."""
+    import spev_tts_b200 as sp
+    from spev_tts_b200 import _lib
+    ctx = sp.Context.get(cuda, fmin=0.0, fmax=8000.0)
+    frames = [800, 33, 1, 2, 64, 517, 95]
+    fb = sp.make_batch(ctx, n_frames=frames, with_chunks=True)
+    g = torch.Generator(device=cuda).manual_seed(5)
+    S = torch.rand(fb.n_frames, _lib.SPEC_LD, generator=g, device=cuda)
+    ph = torch.rand(fb.n_frames, 513, generator=g, device=cuda) * 6.2831853
+    outs = []
+    try:
+        for variant in (0, 1):
+            _lib.check(ctx.lib.spev_set_griffinlim_variant(ctx.handle, variant))
+            outs.append(sp.griffinlim_flat(S, fb, ctx, n_iter=7, init_phase=ph).clone())
+    finally:
+        _lib.check(ctx.lib.spev_set_griffinlim_variant(ctx.handle, 1))
+    assert torch.isfinite(outs[1]).all() and torch.equal(outs[0], outs[1])
