@@ -459,14 +459,15 @@ k_stft_phase_w(BatchView bv, const float* __restrict__ y, const float* __restric
     const int64_t stride = static_cast<int64_t>(gridDim.x) * kWarps;
     int64_t p_static = static_cast<int64_t>(blockIdx.x) * kWarps + warp;
     bool drained = false;
+    unsigned pend = 0;                                   // lane 0: a ticket drawn one call ahead (hides the atomic's latency)
+    auto draw_ahead = [&]() { if (lane == 0) pend = draw_ticket(counter, base); };
     // next (tile, slot) pair of this warp: >= n_pairs when the work is exhausted (a drained warp draws no more)
     auto next_pair = [&]() -> int64_t {
         if (counter == nullptr) { const int64_t p = p_static; p_static += stride; return p; }
         if (drained) return n_pairs;
-        unsigned t = 0;
-        if (lane == 0) t = draw_ticket(counter, base);
-        t = __shfl_sync(0xffffffffu, t, 0);
+        const unsigned t = __shfl_sync(0xffffffffu, pend, 0);
         if (t >= static_cast<unsigned>(n_pairs)) { drained = true; return n_pairs; }
+        draw_ahead();
         return static_cast<int64_t>(t);
     };
     // stage the samples of this warp's next pair that has frames (slots past a partial tile's end have none)
@@ -480,6 +481,7 @@ k_stft_phase_w(BatchView bv, const float* __restrict__ y, const float* __restric
         }
     };
     pdl_wait();                                          // y / ang / tprev come from the previous kernel
+    if (counter != nullptr) draw_ahead();                // (tickets only after the wait: see k_istft)
     PairInfo cur = stage_next();
     cp_async_commit();
 
@@ -746,6 +748,10 @@ k_stft_mel_ws(BatchView bv, const float* __restrict__ samples, float* __restrict
 // ---------------------------------------------------------------------------------------
 // With `counter` the CTAs draw their tiles dynamically (draw_ticket; thread 0 draws three tiles ahead, like the static
 // ring): cfg3's 448 chunk tiles are 3.03 rounds of work on 148 SMs, which the static round-robin pays as 4.
+// BULK: a warp's two spectrum rows (8,272 B) arrive in its region by ONE bulk asynchronous copy instead of 34 scattered
+// 8-byte loads per lane (ncu r01: lg_throttle 1.2 + long_scoreboard 1.7 warps per issue cycle on those loads): no LSU
+// queue pressure, and all 16 warps' rows are in flight at once.
+template <bool BULK>
 __global__ void __launch_bounds__(kThreads, 1)
 k_istft(BatchView bv, const float2* __restrict__ spec, int64_t ld, float* __restrict__ y,
         const float2* __restrict__ g_tw, const float* __restrict__ g_win, unsigned* counter, unsigned base) {
@@ -753,11 +759,16 @@ k_istft(BatchView bv, const float2* __restrict__ spec, int64_t ld, float* __rest
     float2* s_tw = reinterpret_cast<float2*>(smem_raw);
     float* s_win = reinterpret_cast<float*>(s_tw + 1024);
     spev_tile* s_ring = reinterpret_cast<spev_tile*>(s_win + 1024);
-    int* s_tick = reinterpret_cast<int*>(s_ring + kRing);     // [kRing] tile index held by each ring slot, -1: none
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_ring + kRing);   // one mbarrier per warp (BULK)
+    int* s_tick = reinterpret_cast<int*>(s_bar + kWarps);     // [kRing] tile index held by each ring slot, -1: none
     float* s_iw = reinterpret_cast<float*>(s_tick + kRing);   // [256] 1 / sum_q w^2 for interior chunks
     float* s_x = s_iw + kHop;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     load_tables(s_tw, s_win, g_tw, g_win, 1.0f);
+    if (BULK && threadIdx.x < kWarps) bar_init(s_bar + threadIdx.x, 1);
+    if (BULK && threadIdx.x == 0) asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    uint64_t* tbar = s_bar + warp;
+    unsigned tphase = 0;
     __syncthreads();
     for (int s = threadIdx.x; s < kHop; s += blockDim.x) {
         float wss = 0.f;   // same ascending-frame fmaf chain as the edge path below
@@ -786,9 +797,12 @@ k_istft(BatchView bv, const float2* __restrict__ spec, int64_t ld, float* __rest
         s_tick[j & 3] = t;
         if (t >= 0) fetch_desc(s_ring + (j & 3), bv.ctiles + t);
     };
+    // Tickets may only be drawn once every earlier launch of this kernel has finished drawing: with programmatic
+    // dependent launch the prologue above can run while the launch before the previous kernel is still at work, and
+    // its tickets would interleave with ours.  griddepcontrol.wait returns when the whole chain behind us is complete.
+    pdl_wait();   // the spectra come from the previous kernel
     for (int j = 0; j < 3; ++j) claim(j);
     cp_async_commit();
-    pdl_wait();   // the spectra come from the previous kernel
 
     for (int i = 0;; ++i) {
         cp_async_wait_all();
@@ -799,6 +813,18 @@ k_istft(BatchView bv, const float2* __restrict__ spec, int64_t ld, float* __rest
         cp_async_commit();
         const int c0 = d.t0, T = d.T, nchunks = d.n;
         const int lfa = 2 * warp;
+        // local frame lf <-> item frame t = c0 - 1 + lf ; needed: lf in [0, nchunks + 3)
+        const int ta = c0 - 1 + lfa, tb = ta + 1;
+        const bool a_valid = lfa < nchunks + 3 && ta >= 0 && ta < T;
+        const bool b_valid = lfa + 1 < nchunks + 3 && tb >= 0 && tb < T;
+        if (BULK && (a_valid || b_valid) && lane == 0) {      // rows a, b -> region[0 ..], region[ld ..] (float2 units)
+            const uint32_t bytes = (a_valid && b_valid) ? static_cast<uint32_t>(ld * 8 + (kBins + 1) * 8)
+                                                        : static_cast<uint32_t>((kBins + 1) * 8);
+            const int64_t first_row = a_valid ? 0 : 1;
+            fence_proxy_async();                              // the region was last read by the gather (generic proxy)
+            bar_expect_tx(tbar, bytes);
+            bulk_g2s(reinterpret_cast<float2*>(xw) + first_row * ld, spec + (d.row0 + lfa + first_row) * ld, bytes, tbar);
+        }
         if (s_tick[(i + 1) & 3] >= 0) {   // pull the next tile's spectra of this warp into L2 during this tile's FFT
             const spev_tile& nx = s_ring[(i + 1) & 3];
             const int nta = nx.t0 - 1 + lfa;
@@ -810,13 +836,10 @@ k_istft(BatchView bv, const float2* __restrict__ spec, int64_t ld, float* __rest
                 warp_prefetch_l2(spec + (nx.row0 + r0) * ld, static_cast<int>((r1 - r0 - 1) * ld + kBins) * 8, lane);
         }
 
-        // local frame lf <-> item frame t = c0 - 1 + lf ; needed: lf in [0, nchunks + 3)
-        const int ta = c0 - 1 + lfa, tb = ta + 1;
-        const bool a_valid = lfa < nchunks + 3 && ta >= 0 && ta < T;
-        const bool b_valid = lfa + 1 < nchunks + 3 && tb >= 0 && tb < T;
         if (a_valid || b_valid) {
-            const float2* A = spec + (d.row0 + lfa) * ld;
+            const float2* A = BULK ? reinterpret_cast<const float2*>(xw) : spec + (d.row0 + lfa) * ld;
             const float2* B = A + ld;
+            if (BULK) { bar_wait(tbar, tphase); tphase ^= 1; }
             float2 v[32];
             float2 m[16];
             static_for<0, 16>([&](auto jc) {
@@ -980,7 +1003,7 @@ static size_t smem_prog(const spev_ctx* c) { return sizeof(float4) * c->prog_gro
 static size_t smem_stft(size_t prog_bytes) {
     return smem_common() + sizeof(float) * 2 * kStageSamples + sizeof(float) * kWarps * kWarpRegionWords + prog_bytes;
 }
-static size_t smem_istft() { return smem_common() + sizeof(int) * kRing + sizeof(float) * kHop + sizeof(float) * kWarps * kWarpRegionWords; }
+static size_t smem_istft() { return smem_common() + sizeof(uint64_t) * kWarps + sizeof(int) * kRing + sizeof(float) * kHop + sizeof(float) * kWarps * kWarpRegionWords; }
 
 // Launch with the programmatic-stream-serialization attribute (PDL).
 template <class... KArgs, class... Args>
@@ -1095,9 +1118,15 @@ int launch_istft(spev_ctx* ctx, const spev_batch* b, const void* spec, int64_t l
     if (rc) return rc;
     if (b->n_ctiles == 0) return SPEV_OK;
     SPEV_REQUIRE(spec && y && ld >= kBins, SPEV_E_INVALID, "istft: null buffer or ld < 513");
-    return launch_pdl(k_istft, fft_grid(ctx, b->n_ctiles), kThreads, smem_istft(), st, view_of(b), static_cast<const float2*>(spec), ld, y,
-                      static_cast<const float2*>(ctx->d_tw), static_cast<const float*>(ctx->d_window),
-                      ctx->gl_variant == 0 ? static_cast<unsigned*>(nullptr) : counter, base);
+    // bulk staging needs 16-byte aligned rows with one readable pad column, two rows per warp region
+    const bool bulk = ctx->gl_variant != 0 && (reinterpret_cast<uintptr_t>(spec) & 15) == 0 && ld % 2 == 0 && ld > kBins &&
+                      static_cast<size_t>(ld) * 8 + (kBins + 1) * 8 <= sizeof(float) * kWarpRegionWords;
+    unsigned* ctr = ctx->gl_variant == 0 ? nullptr : counter;
+    if (bulk)
+        return launch_pdl(k_istft<true>, fft_grid(ctx, b->n_ctiles), kThreads, smem_istft(), st, view_of(b), static_cast<const float2*>(spec),
+                          ld, y, static_cast<const float2*>(ctx->d_tw), static_cast<const float*>(ctx->d_window), ctr, base);
+    return launch_pdl(k_istft<false>, fft_grid(ctx, b->n_ctiles), kThreads, smem_istft(), st, view_of(b), static_cast<const float2*>(spec),
+                      ld, y, static_cast<const float2*>(ctx->d_tw), static_cast<const float*>(ctx->d_window), ctr, base);
 }
 
 // Opt every FFT kernel into the full shared-memory carve-out ONCE per ctx (per device) -- r01 re-issued
@@ -1113,7 +1142,7 @@ int spectral_init(spev_ctx*) {
     opt(k_stft_mel_ws<5>); opt(k_stft_mel_ws<6>); opt(k_stft_mel_ws<7>); opt(k_stft_mel_ws<8>);
     opt(k_stft_phase<0>); opt(k_stft_phase<1>);
     opt(k_stft_phase_w<0, false>); opt(k_stft_phase_w<1, false>); opt(k_stft_phase_w<1, true>);
-    opt(k_istft);
+    opt(k_istft<true>); opt(k_istft<false>);
     return rc;
 }
 

@@ -226,16 +226,19 @@ def test_griffinlim_kernel_variants_agree(cuda):
     import spev_tts_b200 as sp
     from spev_tts_b200 import _lib
     ctx = sp.Context.get(cuda, fmin=0.0, fmax=8000.0)
-    frames = [800, 33, 1, 2, 64, 517, 95]
-    fb = sp.make_batch(ctx, n_frames=frames, with_chunks=True)
-    g = torch.Generator(device=cuda).manual_seed(5)
-    S = torch.rand(fb.n_frames, _lib.SPEC_LD, generator=g, device=cuda)
-    ph = torch.rand(fb.n_frames, 513, generator=g, device=cuda) * 6.2831853
-    outs = []
-    try:
-        for variant in (0, 1):
-            _lib.check(ctx.lib.spev_set_griffinlim_variant(ctx.handle, variant))
-            outs.append(sp.griffinlim_flat(S, fb, ctx, n_iter=7, init_phase=ph).clone())
-    finally:
-        _lib.check(ctx.lib.spev_set_griffinlim_variant(ctx.handle, 1))
-    assert torch.isfinite(outs[1]).all() and torch.equal(outs[0], outs[1])
+    # a ragged batch, a small single item (grids far below the SM count: successive launches overlap under programmatic
+    # dependent launch, which the ticket scheme must survive) and a batch larger than one round of tiles
+    for frames, n_iter in (([800, 33, 1, 2, 64, 517, 95], 7), ([300], 25), ([40] * 7, 25), ([800] * 16, 3)):
+        fb = sp.make_batch(ctx, n_frames=frames, with_chunks=True)
+        g = torch.Generator(device=cuda).manual_seed(5)
+        S = torch.rand(fb.n_frames, _lib.SPEC_LD, generator=g, device=cuda)
+        ph = torch.rand(fb.n_frames, 513, generator=g, device=cuda) * 6.2831853
+        outs = []
+        try:
+            for variant in (0, 1, 1):
+                _lib.check(ctx.lib.spev_set_griffinlim_variant(ctx.handle, variant))
+                outs.append(sp.griffinlim_flat(S, fb, ctx, n_iter=n_iter, init_phase=ph).clone())
+        finally:
+            _lib.check(ctx.lib.spev_set_griffinlim_variant(ctx.handle, 1))
+        assert torch.isfinite(outs[1]).all(), frames
+        assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2]), frames
