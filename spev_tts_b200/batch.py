@@ -114,6 +114,18 @@ class Context:
                 cls._cache[key] = ctx
         return ctx
 
+    def uniform_batch(self, n_items: int, n_frames: int, with_chunks: bool = True) -> "FlatBatch":
+        """Descriptor of ``n_items`` equal-length spectrogram items, cached: the vocoder is called over and over with
+        the same shapes, and planning + pinned staging + upload cost more than the kernels of a short utterance."""
+        key = (int(n_items), int(n_frames), bool(with_chunks))
+        cache = self.__dict__.setdefault("_uniform", {})
+        fb = cache.get(key)
+        if fb is None:
+            if len(cache) >= 64:
+                cache.pop(next(iter(cache)))
+            fb = cache[key] = make_batch(self, n_frames=[n_frames] * n_items, with_chunks=with_chunks)
+        return fb
+
     def set_tensor_core(self, enable: bool) -> None:
         """A/B switch: False forces the FFMA kernel for the mel->magnitude projection."""
         _lib.check(self.lib.spev_set_tensor_core(self.handle, 1 if enable else 0), "spev_set_tensor_core")

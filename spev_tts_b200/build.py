@@ -11,7 +11,7 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libspev_b200.so")
-SOURCES = ["abi.cu", "spectral.cu", "lr.cu", "gemm_tc.cu", "features.cu", "collate.cu", "pyin.cu"]
+SOURCES = ["abi.cu", "spectral.cu", "lr.cu", "gemm_tc.cu", "features.cu", "collate.cu", "pyin.cu", "nnls.cu"]
 HEADERS = ["fft_core.cuh", "spev_internal.cuh", "tile_pipe.cuh", os.path.join("..", "..", "include", "spev_b200.h")]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]

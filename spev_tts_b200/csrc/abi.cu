@@ -36,6 +36,7 @@ int launch_stft_phase(spev_ctx*, const spev_batch*, const float*, const float*, 
                       unsigned* counter = nullptr, unsigned base = 0);
 int launch_istft(spev_ctx*, const spev_batch*, const void*, int64_t, float*, cudaStream_t, unsigned* counter = nullptr, unsigned base = 0);
 int fft_grid(const spev_ctx*, int64_t);
+int launch_nnls_objective(spev_ctx*, const void*, int, int64_t, const float*, int, int, int64_t, int64_t, int, double*, double*, double*, cudaStream_t);
 int spectral_init(spev_ctx*);
 int launch_gl_init(spev_ctx*, const float*, int64_t, const float*, uint64_t, void*, int64_t, int64_t, cudaStream_t);
 int launch_mel_to_mag(spev_ctx*, const spev_batch*, const float*, int, int, float*, int64_t, cudaStream_t);
@@ -221,7 +222,7 @@ int spev_create(spev_ctx** out, int device, int sr, int n_fft, int hop, int win,
     spev_ctx* c = new spev_ctx();
     c->device = device; c->sr = sr; c->n_fft = n_fft; c->hop = hop; c->win = kNfft; c->n_mels = n_mels;
     c->fmin = fmin; c->fmax = fmax; c->num_sms = c->num_sms_device = prop.multiProcessorCount; c->tma = nullptr; c->use_tc = 1; c->k1_variant = 1; c->gl_variant = 1;
-    c->d_tw = nullptr; c->d_window = nullptr; c->d_win2048 = nullptr; c->d_tw2048 = nullptr; c->d_basis_pad = c->d_basis_hi = c->d_basis_lo = nullptr;
+    c->d_tw = nullptr; c->d_window = nullptr; c->d_win2048 = nullptr; c->d_tw2048 = nullptr; c->d_basis = c->d_basis_pad = c->d_basis_hi = c->d_basis_lo = nullptr;
     c->d_pinv_t = c->d_pinv_hi = c->d_pinv_lo = nullptr;
     c->d_prog_w = nullptr; c->d_prog_h = nullptr;
 
@@ -311,7 +312,7 @@ int spev_create(spev_ctx** out, int device, int sr, int n_fft, int hop, int win,
     int rc = SPEV_OK;
     if ((rc = upload(&c->d_tw, tw)) || (rc = upload(&c->d_window, c->h_window)) ||
         (rc = upload(&c->d_win2048, win2048)) || (rc = upload(&c->d_tw2048, tw2048)) ||
-        (rc = upload(&c->d_basis_pad, basis_pad)) || (rc = upload(&c->d_basis_hi, b_hi)) ||
+        (rc = upload(&c->d_basis, c->h_basis)) || (rc = upload(&c->d_basis_pad, basis_pad)) || (rc = upload(&c->d_basis_hi, b_hi)) ||
         (rc = upload(&c->d_basis_lo, b_lo)) || (rc = upload(&c->d_pinv_t, pinv_t)) ||
         (rc = upload(&c->d_prog_w, prog_w)) || (rc = upload(&c->d_prog_h, prog_h)) ||
         (rc = gemm_tc_init(c)) || (rc = spectral_init(c))) {
@@ -326,7 +327,7 @@ void spev_destroy(spev_ctx* c) {
     if (!c) return;
     DeviceGuard guard(c);
     gemm_tc_destroy(c);
-    cudaFree(c->d_tw); cudaFree(c->d_window); cudaFree(c->d_win2048); cudaFree(c->d_tw2048); cudaFree(c->d_basis_pad); cudaFree(c->d_basis_hi);
+    cudaFree(c->d_tw); cudaFree(c->d_window); cudaFree(c->d_win2048); cudaFree(c->d_tw2048); cudaFree(c->d_basis); cudaFree(c->d_basis_pad); cudaFree(c->d_basis_hi);
     cudaFree(c->d_basis_lo); cudaFree(c->d_pinv_t); cudaFree(c->d_pinv_hi); cudaFree(c->d_pinv_lo);
     cudaFree(c->d_prog_w); cudaFree(c->d_prog_h);
     delete c;
@@ -465,6 +466,14 @@ int spev_mel_to_mag(spev_ctx* c, const spev_batch* b, const float* mel, int layo
                        ld_s >= kSpecLd;
     if (tc_ok) return launch_mel_to_mag_tc(c, mel, b->n_frames, is_log, S, ld_s, static_cast<cudaStream_t>(stream));
     return launch_mel_to_mag(c, b, mel, layout, is_log, S, ld_s, static_cast<cudaStream_t>(stream));
+}
+
+int spev_nnls_objective(spev_ctx* c, const void* x, int x_mode, int64_t ld_x, const float* mel, int is_log, int L, int64_t T,
+                        int64_t t0, int tb, double* value_parts, double* grad, double* pg_max, void* stream) {
+    SPEV_ON_CTX_DEVICE(c);
+    SPEV_REQUIRE(x_mode == 0 || x_mode == 1, SPEV_E_INVALID, "spev_nnls_objective: x_mode must be 0 or 1");
+    return launch_nnls_objective(c, x, x_mode, ld_x, mel, is_log, L, T, t0, tb, value_parts, grad, pg_max,
+                                 static_cast<cudaStream_t>(stream));
 }
 
 int spev_istft(spev_ctx* c, const spev_batch* b, const void* spec, int64_t ld, float* y, void* stream) {

@@ -192,11 +192,77 @@ def mel_to_mag_flat(mel: torch.Tensor, batch: FlatBatch, ctx: Context, *, layout
     return out
 
 
-def mel_to_stft(M: ArrayLike, *, sr=22050, n_fft=2048, power=2.0, fmin=0.0, fmax=None, device=None):
+MAX_MEM_BLOCK = 2 ** 18      # librosa.util.utils.MAX_MEM_BLOCK: nnls solves this many bytes of columns at a time
+NNLS_PGTOL = 1e-5            # scipy.optimize.fmin_l_bfgs_b default pgtol
+
+
+def nnls_refine(S: torch.Tensor, mel_rows: torch.Tensor, ctx: Context, b: int, T: int, *, is_log: bool) -> int:
+    """The L-BFGS-B part of ``librosa.util.nnls`` (inside ``mel_to_stft``, ``spev_real_metrics.py:730``), in place on the
+    warm start ``S = clip(pinv(A) M, 0) ** 0.5`` (``[b*T, 520]`` magnitude rows; ``mel_rows``: ``[b*T, n_mels]``).
+
+    librosa cuts the columns into blocks of ``MAX_MEM_BLOCK // (prod(lead) * n_mels * 4)`` and runs scipy's L-BFGS-B on
+    each, started at the warm start.  Its first act is the convergence test ``max |projected gradient| <= pgtol``; the
+    objective carries a ``1 / B.size`` factor, so for blocks of >~ 40 columns of reference-range input the test passes
+    at once and the warm start IS the answer.  One launch of ``spev_nnls_objective`` evaluates that test for every
+    block (float64, as in librosa); only blocks that fail it -- short utterances, short remainder blocks -- are handed
+    to ``scipy.optimize.fmin_l_bfgs_b`` (the very routine librosa calls, same arguments), with objective and gradient
+    evaluated on the GPU.  Returns the number of blocks that iterated."""
+    n_mels = ctx.n_mels
+    n_columns = max(1, MAX_MEM_BLOCK // (b * n_mels * 4))
+    blocks = [(0, T)] if T <= n_columns else [(s0, min(T, s0 + n_columns)) for s0 in range(0, T, n_columns)]
+    dev = S.device
+    lib, st = ctx.lib, stream_ptr(dev)
+    pg = torch.empty(b * T, dtype=torch.float64, device=dev)          # per column, block after block
+    val = torch.empty(b * T, dtype=torch.float64, device=dev)
+    off = 0
+    for t0, t1 in blocks:
+        _lib.check(lib.spev_nnls_objective(ctx.handle, S.data_ptr(), 1, S.shape[1], mel_rows.data_ptr(), 1 if is_log else 0,
+                                           b, T, t0, t1 - t0, val[off:].data_ptr(), None, pg[off:].data_ptr(), st),
+                   "spev_nnls_objective")
+        off += b * (t1 - t0)
+    pg_host = pg.cpu().numpy()                                         # the one synchronisation of the check
+    todo, off = [], 0
+    for t0, t1 in blocks:
+        n = b * (t1 - t0)
+        if pg_host[off: off + n].max(initial=0.0) > NNLS_PGTOL:
+            todo.append((t0, t1))
+        off += n
+    if not todo:
+        return 0
+    try:
+        from scipy.optimize import fmin_l_bfgs_b
+    except ImportError as e:    # pragma: no cover
+        raise RuntimeError("mel_to_stft(nnls='librosa') needs scipy (librosa's own dependency) for the L-BFGS-B "
+                           "iterations of short blocks; pass nnls='pinv' for the warm start only") from e
+    Sv = S.view(b, T, S.shape[1])
+    for t0, t1 in todo:
+        tb = t1 - t0
+        x0 = Sv[:, t0:t1, : _lib.N_BINS].permute(0, 2, 1).double().square().contiguous()   # [b, 513, tb], librosa's order
+        xd = torch.empty_like(x0)
+        gd = torch.empty_like(x0)
+        vd = torch.empty(b * tb, dtype=torch.float64, device=dev)
+        pd = torch.empty(b * tb, dtype=torch.float64, device=dev)
+
+        def fun(xflat):
+            xd.copy_(torch.from_numpy(xflat).view_as(xd))
+            _lib.check(lib.spev_nnls_objective(ctx.handle, xd.data_ptr(), 0, 0, mel_rows.data_ptr(), 1 if is_log else 0,
+                                               b, T, t0, tb, vd.data_ptr(), gd.data_ptr(), pd.data_ptr(), st),
+                       "spev_nnls_objective")
+            return float(vd.sum().item()), gd.cpu().numpy().reshape(-1)
+        x, _, _ = fmin_l_bfgs_b(fun, x0.cpu().numpy().reshape(-1), bounds=[(0, None)] * x0.numel(), m=_lib.N_BINS)
+        xs = torch.from_numpy(x).view_as(xd).to(dev).to(torch.float32).sqrt()               # astype(f32) then ** 0.5
+        Sv[:, t0:t1, : _lib.N_BINS] = xs.permute(0, 2, 1)
+    return len(todo)
+
+
+def mel_to_stft(M: ArrayLike, *, sr=22050, n_fft=2048, power=2.0, fmin=0.0, fmax=None, nnls="librosa", device=None):
     """Drop-in for ``librosa.feature.inverse.mel_to_stft`` -> ``[..., 513, T]`` magnitudes.
-    Computes the NNLS warm start ``clip(pinv(basis) @ M, 0) ** 0.5`` (which librosa's L-BFGS-B
-    returns unchanged for reference-range inputs; see DESIGN.md "NNLS")."""
+    ``nnls="librosa"`` (default): librosa's result -- the warm start ``clip(pinv(basis) @ M, 0)`` refined by L-BFGS-B
+    wherever librosa's own solver iterates (``nnls_refine``); ``nnls="pinv"``: the warm start only (no host
+    synchronisation; identical for reference-range inputs of >~ 40 frames, see DESIGN.md "NNLS")."""
     _check_fixed(n_fft, HOP, None, "hann", True, "constant", power)
+    if nnls not in ("librosa", "pinv"):
+        raise ValueError("nnls must be 'librosa' or 'pinv'")
     t, was_numpy = _to_device(M, device)
     lead, n_mels, T = t.shape[:-2], t.shape[-2], t.shape[-1]
     b = int(np.prod(lead)) if lead else 1
@@ -205,6 +271,8 @@ def mel_to_stft(M: ArrayLike, *, sr=22050, n_fft=2048, power=2.0, fmin=0.0, fmax
     # [b, n_mels, T] -> frame-major [b*T, n_mels]: the layout the tcgen05 GEMM path takes
     tm = t.reshape(b, n_mels, T).transpose(1, 2).contiguous().view(-1)
     S = mel_to_mag_flat(tm, batch, ctx, layout=0, is_log=False)
+    if nnls == "librosa" and b * T > 0:
+        nnls_refine(S, tm.view(b * T, n_mels), ctx, b, T, is_log=False)
     out = S.view(b, T, _lib.SPEC_LD)[:, :, : _lib.N_BINS].permute(0, 2, 1).reshape(*lead, _lib.N_BINS, T)
     return _ret(out, was_numpy)
 
@@ -260,20 +328,25 @@ def griffinlim(S: ArrayLike, *, n_iter=32, hop_length=None, win_length=None, n_f
 def mel_to_audio(M: ArrayLike, *, sr=22050, n_fft=2048, hop_length=None, win_length=None, window="hann",
                  center=True, pad_mode="constant", power=2.0, n_iter=32, length=None, dtype=np.float32,
                  fmin=0.0, fmax=None, momentum=0.99, init_phase: Optional[ArrayLike] = None,
-                 random_state=None, is_log=False, device=None):
+                 random_state=None, is_log=False, nnls="librosa", device=None):
     """Drop-in for ``librosa.feature.inverse.mel_to_audio`` (call site
     ``spev_real_metrics.py:730-733``): ``[..., n_mels, T]`` mel power -> ``[..., (T-1)*hop]``.
-    ``is_log=True`` fuses the reference's ``np.exp`` (``:729``) into the first kernel."""
+    ``is_log=True`` fuses the reference's ``np.exp`` (``:729``) into the first kernel.  ``nnls``: see ``mel_to_stft``
+    (``"pinv"`` keeps the whole call free of host synchronisation)."""
     _check_fixed(n_fft, hop_length, win_length, window, center, pad_mode, power)
+    if nnls not in ("librosa", "pinv"):
+        raise ValueError("nnls must be 'librosa' or 'pinv'")
     if length is not None:
         raise NotImplementedError("mel_to_audio(length=...) is not on the reference path")
     t, was_numpy = _to_device(M, device)
     lead, n_mels, T = t.shape[:-2], t.shape[-2], t.shape[-1]
     b = int(np.prod(lead)) if lead else 1
     ctx = Context.get(t.device, sr=sr, n_mels=n_mels, fmin=fmin, fmax=fmax)
-    batch = make_batch(ctx, n_frames=[T] * b, with_chunks=True)
+    batch = ctx.uniform_batch(b, T, with_chunks=True)
     tm = t.reshape(b, n_mels, T).transpose(1, 2).contiguous().view(-1)   # frame-major -> tensor-core GEMM
     S = mel_to_mag_flat(tm, batch, ctx, layout=0, is_log=is_log)
+    if nnls == "librosa" and b * T > 0:
+        nnls_refine(S, tm.view(b * T, n_mels), ctx, b, T, is_log=is_log)
     ph = _phase_to_internal(init_phase, b, T, t.device) if init_phase is not None else None
     seed = int(np.random.SeedSequence(random_state).generate_state(2, dtype=np.uint32).view(np.uint64)[0])
     y = griffinlim_flat(S, batch, ctx, n_iter=n_iter, momentum=momentum, init_phase=ph, seed=seed)

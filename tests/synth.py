@@ -222,7 +222,7 @@ def _cfg3_oracle_job(args):
     b, n_iters, sr, T = args
     from oracle import librosa_restated as lr
     lm = lr.reference_logmel(speechy(seed=300 + b, n=(T - 1) * HOP, sr=sr), sr=sr).T.copy()
-    S = lr.mel_to_stft(np.exp(lm), sr=sr, n_fft=1024, fmin=0, fmax=8000, lbfgs=False)
+    S = lr.mel_to_stft(np.exp(lm), sr=sr, n_fft=1024, fmin=0, fmax=8000, lbfgs=True)      # librosa's own solver
     ph = init_phase((513, T), seed=3000 + b)
     return b, [lr.spectral_convergence(lr.griffinlim(S, n_iter=n, hop_length=HOP, n_fft=1024, init_phase=ph), S)
                for n in n_iters]
