@@ -109,37 +109,51 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
-template <int BN>
+// One CTA owns MT consecutive 128-row tiles of A and keeps their MT accumulators side by side in TMEM.  The K loop
+// runs over (k-chunk, tile) pairs: a chunk of the pre-split B operand (hi + lo) is loaded ONCE per k-chunk into its
+// own 2-slot ring and used by all MT tiles, while the A tiles stream through a ring of their own.  With MT = 1 every
+// CTA re-reads the whole B operand (333 KB for the mel basis) from L2 per 128 rows -- more bytes than the A tile it
+// multiplies (266 KB), and the L2 -> SM path, not HBM, was the limiter (r01: 49 % of the HBM roofline, tensor pipe
+// 31 %); MT = 3 cuts the B traffic to a third.
+template <int BN, int MT>
 struct TcSmem {
-    static constexpr int kStages = 2;                  // 2 x 52 KB (BN=80): two CTAs per SM keep 4 stages of loads in flight
-    static constexpr int kCtas = BN > 128 ? 1 : 2;
+    static constexpr int kStagesA = 2;                 // A ring (per stage: landed tile + its tf32 residual)
+    static constexpr int kSlotsB = 2;                  // B ring (per slot: B_hi + B_lo chunk)
+    static constexpr int kCtas = BN > 128 ? 1 : 2;     // two CTAs per SM: one's epilogue overlaps the other's main loop
     static constexpr uint32_t kBBytes = BN * kBK * 4;
-    static constexpr uint32_t kStage = 2 * kABytes + 2 * kBBytes;
+    static constexpr uint32_t kStageA = 2 * kABytes;
+    static constexpr uint32_t kSlotB = 2 * kBBytes;
     static constexpr uint32_t kBars = 1024;
-    static constexpr uint32_t kTotal = kStages * kStage + kBars + 1024 /*alignment slack*/;
-    static constexpr uint32_t kTmemCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : BN <= 256 ? 256 : 512;
+    static constexpr uint32_t kTotal = kStagesA * kStageA + kSlotsB * kSlotB + kBars + 1024 /*alignment slack*/;
+    static constexpr uint32_t kCols = BN * MT;
+    static constexpr uint32_t kTmemCols = kCols <= 32 ? 32 : kCols <= 64 ? 64 : kCols <= 128 ? 128 : kCols <= 256 ? 256 : 512;
+    static_assert(kCols <= 512 && kTmemCols * kCtas <= 512, "accumulators do not fit TMEM");
 };
 
-template <int BN, int EPI>
-__global__ void __launch_bounds__(kTcThreads, TcSmem<BN>::kCtas)
+template <int BN, int EPI, int MT>
+__global__ void __launch_bounds__(kTcThreads, TcSmem<BN, MT>::kCtas)
 k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
               const __grid_constant__ CUtensorMap map_blo, float* __restrict__ out, TcParams p) {
-    using L = TcSmem<BN>;
-    constexpr int kStages = L::kStages;
+    using L = TcSmem<BN, MT>;
+    constexpr int NSA = L::kStagesA, NSB = L::kSlotsB;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(base + kStages * L::kStage);
-    uint64_t* full = bars;                  // [kStages]  TMA landed
-    uint64_t* split = bars + kStages;       // [kStages]  A_hi/A_lo ready
-    uint64_t* empty = bars + 2 * kStages;   // [kStages]  MMAs done reading the stage
-    uint64_t* tmem_full = bars + 3 * kStages;
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 1);
+    unsigned char* base_b = base + NSA * L::kStageA;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base_b + NSB * L::kSlotB);
+    uint64_t* full_a = bars;                        // [NSA] TMA landed an A tile
+    uint64_t* split = full_a + NSA;                 // [NSA] A_hi / A_lo ready
+    uint64_t* empty_a = split + NSA;                // [NSA] MMAs done reading the A stage
+    uint64_t* full_b = empty_a + NSA;               // [NSB] TMA landed a B chunk
+    uint64_t* empty_b = full_b + NSB;               // [NSB] MMAs of every tile done reading the B chunk
+    uint64_t* tmem_full = empty_b + NSB;
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * BN;
+    const int m0 = blockIdx.x * (kBM * MT), n0 = blockIdx.y * BN;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(full + s, 1); mbar_init(split + s, 128); mbar_init(empty + s, 1); }
+        for (int s = 0; s < NSA; ++s) { mbar_init(full_a + s, 1); mbar_init(split + s, 128); mbar_init(empty_a + s, 1); }
+        for (int s = 0; s < NSB; ++s) { mbar_init(full_b + s, 1); mbar_init(empty_b + s, 1); }
         mbar_init(tmem_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
@@ -155,44 +169,58 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     if (warp == 0) {
         if (lane == 0) {
             for (int kc = 0; kc < p.k_chunks; ++kc) {
-                const int s = kc % kStages, it = kc / kStages;
-                mbar_wait(empty + s, (it & 1) ^ 1);
-                unsigned char* st = base + s * L::kStage;
-                mbar_expect_tx(full + s, kABytes + 2 * L::kBBytes);
-                tma_load_2d(st, &map_a, full + s, kc * kBK, m0);
-                tma_load_2d(st + 2 * kABytes, &map_bhi, full + s, kc * kBK, n0);
-                tma_load_2d(st + 2 * kABytes + L::kBBytes, &map_blo, full + s, kc * kBK, n0);
+                const int sb = kc % NSB;
+                mbar_wait(empty_b + sb, ((kc / NSB) & 1) ^ 1);
+                unsigned char* bs = base_b + sb * L::kSlotB;
+                mbar_expect_tx(full_b + sb, 2 * L::kBBytes);
+                tma_load_2d(bs, &map_bhi, full_b + sb, kc * kBK, n0);
+                tma_load_2d(bs + L::kBBytes, &map_blo, full_b + sb, kc * kBK, n0);
+#pragma unroll 1
+                for (int mt = 0; mt < MT; ++mt) {
+                    const int j = kc * MT + mt, s = j % NSA;
+                    mbar_wait(empty_a + s, ((j / NSA) & 1) ^ 1);
+                    mbar_expect_tx(full_a + s, kABytes);
+                    tma_load_2d(base + s * L::kStageA, &map_a, full_a + s, kc * kBK, m0 + mt * kBM);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_tf32(kBM, BN);
             for (int kc = 0; kc < p.k_chunks; ++kc) {
-                const int s = kc % kStages, it = kc / kStages;
-                mbar_wait(split + s, it & 1);
-                tc_fence_after();
-                const uint32_t a_hi = smem_u32(base + s * L::kStage), a_lo = a_hi + kABytes;
-                const uint32_t b_hi = a_hi + 2 * kABytes, b_lo = b_hi + L::kBBytes;
+                const int sb = kc % NSB;
+                mbar_wait(full_b + sb, (kc / NSB) & 1);
+                const uint32_t b_hi = smem_u32(base_b + sb * L::kSlotB), b_lo = b_hi + L::kBBytes;
+#pragma unroll 1
+                for (int mt = 0; mt < MT; ++mt) {
+                    const int j = kc * MT + mt, s = j % NSA;
+                    mbar_wait(split + s, (j / NSA) & 1);
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_u32(base + s * L::kStageA), a_lo = a_hi + kABytes;
+                    const uint32_t acc = tmem_base + static_cast<uint32_t>(mt * BN);
 #pragma unroll
-                for (int k = 0; k < kBK / 8; ++k) {   // UMMA_K = 8 for tf32 = 32 bytes along the swizzled row
-                    const uint32_t off = k * 32;
-                    const uint64_t dah = umma_desc_sw128(a_hi + off), dal = umma_desc_sw128(a_lo + off);
-                    const uint64_t dbh = umma_desc_sw128(b_hi + off), dbl = umma_desc_sw128(b_lo + off);
-                    tc_mma_tf32(tmem_base, dal, dbh, idesc, (kc | k) != 0);   // small terms first
-                    tc_mma_tf32(tmem_base, dah, dbl, idesc, 1);
-                    tc_mma_tf32(tmem_base, dah, dbh, idesc, 1);
+                    for (int k = 0; k < kBK / 8; ++k) {   // UMMA_K = 8 for tf32 = 32 bytes along the swizzled row
+                        const uint32_t off = k * 32;
+                        const uint64_t dah = umma_desc_sw128(a_hi + off), dal = umma_desc_sw128(a_lo + off);
+                        const uint64_t dbh = umma_desc_sw128(b_hi + off), dbl = umma_desc_sw128(b_lo + off);
+                        tc_mma_tf32(acc, dal, dbh, idesc, (kc | k) != 0);   // small terms first
+                        tc_mma_tf32(acc, dah, dbl, idesc, 1);
+                        tc_mma_tf32(acc, dah, dbh, idesc, 1);
+                    }
+                    tc_commit(empty_a + s);   // implies tcgen05.fence::before_thread_sync
                 }
-                tc_commit(empty + s);   // implies tcgen05.fence::before_thread_sync
+                tc_commit(empty_b + sb);
             }
             tc_commit(tmem_full);
         }
     } else {
         const int t = threadIdx.x - 64;   // 0..127
-        for (int kc = 0; kc < p.k_chunks; ++kc) {
-            const int s = kc % kStages, it = kc / kStages;
-            mbar_wait(full + s, it & 1);
-            float4* a = reinterpret_cast<float4*>(base + s * L::kStage);
-            float4* l = reinterpret_cast<float4*>(base + s * L::kStage + kABytes);
+        const int n_it = p.k_chunks * MT;
+        for (int j = 0; j < n_it; ++j) {
+            const int s = j % NSA;
+            mbar_wait(full_a + s, (j / NSA) & 1);
+            float4* a = reinterpret_cast<float4*>(base + s * L::kStageA);
+            float4* l = reinterpret_cast<float4*>(base + s * L::kStageA + kABytes);
 #pragma unroll
             for (int i = 0; i < static_cast<int>(kABytes / 16 / 128); ++i) {
                 float4 v = a[t + 128 * i];
@@ -212,29 +240,32 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         mbar_wait(tmem_full, 0);
         tc_fence_after();
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
-        const int row = q * 32 + lane;
-        const bool row_ok = m0 + row < p.m_total;
-        float* orow = out + static_cast<int64_t>(m0 + row) * p.ld_out + n0;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 16) {
-            uint32_t r[16];
-            tc_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, r);
-            float v[16];
+        for (int mt = 0; mt < MT; ++mt) {
+            const int row = m0 + mt * kBM + q * 32 + lane;
+            const bool row_ok = row < p.m_total;
+            float* orow = out + static_cast<int64_t>(row) * p.ld_out + n0;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 16) {
+                uint32_t r[16];
+                tc_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(mt * BN + c0), r);
+                float v[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                float x = __uint_as_float(r[j]);
-                if (EPI == EPI_MEL) {
-                    if (p.log_mode) x = fminf(fmaxf(logf(fmaxf(x, p.floor_v)), p.lo), p.hi);
-                } else {
-                    x = sqrtf(fmaxf(x, 0.f));
+                for (int jj = 0; jj < 16; ++jj) {
+                    float x = __uint_as_float(r[jj]);
+                    if (EPI == EPI_MEL) {
+                        if (p.log_mode) x = fminf(fmaxf(logf(fmaxf(x, p.floor_v)), p.lo), p.hi);
+                    } else {
+                        x = sqrtf(fmaxf(x, 0.f));
+                    }
+                    v[jj] = x;
                 }
-                v[j] = x;
-            }
-            if (row_ok) {
+                if (row_ok) {
 #pragma unroll
-                for (int j = 0; j < 16; j += 4)
-                    if (n0 + c0 + j < p.n_valid)   // n_valid is a multiple of 4 (80 / 520)
-                        *reinterpret_cast<float4*>(orow + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    for (int jj = 0; jj < 16; jj += 4)
+                        if (n0 + c0 + jj < p.n_valid)   // n_valid is a multiple of 4 (80 / 520)
+                            *reinterpret_cast<float4*>(orow + c0 + jj) = make_float4(v[jj], v[jj + 1], v[jj + 2], v[jj + 3]);
+                }
             }
         }
     }
@@ -297,6 +328,10 @@ int gemm_tc_init(spev_ctx* c) {
     SPEV_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_pinv_lo), lo.size() * sizeof(float)));
     SPEV_CUDA(cudaMemcpy(c->d_pinv_hi, hi.data(), hi.size() * sizeof(float), cudaMemcpyHostToDevice));
     SPEV_CUDA(cudaMemcpy(c->d_pinv_lo, lo.data(), lo.size() * sizeof(float), cudaMemcpyHostToDevice));
+    SPEV_CUDA(cudaFuncSetAttribute(k_gemm_tf32x3<80, EPI_MEL, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(TcSmem<80, 3>::kTotal)));
+    SPEV_CUDA(cudaFuncSetAttribute(k_gemm_tf32x3<176, EPI_MAG, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(TcSmem<176, 1>::kTotal)));
     if (nm % 4 != 0) return SPEV_OK;   // TMA needs 16-byte row pitches; the TC path is then unavailable
     int rc;
     if ((rc = encode_2d(st, &st->mel_bhi, c->d_basis_hi, nm, kBins, kSpecLd, 80))) return rc;
@@ -311,13 +346,13 @@ void gemm_tc_destroy(spev_ctx* c) {
     c->tma = nullptr;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int MT>
 static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mbh, const CUtensorMap& mbl, float* out, const TcParams& p,
                      int n_tiles, cudaStream_t st) {
-    auto kern = k_gemm_tf32x3<BN, EPI>;
-    SPEV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(TcSmem<BN>::kTotal)));
-    dim3 grid(static_cast<unsigned>((p.m_total + kBM - 1) / kBM), static_cast<unsigned>(n_tiles));
-    kern<<<grid, kTcThreads, TcSmem<BN>::kTotal, st>>>(ma, mbh, mbl, out, p);
+    auto kern = k_gemm_tf32x3<BN, EPI, MT>;
+    using L = TcSmem<BN, MT>;
+    dim3 grid(static_cast<unsigned>((p.m_total + kBM * MT - 1) / (kBM * MT)), static_cast<unsigned>(n_tiles));
+    kern<<<grid, kTcThreads, L::kTotal, st>>>(ma, mbh, mbl, out, p);
     SPEV_CUDA(cudaGetLastError());
     return SPEV_OK;
 }
@@ -337,7 +372,7 @@ int launch_mel_project_tc(spev_ctx* c, const float* power, int64_t n_frames, flo
     TcParams p{};
     p.m_total = static_cast<int>(n_frames); p.k_chunks = (kBins + kBK - 1) / kBK; p.n_valid = 80; p.ld_out = 80;
     p.a_exp = 0; p.log_mode = mode; p.floor_v = floor_v; p.lo = lo; p.hi = hi;
-    return launch_tc<80, EPI_MEL>(ma, st->mel_bhi, st->mel_blo, out, p, 1, stm);
+    return launch_tc<80, EPI_MEL, 3>(ma, st->mel_bhi, st->mel_blo, out, p, 1, stm);
 }
 
 // mel [F, n_mels] frame-major (layout 0) -> S [F, ld_s]
@@ -355,7 +390,7 @@ int launch_mel_to_mag_tc(spev_ctx* c, const float* mel, int64_t n_frames, int is
     TcParams p{};
     p.m_total = static_cast<int>(n_frames); p.k_chunks = (c->n_mels + kBK - 1) / kBK; p.n_valid = kSpecLd; p.ld_out = ld_s;
     p.a_exp = is_log; p.log_mode = 0;
-    return launch_tc<176, EPI_MAG>(ma, st->pinv_bhi, st->pinv_blo, S, p, 3, stm);
+    return launch_tc<176, EPI_MAG, 1>(ma, st->pinv_bhi, st->pinv_blo, S, p, 3, stm);
 }
 
 }  // namespace spev
