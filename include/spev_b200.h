@@ -253,8 +253,9 @@ SPEV_API int spev_copy_segments(const void* src, void* dst, const int64_t* src_o
 /* A/B switch of the fused log-mel kernel: 1 (default) = decoupled warps with split-phase mbarrier synchronisation
  * (k_stft_mel_ws), 0 = the tile kernel with three CTA barriers per tile (k_stft_mel<0>).  Results are bit-identical. */
 SPEV_API int spev_set_logmel_variant(spev_ctx* ctx, int variant);
-/* A/B switch of the Griffin-Lim kernels: 1 (default) = dynamic tile tickets + bulk-staged tprev rows, 0 = the static
- * round-robin tile kernels of round 1.  Same arithmetic, bit-identical results. */
+/* A/B switch of the Griffin-Lim kernels (bit mask): 0 = the round-1 kernels; 1 = warp-independent phase update with
+ * bulk-staged (cp.async.bulk) tprev / spectrum rows; | 2 = dynamic tile tickets in the ISTFT; | 4 = dynamic pair tickets
+ * in the phase update.  Same arithmetic, bit-identical results; the default is the fastest measured on cfg3. */
 SPEV_API int spev_set_griffinlim_variant(spev_ctx* ctx, int variant);
 
 /* Cap the number of CTAs the persistent FFT kernels launch (default: one per SM).  A multi-GPU cache build that

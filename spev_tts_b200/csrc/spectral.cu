@@ -1103,6 +1103,7 @@ int launch_stft_phase(spev_ctx* ctx, const spev_batch* b, const float* y, const 
                           static_cast<float2*>(tprev), ld, alpha, has_prev, tw, win);
     // bulk staging of the tprev rows needs 16-byte aligned rows with one readable pad column, and both rows of a pair
     // must fit the warp's transpose tile
+    if (!(ctx->gl_variant & 4)) counter = nullptr;
     const bool stage_t = (reinterpret_cast<uintptr_t>(tprev) & 15) == 0 && ld % 2 == 0 && ld > kBins &&
                          static_cast<size_t>(ld) * 8 + (kBins + 1) * 8 <= sizeof(float) * kXWords;
     if (stage_t)
@@ -1121,7 +1122,7 @@ int launch_istft(spev_ctx* ctx, const spev_batch* b, const void* spec, int64_t l
     // bulk staging needs 16-byte aligned rows with one readable pad column, two rows per warp region
     const bool bulk = ctx->gl_variant != 0 && (reinterpret_cast<uintptr_t>(spec) & 15) == 0 && ld % 2 == 0 && ld > kBins &&
                       static_cast<size_t>(ld) * 8 + (kBins + 1) * 8 <= sizeof(float) * kWarpRegionWords;
-    unsigned* ctr = ctx->gl_variant == 0 ? nullptr : counter;
+    unsigned* ctr = (ctx->gl_variant & 2) ? counter : nullptr;
     if (bulk)
         return launch_pdl(k_istft<true>, fft_grid(ctx, b->n_ctiles), kThreads, smem_istft(), st, view_of(b), static_cast<const float2*>(spec),
                           ld, y, static_cast<const float2*>(ctx->d_tw), static_cast<const float*>(ctx->d_window), ctr, base);
