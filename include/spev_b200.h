@@ -43,7 +43,7 @@ extern "C" {
 #define SPEV_E_WORKSPACE (-5)   /* workspace too small */
 
 #define SPEV_TILE_FRAMES 32 /* frames per CTA tile (STFT-type kernels); == spev_tile_frames() */
-#define SPEV_TILE_CHUNKS 13 /* 256-sample output chunks per CTA tile (ISTFT: 8 warps = 16 frames, 2 CTAs/SM); == spev_tile_chunks() */
+#define SPEV_TILE_CHUNKS 29 /* 256-sample output chunks per CTA tile (ISTFT); == spev_tile_chunks() */
 #define SPEV_SPEC_LD 520    /* row pitch (elements) of internal [F,513] spectra */
 
 typedef struct spev_ctx spev_ctx;

@@ -36,7 +36,6 @@ int launch_stft_phase(spev_ctx*, const spev_batch*, const float*, const float*, 
                       unsigned* counter = nullptr, unsigned base = 0);
 int launch_istft(spev_ctx*, const spev_batch*, const void*, int64_t, float*, cudaStream_t, unsigned* counter = nullptr, unsigned base = 0);
 int fft_grid(const spev_ctx*, int64_t);
-int istft_grid(const spev_ctx*, int64_t);
 int launch_nnls_objective(spev_ctx*, const void*, int, int64_t, const float*, int, int, int64_t, int64_t, int, double*, double*, double*, cudaStream_t);
 int spectral_init(spev_ctx*);
 int launch_gl_init(spev_ctx*, const float*, int64_t, const float*, uint64_t, void*, int64_t, int64_t, cudaStream_t);
@@ -519,7 +518,7 @@ int spev_griffinlim(spev_ctx* c, const spev_batch* b, const float* S, int64_t ld
     // they only grow during a call -- launch j starts at base j * (work + workers), see draw_ticket()
     unsigned* counters = reinterpret_cast<unsigned*>(tprev + b->n_frames * kSpecLd);
     SPEV_CUDA(cudaMemsetAsync(counters, 0, 256, st));
-    const unsigned per_istft = static_cast<unsigned>(b->n_ctiles + istft_grid(c, b->n_ctiles));
+    const unsigned per_istft = static_cast<unsigned>(b->n_ctiles + fft_grid(c, b->n_ctiles));
     const unsigned per_phase = static_cast<unsigned>(static_cast<int64_t>(b->n_ftiles) * kWarps +
                                                      static_cast<int64_t>(fft_grid(c, b->n_ftiles)) * kWarps);
     // librosa: (momentum / (1 + momentum)) is a Python float applied to a complex64 array

@@ -264,20 +264,9 @@ __device__ __forceinline__ float2 phase_of(float2 reb, float s, float2 tp, float
         a.x = a.x - alpha * tp.x;
         a.y = a.y - alpha * tp.y;
     }
-    // ang = S * a / (|a| + tiny).  For 1e-15 <= |a| <= 1e15 the tiny (1.2e-38) is far below half an ulp of |a| and
-    // |a|^2 neither under- nor overflows, so 1 / (|a| + tiny) == rsqrt(|a|^2) (MUFU.RSQ, 2 ulp) -- one instruction
-    // instead of the IEEE sqrt + divide sequences (~20 instructions per bin; the epilogue was a third of the kernel's
-    // instruction count).  Everything else -- exact zeros (digital silence: 0 / tiny = 0), denormal-range and huge
-    // values, NaN -- takes the literal formula.
-    const float m = fmaf(a.x, a.x, a.y * a.y);
-    float r;
-    if (m >= 1e-30f && m <= 1e30f) {
-        r = rsqrtf(m) * s;
-    } else {
-        const float den = sqrtf(m) + kTiny;
-        r = (1.0f / den) * s;   // numpy complex/real division multiplies by the reciprocal
-    }
-    return make_float2(a.x * r, a.y * r);
+    const float den = sqrtf(fmaf(a.x, a.x, a.y * a.y)) + kTiny;
+    const float r = 1.0f / den;   // numpy complex/real division multiplies by the reciprocal
+    return make_float2(a.x * r * s, a.y * r * s);
 }
 
 template <int MODE>   // 0: plain STFT into `ang`; 1: Griffin-Lim phase update
@@ -762,16 +751,8 @@ k_stft_mel_ws(BatchView bv, const float* __restrict__ samples, float* __restrict
 // BULK: a warp's two spectrum rows (8,272 B) arrive in its region by ONE bulk asynchronous copy instead of 34 scattered
 // 8-byte loads per lane (ncu r01: lg_throttle 1.2 + long_scoreboard 1.7 warps per issue cycle on those loads): no LSU
 // queue pressure, and all 16 warps' rows are in flight at once.
-// Eight warps (16 frames -> 13 chunks per tile) and TWO CTAs per SM: the start-of-tile load latency and the two CTA
-// barriers of one CTA (ncu on the 16-warp version: 16 % of the stall samples on the spectrum wait, 8 % on barriers,
-// issue-active 47 %) are covered by the other CTA's transform; that buys more than the wider halo (16/13 instead of
-// 32/29 frames per chunk) costs.
-constexpr int kIstftWarps = (kTileChunks + 3) / 2;
-constexpr int kIstftThreads = kIstftWarps * 32;
-static_assert(2 * kIstftWarps - 3 == kTileChunks && kIstftWarps <= kWarps, "SPEV_TILE_CHUNKS must be 2 * warps - 3");
-
 template <bool BULK>
-__global__ void __launch_bounds__(kIstftThreads, kIstftWarps <= 8 ? 2 : 1)
+__global__ void __launch_bounds__(kThreads, 1)
 k_istft(BatchView bv, const float2* __restrict__ spec, int64_t ld, float* __restrict__ y,
         const float2* __restrict__ g_tw, const float* __restrict__ g_win, unsigned* counter, unsigned base) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -779,12 +760,12 @@ k_istft(BatchView bv, const float2* __restrict__ spec, int64_t ld, float* __rest
     float* s_win = reinterpret_cast<float*>(s_tw + 1024);
     spev_tile* s_ring = reinterpret_cast<spev_tile*>(s_win + 1024);
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_ring + kRing);   // one mbarrier per warp (BULK)
-    int* s_tick = reinterpret_cast<int*>(s_bar + kIstftWarps);     // [kRing] tile index held by each ring slot, -1: none
+    int* s_tick = reinterpret_cast<int*>(s_bar + kWarps);     // [kRing] tile index held by each ring slot, -1: none
     float* s_iw = reinterpret_cast<float*>(s_tick + kRing);   // [256] 1 / sum_q w^2 for interior chunks
     float* s_x = s_iw + kHop;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     load_tables(s_tw, s_win, g_tw, g_win, 1.0f);
-    if (BULK && threadIdx.x < kIstftWarps) bar_init(s_bar + threadIdx.x, 1);
+    if (BULK && threadIdx.x < kWarps) bar_init(s_bar + threadIdx.x, 1);
     if (BULK && threadIdx.x == 0) asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     uint64_t* tbar = s_bar + warp;
     unsigned tphase = 0;
@@ -896,7 +877,7 @@ k_istft(BatchView bv, const float2* __restrict__ spec, int64_t ld, float* __rest
         }
         __syncthreads();
         // gather: chunk c = c0 + cl receives frames c-1, c, c+1, c+2 (ascending), local cl..cl+3
-        for (int cl = warp; cl < nchunks; cl += kIstftWarps) {
+        for (int cl = warp; cl < nchunks; cl += kWarps) {
             const int c = c0 + cl;
             float* yo_c = y + d.src0 + static_cast<int64_t>(cl) * kHop;
             if (c >= 1 && c + 2 < T) {   // all four frames exist: table-driven normalisation
@@ -1022,7 +1003,7 @@ static size_t smem_prog(const spev_ctx* c) { return sizeof(float4) * c->prog_gro
 static size_t smem_stft(size_t prog_bytes) {
     return smem_common() + sizeof(float) * 2 * kStageSamples + sizeof(float) * kWarps * kWarpRegionWords + prog_bytes;
 }
-static size_t smem_istft() { return smem_common() + sizeof(uint64_t) * kIstftWarps + sizeof(int) * kRing + sizeof(float) * kHop + sizeof(float) * kIstftWarps * kWarpRegionWords; }
+static size_t smem_istft() { return smem_common() + sizeof(uint64_t) * kWarps + sizeof(int) * kRing + sizeof(float) * kHop + sizeof(float) * kWarps * kWarpRegionWords; }
 
 // Launch with the programmatic-stream-serialization attribute (PDL).
 template <class... KArgs, class... Args>
@@ -1097,9 +1078,6 @@ int launch_stft_mel(spev_ctx* ctx, const spev_batch* b, const float* samples, fl
 
 // Grid of the persistent FFT kernels for n work tiles (also used by the Griffin-Lim driver to compute ticket bases).
 int fft_grid(const spev_ctx* ctx, int64_t n_tiles) { return static_cast<int>(std::min<int64_t>(n_tiles, ctx->num_sms)); }
-int istft_grid(const spev_ctx* ctx, int64_t n_tiles) {   // ISTFT: kIstftWarps <= 8 -> two CTAs per SM
-    return static_cast<int>(std::min<int64_t>(n_tiles, static_cast<int64_t>(ctx->num_sms) * (kIstftWarps <= 8 ? 2 : 1)));
-}
 
 int launch_stft_phase(spev_ctx* ctx, const spev_batch* b, const float* y, const float* S,
                       int64_t ld_s, void* ang, void* tprev, int64_t ld, float alpha, int has_prev,
@@ -1145,11 +1123,10 @@ int launch_istft(spev_ctx* ctx, const spev_batch* b, const void* spec, int64_t l
     const bool bulk = ctx->gl_variant != 0 && (reinterpret_cast<uintptr_t>(spec) & 15) == 0 && ld % 2 == 0 && ld > kBins &&
                       static_cast<size_t>(ld) * 8 + (kBins + 1) * 8 <= sizeof(float) * kWarpRegionWords;
     unsigned* ctr = (ctx->gl_variant & 2) ? counter : nullptr;
-    const int grid = istft_grid(ctx, b->n_ctiles);
     if (bulk)
-        return launch_pdl(k_istft<true>, grid, kIstftThreads, smem_istft(), st, view_of(b), static_cast<const float2*>(spec),
+        return launch_pdl(k_istft<true>, fft_grid(ctx, b->n_ctiles), kThreads, smem_istft(), st, view_of(b), static_cast<const float2*>(spec),
                           ld, y, static_cast<const float2*>(ctx->d_tw), static_cast<const float*>(ctx->d_window), ctr, base);
-    return launch_pdl(k_istft<false>, grid, kIstftThreads, smem_istft(), st, view_of(b), static_cast<const float2*>(spec),
+    return launch_pdl(k_istft<false>, fft_grid(ctx, b->n_ctiles), kThreads, smem_istft(), st, view_of(b), static_cast<const float2*>(spec),
                       ld, y, static_cast<const float2*>(ctx->d_tw), static_cast<const float*>(ctx->d_window), ctr, base);
 }
 

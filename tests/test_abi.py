@@ -33,7 +33,7 @@ def test_library_builds_and_exports_header_symbols():
     out = subprocess.check_output(["nm", "-D", "--defined-only", sp.LIB_PATH], text=True)
     exported = sorted(l.split()[-1] for l in out.splitlines() if " T " in l)
     assert exported == syms, "library exports symbols outside the header (or misses some)"
-    assert lib.spev_abi_version() == 1 and lib.spev_tile_chunks() in (lib.spev_tile_frames() - 3, lib.spev_tile_frames() // 2 - 3)
+    assert lib.spev_abi_version() == 1 and lib.spev_tile_chunks() == lib.spev_tile_frames() - 3
 
 
 def test_sass_is_sm100a():
