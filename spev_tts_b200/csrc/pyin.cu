@@ -22,6 +22,7 @@
 //   k_pitch_pool      per-phoneme masked mean / std of log-f0 from the decoded states (:399-414).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 #include "spev_internal.cuh"
 #include "tile_pipe.cuh"
@@ -168,6 +169,136 @@ k_yin_cmnd(BatchView bv, const float* __restrict__ samples, float* __restrict__ 
         if (tau >= min_period && tau <= max_period) {
             const float cm = cum / static_cast<float>(tau);
             yin[(d.row0 + fl) * n_lags + (tau - min_period)] = dval / (cm + 1.17549435e-38f);
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// P1 (round 2): the same curve from SHARED partial sums.
+// Consecutive frames overlap by 75 % (hop 256, window 1024): the autocorrelation of frame f is the sum of eight
+// 128-sample segment partials  S[s](tau) = sum_{m in segment s} z[m] z[m + tau],  s = 2f .. 2f + 7, and a segment is
+// shared by the four frames that cover it.  k_yin_cmnd above recomputes every segment for each of them (393 k FMA
+// per frame); here a CTA takes a run of up to 16 consecutive frames of one item, computes its 2*16 + 6 = 38 segment
+// partials ONCE (the same 8-lag x 16-sample register tile, the same summation order) and every frame adds its eight
+// in the same pairwise order -- bit-identical autocorrelations for 2.4 instead of 8 segments per frame.  The per-frame
+// rest (energy prefix sums, differences, cumulative mean) is one warp per frame, no CTA barrier.
+// ----------------------------------------------------------------------------------------------
+constexpr int kCmndGroup = 16;                         // frames per pass = warps per CTA
+constexpr int kCmndThreads = kCmndGroup * 32;
+__global__ void __launch_bounds__(kCmndThreads)
+k_yin_cmnd_shared(BatchView bv, const float* __restrict__ samples, float* __restrict__ yin, int frame_length, int win,
+                  int min_period, int max_period, int O /* lag octets: lags 0 .. 8*O-1 */) {
+    extern __shared__ __align__(16) float sm[];
+    const int L8 = 8 * O;                               // lags held per segment
+    const int need = win + L8;                          // z samples one frame touches
+    const int zmax = (kCmndGroup - 1) * kHop + need;    // z samples of a full group
+    const int nplane = (zmax + 7) / 8 + 4;              // float4 per plane (+ slack for the 24-sample B reads)
+    float* s_z = sm;                                                     // [zmax] linear (prefix sums)
+    float4* s_ev = reinterpret_cast<float4*>(sm + ((zmax + 3) & ~3));    // float4 2n   of z
+    float4* s_od = s_ev + nplane + 4;                                    // float4 2n+1 of z (bank offset, see above)
+    float* s_part = reinterpret_cast<float*>(s_od + nplane);             // [2*G + 6][L8] segment partials
+    float* s_e = s_part + (2 * kCmndGroup + 6) * L8;                     // [G][need + 1] per-frame prefix sums of z^2
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_lags = max_period - min_period + 1;
+    const int per_tile = (kTileFrames + kCmndGroup - 1) / kCmndGroup;
+    const int64_t n_groups = static_cast<int64_t>(bv.n_ftiles) * per_tile;
+    for (int64_t gi = blockIdx.x; gi < n_groups; gi += gridDim.x) {
+        const spev_tile d = bv.ftiles[gi / per_tile];
+        const int f0 = static_cast<int>(gi % per_tile) * kCmndGroup;
+        const int ng = min(kCmndGroup, d.n - f0);
+        if (ng <= 0) continue;                          // (uniform per CTA)
+        const int nseg = 2 * (ng - 1) + 8;
+        const int count = (ng - 1) * kHop + need;
+        // the frame_length window starts frame_length/2 before the frame centre; src0 is n_fft/2 before it; z skips sample 0
+        const int64_t first = d.src0 - (frame_length / 2 - kNfft / 2) + static_cast<int64_t>(f0) * kHop + 1;
+        __syncthreads();
+        {
+            const int i_lo = static_cast<int>(max(static_cast<int64_t>(0), min(static_cast<int64_t>(count), d.lo - first)));
+            const int i_hi = static_cast<int>(max(static_cast<int64_t>(0), min(static_cast<int64_t>(count), d.hi - first)));
+            const float* src = samples + first;
+            float* ev = reinterpret_cast<float*>(s_ev);
+            float* od = reinterpret_cast<float*>(s_od);
+            for (int m = threadIdx.x; m < count + 32; m += blockDim.x) {      // + 32: the B tiles read a little past `count`
+                const float v = (m >= i_lo && m < i_hi) ? __ldg(src + m) : 0.f;
+                if (m < zmax) s_z[m] = v;
+                if ((m >> 3) < nplane) ((m & 4) ? od : ev)[((m >> 3) << 2) | (m & 3)] = v;
+            }
+        }
+        __syncthreads();
+        // ---- segment partials: work item = (segment, lag octet), 8-lag x 16-sample register tile ----
+        for (int w = threadIdx.x; w < nseg * O; w += blockDim.x) {
+            const int sg = w / O, o = w - sg * O;
+            float c[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) c[r] = 0.f;
+            const int n_begin = sg * 16;                // float4-pair index of the segment's first sample
+#pragma unroll 1
+            for (int it = 0; it < 8; ++it) {
+                const int n = n_begin + 2 * it;
+                float A[16], B[24];
+                *reinterpret_cast<float4*>(A) = s_ev[n];       *reinterpret_cast<float4*>(A + 4) = s_od[n];
+                *reinterpret_cast<float4*>(A + 8) = s_ev[n + 1]; *reinterpret_cast<float4*>(A + 12) = s_od[n + 1];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    *reinterpret_cast<float4*>(B + 8 * k) = s_ev[n + o + k];
+                    *reinterpret_cast<float4*>(B + 8 * k + 4) = s_od[n + o + k];
+                }
+#pragma unroll
+                for (int m = 0; m < 16; ++m)
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) c[r] = fmaf(A[m], B[m + r], c[r]);
+            }
+            float* dst = s_part + sg * L8 + 8 * o;
+            *reinterpret_cast<float4*>(dst) = make_float4(c[0], c[1], c[2], c[3]);
+            *reinterpret_cast<float4*>(dst + 4) = make_float4(c[4], c[5], c[6], c[7]);
+        }
+        // ---- per-frame prefix sums of z^2 (numpy: cumsum in the input dtype), one warp per frame ----
+        if (warp < ng) {
+            const float* z = s_z + warp * kHop;
+            float* e = s_e + warp * (need + 1);
+            const int per = (need + 31) / 32;
+            const int b0 = min(need, lane * per), b1 = min(need, b0 + per);
+            float loc = 0.f;
+            for (int i = b0; i < b1; ++i) loc = fmaf(z[i], z[i], loc);
+            float run = loc;
+#pragma unroll
+            for (int o2 = 1; o2 < 32; o2 <<= 1) { const float t = __shfl_up_sync(0xffffffffu, run, o2); if (lane >= o2) run += t; }
+            run -= loc;                                  // exclusive
+            for (int i = b0; i < b1; ++i) { e[i] = run; run = fmaf(z[i], z[i], run); }
+            if (b1 == need && b0 < need) e[need] = run;
+        }
+        __syncthreads();
+        // ---- difference function, cumulative mean normalisation: one warp per frame, lags in chunks of 32 ----
+        if (warp < ng) {
+            const float* e = s_e + warp * (need + 1);
+            const float* part = s_part + (2 * warp) * L8;
+            float carry = 0.f;
+            float e_0 = e[win] - e[0];
+            if (fabsf(e_0) < 1e-6f) e_0 = 0.f;
+            float* out = yin + (d.row0 + f0 + warp) * n_lags;
+            for (int t0 = 0; t0 <= max_period; t0 += 32) {
+                const int tau = t0 + lane;
+                float dval = 0.f;
+                if (tau >= 1 && tau <= max_period) {
+                    float p[kCmndSeg];
+#pragma unroll
+                    for (int k = 0; k < kCmndSeg; ++k) p[k] = part[k * L8 + tau];
+                    float acf = ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
+                    float e_tau = e[tau + win] - e[tau];    // samples tau+1 .. tau+W of the frame
+                    if (fabsf(acf) < 1e-6f) acf = 0.f;      // the reference's clean-ups
+                    if (fabsf(e_tau) < 1e-6f) e_tau = 0.f;
+                    dval = e_0 + e_tau - 2.f * acf;
+                }
+                float cum = dval;
+#pragma unroll
+                for (int o2 = 1; o2 < 32; o2 <<= 1) { const float t = __shfl_up_sync(0xffffffffu, cum, o2); if (lane >= o2) cum += t; }
+                cum += carry;                               // sum of d(1..tau)
+                carry = __shfl_sync(0xffffffffu, cum, 31);
+                if (tau >= min_period && tau <= max_period) {
+                    const float cm = cum / static_cast<float>(tau);
+                    out[tau - min_period] = dval / (cm + 1.17549435e-38f);
+                }
+            }
         }
     }
 }
@@ -763,6 +894,20 @@ int spev_pyin_cmnd(spev_pyin* c, const spev_batch* b, const float* samples, floa
     const int grid = static_cast<int>(std::min<int64_t>(slots, 148 * 64));
     const int octets = ((c->max_period + 1 + 7) / 8 + 3) / 4 * 4;     // whole warps: 8 * octets threads
     const int threads = 8 * octets;
+    {   // shared-partials kernel (default): one CTA per run of 16 frames
+        const int L8 = 8 * octets, need = c->win_length + L8, zmax = (kCmndGroup - 1) * kHop + need, nplane = (zmax + 7) / 8 + 4;
+        const size_t smem = sizeof(float) * (((zmax + 3) & ~3) + 4 * (2 * nplane + 4) + (2 * kCmndGroup + 6) * L8 +
+                                             kCmndGroup * (need + 1) + 8);
+        static const bool use_shared = std::getenv("SPEV_PYIN_CMND_PER_FRAME") == nullptr;
+        if (use_shared && c->win_length == 1024 && c->frame_length == 2048 && smem <= 232448) {
+            const int64_t groups = static_cast<int64_t>(b->n_ftiles) * ((kTileFrames + kCmndGroup - 1) / kCmndGroup);
+            SPEV_CUDA(cudaFuncSetAttribute(k_yin_cmnd_shared, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+            k_yin_cmnd_shared<<<static_cast<int>(std::min<int64_t>(groups, 148 * 32)), kCmndThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+                view_of(b), samples, yin, c->frame_length, c->win_length, c->min_period, c->max_period, octets);
+            SPEV_CUDA(cudaGetLastError());
+            return SPEV_OK;
+        }
+    }
     k_yin_cmnd<<<grid, threads, sizeof(float) * (4096 + 16 + 2048 + 8 + kCmndSeg * threads + 32), static_cast<cudaStream_t>(stream)>>>(
         view_of(b), samples, yin, c->frame_length, c->win_length, c->min_period, c->max_period);
     SPEV_CUDA(cudaGetLastError());

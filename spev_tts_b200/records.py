@@ -81,10 +81,15 @@ def plan_records(n_samples: Sequence[int], phones: Sequence[Optional[Sequence[st
 def _upload(waves: Sequence[np.ndarray], device) -> Tuple[torch.Tensor, np.ndarray, np.ndarray]:
     lens = np.array([len(w) for w in waves], dtype=np.int64)
     starts = aligned_offsets(lens)                           # [U+1], last entry = buffer size
-    host = torch.zeros(int(starts[-1]) + 4, dtype=torch.float32, pin_memory=True)
+    # pinned staging from torch's caching host allocator (a repeat build of similar size pays no cudaHostAlloc); only
+    # the <= 3 alignment samples after each item and the 4-sample tail are zeroed, not the whole buffer
+    host = torch.empty(int(starts[-1]) + 4, dtype=torch.float32, pin_memory=True)
     hv = host.numpy()
-    for w, s in zip(waves, starts[:-1]):
-        hv[s: s + len(w)] = np.asarray(w, dtype=np.float32)
+    for w, s, e in zip(waves, starts[:-1], starts[1:]):
+        n = len(w)
+        hv[s: s + n] = w
+        hv[s + n: e] = 0.0
+    hv[starts[-1]:] = 0.0
     return host.to(device, non_blocking=True), lens, starts[:-1]
 
 
