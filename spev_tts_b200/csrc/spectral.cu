@@ -607,11 +607,9 @@ k_stft_phase_w(BatchView bv, const float* __restrict__ y, const float* __restric
 //     (lane <-> frame) -- the only cross-warp exchange;
 //   * all synchronisation is SPLIT-PHASE on four mbarriers (FULL: P written, EMPTY: P consumed, OUT: mel rows
 //     staged, COPIED: rows stored): a warp arrives as soon as its share is done and waits only where it needs the
-//     others'.  A warp transforms tile i completely, keeps its |X|^2 in registers, and only then runs the mel phase of
-//     tile i-1 -- so FULL has a whole transform of slack and warps drift apart by up to a tile; the one tight
-//     synchronisation per tile is EMPTY (everybody done with P of tile i-1) right before |X|^2 of tile i is written.
-//     (First version: mel phase between the two halves of the transform -- a third of a tile of slack; ncu showed ~50
-//     polls per FULL wait, 12 % of all executed instructions.)
+//     others', with the copy-out of the previous tile and the register-only first half of its next transform
+//     (frame loads, 32-point DFTs, twiddles) in between.  Warps drift apart by up to about a third of a tile, so
+//     the mel chains and exchanges of some overlap the FFT arithmetic of others.
 // Shared memory: twiddles 8 KB, window 4 KB, 16 regions x 8,480 B, P 66,048 B, staged rows 10,368 B, mel program.
 // ---------------------------------------------------------------------------------------
 constexpr int kPRow2 = 2 * kPSlot;               // words per frame PAIR in P: 1032 == 2 (mod 8) in 16-byte units
@@ -682,20 +680,24 @@ k_stft_mel_ws(BatchView bv, const float* __restrict__ samples, float* __restrict
     cp_async_commit();
 
     for (int i = 0; i < my_n; ++i) {
-        // ---- the whole transform of tile i; |X|^2 stays in registers (34 values) ----
-        float pa[16], pb[16], pa512 = 0.f, pb512 = 0.f;
-        PairInfo nxt{0, 0, 0};
+        // ---- front half of tile i's transform: registers only ----
+        float2 v[32];
         cp_async_wait_all();
         __syncwarp();
         if (cur.valid) {
-            float2 v[32];
             load_frame_pair(v, region, s_win, 0, cur.b_valid != 0, lane);
             dft32<-1>(v);
             static_for<1, 32>([&](auto k1c) {
                 constexpr int k1 = decltype(k1c)::value;
                 v[k1] = cmul(v[k1], s_tw[k1 * 32 + lane]);
             });
-            __syncwarp();                              // staged samples consumed: the region becomes the exchange tile
+        }
+        __syncwarp();                                  // staged samples consumed: the region may be overwritten
+        // ---- previous tile: mel phase (needs all warps' P; they had the whole front half above to get there) ----
+        if (i >= 1) mel_phase(i - 1);
+        // ---- back half: exchange, second DFT, Hermitian split, |X|^2 -> P ----
+        PairInfo nxt{0, 0, 0};
+        if (cur.valid) {
             static_for<0, 32>([&](auto k1c) {
                 constexpr int k1 = decltype(k1c)::value;
                 xb[k1 * kXPitch + lane] = v[k1];
@@ -706,47 +708,34 @@ k_stft_mel_ws(BatchView bv, const float* __restrict__ samples, float* __restrict
                 v[n2] = xb[lane * kXPitch + n2];
             });
             __syncwarp();                              // tile read back: free for the next pair's samples
-            if (i + 1 < my_n)
-                nxt = stage_pair(region, samples, bv.ftiles,
-                                 (static_cast<int64_t>(first) + static_cast<int64_t>(i + 1) * stride) * kWarps + warp, n_pairs, lane);
-            cp_async_commit();
+        }
+        if (i + 1 < my_n)
+            nxt = stage_pair(region, samples, bv.ftiles, (static_cast<int64_t>(first) + static_cast<int64_t>(i + 1) * stride) * kWarps + warp,
+                             n_pairs, lane);
+        cp_async_commit();
+        if (cur.valid) {
             dft32<-1>(v);
             float2 p[16];
             fetch_mirror(v, p, lane);
-            pa512 = 4.f * v[16].x * v[16].x; pb512 = 4.f * v[16].y * v[16].y;   // bin 512: X = 2 * Z' (window carries 1/2)
+            if (i >= 1) bar_wait(b_empty, (i - 1) & 1);   // everybody has finished reading P of tile i-1
+            const float pa512 = 4.f * v[16].x * v[16].x, pb512 = 4.f * v[16].y * v[16].y;
             static_for<0, 16>([&](auto kc) {
                 constexpr int k2 = decltype(kc)::value;
                 float2 xa, xb2;
                 split_pair_prescaled(v[k2], p[k2], xa, xb2);
-                pa[k2] = fmaf(xa.x, xa.x, xa.y * xa.y);
-                pb[k2] = fmaf(xb2.x, xb2.x, xb2.y * xb2.y);
-            });
-        } else {
-            __syncwarp();
-            if (i + 1 < my_n)
-                nxt = stage_pair(region, samples, bv.ftiles,
-                                 (static_cast<int64_t>(first) + static_cast<int64_t>(i + 1) * stride) * kWarps + warp, n_pairs, lane);
-            cp_async_commit();
-        }
-        // ---- previous tile: mel phase.  Its FULL barrier completed a whole transform ago for all but the slowest warp ----
-        if (i >= 1) {
-            mel_phase(i - 1);
-            bar_wait(b_empty, (i - 1) & 1);            // everybody has finished reading P of tile i-1 (the one tight sync)
-        }
-        if (cur.valid) {
-            static_for<0, 16>([&](auto kc) {
-                constexpr int k2 = decltype(kc)::value;
-                pw[lane + 32 * k2] = pa[k2];
-                pw[kPSlot + lane + 32 * k2] = pb[k2];
+                pw[lane + 32 * k2] = fmaf(xa.x, xa.x, xa.y * xa.y);
+                pw[kPSlot + lane + 32 * k2] = fmaf(xb2.x, xb2.x, xb2.y * xb2.y);
             });
             if (lane < 4) {   // bin 512 + three zero words so that padded float4 band reads stay clean
                 pw[512 + lane] = lane == 0 ? pa512 : 0.f;
                 pw[kPSlot + 512 + lane] = lane == 0 ? pb512 : 0.f;
             }
+        } else if (i >= 1) {
+            bar_wait(b_empty, (i - 1) & 1);            // keep the phase bookkeeping uniform
         }
         __syncwarp();
         if (lane == 0) bar_arrive(b_full);
-        // ---- the previous tile's staged rows (everybody's bands are in: we are past its EMPTY barrier) ----
+        // ---- the previous tile's staged rows (everybody's bands arrived before their own back half) ----
         if (i >= 1) copy_out(i - 1);
         cur = nxt;
     }
