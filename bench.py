@@ -41,9 +41,10 @@ sys.path.insert(0, ROOT)
 
 SR, HOP, N_MELS = 22050, 256, 80
 ALG_BYTES_PER_FRAME = 1344          # 256 new samples * 4 B read + 80 * 4 B written
-NCU_DRAM_BYTES_PER_FRAME = 1339.6   # dram__bytes_read+write of k_stft_mel<0> / frames, profiles/r01e_ncu_forward_kernels.txt
-NCU_TRAFFIC_SOURCE = "ncu --set full, profiles/r01e_ncu_forward_kernels.txt (1,339.6 B/frame measured)"
-NCU_ISSUE_NOTE = {"warp_instr_per_frame": 1090, "issue_active_pct": 65.0, "lsu_wavefront_pct": 61.3,
+NCU_DRAM_BYTES_PER_FRAME = 1320.2   # (dram__bytes_read + dram__bytes_write) of k_stft_mel<0,5> / frames, profiles/r02_ncu_k_stft_mel.txt
+NCU_TRAFFIC_SOURCE = ("ncu --set full, profiles/r02_ncu_k_stft_mel.txt: 736.7 MB read + 212.6 MB written for 719,053 frames "
+                      "= 1,320 B/frame (below the 1,344 algorithmic bytes: rows of neighbouring tiles share DRAM sectors)")
+NCU_ISSUE_NOTE = {"warp_instr_per_frame": 1042, "issue_active_pct": 65.2, "lsu_wavefront_pct": 61.4, "fma_pipe_pct": 40.8,
                   "note": "co-limited by issue slots and the shared-memory pipe, not HBM"}
 GL_BYTES_PER_FRAME_ITER = 20516
 N_UTTS = 13100
