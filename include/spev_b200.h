@@ -162,7 +162,9 @@ SPEV_API int spev_set_tensor_core(spev_ctx* ctx, int enable);
  *     f(x) = 0.5 / size * || A x - B ||^2,   grad = A^T (A x - B) / size,   size = L * n_mels * tb,
  * evaluated in float64 like librosa's (scipy hands its objective a float64 x); A = the ctx's mel basis, B = mel columns.
  *   x        : x_mode 0: device float64 [L, 513, tb] (librosa's own element order);
- *              x_mode 1: device float32 magnitude rows S [L*T, ld_x] as written by spev_mel_to_mag -> x = S^2 (the warm start)
+ *              x_mode 1: device float32 magnitude rows S [L*T, ld_x] as written by spev_mel_to_mag -> x = S^2 (the warm start);
+ *              x_mode 2: as 1, but the arithmetic in float32 -- a cheap screening pass; re-evaluate blocks whose pg_max lies
+ *                        within 10 % of pgtol with x_mode 1 before deciding
  *   mel      : device float32 [L*T, n_mels] frame-major mel power (or log-mel with is_log != 0)
  *   value_parts [L*tb] float64: per-column share of f (f = their sum, column order (l, t));
  *   grad     [L, 513, tb] float64 or NULL;   pg_max [L*tb]: per-column max |projected gradient| for the bound x >= 0

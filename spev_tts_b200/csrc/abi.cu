@@ -472,7 +472,7 @@ int spev_mel_to_mag(spev_ctx* c, const spev_batch* b, const float* mel, int layo
 int spev_nnls_objective(spev_ctx* c, const void* x, int x_mode, int64_t ld_x, const float* mel, int is_log, int L, int64_t T,
                         int64_t t0, int tb, double* value_parts, double* grad, double* pg_max, void* stream) {
     SPEV_ON_CTX_DEVICE(c);
-    SPEV_REQUIRE(x_mode == 0 || x_mode == 1, SPEV_E_INVALID, "spev_nnls_objective: x_mode must be 0 or 1");
+    SPEV_REQUIRE(x_mode >= 0 && x_mode <= 2, SPEV_E_INVALID, "spev_nnls_objective: x_mode must be 0, 1 or 2");
     return launch_nnls_objective(c, x, x_mode, ld_x, mel, is_log, L, T, t0, tb, value_parts, grad, pg_max,
                                  static_cast<cudaStream_t>(stream));
 }

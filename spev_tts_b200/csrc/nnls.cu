@@ -16,50 +16,53 @@ constexpr int kNnlsThreads = 256;
 
 // XMODE 0: x float64 in librosa's order [L, 513, tb];  1: x = S^2 from float32 magnitude rows S (row = l*T + t0 + t,
 // pitch ld_x) -- the warm start clip(pinv B, 0) as spev_mel_to_mag leaves it (its square root)
-template <int XMODE>
+// Real = double: librosa's precision (every call that feeds L-BFGS-B).  Real = float: the screening pass over all blocks
+// of a call -- it only has to decide "projected gradient above or below pgtol", and blocks it finds within 10 % of the
+// threshold are re-evaluated in double by the caller.
+template <int XMODE, class Real>
 __global__ void __launch_bounds__(kNnlsThreads)
 k_nnls_objective(const void* __restrict__ xv, int64_t ld_x, const float* __restrict__ mel /*[L*T, n_mels]*/, int is_log,
                  const float* __restrict__ basis /*[n_mels, 513]*/, int n_mels, int L, int64_t T, int64_t t0, int tb,
                  double inv_size, double* __restrict__ value_parts, double* __restrict__ grad /*[L,513,tb] or null*/,
                  double* __restrict__ pg_max) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* s_x = reinterpret_cast<double*>(smem_raw);       // [513]
-    double* s_r = s_x + kBins + 1;                            // [n_mels]
+    Real* s_x = reinterpret_cast<Real*>(smem_raw);           // [513]
+    Real* s_r = s_x + kBins + 1;                              // [n_mels]
     __shared__ double s_red[kNnlsThreads / 32];
     const int col = blockIdx.x;                               // (l, t)
     const int l = col / tb, t = col - l * tb;
     const int64_t row = static_cast<int64_t>(l) * T + t0 + t;
     for (int k = threadIdx.x; k < kBins; k += blockDim.x) {
-        if (XMODE == 0) s_x[k] = static_cast<const double*>(xv)[(static_cast<int64_t>(l) * kBins + k) * tb + t];
-        else { const double sv = static_cast<double>(static_cast<const float*>(xv)[row * ld_x + k]); s_x[k] = sv * sv; }
+        if (XMODE == 0) s_x[k] = static_cast<Real>(static_cast<const double*>(xv)[(static_cast<int64_t>(l) * kBins + k) * tb + t]);
+        else { const Real sv = static_cast<Real>(static_cast<const float*>(xv)[row * ld_x + k]); s_x[k] = sv * sv; }
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     for (int m = warp; m < n_mels; m += nw) {                 // r[m] = sum_k A[m,k] x[k] - B[m]
         const float* a = basis + static_cast<int64_t>(m) * kBins;
-        double acc = 0.0;
-        for (int k = lane; k < kBins; k += 32) acc = fma(static_cast<double>(__ldg(a + k)), s_x[k], acc);
+        Real acc = 0;
+        for (int k = lane; k < kBins; k += 32) acc = fma(static_cast<Real>(__ldg(a + k)), s_x[k], acc);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         if (lane == 0) {
             float b = mel[row * n_mels + m];
             if (is_log) b = expf(b);
-            s_r[m] = acc - static_cast<double>(b);
+            s_r[m] = acc - static_cast<Real>(b);
         }
     }
     __syncthreads();
     double pg = 0.0;
     for (int k = threadIdx.x; k < kBins; k += blockDim.x) {   // g[k] = inv_size * sum_m A[m,k] r[m]
-        double acc = 0.0;
-        for (int m = 0; m < n_mels; ++m) acc = fma(static_cast<double>(__ldg(basis + static_cast<int64_t>(m) * kBins + k)), s_r[m], acc);
-        const double g = acc * inv_size;
+        Real acc = 0;
+        for (int m = 0; m < n_mels; ++m) acc = fma(static_cast<Real>(__ldg(basis + static_cast<int64_t>(m) * kBins + k)), s_r[m], acc);
+        const double g = static_cast<double>(acc) * inv_size;
         if (grad) grad[(static_cast<int64_t>(l) * kBins + k) * tb + t] = g;
         // L-BFGS-B projgr with a lower bound only: g < 0 -> |g|, else min(x - 0, g)
-        const double p = g < 0.0 ? -g : fmin(s_x[k], g);
+        const double p = g < 0.0 ? -g : fmin(static_cast<double>(s_x[k]), g);
         pg = fmax(pg, p);
     }
     double v = 0.0;
-    for (int m = threadIdx.x; m < n_mels; m += blockDim.x) v += s_r[m] * s_r[m];
+    for (int m = threadIdx.x; m < n_mels; m += blockDim.x) v += static_cast<double>(s_r[m]) * static_cast<double>(s_r[m]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         pg = fmax(pg, __shfl_xor_sync(0xffffffffu, pg, o));
@@ -83,21 +86,25 @@ k_nnls_objective(const void* __restrict__ xv, int64_t ld_x, const float* __restr
     }
 }
 
-int launch_nnls_objective(spev_ctx* ctx, const void* x, int x_is_f32_rows, int64_t ld_x, const float* mel, int is_log, int L,
+int launch_nnls_objective(spev_ctx* ctx, const void* x, int x_mode, int64_t ld_x, const float* mel, int is_log, int L,
                           int64_t T, int64_t t0, int tb, double* value_parts, double* grad, double* pg_max, cudaStream_t st) {
     SPEV_REQUIRE(ctx && x && mel && value_parts && pg_max, SPEV_E_INVALID, "nnls_objective: null argument");
     SPEV_REQUIRE(L > 0 && tb > 0 && t0 >= 0 && t0 + tb <= T, SPEV_E_INVALID, "nnls_objective: bad block [%lld, %lld) of %lld",
                  static_cast<long long>(t0), static_cast<long long>(t0 + tb), static_cast<long long>(T));
+    const int x_is_f32_rows = x_mode != 0;            // 1: float64 arithmetic, 2: float32 screening pass
     SPEV_REQUIRE(!x_is_f32_rows || ld_x >= kBins, SPEV_E_INVALID, "nnls_objective: ld_x < 513");
     const double inv_size = 1.0 / (static_cast<double>(L) * ctx->n_mels * tb);      // 1 / B.size
     const size_t smem = sizeof(double) * (kBins + 1 + ctx->n_mels);
     const int grid = L * tb;
-    if (x_is_f32_rows)
-        k_nnls_objective<1><<<grid, kNnlsThreads, smem, st>>>(x, ld_x, mel, is_log, ctx->d_basis, ctx->n_mels, L, T, t0, tb, inv_size,
-                                                             value_parts, grad, pg_max);
+    if (x_mode == 2)
+        k_nnls_objective<1, float><<<grid, kNnlsThreads, smem, st>>>(x, ld_x, mel, is_log, ctx->d_basis, ctx->n_mels, L, T, t0, tb,
+                                                                    inv_size, value_parts, grad, pg_max);
+    else if (x_mode == 1)
+        k_nnls_objective<1, double><<<grid, kNnlsThreads, smem, st>>>(x, ld_x, mel, is_log, ctx->d_basis, ctx->n_mels, L, T, t0, tb,
+                                                                     inv_size, value_parts, grad, pg_max);
     else
-        k_nnls_objective<0><<<grid, kNnlsThreads, smem, st>>>(x, 0, mel, is_log, ctx->d_basis, ctx->n_mels, L, T, t0, tb, inv_size,
-                                                             value_parts, grad, pg_max);
+        k_nnls_objective<0, double><<<grid, kNnlsThreads, smem, st>>>(x, 0, mel, is_log, ctx->d_basis, ctx->n_mels, L, T, t0, tb,
+                                                                     inv_size, value_parts, grad, pg_max);
     SPEV_CUDA(cudaGetLastError());
     return SPEV_OK;
 }

@@ -214,19 +214,21 @@ def nnls_refine(S: torch.Tensor, mel_rows: torch.Tensor, ctx: Context, b: int, T
     lib, st = ctx.lib, stream_ptr(dev)
     pg = torch.empty(b * T, dtype=torch.float64, device=dev)          # per column, block after block
     val = torch.empty(b * T, dtype=torch.float64, device=dev)
-    off = 0
-    for t0, t1 in blocks:
-        _lib.check(lib.spev_nnls_objective(ctx.handle, S.data_ptr(), 1, S.shape[1], mel_rows.data_ptr(), 1 if is_log else 0,
-                                           b, T, t0, t1 - t0, val[off:].data_ptr(), None, pg[off:].data_ptr(), st),
-                   "spev_nnls_objective")
-        off += b * (t1 - t0)
-    pg_host = pg.cpu().numpy()                                         # the one synchronisation of the check
-    todo, off = [], 0
-    for t0, t1 in blocks:
-        n = b * (t1 - t0)
-        if pg_host[off: off + n].max(initial=0.0) > NNLS_PGTOL:
-            todo.append((t0, t1))
-        off += n
+    def screen(mode, which):
+        off_ = {blk: o for blk, o in zip(blocks, np.cumsum([0] + [b * (t1 - t0) for t0, t1 in blocks[:-1]]))}
+        for t0, t1 in which:
+            o = int(off_[(t0, t1)])
+            _lib.check(lib.spev_nnls_objective(ctx.handle, S.data_ptr(), mode, S.shape[1], mel_rows.data_ptr(), 1 if is_log else 0,
+                                               b, T, t0, t1 - t0, val[o:].data_ptr(), None, pg[o:].data_ptr(), st),
+                       "spev_nnls_objective")
+        host = pg.cpu().numpy()                                        # (one synchronisation per pass)
+        return {(t0, t1): float(host[int(off_[(t0, t1)]): int(off_[(t0, t1)]) + b * (t1 - t0)].max(initial=0.0)) for t0, t1 in which}
+    # float32 screening pass over every block; blocks within 10 % of the threshold are decided in float64
+    norm = screen(2, blocks)
+    near = [blk for blk, v in norm.items() if 0.9 * NNLS_PGTOL <= v <= 1.1 * NNLS_PGTOL]
+    if near:
+        norm.update(screen(1, near))
+    todo = [blk for blk in blocks if norm[blk] > NNLS_PGTOL]
     if not todo:
         return 0
     try:
