@@ -159,7 +159,8 @@ SPEV_API int spev_set_tensor_core(spev_ctx* ctx, int enable);
 
 /* Objective of librosa.util.nnls (the solver inside librosa.feature.inverse.mel_to_stft, spev_real_metrics.py:730) for
  * one block of tb columns starting at column t0 of L stacked items of T columns each:
- *     f(x) = 0.5 / size * || A x - B ||^2,   grad = A^T (A x - B) / size,   size = L * n_mels * tb,
+ *     f(x) = 0.5 / size * || A x - B ||^2,   grad = A^T (A x - B) / size,   size = L * n_mels * (size_cols ? size_cols : tb)
+ *     (size_cols lets one launch cover several of librosa's equal-sized blocks: tb = their total, size_cols = one block),
  * evaluated in float64 like librosa's (scipy hands its objective a float64 x); A = the ctx's mel basis, B = mel columns.
  *   x        : x_mode 0: device float64 [L, 513, tb] (librosa's own element order);
  *              x_mode 1: device float32 magnitude rows S [L*T, ld_x] as written by spev_mel_to_mag -> x = S^2 (the warm start);
@@ -170,7 +171,8 @@ SPEV_API int spev_set_tensor_core(spev_ctx* ctx, int enable);
  *   grad     [L, 513, tb] float64 or NULL;   pg_max [L*tb]: per-column max |projected gradient| for the bound x >= 0
  *              (L-BFGS-B's convergence measure: it returns the start point when max(pg_max) <= pgtol = 1e-5). */
 SPEV_API int spev_nnls_objective(spev_ctx* ctx, const void* x, int x_mode, int64_t ld_x, const float* mel, int is_log,
-                                 int L, int64_t T, int64_t t0, int tb, double* value_parts, double* grad, double* pg_max,
+                                 int L, int64_t T, int64_t t0, int tb, int size_cols, double* value_parts, double* grad,
+                                 double* pg_max,
                                  void* stream);
 
 /* ISTFT (irFFT-1024, Hann, gather overlap-add, window-sum-square normalisation).

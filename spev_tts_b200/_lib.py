@@ -68,7 +68,7 @@ _SIGS = {
                                   C.c_void_p, C.c_int64, C.c_void_p]),
     "spev_set_tensor_core": (C.c_int, [C.c_void_p, C.c_int]),
     "spev_nnls_objective": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_int64,
-                                      C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+                                      C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "spev_istft": (C.c_int, [C.c_void_p, C.POINTER(SpevBatch), C.c_void_p, C.c_int64, C.c_void_p,
                              C.c_void_p]),
     "spev_stft": (C.c_int, [C.c_void_p, C.POINTER(SpevBatch), C.c_void_p, C.c_void_p, C.c_int64,

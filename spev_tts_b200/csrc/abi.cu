@@ -36,7 +36,7 @@ int launch_stft_phase(spev_ctx*, const spev_batch*, const float*, const float*, 
                       unsigned* counter = nullptr, unsigned base = 0);
 int launch_istft(spev_ctx*, const spev_batch*, const void*, int64_t, float*, cudaStream_t, unsigned* counter = nullptr, unsigned base = 0);
 int fft_grid(const spev_ctx*, int64_t);
-int launch_nnls_objective(spev_ctx*, const void*, int, int64_t, const float*, int, int, int64_t, int64_t, int, double*, double*, double*, cudaStream_t);
+int launch_nnls_objective(spev_ctx*, const void*, int, int64_t, const float*, int, int, int64_t, int64_t, int, int, double*, double*, double*, cudaStream_t);
 int spectral_init(spev_ctx*);
 int launch_gl_init(spev_ctx*, const float*, int64_t, const float*, uint64_t, void*, int64_t, int64_t, cudaStream_t);
 int launch_mel_to_mag(spev_ctx*, const spev_batch*, const float*, int, int, float*, int64_t, cudaStream_t);
@@ -470,10 +470,10 @@ int spev_mel_to_mag(spev_ctx* c, const spev_batch* b, const float* mel, int layo
 }
 
 int spev_nnls_objective(spev_ctx* c, const void* x, int x_mode, int64_t ld_x, const float* mel, int is_log, int L, int64_t T,
-                        int64_t t0, int tb, double* value_parts, double* grad, double* pg_max, void* stream) {
+                        int64_t t0, int tb, int size_cols, double* value_parts, double* grad, double* pg_max, void* stream) {
     SPEV_ON_CTX_DEVICE(c);
     SPEV_REQUIRE(x_mode >= 0 && x_mode <= 2, SPEV_E_INVALID, "spev_nnls_objective: x_mode must be 0, 1 or 2");
-    return launch_nnls_objective(c, x, x_mode, ld_x, mel, is_log, L, T, t0, tb, value_parts, grad, pg_max,
+    return launch_nnls_objective(c, x, x_mode, ld_x, mel, is_log, L, T, t0, tb, size_cols, value_parts, grad, pg_max,
                                  static_cast<cudaStream_t>(stream));
 }
 

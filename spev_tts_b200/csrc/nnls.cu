@@ -87,13 +87,14 @@ k_nnls_objective(const void* __restrict__ xv, int64_t ld_x, const float* __restr
 }
 
 int launch_nnls_objective(spev_ctx* ctx, const void* x, int x_mode, int64_t ld_x, const float* mel, int is_log, int L,
-                          int64_t T, int64_t t0, int tb, double* value_parts, double* grad, double* pg_max, cudaStream_t st) {
+                          int64_t T, int64_t t0, int tb, int size_cols, double* value_parts, double* grad, double* pg_max, cudaStream_t st) {
     SPEV_REQUIRE(ctx && x && mel && value_parts && pg_max, SPEV_E_INVALID, "nnls_objective: null argument");
     SPEV_REQUIRE(L > 0 && tb > 0 && t0 >= 0 && t0 + tb <= T, SPEV_E_INVALID, "nnls_objective: bad block [%lld, %lld) of %lld",
                  static_cast<long long>(t0), static_cast<long long>(t0 + tb), static_cast<long long>(T));
     const int x_is_f32_rows = x_mode != 0;            // 1: float64 arithmetic, 2: float32 screening pass
     SPEV_REQUIRE(!x_is_f32_rows || ld_x >= kBins, SPEV_E_INVALID, "nnls_objective: ld_x < 513");
-    const double inv_size = 1.0 / (static_cast<double>(L) * ctx->n_mels * tb);      // 1 / B.size
+    SPEV_REQUIRE(size_cols >= 0, SPEV_E_INVALID, "nnls_objective: size_cols < 0");
+    const double inv_size = 1.0 / (static_cast<double>(L) * ctx->n_mels * (size_cols > 0 ? size_cols : tb));      // 1 / B.size
     const size_t smem = sizeof(double) * (kBins + 1 + ctx->n_mels);
     const int grid = L * tb;
     if (x_mode == 2)

@@ -214,20 +214,32 @@ def nnls_refine(S: torch.Tensor, mel_rows: torch.Tensor, ctx: Context, b: int, T
     lib, st = ctx.lib, stream_ptr(dev)
     pg = torch.empty(b * T, dtype=torch.float64, device=dev)          # per column, block after block
     val = torch.empty(b * T, dtype=torch.float64, device=dev)
-    def screen(mode, which):
-        off_ = {blk: o for blk, o in zip(blocks, np.cumsum([0] + [b * (t1 - t0) for t0, t1 in blocks[:-1]]))}
-        for t0, t1 in which:
-            o = int(off_[(t0, t1)])
+    # Screening: librosa's blocks are equal-sized except the last, so all full blocks go in ONE launch (columns
+    # [0, n_full * n_columns), objective scaled for one block) and the remainder in a second; pg comes back per column
+    # in (item, column-of-the-launch) order.
+    n_full = T // n_columns if T > n_columns else 0
+    launches = []                                   # (t0, tb, size_cols, offset into pg)
+    if n_full:
+        launches.append((0, n_full * n_columns, n_columns, 0))
+    if T - n_full * n_columns > 0:
+        launches.append((n_full * n_columns, T - n_full * n_columns, 0, b * n_full * n_columns))
+
+    def screen(mode):
+        for t0, tb, sc, o in launches:
             _lib.check(lib.spev_nnls_objective(ctx.handle, S.data_ptr(), mode, S.shape[1], mel_rows.data_ptr(), 1 if is_log else 0,
-                                               b, T, t0, t1 - t0, val[o:].data_ptr(), None, pg[o:].data_ptr(), st),
+                                               b, T, t0, tb, sc, val[o:].data_ptr(), None, pg[o:].data_ptr(), st),
                        "spev_nnls_objective")
-        host = pg.cpu().numpy()                                        # (one synchronisation per pass)
-        return {(t0, t1): float(host[int(off_[(t0, t1)]): int(off_[(t0, t1)]) + b * (t1 - t0)].max(initial=0.0)) for t0, t1 in which}
-    # float32 screening pass over every block; blocks within 10 % of the threshold are decided in float64
-    norm = screen(2, blocks)
-    near = [blk for blk, v in norm.items() if 0.9 * NNLS_PGTOL <= v <= 1.1 * NNLS_PGTOL]
-    if near:
-        norm.update(screen(1, near))
+        host = pg.cpu().numpy()                     # (one synchronisation per pass)
+        out = {}
+        for t0, tb, sc, o in launches:
+            cols = host[o: o + b * tb].reshape(b, tb)
+            for s0 in range(0, tb, sc or tb):
+                out[(t0 + s0, t0 + min(tb, s0 + (sc or tb)))] = float(cols[:, s0: s0 + (sc or tb)].max(initial=0.0))
+        return out
+    # float32 screening pass; if any block lies within 10 % of the threshold the pass is repeated in float64
+    norm = screen(2)
+    if any(0.9 * NNLS_PGTOL <= v <= 1.1 * NNLS_PGTOL for v in norm.values()):
+        norm = screen(1)
     todo = [blk for blk in blocks if norm[blk] > NNLS_PGTOL]
     if not todo:
         return 0
@@ -248,7 +260,7 @@ def nnls_refine(S: torch.Tensor, mel_rows: torch.Tensor, ctx: Context, b: int, T
         def fun(xflat):
             xd.copy_(torch.from_numpy(xflat).view_as(xd))
             _lib.check(lib.spev_nnls_objective(ctx.handle, xd.data_ptr(), 0, 0, mel_rows.data_ptr(), 1 if is_log else 0,
-                                               b, T, t0, tb, vd.data_ptr(), gd.data_ptr(), pd.data_ptr(), st),
+                                               b, T, t0, tb, 0, vd.data_ptr(), gd.data_ptr(), pd.data_ptr(), st),
                        "spev_nnls_objective")
             return float(vd.sum().item()), gd.cpu().numpy().reshape(-1)
         x, _, _ = fmin_l_bfgs_b(fun, x0.cpu().numpy().reshape(-1), bounds=[(0, None)] * x0.numel(), m=_lib.N_BINS)
