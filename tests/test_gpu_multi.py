@@ -64,6 +64,65 @@ def test_sharded_build_gather_assemble_equals_single_gpu():
     assert res == {0: True, 1: True}
 
 
+def _pipeline_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    import spev_tts_b200 as sp
+    from spev_tts_b200 import cache
+    lens = synth.utterance_lengths(seed=34, n_utts=300)
+    rng = np.random.default_rng(34)
+    ys = [(0.05 * rng.standard_normal(int(n))).astype(np.float32) for n in lens]     # same corpus on every rank
+    plan = cache.plan_shards(lens, world, n_chunks=3)
+    ok = True
+    ref = fo = None
+    if rank == 0:
+        ref, fb = sp.logmel_flat(torch.from_numpy(np.concatenate(ys)).to(dev), lens)   # one GPU, whole corpus
+        fo = fb.frame_off
+    for transport in ("nccl", "p2p"):
+        bld = cache.ShardedCacheBuilder(plan, rank, dev, dst=0, transport=transport, reserve_sms=16)
+        buf = np.zeros(int(bld.sample_off[-1]), np.float32)
+        for s0, u in zip(bld.sample_off[:-1], plan.shards[rank]):
+            buf[s0: s0 + lens[u]] = ys[u]
+        samples = torch.from_numpy(buf).to(dev)
+        out = bld.alloc_out()
+        for overlap in (False, True, True):                      # the last one back to back with the previous step
+            if rank == 0:
+                out.fill_(float("nan"))
+            bld.build(samples, out, gather=True, overlap=overlap)
+            torch.cuda.synchronize(dev)
+            dist.barrier()
+            if rank == 0:
+                gc = cache.GatheredCache(out, plan)
+                full, fo2 = gc.corpus_order()
+                ok = ok and bool(torch.equal(full, ref)) and np.array_equal(fo2, fo)
+                ok = ok and all(bool(torch.equal(gc.utterance(u), ref[fo[u]: fo[u + 1]])) for u in (0, 7, 150, 299))
+            dist.barrier()
+        del out, bld
+    q.put((rank, ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_sharded_builder_both_transports_equal_single_gpu():
+    """ShardedCacheBuilder.build (kernel per chunk + gather into rank 0), NCCL and p2p (symmetric-memory window, copy-engine
+    pushes), serial and overlapped: the root's gathered cache == the single-GPU cache of the whole corpus, bit for bit."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_pipeline_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert res == {0: True, 1: True}
+
+
 def _records_worker(rank, world, port, tmp, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
