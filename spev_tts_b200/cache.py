@@ -404,7 +404,10 @@ class ShardedCacheBuilder:
         if kernel is not None:
             self.ctx = None
             return
-        self.ctx = Context.get(self.device, sr=sr, n_mels=n_mels)
+        # a PRIVATE context: build() changes its SM limit while transfers are in flight, which must not leak into the
+        # shared per-device context other callers (threads) get from Context.get
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.ctx = Context(idx, sr, 1024, HOP, 1024, n_mels, 0.0, None)
         self.batch_all = make_batch(self.ctx, n_samples=self.lens, sample_off=self.sample_off)
         self.batch_chunk = [make_batch(self.ctx, n_samples=self.lens[a:b], sample_off=self.sample_off[a:b])
                             for a, b in plan.chunks[rank]]
@@ -442,8 +445,10 @@ class ShardedCacheBuilder:
             a, b = (0, len(self.lens)) if k is None else self.plan.chunks[self.rank][k]
             self._kernel_hook(samples, out_rows, a, b)
             return
-        spectral.logmel_flat(samples, None, sr=self.sr, n_mels=self.n_mels, out=out_rows,
-                             batch=self.batch_all if k is None else self.batch_chunk[k])
+        batch = self.batch_all if k is None else self.batch_chunk[k]
+        _lib.check(self.ctx.lib.spev_logmel(self.ctx.handle, batch.desc, samples.data_ptr(), out_rows.data_ptr(), 1,
+                                            spectral.REF_LOG_FLOOR, spectral.REF_LOG_LO, spectral.REF_LOG_HI,
+                                            torch.cuda.current_stream(self.device).cuda_stream), "spev_logmel")
 
     def _limit(self, on: bool) -> None:
         if self.ctx is None:
