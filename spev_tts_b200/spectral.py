@@ -196,6 +196,14 @@ MAX_MEM_BLOCK = 2 ** 18      # librosa.util.utils.MAX_MEM_BLOCK: nnls solves thi
 NNLS_PGTOL = 1e-5            # scipy.optimize.fmin_l_bfgs_b default pgtol
 
 
+def nnls_blocks(b: int, T: int, n_mels: int):
+    """librosa.util.nnls's column blocks for ``b`` stacked ``[n_mels, T]`` float32 items:
+    ``n_columns = max(1, MAX_MEM_BLOCK // (prod(B.shape[:-1]) * itemsize))``; one block if ``T <= n_columns``."""
+    n_columns = max(1, MAX_MEM_BLOCK // (b * n_mels * 4))
+    blocks = [(0, T)] if T <= n_columns else [(s0, min(T, s0 + n_columns)) for s0 in range(0, T, n_columns)]
+    return n_columns, blocks
+
+
 def nnls_refine(S: torch.Tensor, mel_rows: torch.Tensor, ctx: Context, b: int, T: int, *, is_log: bool) -> int:
     """The L-BFGS-B part of ``librosa.util.nnls`` (inside ``mel_to_stft``, ``spev_real_metrics.py:730``), in place on the
     warm start ``S = clip(pinv(A) M, 0) ** 0.5`` (``[b*T, 520]`` magnitude rows; ``mel_rows``: ``[b*T, n_mels]``).
@@ -208,8 +216,7 @@ def nnls_refine(S: torch.Tensor, mel_rows: torch.Tensor, ctx: Context, b: int, T
     to ``scipy.optimize.fmin_l_bfgs_b`` (the very routine librosa calls, same arguments), with objective and gradient
     evaluated on the GPU.  Returns the number of blocks that iterated."""
     n_mels = ctx.n_mels
-    n_columns = max(1, MAX_MEM_BLOCK // (b * n_mels * 4))
-    blocks = [(0, T)] if T <= n_columns else [(s0, min(T, s0 + n_columns)) for s0 in range(0, T, n_columns)]
+    n_columns, blocks = nnls_blocks(b, T, n_mels)
     dev = S.device
     lib, st = ctx.lib, stream_ptr(dev)
     pg = torch.empty(b * T, dtype=torch.float64, device=dev)          # per column, block after block

@@ -161,3 +161,15 @@ def test_logmel_chain_against_transformers_audio_utils(monkeypatch):
         assert np.abs(S - M).max() <= 1e-6 * np.abs(M).max()
         lm = np.clip(np.log(np.clip(S, 1e-5, None)), -10.0, 2.0).T
         assert np.abs(lm - lr.reference_logmel(y)).max() <= 5e-6
+
+
+def test_product_nnls_block_partition_matches_librosa_rule():
+    """The host-side block partition of the product's NNLS refinement == the rule of librosa.util.nnls as restated in the
+    oracle (MAX_MEM_BLOCK // (prod(lead) * n_mels * itemsize) columns per block; a single block if T fits)."""
+    from spev_tts_b200.spectral import nnls_blocks
+    for b, T in ((1, 1), (1, 10), (1, 819), (1, 820), (1, 1638), (1, 2000), (16, 800), (16, 51), (16, 52), (3, 700)):
+        n_columns = max(lr.MAX_MEM_BLOCK // (b * 80 * 4), 1)                  # oracle's nnls()
+        want = [(0, T)] if T <= n_columns else [(s, min(s + n_columns, T)) for s in range(0, T, n_columns)]
+        got_cols, got = nnls_blocks(b, T, 80)
+        assert got_cols == n_columns and got == want, (b, T)
+    assert nnls_blocks(1, 800, 80)[0] == 819 and nnls_blocks(16, 800, 80)[0] == 51   # SURVEY A.5
