@@ -148,3 +148,79 @@ def test_pyin_kernels_stay_in_bounds(cuda, lens):
     _lib.check(p.lib.spev_pitch_pool(p.handle, states.ptr(), fo.data_ptr(), durs.data_ptr(), po.data_ptr(), len(lens),
                                      5.2, 0.3, -2.5, 2.5, 1.5, pitch.ptr(), rough.ptr(), st))
     assert bool(torch.isfinite(pitch.check("pitch")).all()) and bool(torch.isfinite(rough.check("rough")).all())
+
+
+@pytest.mark.parametrize("B,T,H,n_feat", [(1, 1, 1, 0), (3, 7, 5, 2), (4, 33, 256, 5), (2, 50, 12, 5)])
+def test_backward_kernels_stay_in_bounds(cuda, B, T, H, n_feat):
+    """spev_lr_expand_backward / spev_variance_fuse_backward: every gradient buffer fully written, nothing around it."""
+    from spev_tts_b200 import _lib
+    from spev_tts_b200.length_regulator import plan
+    lib = _lib.load()
+    rng = np.random.default_rng(B * 100 + T)
+    dur = torch.from_numpy(rng.integers(0, 6, (B, T))).to(cuda)
+    p = plan(dur)
+    st = torch.cuda.current_stream(cuda).cuda_stream
+    go = torch.randn(B, p.max_len, H, device=cuda)
+    gx = Guarded(B * T * H, cuda)
+    gfo = torch.randn(max(n_feat, 1), B, p.max_len, device=cuda)
+    feats = torch.randn(max(n_feat, 1), B, T, device=cuda) * 2
+    gf = Guarded(max(n_feat, 1) * B * T, cuda)
+    lo = (C.c_float * 5)(-3, -3, 0, 0, -3); hi = (C.c_float * 5)(3, 3, 1, 2, 3)
+    _lib.check(lib.spev_lr_expand_backward(go.data_ptr(), 0, H, gfo.data_ptr() if n_feat else None, n_feat,
+                                           feats.data_ptr() if n_feat else None, C.cast(lo, C.c_void_p) if n_feat else None,
+                                           C.cast(hi, C.c_void_p) if n_feat else None, p.cumsum.data_ptr(), B, T, p.max_len,
+                                           gx.ptr(), gf.ptr() if n_feat else None, st))
+    assert bool(torch.isfinite(gx.check("grad_x")).all())
+    if n_feat:
+        assert bool(torch.isfinite(gf.check("grad_feats")[: n_feat * B * T]).all())
+    if n_feat:                                                   # fused variance adaptor backward
+        w = torch.randn(n_feat, H, 3, device=cuda)
+        gx2, gf2 = Guarded(B * T * H, cuda), Guarded(n_feat * B * T, cuda)
+        gw, gb = Guarded(n_feat * H * 3, cuda), Guarded(n_feat * H, cuda)
+        nws = lib.spev_variance_fuse_backward_workspace_bytes(n_feat, B, H, p.max_len)
+        ws = Guarded((nws + 3) // 4, cuda)
+        _lib.check(lib.spev_variance_fuse_backward(go.data_ptr(), feats.data_ptr(), n_feat, C.cast(lo, C.c_void_p),
+                                                   C.cast(hi, C.c_void_p), w.data_ptr(), p.cumsum.data_ptr(), B, T, H, p.max_len,
+                                                   gx2.ptr(), gf2.ptr(), gw.ptr(), gb.ptr(), ws.ptr(), nws, st))
+        ws.check("variance backward workspace")
+        for g, name in ((gx2, "grad_x"), (gf2, "grad_feats"), (gw, "grad_w"), (gb, "grad_b")):
+            assert bool(torch.isfinite(g.check(name)).all()), name
+        assert torch.equal(gx2.view, gx.view)                    # same segment sums as the plain expand backward
+
+
+def test_copy_segments_and_nnls_objective_stay_in_bounds(cuda):
+    import spev_tts_b200 as sp
+    from spev_tts_b200 import _lib, cache
+    rng = np.random.default_rng(3)
+    rows = rng.integers(0, 70, 23)                               # ragged runs of 7-float rows, some empty
+    src = torch.randn(int(rows.sum()), 7, device=cuda)
+    so = np.concatenate([[0], np.cumsum(rows)])[:-1]
+    perm = rng.permutation(len(rows))
+    do = np.zeros(len(rows), np.int64)
+    do[perm] = np.concatenate([[0], np.cumsum(rows[perm])])[:-1]
+    g = Guarded(src.numel(), cuda)
+    dst = g.view.view(-1, 7)
+    cache.copy_segments(src, dst, so, do, rows)
+    out = g.check("spev_copy_segments").view(-1, 7)
+    for i in range(len(rows)):
+        assert torch.equal(out[do[i]: do[i] + rows[i]], src[so[i]: so[i] + rows[i]])
+    # NNLS objective: per-column outputs and the gradient block
+    ctx = sp.Context.get(cuda, fmin=0.0, fmax=8000.0)
+    L, T, t0, tb = 3, 19, 4, 11
+    mel = torch.rand(L * T, 80, device=cuda)
+    x = torch.rand(L, 513, tb, device=cuda, dtype=torch.float64)
+    val, pgm = Guarded(L * tb, cuda, words_per_elem=2), Guarded(L * tb, cuda, words_per_elem=2)
+    grad = Guarded(L * 513 * tb, cuda, words_per_elem=2)
+    _lib.check(ctx.lib.spev_nnls_objective(ctx.handle, x.data_ptr(), 0, 0, mel.data_ptr(), 0, L, T, t0, tb, 0, val.ptr(), grad.ptr(),
+                                           pgm.ptr(), torch.cuda.current_stream(cuda).cuda_stream))
+    for gd, name in ((val, "value_parts"), (pgm, "pg_max"), (grad, "grad")):
+        v = gd.check(name).view(torch.float64)
+        assert bool(torch.isfinite(v).all()), name
+    # and the numbers: f = 0.5/size ||A x - B||^2, g = A^T (A x - B) / size, in float64
+    A = torch.from_numpy(ctx.mel_basis()).to(cuda).double()
+    Bm = mel.view(L, T, 80)[:, t0: t0 + tb].permute(0, 2, 1).double()          # [L, 80, tb]
+    r = torch.einsum("mf,lft->lmt", A, x) - Bm
+    size = L * 80 * tb
+    assert abs(float(val.view.view(torch.float64).sum()) - float(0.5 / size * (r ** 2).sum())) <= 1e-12
+    gref = torch.einsum("mf,lmt->lft", A, r) / size
+    assert float((grad.view.view(torch.float64).view(L, 513, tb) - gref).abs().max()) <= 1e-14
