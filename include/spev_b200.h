@@ -244,6 +244,14 @@ SPEV_API int spev_collate(const spev_pad_array* arrays_host, int n_arrays, const
                           const int64_t* phone_off, const int64_t* sel, int B, int64_t t_max, int64_t p_max,
                           void* stream);
 
+/* Batched 2-D transpose, dst[b][c][r] = src[b][r][c] (pitches and batch strides in ELEMENTS of elem_bytes = 4 or 8):
+ * the layout change between librosa's [..., bins, T] arrays (the shapes at spev_real_metrics.py:363 and :730-733) and
+ * the frame-major rows [F, pitch] the kernels work on, e.g. a [b, 80, T] mel -> rows [b*T, 80], or magnitude rows
+ * [b*T, 520] -> [b, 513, T] (rows = T, cols = 513, src_pitch = 520). */
+SPEV_API int spev_transpose_batched(const void* src, void* dst, int elem_bytes, int64_t batches, int rows, int cols,
+                                    int64_t src_pitch, int64_t src_batch, int64_t dst_pitch, int64_t dst_batch,
+                                    void* stream);
+
 /* Segmented device copy: dst[dst_off[i] .. +nbytes[i]) = src[src_off[i] .. +nbytes[i]) for n_segments runs of bytes
  * (all tables on the device; piece_off[i] = first 16 KB piece of segment i, piece_off is the exclusive prefix sum of
  * ceil(nbytes[i] / spev_copy_segments_piece_bytes()), n_pieces its total).  Used to put gathered cache shards

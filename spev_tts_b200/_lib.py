@@ -87,6 +87,8 @@ _SIGS = {
                                         C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
     "spev_collate": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64,
                                C.c_void_p]),
+    "spev_transpose_batched": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int64, C.c_int64,
+                                         C.c_int64, C.c_int64, C.c_void_p]),
     "spev_copy_segments_piece_bytes": (C.c_int, []),
     "spev_copy_segments": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                      C.c_int64, C.c_void_p]),

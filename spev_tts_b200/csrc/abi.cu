@@ -51,6 +51,7 @@ int launch_variance_fuse_backward(const float*, const float*, int, const float*,
 int launch_variance_fuse(const float*, const float*, int, const float*, const float*, const float*, const float*, const int32_t*, int, int, int, float*, float*, int64_t, cudaStream_t);
 int launch_pcm16_to_f32(const int16_t*, int64_t, float*, cudaStream_t);
 int launch_collate(const spev_pad_array*, int, const int64_t*, const int64_t*, const int64_t*, int, int64_t, int64_t, cudaStream_t);
+int launch_transpose(const void*, void*, int, int64_t, int, int, int64_t, int64_t, int64_t, int64_t, cudaStream_t);
 int launch_copy_segments(const void*, void*, const int64_t*, const int64_t*, const int64_t*, const int64_t*, int, int64_t, cudaStream_t);
 int launch_bucketize_embed(const float*, int64_t, const float*, int, int, const float*, int, int64_t*, float*, int, cudaStream_t);
 int launch_frame_features(spev_ctx*, const spev_batch*, const float*, float*, float*, cudaStream_t);
@@ -554,6 +555,12 @@ int spev_segment_pool_log(const float* curve, float log_eps, const int64_t* fram
 int spev_collate(const spev_pad_array* arrays, int n_arrays, const int64_t* frame_off, const int64_t* phone_off,
                  const int64_t* sel, int B, int64_t t_max, int64_t p_max, void* stream) {
     return launch_collate(arrays, n_arrays, frame_off, phone_off, sel, B, t_max, p_max, static_cast<cudaStream_t>(stream));
+}
+
+int spev_transpose_batched(const void* src, void* dst, int elem_bytes, int64_t batches, int rows, int cols, int64_t src_pitch,
+                           int64_t src_batch, int64_t dst_pitch, int64_t dst_batch, void* stream) {
+    return launch_transpose(src, dst, elem_bytes, batches, rows, cols, src_pitch, src_batch, dst_pitch, dst_batch,
+                            static_cast<cudaStream_t>(stream));
 }
 
 int spev_copy_segments_piece_bytes(void) { return 256 * 16 * 4; }

@@ -121,4 +121,50 @@ int launch_copy_segments(const void* src, void* dst, const int64_t* src_off, con
     return SPEV_OK;
 }
 
+// ---- batched 2-D transpose: dst[b][c][r] = src[b][r][c] -------------------------------------------------------------
+// librosa lays spectra and mels out as [..., bins, T]; the kernels here work on frame-major rows [F, pitch].  This is
+// the layout change between the two (32 x 32 tiles through padded shared memory, coalesced on both sides), for 4-byte
+// (float) and 8-byte (complex64) elements, with independent row pitches and batch strides on either side so that the
+// 520-column padded spectra are read / written in place.
+template <class T>
+__global__ void __launch_bounds__(256)
+k_transpose(const T* __restrict__ src, T* __restrict__ dst, int rows, int cols, int64_t src_pitch, int64_t src_batch,
+            int64_t dst_pitch, int64_t dst_batch) {
+    __shared__ T tile[32][33];
+    const int64_t b = blockIdx.z;
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;        // 32 x 8
+    const T* s = src + b * src_batch;
+    T* d = dst + b * dst_batch;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+        const int r = r0 + ty + j, c = c0 + tx;
+        if (r < rows && c < cols) tile[ty + j][tx] = s[static_cast<int64_t>(r) * src_pitch + c];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+        const int c = c0 + ty + j, r = r0 + tx;
+        if (r < rows && c < cols) d[static_cast<int64_t>(c) * dst_pitch + r] = tile[tx][ty + j];
+    }
+}
+
+int launch_transpose(const void* src, void* dst, int elem_bytes, int64_t batches, int rows, int cols, int64_t src_pitch,
+                     int64_t src_batch, int64_t dst_pitch, int64_t dst_batch, cudaStream_t st) {
+    SPEV_REQUIRE(batches >= 0 && rows >= 0 && cols >= 0, SPEV_E_INVALID, "transpose: negative shape");
+    if (batches == 0 || rows == 0 || cols == 0) return SPEV_OK;
+    SPEV_REQUIRE(src && dst && src_pitch >= cols && dst_pitch >= rows, SPEV_E_INVALID, "transpose: null buffer or pitch < extent");
+    SPEV_REQUIRE(elem_bytes == 4 || elem_bytes == 8, SPEV_E_UNSUPPORTED, "transpose: 4- or 8-byte elements only");
+    SPEV_REQUIRE(batches <= 65535, SPEV_E_UNSUPPORTED, "transpose: more than 65535 batches");
+    dim3 grid(static_cast<unsigned>((cols + 31) / 32), static_cast<unsigned>((rows + 31) / 32), static_cast<unsigned>(batches));
+    if (elem_bytes == 4)
+        k_transpose<float><<<grid, 256, 0, st>>>(static_cast<const float*>(src), static_cast<float*>(dst), rows, cols, src_pitch,
+                                                src_batch, dst_pitch, dst_batch);
+    else
+        k_transpose<float2><<<grid, 256, 0, st>>>(static_cast<const float2*>(src), static_cast<float2*>(dst), rows, cols, src_pitch,
+                                                 src_batch, dst_pitch, dst_batch);
+    SPEV_CUDA(cudaGetLastError());
+    return SPEV_OK;
+}
+
 }  // namespace spev

@@ -44,6 +44,30 @@ def _ret(t: torch.Tensor, was_numpy: bool):
     return t.cpu().numpy() if was_numpy else t
 
 
+def items_to_rows(t: torch.Tensor, pitch: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """librosa layout ``[b, R, T]`` -> frame-major rows ``[b*T, pitch]`` (first ``R`` columns; ``pitch`` defaults to ``R``)
+    in one launch of ``spev_transpose_batched`` (float32 or complex64).  Pad columns are left as they are."""
+    b, R, T = t.shape
+    pitch = R if pitch is None else pitch
+    t = t.contiguous()
+    if out is None:
+        out = torch.empty((b * T, pitch), dtype=t.dtype, device=t.device)
+    with torch.cuda.device(t.device):
+        _lib.check(_lib.load().spev_transpose_batched(t.data_ptr(), out.data_ptr(), t.element_size(), b, R, T, T, R * T,
+                                                      pitch, T * pitch, stream_ptr(t.device)), "spev_transpose_batched")
+    return out
+
+
+def rows_to_items(rows: torch.Tensor, b: int, T: int, R: int) -> torch.Tensor:
+    """frame-major rows ``[b*T, pitch]`` -> librosa layout ``[b, R, T]`` (the first ``R`` columns of every row)."""
+    pitch = rows.shape[1]
+    out = torch.empty((b, R, T), dtype=rows.dtype, device=rows.device)
+    with torch.cuda.device(rows.device):
+        _lib.check(_lib.load().spev_transpose_batched(rows.data_ptr(), out.data_ptr(), rows.element_size(), b, T, R, pitch,
+                                                      T * pitch, T, R * T, stream_ptr(rows.device)), "spev_transpose_batched")
+    return out
+
+
 def _check_fixed(n_fft, hop_length, win_length, window, center, pad_mode, power=2.0):
     if hop_length is None:
         hop_length = (win_length or n_fft) // 4
@@ -89,7 +113,7 @@ def melspectrogram(*, y: ArrayLike, sr=22050, n_fft=2048, hop_length=512, win_le
     b = int(np.prod(lead)) if lead else 1
     mel, fb = logmel_flat(t.reshape(-1), [n] * b, sr=sr, n_mels=n_mels, fmin=fmin, fmax=fmax, log=False)
     T = 1 + n // HOP
-    mel = mel.view(*lead, T, n_mels).transpose(-1, -2)
+    mel = rows_to_items(mel, b, T, n_mels).view(*lead, n_mels, T)
     return _ret(mel, was_numpy)
 
 
@@ -131,8 +155,7 @@ def _spec_to_internal(X: torch.Tensor) -> torch.Tensor:
     """[B, 513, T] complex64 -> [B*T, 520] complex64 (frame-major rows, pitch 520)."""
     B, nb, T = X.shape
     buf = torch.zeros((B * T, _lib.SPEC_LD), dtype=torch.complex64, device=X.device)
-    buf[:, :nb] = X.permute(0, 2, 1).reshape(B * T, nb)
-    return buf
+    return items_to_rows(X, _lib.SPEC_LD, out=buf)
 
 
 def stft(y: ArrayLike, *, n_fft=2048, hop_length=None, win_length=None, window="hann", center=True,
@@ -155,7 +178,9 @@ def stft(y: ArrayLike, *, n_fft=2048, hop_length=None, win_length=None, window="
     spec = torch.empty((b * Tc, _lib.SPEC_LD), dtype=torch.complex64, device=t.device)
     _lib.check(ctx.lib.spev_stft(ctx.handle, batch.desc, t.data_ptr(), spec.data_ptr(), _lib.SPEC_LD,
                                  stream_ptr(t.device)), "spev_stft")
-    out = spec.view(b, Tc, _lib.SPEC_LD)[:, :T, : _lib.N_BINS].permute(0, 2, 1)
+    out = rows_to_items(spec, b, Tc, _lib.N_BINS)
+    if Tc != T:
+        out = out[:, :, :T].contiguous()
     out = out.reshape(*lead, _lib.N_BINS, T)
     return _ret(out, was_numpy)
 
@@ -290,11 +315,11 @@ def mel_to_stft(M: ArrayLike, *, sr=22050, n_fft=2048, power=2.0, fmin=0.0, fmax
     ctx = Context.get(t.device, sr=sr, n_mels=n_mels, fmin=fmin, fmax=fmax)
     batch = make_batch(ctx, n_frames=[T] * b)
     # [b, n_mels, T] -> frame-major [b*T, n_mels]: the layout the tcgen05 GEMM path takes
-    tm = t.reshape(b, n_mels, T).transpose(1, 2).contiguous().view(-1)
+    tm = items_to_rows(t.reshape(b, n_mels, T)).view(-1)
     S = mel_to_mag_flat(tm, batch, ctx, layout=0, is_log=False)
     if nnls == "librosa" and b * T > 0:
         nnls_refine(S, tm.view(b * T, n_mels), ctx, b, T, is_log=False)
-    out = S.view(b, T, _lib.SPEC_LD)[:, :, : _lib.N_BINS].permute(0, 2, 1).reshape(*lead, _lib.N_BINS, T)
+    out = rows_to_items(S, b, T, _lib.N_BINS).reshape(*lead, _lib.N_BINS, T)
     return _ret(out, was_numpy)
 
 
@@ -319,7 +344,7 @@ def griffinlim_flat(S: torch.Tensor, batch: FlatBatch, ctx: Context, *, n_iter=3
 
 def _phase_to_internal(init_phase: ArrayLike, b: int, T: int, device) -> torch.Tensor:
     p, _ = _to_device(init_phase, device)
-    return p.reshape(b, _lib.N_BINS, T).permute(0, 2, 1).contiguous().view(b * T, _lib.N_BINS)
+    return items_to_rows(p.reshape(b, _lib.N_BINS, T))
 
 
 def griffinlim(S: ArrayLike, *, n_iter=32, hop_length=None, win_length=None, n_fft=None, window="hann",
@@ -338,8 +363,7 @@ def griffinlim(S: ArrayLike, *, n_iter=32, hop_length=None, win_length=None, n_f
     b = int(np.prod(lead)) if lead else 1
     ctx = Context.get(t.device)
     batch = make_batch(ctx, n_frames=[T] * b, with_chunks=True)
-    Sf = torch.zeros((b * T, _lib.SPEC_LD), dtype=torch.float32, device=t.device)
-    Sf[:, :nb] = t.reshape(b, nb, T).permute(0, 2, 1).reshape(b * T, nb)
+    Sf = items_to_rows(t.reshape(b, nb, T), _lib.SPEC_LD, out=torch.zeros((b * T, _lib.SPEC_LD), dtype=torch.float32, device=t.device))
     ph = _phase_to_internal(init_phase, b, T, t.device) if init_phase is not None else None
     seed = int(np.random.SeedSequence(random_state).generate_state(2, dtype=np.uint32).view(np.uint64)[0])
     y = griffinlim_flat(Sf, batch, ctx, n_iter=n_iter, momentum=momentum, init_phase=ph, seed=seed)
@@ -364,7 +388,7 @@ def mel_to_audio(M: ArrayLike, *, sr=22050, n_fft=2048, hop_length=None, win_len
     b = int(np.prod(lead)) if lead else 1
     ctx = Context.get(t.device, sr=sr, n_mels=n_mels, fmin=fmin, fmax=fmax)
     batch = ctx.uniform_batch(b, T, with_chunks=True)
-    tm = t.reshape(b, n_mels, T).transpose(1, 2).contiguous().view(-1)   # frame-major -> tensor-core GEMM
+    tm = items_to_rows(t.reshape(b, n_mels, T)).view(-1)                  # frame-major -> tensor-core GEMM
     S = mel_to_mag_flat(tm, batch, ctx, layout=0, is_log=is_log)
     if nnls == "librosa" and b * T > 0:
         nnls_refine(S, tm.view(b * T, n_mels), ctx, b, T, is_log=is_log)
