@@ -750,12 +750,7 @@ k_stft_mel_ws(BatchView bv, const float* __restrict__ samples, float* __restrict
 // ring): cfg3's 448 chunk tiles are 3.03 rounds of work on 148 SMs, which the static round-robin pays as 4.
 // BULK: a warp's two spectrum rows (8,272 B) arrive in its region by ONE bulk asynchronous copy instead of 34 scattered
 // 8-byte loads per lane (ncu r01: lg_throttle 1.2 + long_scoreboard 1.7 warps per issue cycle on those loads): no LSU
-// queue pressure, and all 16 warps' rows are in flight at once.  The wait for them would be exposed at the start of
-// every tile (the region only frees up when the previous gather ends: 16 % of the stall samples), so the shared memory
-// the kernel has left holds kIstftPf extra row slots: warps 0 .. kIstftPf-1 fetch their NEXT tile's rows into their
-// slot as soon as the current rows are in registers -- a whole tile ahead -- and start each tile without waiting;
-// the other warps' wait is covered by their work.
-constexpr int kIstftPf = 9;
+// queue pressure, and all 16 warps' rows are in flight at once.
 template <bool BULK>
 __global__ void __launch_bounds__(kThreads, 1)
 k_istft(BatchView bv, const float2* __restrict__ spec, int64_t ld, float* __restrict__ y,
@@ -782,26 +777,7 @@ k_istft(BatchView bv, const float2* __restrict__ spec, int64_t ld, float* __rest
         s_iw[s] = 1.0f / wss;
     }
     float* xw = s_x + warp * kWarpRegionWords;
-    float* s_pf = s_x + kWarps * kWarpRegionWords;            // [kIstftPf] prefetch slots, one region's size each
-    float2* rows_in = BULK && warp < kIstftPf ? reinterpret_cast<float2*>(s_pf + warp * kWarpRegionWords)
-                                              : reinterpret_cast<float2*>(xw);
-    bool pf_pending = false;                                  // this warp's rows for the upcoming tile are already in flight
     const int pl = (32 - lane) & 31;
-    // rows of this warp in tile t: start the bulk copy into rows_in (row a at [0], row b at [ld]); false if it has none
-    auto issue_rows = [&](const spev_tile& t) -> bool {
-        const int lf = 2 * warp, fa_t = t.t0 - 1 + lf;
-        const bool av = lf < t.n + 3 && fa_t >= 0 && fa_t < t.T;
-        const bool bvv = lf + 1 < t.n + 3 && fa_t + 1 >= 0 && fa_t + 1 < t.T;
-        if (!(av || bvv)) return false;
-        if (lane == 0) {
-            const uint32_t bytes = (av && bvv) ? static_cast<uint32_t>(ld * 8 + (kBins + 1) * 8) : static_cast<uint32_t>((kBins + 1) * 8);
-            const int64_t first_row = av ? 0 : 1;
-            fence_proxy_async();                              // the buffer was last read through the generic proxy
-            bar_expect_tx(tbar, bytes);
-            bulk_g2s(rows_in + first_row * ld, spec + (t.row0 + lf + first_row) * ld, bytes, tbar);
-        }
-        return true;
-    };
 
     const int stride = gridDim.x;
     pdl_launch_dependents();
@@ -841,7 +817,14 @@ k_istft(BatchView bv, const float2* __restrict__ spec, int64_t ld, float* __rest
         const int ta = c0 - 1 + lfa, tb = ta + 1;
         const bool a_valid = lfa < nchunks + 3 && ta >= 0 && ta < T;
         const bool b_valid = lfa + 1 < nchunks + 3 && tb >= 0 && tb < T;
-        if (BULK && !pf_pending) issue_rows(d);               // (a slot warp's rows were started one tile ago)
+        if (BULK && (a_valid || b_valid) && lane == 0) {      // rows a, b -> region[0 ..], region[ld ..] (float2 units)
+            const uint32_t bytes = (a_valid && b_valid) ? static_cast<uint32_t>(ld * 8 + (kBins + 1) * 8)
+                                                        : static_cast<uint32_t>((kBins + 1) * 8);
+            const int64_t first_row = a_valid ? 0 : 1;
+            fence_proxy_async();                              // the region was last read by the gather (generic proxy)
+            bar_expect_tx(tbar, bytes);
+            bulk_g2s(reinterpret_cast<float2*>(xw) + first_row * ld, spec + (d.row0 + lfa + first_row) * ld, bytes, tbar);
+        }
         if (s_tick[(i + 1) & 3] >= 0) {   // pull the next tile's spectra of this warp into L2 during this tile's FFT
             const spev_tile& nx = s_ring[(i + 1) & 3];
             const int nta = nx.t0 - 1 + lfa;
@@ -854,7 +837,7 @@ k_istft(BatchView bv, const float2* __restrict__ spec, int64_t ld, float* __rest
         }
 
         if (a_valid || b_valid) {
-            const float2* A = BULK ? rows_in : spec + (d.row0 + lfa) * ld;
+            const float2* A = BULK ? reinterpret_cast<const float2*>(xw) : spec + (d.row0 + lfa) * ld;
             const float2* B = A + ld;
             if (BULK) { bar_wait(tbar, tphase); tphase ^= 1; }
             float2 v[32];
@@ -882,11 +865,6 @@ k_istft(BatchView bv, const float2* __restrict__ spec, int64_t ld, float* __rest
                 }
                 v[16 + ii] = r;
             });
-            pf_pending = false;
-            if (BULK && warp < kIstftPf) {                    // rows are in registers: fetch the next tile's into the slot
-                __syncwarp();
-                if (s_tick[(i + 1) & 3] >= 0) pf_pending = issue_rows(s_ring[(i + 1) & 3]);
-            }
             warp_fft1024<1>(v, reinterpret_cast<float2*>(xw), s_tw, lane);
             __syncwarp();   // transpose tile dead -> reuse for the two windowed real frames
             static_for<0, 32>([&](auto kc) {
@@ -1025,7 +1003,7 @@ static size_t smem_prog(const spev_ctx* c) { return sizeof(float4) * c->prog_gro
 static size_t smem_stft(size_t prog_bytes) {
     return smem_common() + sizeof(float) * 2 * kStageSamples + sizeof(float) * kWarps * kWarpRegionWords + prog_bytes;
 }
-static size_t smem_istft() { return smem_common() + sizeof(uint64_t) * kWarps + sizeof(int) * kRing + sizeof(float) * kHop + sizeof(float) * (kWarps + kIstftPf) * kWarpRegionWords; }
+static size_t smem_istft() { return smem_common() + sizeof(uint64_t) * kWarps + sizeof(int) * kRing + sizeof(float) * kHop + sizeof(float) * kWarps * kWarpRegionWords; }
 
 // Launch with the programmatic-stream-serialization attribute (PDL).
 template <class... KArgs, class... Args>
