@@ -134,8 +134,6 @@ class _ExpandFn(torch.autograd.Function):
         ctx.save_for_backward(feats if (feats is not None and clamps is not None) else None)
         ctx.n_feat = 0 if feats is None else feats.shape[0]
         out, fo = _expand_raw(x, p, feats, clamps)
-        if out is None:
-            ctx.mark_non_differentiable()
         return out, fo
 
     @staticmethod
