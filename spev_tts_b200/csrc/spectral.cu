@@ -433,7 +433,7 @@ __device__ __forceinline__ PairInfo stage_pair(float* region, const float* __res
 // (ncu before: long_scoreboard 2.5 warps per issue cycle on exactly those loads).
 constexpr int kWsRegionWords = kXWords + kNfft + kHop;   // transpose tile + 1280 staged samples of the NEXT pair
 
-template <int MODE, bool STAGE_T>   // MODE 0: plain STFT into `ang`; 1: Griffin-Lim phase update
+template <int MODE, bool STAGE_T, bool FUSE = false>   // MODE 0: plain STFT into `ang`; 1: Griffin-Lim phase update
 __global__ void __launch_bounds__(kThreads, 1)
 k_stft_phase_w(BatchView bv, const float* __restrict__ y, const float* __restrict__ S, int64_t ld_s,
                float2* __restrict__ ang, float2* tprev, int64_t ld, float alpha, int has_prev,
@@ -454,6 +454,7 @@ k_stft_phase_w(BatchView bv, const float* __restrict__ y, const float* __restric
     float2* xb = reinterpret_cast<float2*>(tile);
     uint64_t* tbar = s_bar + warp;
     unsigned tphase = 0;
+    const int pl = (32 - lane) & 31;
 
     const int64_t n_pairs = static_cast<int64_t>(bv.n_ftiles) * kWarps;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * kWarps;
@@ -533,6 +534,7 @@ k_stft_phase_w(BatchView bv, const float* __restrict__ y, const float* __restric
         fetch_mirror(v, pm, lane);
         const float2* tsm = reinterpret_cast<const float2*>(tile);   // staged rows: a at [0, 514), b at [ld, ld + 514)
         if (staged) { bar_wait(tbar, tphase); tphase ^= 1; }
+        float nyq_a = 0.f, nyq_b = 0.f;                  // FUSE: Re(ang[512]) of the two frames (lane 0)
         static_for<0, 4>([&](auto gc) {
             constexpr int g = decltype(gc)::value;
             float2 tpa[4], tpb[4];
@@ -561,13 +563,26 @@ k_stft_phase_w(BatchView bv, const float* __restrict__ y, const float* __restric
                 if (MODE == 0) {
                     ang[ra + k] = xa;
                     if (b_valid) ang[rb + k] = xbv;
-                } else {
+                } else if (!FUSE) {
                     ang[ra + k] = phase_of(xa, s_a[q], tpa[q], alpha, has_prev);
                     tprev[ra + k] = xa;
                     if (b_valid) {
                         ang[rb + k] = phase_of(xbv, s_b[q], tpb[q], alpha, has_prev);
                         tprev[rb + k] = xbv;
                     }
+                } else {
+                    // the new spectra never leave the registers: pack them (A + iB, and conj(A) + i conj(B) for the
+                    // mirror half) exactly as k_istft packs the rows it loads
+                    float2 a = phase_of(xa, s_a[q], tpa[q], alpha, has_prev);
+                    float2 b = make_float2(0.f, 0.f);
+                    tprev[ra + k] = xa;
+                    if (b_valid) {
+                        b = phase_of(xbv, s_b[q], tpb[q], alpha, has_prev);
+                        tprev[rb + k] = xbv;
+                    }
+                    if (k2 == 0 && lane == 0) { a.y = 0.f; b.y = 0.f; }   // irfft ignores Im(DC)
+                    v[k2] = make_float2(a.x - b.y, a.y + b.x);
+                    pm[k2] = make_float2(a.x + b.y, b.x - a.y);
                 }
             });
         });
@@ -580,14 +595,47 @@ k_stft_phase_w(BatchView bv, const float* __restrict__ y, const float* __restric
             } else {
                 const float2 z = make_float2(0.f, 0.f);
                 const float2 ta = !has_prev ? z : (staged ? tsm[512] : tprev[ra + 512]);
-                ang[ra + 512] = phase_of(xa, sa[512], ta, alpha, has_prev);
+                const float2 na = phase_of(xa, sa[512], ta, alpha, has_prev);
+                if (FUSE) nyq_a = na.x; else ang[ra + 512] = na;
                 tprev[ra + 512] = xa;
                 if (b_valid) {
                     const float2 tb = !has_prev ? z : (staged ? tsm[ld + 512] : tprev[rb + 512]);
-                    ang[rb + 512] = phase_of(xbv, sb[512], tb, alpha, has_prev);
+                    const float2 nb = phase_of(xbv, sb[512], tb, alpha, has_prev);
+                    if (FUSE) nyq_b = nb.x; else ang[rb + 512] = nb;
                     tprev[rb + 512] = xbv;
                 }
             }
+        }
+        if (FUSE) {
+            // ---- inverse transform of the pair straight from the registers, Hann, and the overlap-add of the
+            // pair's two frames (frame b = frame a shifted by 8 rows of 32 samples: the same lane) ----
+            static_for<0, 16>([&](auto ic) {
+                constexpr int ii = decltype(ic)::value;
+                float2 r;
+                r.x = __shfl_sync(0xffffffffu, pm[15 - ii].x, pl);
+                r.y = __shfl_sync(0xffffffffu, pm[15 - ii].y, pl);
+                if (lane == 0) {
+                    if constexpr (ii == 0) r = make_float2(nyq_a, nyq_b);
+                    else r = pm[16 - ii];
+                }
+                v[16 + ii] = r;
+            });
+            __syncwarp();                                // staged tprev rows consumed: the tile is free for the exchange
+            warp_fft1024<1>(v, xb, s_tw, lane);
+            // s_win holds Hann / 2 (forward scaling); Hann / 1024 = s_win / 512 exactly
+            static_for<0, 32>([&](auto kc) {
+                constexpr int k2 = decltype(kc)::value;
+                const float w = s_win[lane + 32 * k2] * (1.0f / 512.0f);
+                v[k2].x *= w;
+                v[k2].y = b_valid ? v[k2].y * w : 0.f;
+            });
+            float* seg = reinterpret_cast<float*>(ang + ra) + lane;
+            static_for<0, 40>([&](auto jc) {
+                constexpr int j = decltype(jc)::value;
+                if constexpr (j < 8) seg[32 * j] = v[j].x;
+                else if constexpr (j < 32) seg[32 * j] = v[j].x + v[j - 8].y;
+                else { if (b_valid) seg[32 * j] = v[j - 8].y; }
+            });
         }
         __syncwarp();                                    // staged rows consumed: the tile is free for the next exchange
         cur = nxt;
@@ -915,6 +963,91 @@ k_istft(BatchView bv, const float2* __restrict__ spec, int64_t ld, float* __rest
 }
 
 // ---------------------------------------------------------------------------------------
+// K4p: overlap-add of PAIR segments (the fused Griffin-Lim iteration)
+//
+// k_stft_phase_w<1, *, true> leaves, for every frame pair (2j, 2j+1) of an item, the 1280-sample sum of its two
+// windowed inverse-transform frames at row (item row + 2j) of the `ang` workspace (float view, 2 * ld floats per row;
+// a lone last frame leaves its 1024 samples).  Padded chunk q = c + 2 of output chunk c lies in the segments of pairs
+// j with 0 <= q - 2j <= 4 -- two or three of them --, summed here in ascending pair order and normalised by the
+// window-sum-square exactly as k_istft does (table for interior chunks, per-sample sum over the existing frames at
+// the item edges).  One warp per chunk, 16-byte loads and stores, no shared-memory staging: a pure streaming kernel.
+// ---------------------------------------------------------------------------------------
+constexpr int kOlaWarps = 8;
+constexpr int kOlaParts = (kTileChunks + kOlaWarps - 1) / kOlaWarps;   // CTAs per chunk tile
+
+__global__ void __launch_bounds__(kOlaWarps * 32)
+k_ola_pairs(BatchView bv, const float* __restrict__ seg, int64_t ld_f, float* __restrict__ y,
+            const float* __restrict__ g_win) {
+    __shared__ __align__(16) float s_win[kNfft];
+    __shared__ __align__(16) float s_iw[kHop];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    pdl_launch_dependents();
+    for (int i = threadIdx.x; i < kNfft; i += blockDim.x) s_win[i] = g_win[i];
+    __syncthreads();
+    for (int s = threadIdx.x; s < kHop; s += blockDim.x) {
+        float wss = 0.f;   // same ascending-frame fmaf chain as k_istft
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const float w = s_win[768 - 256 * q + s]; wss = fmaf(w, w, wss); }
+        s_iw[s] = 1.0f / wss;
+    }
+    __syncthreads();
+    const int tile = blockIdx.x / kOlaParts, cl = (blockIdx.x % kOlaParts) * kOlaWarps + warp;
+    const spev_tile* d = bv.ctiles + tile;
+    const int n = __ldg(&d->n);
+    if (cl >= n) return;
+    const int c = __ldg(&d->t0) + cl, T = __ldg(&d->T);
+    const int64_t item_row = __ldg(&d->row0) - __ldg(&d->t0) + 1;
+    float* yo = y + __ldg(&d->src0) + static_cast<int64_t>(cl) * kHop;
+    const int n_pairs = (T + 1) >> 1;
+    const int jlo = max(0, (c - 1) >> 1), jhi = min(n_pairs - 1, (c + 2) >> 1);
+    pdl_wait();   // the segments come from the previous kernel
+    float4 p0[3], p1[3];
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+        const int j = jlo + u;
+        const int off = (c + 2 - 2 * j) * kHop;
+        // a lone last frame (2j + 1 == T) has no fifth chunk
+        const bool ok = j <= jhi && !(off == kNfft && 2 * j + 1 >= T);
+        p0[u] = p1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok) {
+            const float4* src = reinterpret_cast<const float4*>(seg + (item_row + 2 * j) * ld_f + off);
+            p0[u] = src[lane];
+            p1[u] = src[32 + lane];
+        }
+    }
+    auto add3 = [](const float4 (&p)[3]) {
+        return make_float4((p[0].x + p[1].x) + p[2].x, (p[0].y + p[1].y) + p[2].y, (p[0].z + p[1].z) + p[2].z,
+                           (p[0].w + p[1].w) + p[2].w);
+    };
+    float4 r0 = add3(p0), r1 = add3(p1);
+    const int s0 = 4 * lane, s1 = 128 + 4 * lane;
+    if (c >= 1 && c + 2 < T) {
+        const float4 w0 = *reinterpret_cast<const float4*>(s_iw + s0), w1 = *reinterpret_cast<const float4*>(s_iw + s1);
+        r0 = make_float4(r0.x * w0.x, r0.y * w0.y, r0.z * w0.z, r0.w * w0.w);
+        r1 = make_float4(r1.x * w1.x, r1.y * w1.y, r1.z * w1.z, r1.w * w1.w);
+    } else {
+        auto norm = [&](float sum, int s) {
+            float wss = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int t = c - 1 + q;
+                if (t >= 0 && t < T) { const float w = s_win[768 - 256 * q + s]; wss = fmaf(w, w, wss); }
+            }
+            return wss > kTiny ? sum / wss : sum;
+        };
+        r0 = make_float4(norm(r0.x, s0), norm(r0.y, s0 + 1), norm(r0.z, s0 + 2), norm(r0.w, s0 + 3));
+        r1 = make_float4(norm(r1.x, s1), norm(r1.y, s1 + 1), norm(r1.z, s1 + 2), norm(r1.w, s1 + 3));
+    }
+    if ((reinterpret_cast<uintptr_t>(yo) & 15) == 0) {
+        reinterpret_cast<float4*>(yo)[lane] = r0;
+        reinterpret_cast<float4*>(yo)[32 + lane] = r1;
+    } else {
+        yo[s0] = r0.x; yo[s0 + 1] = r0.y; yo[s0 + 2] = r0.z; yo[s0 + 3] = r0.w;
+        yo[s1] = r1.x; yo[s1 + 1] = r1.y; yo[s1 + 2] = r1.z; yo[s1 + 3] = r1.w;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Griffin-Lim initial state: ang = S * exp(i * phase)
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
@@ -1081,7 +1214,7 @@ int fft_grid(const spev_ctx* ctx, int64_t n_tiles) { return static_cast<int>(std
 
 int launch_stft_phase(spev_ctx* ctx, const spev_batch* b, const float* y, const float* S,
                       int64_t ld_s, void* ang, void* tprev, int64_t ld, float alpha, int has_prev,
-                      bool phase, cudaStream_t st, unsigned* counter, unsigned base) {
+                      bool phase, cudaStream_t st, unsigned* counter, unsigned base, bool fuse) {
     int rc = check_batch(ctx, b, false);
     if (rc) return rc;
     if (b->n_ftiles == 0) return SPEV_OK;
@@ -1106,11 +1239,31 @@ int launch_stft_phase(spev_ctx* ctx, const spev_batch* b, const float* y, const 
     if (!(ctx->gl_variant & 4)) counter = nullptr;
     const bool stage_t = (reinterpret_cast<uintptr_t>(tprev) & 15) == 0 && ld % 2 == 0 && ld > kBins &&
                          static_cast<size_t>(ld) * 8 + (kBins + 1) * 8 <= sizeof(float) * kXWords;
+    if (fuse) {
+        // fused iteration: the new spectra are inverse-transformed in registers and leave as pair segments in `ang`
+        SPEV_REQUIRE((reinterpret_cast<uintptr_t>(ang) & 15) == 0 && ld % 2 == 0 && ld * 2 >= kNfft, SPEV_E_INVALID,
+                     "fused phase update: segment rows need 16-byte alignment and >= 1024 floats per row");
+        if (stage_t)
+            return launch_pdl(k_stft_phase_w<1, true, true>, grid, kThreads, smem_ws_phase(), st, view_of(b), y, S, ld_s,
+                              static_cast<float2*>(ang), static_cast<float2*>(tprev), ld, alpha, has_prev, tw, win, counter, base);
+        return launch_pdl(k_stft_phase_w<1, false, true>, grid, kThreads, smem_ws_phase(), st, view_of(b), y, S, ld_s,
+                          static_cast<float2*>(ang), static_cast<float2*>(tprev), ld, alpha, has_prev, tw, win, counter, base);
+    }
     if (stage_t)
         return launch_pdl(k_stft_phase_w<1, true>, grid, kThreads, smem_ws_phase(), st, view_of(b), y, S, ld_s, static_cast<float2*>(ang),
                           static_cast<float2*>(tprev), ld, alpha, has_prev, tw, win, counter, base);
     return launch_pdl(k_stft_phase_w<1, false>, grid, kThreads, smem_ws_phase(), st, view_of(b), y, S, ld_s, static_cast<float2*>(ang),
                       static_cast<float2*>(tprev), ld, alpha, has_prev, tw, win, counter, base);
+}
+
+// Overlap-add of the pair segments the fused phase update left in `seg` (rows of 2 * ld floats) into y.
+int launch_ola_pairs(spev_ctx* ctx, const spev_batch* b, const void* seg, int64_t ld, float* y, cudaStream_t st) {
+    int rc = check_batch(ctx, b, true);
+    if (rc) return rc;
+    if (b->n_ctiles == 0) return SPEV_OK;
+    SPEV_REQUIRE(seg && y, SPEV_E_INVALID, "ola: null buffer");
+    return launch_pdl(k_ola_pairs, b->n_ctiles * kOlaParts, kOlaWarps * 32, 0, st, view_of(b), static_cast<const float*>(seg),
+                      2 * ld, y, static_cast<const float*>(ctx->d_window));
 }
 
 int launch_istft(spev_ctx* ctx, const spev_batch* b, const void* spec, int64_t ld, float* y,
@@ -1143,6 +1296,7 @@ int spectral_init(spev_ctx*) {
     opt(k_stft_mel_ws<5>); opt(k_stft_mel_ws<6>); opt(k_stft_mel_ws<7>); opt(k_stft_mel_ws<8>);
     opt(k_stft_phase<0>); opt(k_stft_phase<1>);
     opt(k_stft_phase_w<0, false>); opt(k_stft_phase_w<1, false>); opt(k_stft_phase_w<1, true>);
+    opt(k_stft_phase_w<1, false, true>); opt(k_stft_phase_w<1, true, true>);
     opt(k_istft<true>); opt(k_istft<false>);
     return rc;
 }

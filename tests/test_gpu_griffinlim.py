@@ -264,6 +264,41 @@ def test_griffinlim_kernel_variants_agree(cuda):
                 _lib.check(ctx.lib.spev_set_griffinlim_variant(ctx.handle, variant))
                 outs.append(sp.griffinlim_flat(S, fb, ctx, n_iter=n_iter, init_phase=ph).clone())
         finally:
-            _lib.check(ctx.lib.spev_set_griffinlim_variant(ctx.handle, 1))
+            _lib.check(ctx.lib.spev_set_griffinlim_variant(ctx.handle, 9))
         assert torch.isfinite(outs[1]).all(), frames
         assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2]), frames
+
+
+def test_griffinlim_fused_iteration_matches_two_kernel_path(cuda):
+    """The fused iteration (default, variant 9: the new spectra are inverse-transformed in registers inside the phase
+    update and leave as pair segments; k_ola_pairs overlap-adds them) against the two-kernel path (variant 1: spectra
+    through HBM, k_istft): same arithmetic per frame, only the order of the <= 4 overlap-add terms differs (pairs first),
+    so a few iterations agree to rounding; static and dynamic pair scheduling are bit-identical to each other."""
+    import spev_tts_b200 as sp
+    from spev_tts_b200 import _lib
+    ctx = sp.Context.get(cuda, fmin=0.0, fmax=8000.0)
+    for frames, n_iter, tol in (([800, 33, 1, 2, 3, 4, 5, 64, 517, 95, 31], 1, 2e-6), ([800, 33, 1, 2, 3, 4, 5, 64, 517, 95, 31], 3, 1e-5),
+                                ([7] * 40, 2, 1e-5), ([800] * 16, 2, 1e-5), ([301], 0, 0.0)):
+        fb = sp.make_batch(ctx, n_frames=frames, with_chunks=True)
+        g = torch.Generator(device=cuda).manual_seed(11)
+        S = torch.rand(fb.n_frames, _lib.SPEC_LD, generator=g, device=cuda)
+        ph = torch.rand(fb.n_frames, 513, generator=g, device=cuda) * 6.2831853
+        outs = {}
+        try:
+            for variant in (1, 9, 13):
+                _lib.check(ctx.lib.spev_set_griffinlim_variant(ctx.handle, variant))
+                outs[variant] = sp.griffinlim_flat(S, fb, ctx, n_iter=n_iter, init_phase=ph).clone()
+        finally:
+            _lib.check(ctx.lib.spev_set_griffinlim_variant(ctx.handle, 9))
+        assert torch.isfinite(outs[9]).all(), frames
+        assert torch.equal(outs[9], outs[13]), frames
+        a, b = outs[1].double(), outs[9].double()
+        # per item (a short item must not hide behind a long one)
+        off = 0
+        for T in frames:
+            n = (T - 1) * 256
+            if n:
+                ia, ib = a[off:off + n], b[off:off + n]
+                err = float((ia - ib).norm() / ia.norm().clamp_min(1e-30))
+                assert err <= tol, (frames, n_iter, T, err)
+            off += n
