@@ -898,9 +898,13 @@ def bench_griffinlim(sp, dev, hbm_peak, args):
     return {"metric": "Griffin-Lim audio-s/s", "value": audio_s / (ms * 1e-3), "unit": "audio-s/s",
             "config": {"workload": "cfg3: 16 x [80,800] log-mel, 60 iterations, momentum 0.99; L2 flushed between steps"},
             "ms_per_step": ms, "launches_per_step": 2 * n_iter + 3,
-            "roofline": {"bound": "hbm", "kernels": "k_istft + k_stft_phase<1>", "achieved": alg / (ms * 1e-3) / 1e9,
+            "roofline": {"bound": "hbm", "kernels": "k_gl_fused (STFT + phase update + inverse transform) + k_ola_pairs",
+                         "achieved": alg / (ms * 1e-3) / 1e9,
                          "peak": hbm_peak, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / hbm_peak,
-                         "alg_bytes_per_frame_iter": GL_BYTES_PER_FRAME_ITER},
+                         "alg_bytes_per_frame_iter": GL_BYTES_PER_FRAME_ITER,
+                         "note": "algorithmic bytes are SURVEY 8d's two-kernel figure (20,516 B per frame and iteration); the fused "
+                                 "iteration keeps the new spectra in registers and moves 17,428 B (y 1,024 + tprev 4,104 + S 2,052 "
+                                 "read, tprev 4,104 + pair segment 2,560 written; segment 2,560 read, y 1,024 written)"},
             "e2e": {"value": audio_s / (e2e_ms * 1e-3), "unit": "audio-s/s", "ms_per_step": e2e_ms,
                     "ms_per_call_min_max": [float(min(calls)), float(max(calls))],
                     "api": "Vocoder.infer (host log-mel in, numpy waveform out; mel->linear solved as librosa does: "

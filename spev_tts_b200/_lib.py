@@ -130,6 +130,9 @@ _SIGS = {
 
 EXPORTED_SYMBOLS = tuple(sorted(_SIGS))
 
+# spev_set_griffinlim_variant: the library default (bulk-staged rows | fused iteration | rsqrt phase normalisation)
+GL_VARIANT_DEFAULT = 25
+
 _lib = None
 _lock = threading.Lock()
 

@@ -223,7 +223,7 @@ int spev_create(spev_ctx** out, int device, int sr, int n_fft, int hop, int win,
 
     spev_ctx* c = new spev_ctx();
     c->device = device; c->sr = sr; c->n_fft = n_fft; c->hop = hop; c->win = kNfft; c->n_mels = n_mels;
-    c->fmin = fmin; c->fmax = fmax; c->num_sms = c->num_sms_device = prop.multiProcessorCount; c->tma = nullptr; c->use_tc = 1; c->k1_variant = 0; c->gl_variant = 9;
+    c->fmin = fmin; c->fmax = fmax; c->num_sms = c->num_sms_device = prop.multiProcessorCount; c->tma = nullptr; c->use_tc = 1; c->k1_variant = 0; c->gl_variant = 25;
     c->d_tw = nullptr; c->d_window = nullptr; c->d_win2048 = nullptr; c->d_tw2048 = nullptr; c->d_basis = c->d_basis_pad = c->d_basis_hi = c->d_basis_lo = nullptr;
     c->d_pinv_t = c->d_pinv_hi = c->d_pinv_lo = nullptr;
     c->d_prog_w = nullptr; c->d_prog_h = nullptr;
@@ -311,8 +311,16 @@ int spev_create(spev_ctx** out, int device, int sr, int n_fft, int hop, int win,
         }
     for (size_t i = 0; i < basis_pad.size(); ++i) { b_hi[i] = tf32_trunc(basis_pad[i]); b_lo[i] = basis_pad[i] - b_hi[i]; }
 
+    // d_window = [1024] Hann followed by [256] 1 / sum_q w[768 - 256 q + s]^2: the window-sum-square of interior ISTFT
+    // chunks, accumulated with the same ascending-frame fmaf chain k_istft uses in the kernel (IEEE: same bits)
+    std::vector<float> win_iw(c->h_window);
+    for (int s = 0; s < kHop; ++s) {
+        float wss = 0.f;
+        for (int q = 0; q < 4; ++q) { const float w = c->h_window[768 - 256 * q + s]; wss = std::fmaf(w, w, wss); }
+        win_iw.push_back(1.0f / wss);
+    }
     int rc = SPEV_OK;
-    if ((rc = upload(&c->d_tw, tw)) || (rc = upload(&c->d_window, c->h_window)) ||
+    if ((rc = upload(&c->d_tw, tw)) || (rc = upload(&c->d_window, win_iw)) ||
         (rc = upload(&c->d_win2048, win2048)) || (rc = upload(&c->d_tw2048, tw2048)) ||
         (rc = upload(&c->d_basis, c->h_basis)) || (rc = upload(&c->d_basis_pad, basis_pad)) || (rc = upload(&c->d_basis_hi, b_hi)) ||
         (rc = upload(&c->d_basis_lo, b_lo)) || (rc = upload(&c->d_pinv_t, pinv_t)) ||
@@ -376,9 +384,10 @@ int spev_set_tensor_core(spev_ctx* c, int enable) {
 
 int spev_set_griffinlim_variant(spev_ctx* c, int variant) {
     SPEV_REQUIRE(c, SPEV_E_INVALID, "ctx is null");
-    SPEV_REQUIRE(variant >= 0 && variant <= 15 && (variant == 0 || (variant & 1)), SPEV_E_INVALID,
+    SPEV_REQUIRE(variant >= 0 && variant <= 63 && (variant == 0 || (variant & 1)), SPEV_E_INVALID,
                  "spev_set_griffinlim_variant: 0 (r01 kernels) or 1 (bulk-staged rows) | 2 (dynamic ISTFT tiles) | 4 (dynamic phase-update pairs) "
-                 "| 8 (fused iteration: inverse transform inside the phase update + pair overlap-add; default 9)");
+                 "| 8 (fused iteration: inverse transform inside the phase update + pair overlap-add; default 25 = 1 | 8 | 16) | 16 (rsqrt phase normalisation in the fused kernel) "
+                 "| 32 (straight-line fused body)");
     c->gl_variant = variant;
     return SPEV_OK;
 }

@@ -643,6 +643,224 @@ k_stft_phase_w(BatchView bv, const float* __restrict__ y, const float* __restric
 }
 
 // ---------------------------------------------------------------------------------------
+// K5f: the fused Griffin-Lim iteration (default since r02): STFT of the rebuilt signal, momentum / phase update, and
+// the INVERSE transform of the new spectra without leaving the registers; what goes back to HBM is the pair's
+// 1280-sample overlap-add segment (k_ola_pairs finishes the overlap-add) and the rebuilt spectra for the momentum term.
+//
+// Same work distribution and staging as k_stft_phase_w (warp-independent pairs, cp.async samples one pair ahead, bulk-
+// staged tprev rows), but the body is written ONCE and run twice per pair: pass 0 transforms the samples, pass 1 the
+// new spectra.  The inverse transform is the forward one on swapped components (swap(z) = i conj(z):
+// ifft(V) = swap(fft(swap(V)))), so both passes -- and, inside a pass, both 32-point stages -- execute the same
+// instructions.  The straight-line version (k_stft_phase_w<1, *, true>: four inlined 32-point DFTs, ~75 KB of code)
+// lost 1.3 warps per issue cycle to instruction fetch (ncu `no_instruction`) because its 16 drifting warps walk the
+// whole body at different places; this body is less than half of that.
+// FAST: |a| normalisation by MUFU.RSQ (2 ulp) instead of IEEE sqrt + divide.
+// ---------------------------------------------------------------------------------------
+template <bool FAST>
+__device__ __forceinline__ float2 phase_of_t(float2 reb, float s, float2 tp, float alpha, int has_prev) {
+    if constexpr (!FAST) return phase_of(reb, s, tp, alpha, has_prev);
+    float2 a = reb;
+    if (has_prev) {
+        a.x = a.x - alpha * tp.x;
+        a.y = a.y - alpha * tp.y;
+    }
+    // 1 / (|a| + tiny) == rsqrt(|a|^2) wherever |a|^2 is a normal number; the clamp keeps a == 0 at 0 * finite
+    const float n2 = fmaxf(fmaf(a.x, a.x, a.y * a.y), 1e-36f);
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(n2));
+    r *= s;
+    return make_float2(a.x * r, a.y * r);
+}
+
+template <bool STAGE_T, bool FAST>
+__global__ void __launch_bounds__(kThreads, 1)
+k_gl_fused(BatchView bv, const float* __restrict__ y, const float* __restrict__ S, int64_t ld_s,
+           float* __restrict__ seg_base, float2* tprev, int64_t ld, float alpha, int has_prev,
+           const float2* __restrict__ g_tw, const float* __restrict__ g_win, unsigned* counter, unsigned base) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* s_tw = reinterpret_cast<float2*>(smem_raw);
+    float* s_win = reinterpret_cast<float*>(s_tw + 1024);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_win + 1024);        // one mbarrier per warp
+    float* s_x = reinterpret_cast<float*>(s_bar + kWarps);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    pdl_launch_dependents();
+    load_tables(s_tw, s_win, g_tw, g_win, 0.5f);
+    if (STAGE_T && threadIdx.x < kWarps) bar_init(s_bar + threadIdx.x, 1);
+    if (STAGE_T && threadIdx.x == 0) asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    __syncthreads();                                     // the only CTA-wide barrier
+    float* tile = s_x + warp * kWsRegionWords;           // exchange tile, then the staged tprev rows
+    float* xs = tile + kXWords;                          // samples of the pair being loaded / staged next
+    float2* xb = reinterpret_cast<float2*>(tile);
+    uint64_t* tbar = s_bar + warp;
+    unsigned tphase = 0;
+    const int pl = (32 - lane) & 31;
+
+    const int64_t n_pairs = static_cast<int64_t>(bv.n_ftiles) * kWarps;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * kWarps;
+    int64_t p_static = static_cast<int64_t>(blockIdx.x) * kWarps + warp;
+    bool drained = false;
+    unsigned pend = 0;
+    auto draw_ahead = [&]() { if (lane == 0) pend = draw_ticket(counter, base); };
+    auto next_pair = [&]() -> int64_t {
+        if (counter == nullptr) { const int64_t p = p_static; p_static += stride; return p; }
+        if (drained) return n_pairs;
+        const unsigned t = __shfl_sync(0xffffffffu, pend, 0);
+        if (t >= static_cast<unsigned>(n_pairs)) { drained = true; return n_pairs; }
+        draw_ahead();
+        return static_cast<int64_t>(t);
+    };
+    auto stage_next = [&]() -> PairInfo {
+        PairInfo pi{0, 0, 0};
+        for (;;) {
+            const int64_t p = next_pair();
+            if (p >= n_pairs) return pi;
+            pi = stage_pair(xs, y, bv.ftiles, p, n_pairs, lane);
+            if (pi.valid) return pi;
+        }
+    };
+    pdl_wait();                                          // y / tprev come from the previous kernels
+    if (counter != nullptr) draw_ahead();
+    PairInfo cur = stage_next();
+    cp_async_commit();
+
+    while (cur.valid) {
+        cp_async_wait_all();
+        __syncwarp();
+        const bool b_valid = cur.b_valid != 0;
+        float2 v[32];
+        load_frame_pair(v, xs, s_win, 0, b_valid, lane);
+        __syncwarp();                                    // staged samples consumed
+        const PairInfo nxt = stage_next();               // the next pair's samples have this whole pair's time to arrive
+        cp_async_commit();
+        const int64_t ra = cur.row * ld, rb = ra + ld;
+        const float* sa = S + cur.row * ld_s;
+        const float* sb = sa + ld_s;
+        {
+            const int rows = b_valid ? 2 : 1;
+            warp_prefetch_l2(sa, static_cast<int>((rows - 1) * ld_s + kBins) * 4, lane);
+            if (!STAGE_T && has_prev) warp_prefetch_l2(tprev + ra, static_cast<int>((rows - 1) * ld + kBins) * 8, lane);
+        }
+        const bool staged = STAGE_T && has_prev;
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            // ---- 1024-point forward transform: two 32-point stages around one exchange ----
+#pragma unroll 1
+            for (int stage = 0; stage < 2; ++stage) {
+                dft32<-1>(v);
+                if (stage == 0) {
+                    static_for<1, 32>([&](auto k1c) {
+                        constexpr int k1 = decltype(k1c)::value;
+                        v[k1] = cmul(v[k1], s_tw[k1 * 32 + lane]);
+                    });
+                    __syncwarp();                        // pass 1: everybody has read the staged tprev rows
+                    static_for<0, 32>([&](auto k1c) {
+                        constexpr int k1 = decltype(k1c)::value;
+                        xb[k1 * kXPitch + lane] = v[k1];
+                    });
+                    __syncwarp();
+                    static_for<0, 32>([&](auto n2c) {
+                        constexpr int n2 = decltype(n2c)::value;
+                        v[n2] = xb[lane * kXPitch + n2];
+                    });
+                    __syncwarp();                        // tile read back
+                    if (pass == 0 && staged && lane == 0) {   // pull the pair's tprev rows into the tile: they land during stage 1
+                        const uint32_t bytes = b_valid ? static_cast<uint32_t>(ld * 8 + (kBins + 1) * 8) : static_cast<uint32_t>((kBins + 1) * 8);
+                        fence_proxy_async();
+                        bar_expect_tx(tbar, bytes);
+                        bulk_g2s(tile, tprev + ra, bytes, tbar);
+                    }
+                }
+            }
+            if (pass == 0) {
+                // ---- Hermitian split, phase update; the new spectra are packed (swapped) for the second pass ----
+                float2 pm[16];
+                fetch_mirror(v, pm, lane);
+                const float2* tsm = reinterpret_cast<const float2*>(tile);   // staged rows: a at [0, 514), b at [ld, ld + 514)
+                if (staged) { bar_wait(tbar, tphase); tphase ^= 1; }
+                float nyq_a = 0.f, nyq_b = 0.f;
+                if (lane == 0) {   // bin 512 first: v[16] is overwritten below.  X[512] = 2 * Z'[512] (window carries 1/2)
+                    const float2 xa = make_float2(2.f * v[16].x, 0.f), xbv = make_float2(2.f * v[16].y, 0.f);
+                    const float2 z = make_float2(0.f, 0.f);
+                    const float2 ta = !has_prev ? z : (staged ? tsm[512] : tprev[ra + 512]);
+                    nyq_a = phase_of_t<FAST>(xa, sa[512], ta, alpha, has_prev).x;
+                    tprev[ra + 512] = xa;
+                    if (b_valid) {
+                        const float2 tb = !has_prev ? z : (staged ? tsm[ld + 512] : tprev[rb + 512]);
+                        nyq_b = phase_of_t<FAST>(xbv, sb[512], tb, alpha, has_prev).x;
+                        tprev[rb + 512] = xbv;
+                    }
+                }
+                static_for<0, 4>([&](auto gc) {
+                    constexpr int g = decltype(gc)::value;
+                    float2 tpa[4], tpb[4];
+                    float s_a[4], s_b[4];
+                    static_for<0, 4>([&](auto qc) {
+                        constexpr int q = decltype(qc)::value;
+                        const int k = lane + 32 * (4 * g + q);
+                        s_a[q] = sa[k];
+                        s_b[q] = b_valid ? sb[k] : 0.f;
+                        if (staged) {
+                            tpa[q] = tsm[k];
+                            tpb[q] = b_valid ? tsm[ld + k] : make_float2(0.f, 0.f);
+                        } else {
+                            tpa[q] = has_prev ? tprev[ra + k] : make_float2(0.f, 0.f);
+                            tpb[q] = (has_prev && b_valid) ? tprev[rb + k] : make_float2(0.f, 0.f);
+                        }
+                    });
+                    static_for<0, 4>([&](auto qc) {
+                        constexpr int q = decltype(qc)::value;
+                        constexpr int k2 = 4 * g + q;
+                        const int k = lane + 32 * k2;
+                        float2 xa, xbv;
+                        split_pair_prescaled(v[k2], pm[k2], xa, xbv);
+                        float2 a = phase_of_t<FAST>(xa, s_a[q], tpa[q], alpha, has_prev);
+                        float2 b = make_float2(0.f, 0.f);
+                        tprev[ra + k] = xa;
+                        if (b_valid) {
+                            b = phase_of_t<FAST>(xbv, s_b[q], tpb[q], alpha, has_prev);
+                            tprev[rb + k] = xbv;
+                        }
+                        if (k2 == 0 && lane == 0) { a.y = 0.f; b.y = 0.f; }   // irfft ignores Im(DC)
+                        // V = A + iB and its mirror conj(A) + i conj(B), both with swapped components
+                        v[k2] = make_float2(a.y + b.x, a.x - b.y);
+                        pm[k2] = make_float2(b.x - a.y, a.x + b.y);
+                    });
+                });
+                static_for<0, 16>([&](auto ic) {
+                    constexpr int ii = decltype(ic)::value;
+                    float2 r;
+                    r.x = __shfl_sync(0xffffffffu, pm[15 - ii].x, pl);
+                    r.y = __shfl_sync(0xffffffffu, pm[15 - ii].y, pl);
+                    if (lane == 0) {
+                        if constexpr (ii == 0) r = make_float2(nyq_b, nyq_a);   // irfft ignores Im(Nyquist)
+                        else r = pm[16 - ii];
+                    }
+                    v[16 + ii] = r;
+                });
+            } else {
+                // ---- v = swap(ifft): frame a in .y, frame b in .x.  Hann / 1024 = s_win / 512 exactly; overlap-add of the
+                // pair (frame b = frame a shifted by 8 rows of 32 samples: the same lane) ----
+                static_for<0, 32>([&](auto kc) {
+                    constexpr int k2 = decltype(kc)::value;
+                    const float w = s_win[lane + 32 * k2] * (1.0f / 512.0f);
+                    v[k2].y *= w;
+                    v[k2].x = b_valid ? v[k2].x * w : 0.f;
+                });
+                float* seg = seg_base + 2 * ra + lane;
+                static_for<0, 40>([&](auto jc) {
+                    constexpr int j = decltype(jc)::value;
+                    if constexpr (j < 8) seg[32 * j] = v[j].y;
+                    else if constexpr (j < 32) seg[32 * j] = v[j].y + v[j - 8].x;
+                    else { if (b_valid) seg[32 * j] = v[j - 8].x; }
+                });
+            }
+        }
+        __syncwarp();
+        cur = nxt;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // K1 (default): fused STFT -> power -> mel -> log with DECOUPLED warps
 //
 // Same arithmetic as k_stft_mel<0> (bit-identical results), different schedule.  In the tile kernel above every
@@ -977,20 +1195,10 @@ constexpr int kOlaParts = (kTileChunks + kOlaWarps - 1) / kOlaWarps;   // CTAs p
 
 __global__ void __launch_bounds__(kOlaWarps * 32)
 k_ola_pairs(BatchView bv, const float* __restrict__ seg, int64_t ld_f, float* __restrict__ y,
-            const float* __restrict__ g_win) {
-    __shared__ __align__(16) float s_win[kNfft];
-    __shared__ __align__(16) float s_iw[kHop];
+            const float* __restrict__ g_win /* [1024] Hann, then [256] 1 / sum_q w^2 (ctx table) */) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float* g_iw = g_win + kNfft;
     pdl_launch_dependents();
-    for (int i = threadIdx.x; i < kNfft; i += blockDim.x) s_win[i] = g_win[i];
-    __syncthreads();
-    for (int s = threadIdx.x; s < kHop; s += blockDim.x) {
-        float wss = 0.f;   // same ascending-frame fmaf chain as k_istft
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { const float w = s_win[768 - 256 * q + s]; wss = fmaf(w, w, wss); }
-        s_iw[s] = 1.0f / wss;
-    }
-    __syncthreads();
     const int tile = blockIdx.x / kOlaParts, cl = (blockIdx.x % kOlaParts) * kOlaWarps + warp;
     const spev_tile* d = bv.ctiles + tile;
     const int n = __ldg(&d->n);
@@ -1022,7 +1230,7 @@ k_ola_pairs(BatchView bv, const float* __restrict__ seg, int64_t ld_f, float* __
     float4 r0 = add3(p0), r1 = add3(p1);
     const int s0 = 4 * lane, s1 = 128 + 4 * lane;
     if (c >= 1 && c + 2 < T) {
-        const float4 w0 = *reinterpret_cast<const float4*>(s_iw + s0), w1 = *reinterpret_cast<const float4*>(s_iw + s1);
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(g_iw + s0)), w1 = __ldg(reinterpret_cast<const float4*>(g_iw + s1));
         r0 = make_float4(r0.x * w0.x, r0.y * w0.y, r0.z * w0.z, r0.w * w0.w);
         r1 = make_float4(r1.x * w1.x, r1.y * w1.y, r1.z * w1.z, r1.w * w1.w);
     } else {
@@ -1031,7 +1239,7 @@ k_ola_pairs(BatchView bv, const float* __restrict__ seg, int64_t ld_f, float* __
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const int t = c - 1 + q;
-                if (t >= 0 && t < T) { const float w = s_win[768 - 256 * q + s]; wss = fmaf(w, w, wss); }
+                if (t >= 0 && t < T) { const float w = __ldg(g_win + 768 - 256 * q + s); wss = fmaf(w, w, wss); }
             }
             return wss > kTiny ? sum / wss : sum;
         };
@@ -1236,6 +1444,7 @@ int launch_stft_phase(spev_ctx* ctx, const spev_batch* b, const float* y, const 
                           static_cast<float2*>(tprev), ld, alpha, has_prev, tw, win);
     // bulk staging of the tprev rows needs 16-byte aligned rows with one readable pad column, and both rows of a pair
     // must fit the warp's transpose tile
+    unsigned* const counter_in = counter;
     if (!(ctx->gl_variant & 4)) counter = nullptr;
     const bool stage_t = (reinterpret_cast<uintptr_t>(tprev) & 15) == 0 && ld % 2 == 0 && ld > kBins &&
                          static_cast<size_t>(ld) * 8 + (kBins + 1) * 8 <= sizeof(float) * kXWords;
@@ -1243,11 +1452,21 @@ int launch_stft_phase(spev_ctx* ctx, const spev_batch* b, const float* y, const 
         // fused iteration: the new spectra are inverse-transformed in registers and leave as pair segments in `ang`
         SPEV_REQUIRE((reinterpret_cast<uintptr_t>(ang) & 15) == 0 && ld % 2 == 0 && ld * 2 >= kNfft, SPEV_E_INVALID,
                      "fused phase update: segment rows need 16-byte alignment and >= 1024 floats per row");
-        if (stage_t)
-            return launch_pdl(k_stft_phase_w<1, true, true>, grid, kThreads, smem_ws_phase(), st, view_of(b), y, S, ld_s,
-                              static_cast<float2*>(ang), static_cast<float2*>(tprev), ld, alpha, has_prev, tw, win, counter, base);
-        return launch_pdl(k_stft_phase_w<1, false, true>, grid, kThreads, smem_ws_phase(), st, view_of(b), y, S, ld_s,
-                          static_cast<float2*>(ang), static_cast<float2*>(tprev), ld, alpha, has_prev, tw, win, counter, base);
+        // dynamic pair tickets pay once a warp has many pairs (measured: 0.72 vs 0.67 of the roofline on 138 k frames,
+        // 0.635 vs 0.65 at cfg3's 2.7 pairs per warp): chosen from the batch alone, so every launch of a call agrees
+        if (!(ctx->gl_variant & 4) && b->n_ftiles >= 8 * grid) counter = counter_in;
+        float* seg = static_cast<float*>(ang);
+        const bool fast = (ctx->gl_variant & 16) != 0;
+#define SPEV_GLF(ST, FA) launch_pdl(k_gl_fused<ST, FA>, grid, kThreads, smem_ws_phase(), st, view_of(b), y, S, ld_s, seg, \
+                                    static_cast<float2*>(tprev), ld, alpha, has_prev, tw, win, counter, base)
+        if (ctx->gl_variant & 32)   // straight-line body (A/B: instruction-fetch bound)
+            return stage_t ? launch_pdl(k_stft_phase_w<1, true, true>, grid, kThreads, smem_ws_phase(), st, view_of(b), y, S, ld_s,
+                                        static_cast<float2*>(ang), static_cast<float2*>(tprev), ld, alpha, has_prev, tw, win, counter, base)
+                           : launch_pdl(k_stft_phase_w<1, false, true>, grid, kThreads, smem_ws_phase(), st, view_of(b), y, S, ld_s,
+                                        static_cast<float2*>(ang), static_cast<float2*>(tprev), ld, alpha, has_prev, tw, win, counter, base);
+        if (stage_t) return fast ? SPEV_GLF(true, true) : SPEV_GLF(true, false);
+        return fast ? SPEV_GLF(false, true) : SPEV_GLF(false, false);
+#undef SPEV_GLF
     }
     if (stage_t)
         return launch_pdl(k_stft_phase_w<1, true>, grid, kThreads, smem_ws_phase(), st, view_of(b), y, S, ld_s, static_cast<float2*>(ang),
@@ -1297,6 +1516,7 @@ int spectral_init(spev_ctx*) {
     opt(k_stft_phase<0>); opt(k_stft_phase<1>);
     opt(k_stft_phase_w<0, false>); opt(k_stft_phase_w<1, false>); opt(k_stft_phase_w<1, true>);
     opt(k_stft_phase_w<1, false, true>); opt(k_stft_phase_w<1, true, true>);
+    opt(k_gl_fused<true, true>); opt(k_gl_fused<true, false>); opt(k_gl_fused<false, true>); opt(k_gl_fused<false, false>);
     opt(k_istft<true>); opt(k_istft<false>);
     return rc;
 }

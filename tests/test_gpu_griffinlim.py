@@ -264,13 +264,13 @@ def test_griffinlim_kernel_variants_agree(cuda):
                 _lib.check(ctx.lib.spev_set_griffinlim_variant(ctx.handle, variant))
                 outs.append(sp.griffinlim_flat(S, fb, ctx, n_iter=n_iter, init_phase=ph).clone())
         finally:
-            _lib.check(ctx.lib.spev_set_griffinlim_variant(ctx.handle, 9))
+            _lib.check(ctx.lib.spev_set_griffinlim_variant(ctx.handle, _lib.GL_VARIANT_DEFAULT))
         assert torch.isfinite(outs[1]).all(), frames
         assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2]), frames
 
 
 def test_griffinlim_fused_iteration_matches_two_kernel_path(cuda):
-    """The fused iteration (default, variant 9: the new spectra are inverse-transformed in registers inside the phase
+    """The fused iteration (default, variant 25 = 9 + rsqrt phase normalisation; 9: the new spectra are inverse-transformed in registers inside the phase
     update and leave as pair segments; k_ola_pairs overlap-adds them) against the two-kernel path (variant 1: spectra
     through HBM, k_istft): same arithmetic per frame, only the order of the <= 4 overlap-add terms differs (pairs first),
     so a few iterations agree to rounding; static and dynamic pair scheduling are bit-identical to each other."""
@@ -285,20 +285,22 @@ def test_griffinlim_fused_iteration_matches_two_kernel_path(cuda):
         ph = torch.rand(fb.n_frames, 513, generator=g, device=cuda) * 6.2831853
         outs = {}
         try:
-            for variant in (1, 9, 13):
+            for variant in (1, 9, 13, 25, 41):
                 _lib.check(ctx.lib.spev_set_griffinlim_variant(ctx.handle, variant))
                 outs[variant] = sp.griffinlim_flat(S, fb, ctx, n_iter=n_iter, init_phase=ph).clone()
         finally:
-            _lib.check(ctx.lib.spev_set_griffinlim_variant(ctx.handle, 9))
+            _lib.check(ctx.lib.spev_set_griffinlim_variant(ctx.handle, _lib.GL_VARIANT_DEFAULT))
         assert torch.isfinite(outs[9]).all(), frames
         assert torch.equal(outs[9], outs[13]), frames
-        a, b = outs[1].double(), outs[9].double()
-        # per item (a short item must not hide behind a long one)
-        off = 0
-        for T in frames:
-            n = (T - 1) * 256
-            if n:
-                ia, ib = a[off:off + n], b[off:off + n]
-                err = float((ia - ib).norm() / ia.norm().clamp_min(1e-30))
-                assert err <= tol, (frames, n_iter, T, err)
-            off += n
+        a = outs[1].double()
+        # 9 / 13: rolled body, static / dynamic pairs; 25: the default (rsqrt normalisation); 41: straight-line body
+        for variant in (9, 25, 41):
+            b = outs[variant].double()
+            off = 0   # per item (a short item must not hide behind a long one)
+            for T in frames:
+                n = (T - 1) * 256
+                if n:
+                    ia, ib = a[off:off + n], b[off:off + n]
+                    err = float((ia - ib).norm() / ia.norm().clamp_min(1e-30))
+                    assert err <= tol, (frames, n_iter, variant, T, err)
+                off += n
