@@ -680,19 +680,20 @@ k_gl_fused(BatchView bv, const float* __restrict__ y, const float* __restrict__ 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* s_tw = reinterpret_cast<float2*>(smem_raw);
     float* s_win = reinterpret_cast<float*>(s_tw + 1024);
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_win + 1024);        // one mbarrier per warp
-    float* s_x = reinterpret_cast<float*>(s_bar + kWarps);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_win + 1024);        // two mbarriers per warp: tprev rows, S rows
+    float* s_x = reinterpret_cast<float*>(s_bar + 2 * kWarps);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     pdl_launch_dependents();
     load_tables(s_tw, s_win, g_tw, g_win, 0.5f);
-    if (STAGE_T && threadIdx.x < kWarps) bar_init(s_bar + threadIdx.x, 1);
+    if (STAGE_T && threadIdx.x < 2 * kWarps) bar_init(s_bar + threadIdx.x, 1);
     if (STAGE_T && threadIdx.x == 0) asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     __syncthreads();                                     // the only CTA-wide barrier
     float* tile = s_x + warp * kWsRegionWords;           // exchange tile, then the staged tprev rows
     float* xs = tile + kXWords;                          // samples of the pair being loaded / staged next
     float2* xb = reinterpret_cast<float2*>(tile);
     uint64_t* tbar = s_bar + warp;
-    unsigned tphase = 0;
+    uint64_t* sbar = s_bar + kWarps + warp;
+    unsigned tphase = 0, sphase = 0;
     const int pl = (32 - lane) & 31;
 
     const int64_t n_pairs = static_cast<int64_t>(bv.n_ftiles) * kWarps;
@@ -730,15 +731,26 @@ k_gl_fused(BatchView bv, const float* __restrict__ y, const float* __restrict__ 
         float2 v[32];
         load_frame_pair(v, xs, s_win, 0, b_valid, lane);
         __syncwarp();                                    // staged samples consumed
-        const PairInfo nxt = stage_next();               // the next pair's samples have this whole pair's time to arrive
-        cp_async_commit();
         const int64_t ra = cur.row * ld, rb = ra + ld;
         const float* sa = S + cur.row * ld_s;
-        const float* sb = sa + ld_s;
-        {
+        PairInfo nxt{0, 0, 0};
+        if (STAGE_T) {
+            // the pair's S rows take the sample region's place (bulk copy; they land during the first transform) and the
+            // next pair's samples are staged after the phase update instead -- they have the inverse transform's time to
+            // arrive from L2 (y was written by the kernel just before).  The epilogue then reads S and tprev from shared
+            // memory: no global load on the pair's critical path (ncu before: long_scoreboard 1.6 warps per issue cycle).
+            if (lane == 0) {
+                const uint32_t bytes = b_valid ? static_cast<uint32_t>((ld_s + kPSlot) * 4) : static_cast<uint32_t>(kPSlot * 4);
+                fence_proxy_async();
+                bar_expect_tx(sbar, bytes);
+                bulk_g2s(xs, sa, bytes, sbar);
+            }
+        } else {
+            nxt = stage_next();                          // the next pair's samples have this whole pair's time to arrive
+            cp_async_commit();
             const int rows = b_valid ? 2 : 1;
             warp_prefetch_l2(sa, static_cast<int>((rows - 1) * ld_s + kBins) * 4, lane);
-            if (!STAGE_T && has_prev) warp_prefetch_l2(tprev + ra, static_cast<int>((rows - 1) * ld + kBins) * 8, lane);
+            if (has_prev) warp_prefetch_l2(tprev + ra, static_cast<int>((rows - 1) * ld + kBins) * 8, lane);
         }
         const bool staged = STAGE_T && has_prev;
 #pragma unroll 1
@@ -777,16 +789,19 @@ k_gl_fused(BatchView bv, const float* __restrict__ y, const float* __restrict__ 
                 fetch_mirror(v, pm, lane);
                 const float2* tsm = reinterpret_cast<const float2*>(tile);   // staged rows: a at [0, 514), b at [ld, ld + 514)
                 if (staged) { bar_wait(tbar, tphase); tphase ^= 1; }
+                if (STAGE_T) { bar_wait(sbar, sphase); sphase ^= 1; }
+                const float* ssa = STAGE_T ? xs : sa;    // S rows: staged (row b at ld_s floats) or global
+                const float* ssb = ssa + ld_s;
                 float nyq_a = 0.f, nyq_b = 0.f;
                 if (lane == 0) {   // bin 512 first: v[16] is overwritten below.  X[512] = 2 * Z'[512] (window carries 1/2)
                     const float2 xa = make_float2(2.f * v[16].x, 0.f), xbv = make_float2(2.f * v[16].y, 0.f);
                     const float2 z = make_float2(0.f, 0.f);
                     const float2 ta = !has_prev ? z : (staged ? tsm[512] : tprev[ra + 512]);
-                    nyq_a = phase_of_t<FAST>(xa, sa[512], ta, alpha, has_prev).x;
+                    nyq_a = phase_of_t<FAST>(xa, ssa[512], ta, alpha, has_prev).x;
                     tprev[ra + 512] = xa;
                     if (b_valid) {
                         const float2 tb = !has_prev ? z : (staged ? tsm[ld + 512] : tprev[rb + 512]);
-                        nyq_b = phase_of_t<FAST>(xbv, sb[512], tb, alpha, has_prev).x;
+                        nyq_b = phase_of_t<FAST>(xbv, ssb[512], tb, alpha, has_prev).x;
                         tprev[rb + 512] = xbv;
                     }
                 }
@@ -797,8 +812,8 @@ k_gl_fused(BatchView bv, const float* __restrict__ y, const float* __restrict__ 
                     static_for<0, 4>([&](auto qc) {
                         constexpr int q = decltype(qc)::value;
                         const int k = lane + 32 * (4 * g + q);
-                        s_a[q] = sa[k];
-                        s_b[q] = b_valid ? sb[k] : 0.f;
+                        s_a[q] = ssa[k];
+                        s_b[q] = b_valid ? ssb[k] : 0.f;
                         if (staged) {
                             tpa[q] = tsm[k];
                             tpb[q] = b_valid ? tsm[ld + k] : make_float2(0.f, 0.f);
@@ -837,6 +852,11 @@ k_gl_fused(BatchView bv, const float* __restrict__ y, const float* __restrict__ 
                     }
                     v[16 + ii] = r;
                 });
+                if (STAGE_T) {                           // S rows consumed: the region takes the next pair's samples
+                    __syncwarp();
+                    nxt = stage_next();
+                    cp_async_commit();
+                }
             } else {
                 // ---- v = swap(ifft): frame a in .y, frame b in .x.  Hann / 1024 = s_win / 512 exactly; overlap-add of the
                 // pair (frame b = frame a shifted by 8 rows of 32 samples: the same lane) ----
@@ -1191,7 +1211,8 @@ k_istft(BatchView bv, const float2* __restrict__ spec, int64_t ld, float* __rest
 // the item edges).  One warp per chunk, 16-byte loads and stores, no shared-memory staging: a pure streaming kernel.
 // ---------------------------------------------------------------------------------------
 constexpr int kOlaWarps = 8;
-constexpr int kOlaParts = (kTileChunks + kOlaWarps - 1) / kOlaWarps;   // CTAs per chunk tile
+constexpr int kOlaPerWarp = 1;                                           // chunks per warp (2 measured: no gain)
+constexpr int kOlaParts = (kTileChunks + kOlaWarps * kOlaPerWarp - 1) / (kOlaWarps * kOlaPerWarp);   // CTAs per chunk tile
 
 __global__ void __launch_bounds__(kOlaWarps * 32)
 k_ola_pairs(BatchView bv, const float* __restrict__ seg, int64_t ld_f, float* __restrict__ y,
@@ -1199,59 +1220,70 @@ k_ola_pairs(BatchView bv, const float* __restrict__ seg, int64_t ld_f, float* __
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float* g_iw = g_win + kNfft;
     pdl_launch_dependents();
-    const int tile = blockIdx.x / kOlaParts, cl = (blockIdx.x % kOlaParts) * kOlaWarps + warp;
+    const int tile = blockIdx.x / kOlaParts, cl0 = ((blockIdx.x % kOlaParts) * kOlaWarps + warp) * kOlaPerWarp;
     const spev_tile* d = bv.ctiles + tile;
     const int n = __ldg(&d->n);
-    if (cl >= n) return;
-    const int c = __ldg(&d->t0) + cl, T = __ldg(&d->T);
-    const int64_t item_row = __ldg(&d->row0) - __ldg(&d->t0) + 1;
-    float* yo = y + __ldg(&d->src0) + static_cast<int64_t>(cl) * kHop;
+    if (cl0 >= n) return;
+    const int t0 = __ldg(&d->t0), T = __ldg(&d->T);
+    const int64_t item_row = __ldg(&d->row0) - t0 + 1;
+    float* yo0 = y + __ldg(&d->src0);
     const int n_pairs = (T + 1) >> 1;
-    const int jlo = max(0, (c - 1) >> 1), jhi = min(n_pairs - 1, (c + 2) >> 1);
+    const int s0 = 4 * lane, s1 = 128 + 4 * lane;
+    // constant tables before the wait: they do not depend on the previous kernel
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(g_iw + s0)), w1 = __ldg(reinterpret_cast<const float4*>(g_iw + s1));
     pdl_wait();   // the segments come from the previous kernel
-    float4 p0[3], p1[3];
+    float4 p0[kOlaPerWarp][3], p1[kOlaPerWarp][3];
 #pragma unroll
-    for (int u = 0; u < 3; ++u) {
-        const int j = jlo + u;
-        const int off = (c + 2 - 2 * j) * kHop;
-        // a lone last frame (2j + 1 == T) has no fifth chunk
-        const bool ok = j <= jhi && !(off == kNfft && 2 * j + 1 >= T);
-        p0[u] = p1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ok) {
-            const float4* src = reinterpret_cast<const float4*>(seg + (item_row + 2 * j) * ld_f + off);
-            p0[u] = src[lane];
-            p1[u] = src[32 + lane];
+    for (int e = 0; e < kOlaPerWarp; ++e) {
+        const int c = t0 + cl0 + e;
+        const int jlo = max(0, (c - 1) >> 1), jhi = min(n_pairs - 1, (c + 2) >> 1);
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            const int j = jlo + u;
+            const int off = (c + 2 - 2 * j) * kHop;
+            // a lone last frame (2j + 1 == T) has no fifth chunk
+            const bool ok = cl0 + e < n && j <= jhi && !(off == kNfft && 2 * j + 1 >= T);
+            p0[e][u] = p1[e][u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok) {
+                const float4* src = reinterpret_cast<const float4*>(seg + (item_row + 2 * j) * ld_f + off);
+                p0[e][u] = src[lane];
+                p1[e][u] = src[32 + lane];
+            }
         }
     }
     auto add3 = [](const float4 (&p)[3]) {
         return make_float4((p[0].x + p[1].x) + p[2].x, (p[0].y + p[1].y) + p[2].y, (p[0].z + p[1].z) + p[2].z,
                            (p[0].w + p[1].w) + p[2].w);
     };
-    float4 r0 = add3(p0), r1 = add3(p1);
-    const int s0 = 4 * lane, s1 = 128 + 4 * lane;
-    if (c >= 1 && c + 2 < T) {
-        const float4 w0 = __ldg(reinterpret_cast<const float4*>(g_iw + s0)), w1 = __ldg(reinterpret_cast<const float4*>(g_iw + s1));
-        r0 = make_float4(r0.x * w0.x, r0.y * w0.y, r0.z * w0.z, r0.w * w0.w);
-        r1 = make_float4(r1.x * w1.x, r1.y * w1.y, r1.z * w1.z, r1.w * w1.w);
-    } else {
-        auto norm = [&](float sum, int s) {
-            float wss = 0.f;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int t = c - 1 + q;
-                if (t >= 0 && t < T) { const float w = __ldg(g_win + 768 - 256 * q + s); wss = fmaf(w, w, wss); }
-            }
-            return wss > kTiny ? sum / wss : sum;
-        };
-        r0 = make_float4(norm(r0.x, s0), norm(r0.y, s0 + 1), norm(r0.z, s0 + 2), norm(r0.w, s0 + 3));
-        r1 = make_float4(norm(r1.x, s1), norm(r1.y, s1 + 1), norm(r1.z, s1 + 2), norm(r1.w, s1 + 3));
-    }
-    if ((reinterpret_cast<uintptr_t>(yo) & 15) == 0) {
-        reinterpret_cast<float4*>(yo)[lane] = r0;
-        reinterpret_cast<float4*>(yo)[32 + lane] = r1;
-    } else {
-        yo[s0] = r0.x; yo[s0 + 1] = r0.y; yo[s0 + 2] = r0.z; yo[s0 + 3] = r0.w;
-        yo[s1] = r1.x; yo[s1 + 1] = r1.y; yo[s1 + 2] = r1.z; yo[s1 + 3] = r1.w;
+    for (int e = 0; e < kOlaPerWarp; ++e) {
+        if (cl0 + e >= n) break;
+        const int c = t0 + cl0 + e;
+        float4 r0 = add3(p0[e]), r1 = add3(p1[e]);
+        if (c >= 1 && c + 2 < T) {
+            r0 = make_float4(r0.x * w0.x, r0.y * w0.y, r0.z * w0.z, r0.w * w0.w);
+            r1 = make_float4(r1.x * w1.x, r1.y * w1.y, r1.z * w1.z, r1.w * w1.w);
+        } else {
+            auto norm = [&](float sum, int s) {
+                float wss = 0.f;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int t = c - 1 + q;
+                    if (t >= 0 && t < T) { const float w = __ldg(g_win + 768 - 256 * q + s); wss = fmaf(w, w, wss); }
+                }
+                return wss > kTiny ? sum / wss : sum;
+            };
+            r0 = make_float4(norm(r0.x, s0), norm(r0.y, s0 + 1), norm(r0.z, s0 + 2), norm(r0.w, s0 + 3));
+            r1 = make_float4(norm(r1.x, s1), norm(r1.y, s1 + 1), norm(r1.z, s1 + 2), norm(r1.w, s1 + 3));
+        }
+        float* yo = yo0 + static_cast<int64_t>(cl0 + e) * kHop;
+        if ((reinterpret_cast<uintptr_t>(yo) & 15) == 0) {
+            reinterpret_cast<float4*>(yo)[lane] = r0;
+            reinterpret_cast<float4*>(yo)[32 + lane] = r1;
+        } else {
+            yo[s0] = r0.x; yo[s0 + 1] = r0.y; yo[s0 + 2] = r0.z; yo[s0 + 3] = r0.w;
+            yo[s1] = r1.x; yo[s1 + 1] = r1.y; yo[s1 + 2] = r1.z; yo[s1 + 3] = r1.w;
+        }
     }
 }
 
@@ -1339,6 +1371,7 @@ k_mel_to_mag(BatchView bv, const float* __restrict__ mel, int layout, int is_log
 // host-side launchers
 // ---------------------------------------------------------------------------------------
 static size_t smem_common() { return sizeof(float2) * 1024 + sizeof(float) * 1024 + sizeof(spev_tile) * kRing; }
+static size_t smem_gl_fused() { return sizeof(float2) * 1024 + sizeof(float) * 1024 + sizeof(uint64_t) * 2 * kWarps + sizeof(float) * kWarps * kWsRegionWords; }
 static size_t smem_ws_phase() { return sizeof(float2) * 1024 + sizeof(float) * 1024 + sizeof(uint64_t) * kWarps + sizeof(float) * kWarps * kWsRegionWords; }
 static size_t smem_prog(const spev_ctx* c) { return sizeof(float4) * c->prog_groups + sizeof(int4) * kWarps * c->prog_nb; }
 static size_t smem_stft(size_t prog_bytes) {
@@ -1457,14 +1490,17 @@ int launch_stft_phase(spev_ctx* ctx, const spev_batch* b, const float* y, const 
         if (!(ctx->gl_variant & 4) && b->n_ftiles >= 8 * grid) counter = counter_in;
         float* seg = static_cast<float*>(ang);
         const bool fast = (ctx->gl_variant & 16) != 0;
-#define SPEV_GLF(ST, FA) launch_pdl(k_gl_fused<ST, FA>, grid, kThreads, smem_ws_phase(), st, view_of(b), y, S, ld_s, seg, \
+#define SPEV_GLF(ST, FA) launch_pdl(k_gl_fused<ST, FA>, grid, kThreads, smem_gl_fused(), st, view_of(b), y, S, ld_s, seg, \
                                     static_cast<float2*>(tprev), ld, alpha, has_prev, tw, win, counter, base)
         if (ctx->gl_variant & 32)   // straight-line body (A/B: instruction-fetch bound)
             return stage_t ? launch_pdl(k_stft_phase_w<1, true, true>, grid, kThreads, smem_ws_phase(), st, view_of(b), y, S, ld_s,
                                         static_cast<float2*>(ang), static_cast<float2*>(tprev), ld, alpha, has_prev, tw, win, counter, base)
                            : launch_pdl(k_stft_phase_w<1, false, true>, grid, kThreads, smem_ws_phase(), st, view_of(b), y, S, ld_s,
                                         static_cast<float2*>(ang), static_cast<float2*>(tprev), ld, alpha, has_prev, tw, win, counter, base);
-        if (stage_t) return fast ? SPEV_GLF(true, true) : SPEV_GLF(true, false);
+        // bulk staging of the S rows: 16-byte aligned rows, both rows (+ 3 pad columns) inside the 1280-float sample region
+        const bool stage_s = stage_t && (reinterpret_cast<uintptr_t>(S) & 15) == 0 && ld_s % 4 == 0 && ld_s >= kPSlot &&
+                             ld_s + kPSlot <= kNfft + kHop;
+        if (stage_s) return fast ? SPEV_GLF(true, true) : SPEV_GLF(true, false);
         return fast ? SPEV_GLF(false, true) : SPEV_GLF(false, false);
 #undef SPEV_GLF
     }
