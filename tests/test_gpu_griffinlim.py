@@ -304,3 +304,24 @@ def test_griffinlim_fused_iteration_matches_two_kernel_path(cuda):
                     err = float((ia - ib).norm() / ia.norm().clamp_min(1e-30))
                     assert err <= tol, (frames, n_iter, variant, T, err)
                 off += n
+
+
+def test_griffinlim_fused_silent_bins_and_items(cuda):
+    """Zero magnitudes (silent bins, a silent item): the phase normalisation divides 0 by (0 + tiny) in librosa; the fused
+    kernel's rsqrt path clamps |a|^2 instead.  Both give exactly 0 -- no NaN / Inf, a silent item stays silent -- and the
+    non-silent item still matches the oracle."""
+    import spev_tts_b200 as sp
+    _, S = _state(40, T=60, B=2)
+    S = S.copy()
+    S[1] = 0.0                      # a silent item
+    S[0, 300:, :] = 0.0             # silent upper bins
+    S[0, :, 20:25] = 0.0            # silent frames
+    ph = synth.init_phase(S.shape, seed=41)
+    for n_iter in (1, 5):
+        got = sp.griffinlim(S, n_iter=n_iter, hop_length=256, n_fft=1024, init_phase=ph)
+        assert np.isfinite(got).all()
+        assert not got[1].any()
+        ref = lr.griffinlim(S[:1], n_iter=n_iter, hop_length=256, n_fft=1024, init_phase=ph[:1])
+        assert abs(lr.spectral_convergence(got[0], S[0]) - lr.spectral_convergence(ref[0], S[0])) <= 1e-3
+        if n_iter == 1:
+            assert rel_l2(got[:1], ref) <= 1e-5
