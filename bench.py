@@ -465,8 +465,12 @@ def run_ours(args):
                "api": "spev_tts_b200.cache.LogMelCacheBuilder.build (pinned host in/out, 3-stream pipeline)",
                "bytes_note": "per rank (its shard); all ranks copy concurrently",
                "roofline": {"bound": "pcie", "peak": pcie, "floor_ms": floor_ms, "frac": floor_ms / e2e_ms,
+                            "duplex_floor_ms": (h2d_b + d2h_b) / pcie["duplex_GBps"] / 1e6,
+                            "frac_of_duplex_floor": (h2d_b + d2h_b) / pcie["duplex_GBps"] / 1e6 / e2e_ms,
                             "note": "floor = max(H2D bytes / measured pinned H2D GB/s, D2H bytes / measured D2H GB/s) "
-                                    "of rank 0 measured ALONE in this run (PCIe is full duplex); at N > 1 compare with "
+                                    "of rank 0 measured ALONE in this run (PCIe is full duplex); duplex_floor = all bytes / "
+                                    "the rate measured with both directions copying at once (what the pipelined build "
+                                    "actually faces: the two directions share the host side); at N > 1 compare with "
                                     "all_ranks_at_once: the shared host side is the limiter"},
                "host_numa_binding_rank0": numa}
         # extra: the same corpus as 16-bit PCM on the host (the on-disk format of LJSpeech-style

@@ -274,7 +274,8 @@ SPEV_API int spev_set_logmel_variant(spev_ctx* ctx, int variant);
  * update inverse-transforms the new spectra in registers and writes pair overlap-add segments (k_gl_fused), a streaming
  * kernel finishes the overlap-add (k_ola_pairs) -- the spectra never travel through HBM; | 16 = rsqrt phase
  * normalisation in the fused kernel (2 ulp instead of IEEE sqrt + divide); | 32 = straight-line fused body (A/B of the
- * rolled two-pass body).  Default 25 = 1 | 8 | 16.  Variants 0..7 are bit-identical to each other; the fused ones add
+ * rolled two-pass body); | 64 = L2 eviction hints in the fused kernels (the momentum spectra stream through
+ * evict-first, S / pair segments / y are kept evict-last).  Default 89 = 1 | 8 | 16 | 64.  Variants 0..7 are bit-identical to each other; the fused ones add
  * the <= 4 overlap-add terms in pair order and agree with them to rounding (tests/test_gpu_griffinlim.py). */
 SPEV_API int spev_set_griffinlim_variant(spev_ctx* ctx, int variant);
 

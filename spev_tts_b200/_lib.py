@@ -130,8 +130,8 @@ _SIGS = {
 
 EXPORTED_SYMBOLS = tuple(sorted(_SIGS))
 
-# spev_set_griffinlim_variant: the library default (bulk-staged rows | fused iteration | rsqrt phase normalisation)
-GL_VARIANT_DEFAULT = 25
+# spev_set_griffinlim_variant: the library default (bulk-staged rows | fused iteration | rsqrt phase normalisation | L2 hints)
+GL_VARIANT_DEFAULT = 89
 
 _lib = None
 _lock = threading.Lock()

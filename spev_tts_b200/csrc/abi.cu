@@ -223,7 +223,7 @@ int spev_create(spev_ctx** out, int device, int sr, int n_fft, int hop, int win,
 
     spev_ctx* c = new spev_ctx();
     c->device = device; c->sr = sr; c->n_fft = n_fft; c->hop = hop; c->win = kNfft; c->n_mels = n_mels;
-    c->fmin = fmin; c->fmax = fmax; c->num_sms = c->num_sms_device = prop.multiProcessorCount; c->tma = nullptr; c->use_tc = 1; c->k1_variant = 0; c->gl_variant = 25;
+    c->fmin = fmin; c->fmax = fmax; c->num_sms = c->num_sms_device = prop.multiProcessorCount; c->tma = nullptr; c->use_tc = 1; c->k1_variant = 0; c->gl_variant = 89;
     c->d_tw = nullptr; c->d_window = nullptr; c->d_win2048 = nullptr; c->d_tw2048 = nullptr; c->d_basis = c->d_basis_pad = c->d_basis_hi = c->d_basis_lo = nullptr;
     c->d_pinv_t = c->d_pinv_hi = c->d_pinv_lo = nullptr;
     c->d_prog_w = nullptr; c->d_prog_h = nullptr;
@@ -384,10 +384,10 @@ int spev_set_tensor_core(spev_ctx* c, int enable) {
 
 int spev_set_griffinlim_variant(spev_ctx* c, int variant) {
     SPEV_REQUIRE(c, SPEV_E_INVALID, "ctx is null");
-    SPEV_REQUIRE(variant >= 0 && variant <= 63 && (variant == 0 || (variant & 1)), SPEV_E_INVALID,
+    SPEV_REQUIRE(variant >= 0 && variant <= 127 && (variant == 0 || (variant & 1)), SPEV_E_INVALID,
                  "spev_set_griffinlim_variant: 0 (r01 kernels) or 1 (bulk-staged rows) | 2 (dynamic ISTFT tiles) | 4 (dynamic phase-update pairs) "
-                 "| 8 (fused iteration: inverse transform inside the phase update + pair overlap-add; default 25 = 1 | 8 | 16) | 16 (rsqrt phase normalisation in the fused kernel) "
-                 "| 32 (straight-line fused body)");
+                 "| 8 (fused iteration: inverse transform inside the phase update + pair overlap-add; default 89 = 1 | 8 | 16 | 64) | 16 (rsqrt phase normalisation in the fused kernel) "
+                 "| 32 (straight-line fused body) | 64 (L2 eviction hints: momentum spectra stream, S / segments / y stay)");
     c->gl_variant = variant;
     return SPEV_OK;
 }

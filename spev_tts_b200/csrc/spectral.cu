@@ -676,7 +676,7 @@ template <bool STAGE_T, bool FAST>
 __global__ void __launch_bounds__(kThreads, 1)
 k_gl_fused(BatchView bv, const float* __restrict__ y, const float* __restrict__ S, int64_t ld_s,
            float* __restrict__ seg_base, float2* tprev, int64_t ld, float alpha, int has_prev,
-           const float2* __restrict__ g_tw, const float* __restrict__ g_win, unsigned* counter, unsigned base) {
+           const float2* __restrict__ g_tw, const float* __restrict__ g_win, unsigned* counter, unsigned base, int l2_hints) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* s_tw = reinterpret_cast<float2*>(smem_raw);
     float* s_win = reinterpret_cast<float*>(s_tw + 1024);
@@ -695,6 +695,8 @@ k_gl_fused(BatchView bv, const float* __restrict__ y, const float* __restrict__ 
     uint64_t* sbar = s_bar + kWarps + warp;
     unsigned tphase = 0, sphase = 0;
     const int pl = (32 - lane) & 31;
+    // tprev streams through (read once, rewritten, next use a whole iteration away); S and the segments are re-used soon
+    const uint64_t pol_stream = l2_policy(l2_hints ? 1 : 0), pol_keep = l2_policy(l2_hints ? 2 : 0);
 
     const int64_t n_pairs = static_cast<int64_t>(bv.n_ftiles) * kWarps;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * kWarps;
@@ -743,7 +745,7 @@ k_gl_fused(BatchView bv, const float* __restrict__ y, const float* __restrict__ 
                 const uint32_t bytes = b_valid ? static_cast<uint32_t>((ld_s + kPSlot) * 4) : static_cast<uint32_t>(kPSlot * 4);
                 fence_proxy_async();
                 bar_expect_tx(sbar, bytes);
-                bulk_g2s(xs, sa, bytes, sbar);
+                bulk_g2s_hint(xs, sa, bytes, sbar, pol_keep);
             }
         } else {
             nxt = stage_next();                          // the next pair's samples have this whole pair's time to arrive
@@ -779,7 +781,7 @@ k_gl_fused(BatchView bv, const float* __restrict__ y, const float* __restrict__ 
                         const uint32_t bytes = b_valid ? static_cast<uint32_t>(ld * 8 + (kBins + 1) * 8) : static_cast<uint32_t>((kBins + 1) * 8);
                         fence_proxy_async();
                         bar_expect_tx(tbar, bytes);
-                        bulk_g2s(tile, tprev + ra, bytes, tbar);
+                        bulk_g2s_hint(tile, tprev + ra, bytes, tbar, pol_stream);
                     }
                 }
             }
@@ -798,11 +800,11 @@ k_gl_fused(BatchView bv, const float* __restrict__ y, const float* __restrict__ 
                     const float2 z = make_float2(0.f, 0.f);
                     const float2 ta = !has_prev ? z : (staged ? tsm[512] : tprev[ra + 512]);
                     nyq_a = phase_of_t<FAST>(xa, ssa[512], ta, alpha, has_prev).x;
-                    tprev[ra + 512] = xa;
+                    st_hint(tprev + ra + 512, xa, pol_stream);
                     if (b_valid) {
                         const float2 tb = !has_prev ? z : (staged ? tsm[ld + 512] : tprev[rb + 512]);
                         nyq_b = phase_of_t<FAST>(xbv, ssb[512], tb, alpha, has_prev).x;
-                        tprev[rb + 512] = xbv;
+                        st_hint(tprev + rb + 512, xbv, pol_stream);
                     }
                 }
                 static_for<0, 4>([&](auto gc) {
@@ -830,10 +832,10 @@ k_gl_fused(BatchView bv, const float* __restrict__ y, const float* __restrict__ 
                         split_pair_prescaled(v[k2], pm[k2], xa, xbv);
                         float2 a = phase_of_t<FAST>(xa, s_a[q], tpa[q], alpha, has_prev);
                         float2 b = make_float2(0.f, 0.f);
-                        tprev[ra + k] = xa;
+                        st_hint(tprev + ra + k, xa, pol_stream);
                         if (b_valid) {
                             b = phase_of_t<FAST>(xbv, s_b[q], tpb[q], alpha, has_prev);
-                            tprev[rb + k] = xbv;
+                            st_hint(tprev + rb + k, xbv, pol_stream);
                         }
                         if (k2 == 0 && lane == 0) { a.y = 0.f; b.y = 0.f; }   // irfft ignores Im(DC)
                         // V = A + iB and its mirror conj(A) + i conj(B), both with swapped components
@@ -869,9 +871,9 @@ k_gl_fused(BatchView bv, const float* __restrict__ y, const float* __restrict__ 
                 float* seg = seg_base + 2 * ra + lane;
                 static_for<0, 40>([&](auto jc) {
                     constexpr int j = decltype(jc)::value;
-                    if constexpr (j < 8) seg[32 * j] = v[j].y;
-                    else if constexpr (j < 32) seg[32 * j] = v[j].y + v[j - 8].x;
-                    else { if (b_valid) seg[32 * j] = v[j - 8].x; }
+                    if constexpr (j < 8) st_hint(seg + 32 * j, v[j].y, pol_keep);
+                    else if constexpr (j < 32) st_hint(seg + 32 * j, v[j].y + v[j - 8].x, pol_keep);
+                    else { if (b_valid) st_hint(seg + 32 * j, v[j - 8].x, pol_keep); }
                 });
             }
         }
@@ -1216,7 +1218,7 @@ constexpr int kOlaParts = (kTileChunks + kOlaWarps * kOlaPerWarp - 1) / (kOlaWar
 
 __global__ void __launch_bounds__(kOlaWarps * 32)
 k_ola_pairs(BatchView bv, const float* __restrict__ seg, int64_t ld_f, float* __restrict__ y,
-            const float* __restrict__ g_win /* [1024] Hann, then [256] 1 / sum_q w^2 (ctx table) */) {
+            const float* __restrict__ g_win /* [1024] Hann, then [256] 1 / sum_q w^2 (ctx table) */, int l2_hints) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float* g_iw = g_win + kNfft;
     pdl_launch_dependents();
@@ -1278,8 +1280,16 @@ k_ola_pairs(BatchView bv, const float* __restrict__ seg, int64_t ld_f, float* __
         }
         float* yo = yo0 + static_cast<int64_t>(cl0 + e) * kHop;
         if ((reinterpret_cast<uintptr_t>(yo) & 15) == 0) {
-            reinterpret_cast<float4*>(yo)[lane] = r0;
-            reinterpret_cast<float4*>(yo)[32 + lane] = r1;
+            if (l2_hints) {   // y is read back by the next kernel: keep it in L2
+                const uint64_t pol = l2_policy(2);
+                asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;\n" ::"l"(reinterpret_cast<float4*>(yo) + lane),
+                             "f"(r0.x), "f"(r0.y), "f"(r0.z), "f"(r0.w), "l"(pol) : "memory");
+                asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;\n" ::"l"(reinterpret_cast<float4*>(yo) + 32 + lane),
+                             "f"(r1.x), "f"(r1.y), "f"(r1.z), "f"(r1.w), "l"(pol) : "memory");
+            } else {
+                reinterpret_cast<float4*>(yo)[lane] = r0;
+                reinterpret_cast<float4*>(yo)[32 + lane] = r1;
+            }
         } else {
             yo[s0] = r0.x; yo[s0 + 1] = r0.y; yo[s0 + 2] = r0.z; yo[s0 + 3] = r0.w;
             yo[s1] = r1.x; yo[s1 + 1] = r1.y; yo[s1 + 2] = r1.z; yo[s1 + 3] = r1.w;
@@ -1491,7 +1501,7 @@ int launch_stft_phase(spev_ctx* ctx, const spev_batch* b, const float* y, const 
         float* seg = static_cast<float*>(ang);
         const bool fast = (ctx->gl_variant & 16) != 0;
 #define SPEV_GLF(ST, FA) launch_pdl(k_gl_fused<ST, FA>, grid, kThreads, smem_gl_fused(), st, view_of(b), y, S, ld_s, seg, \
-                                    static_cast<float2*>(tprev), ld, alpha, has_prev, tw, win, counter, base)
+                                    static_cast<float2*>(tprev), ld, alpha, has_prev, tw, win, counter, base, (ctx->gl_variant & 64) ? 1 : 0)
         if (ctx->gl_variant & 32)   // straight-line body (A/B: instruction-fetch bound)
             return stage_t ? launch_pdl(k_stft_phase_w<1, true, true>, grid, kThreads, smem_ws_phase(), st, view_of(b), y, S, ld_s,
                                         static_cast<float2*>(ang), static_cast<float2*>(tprev), ld, alpha, has_prev, tw, win, counter, base)
@@ -1518,7 +1528,7 @@ int launch_ola_pairs(spev_ctx* ctx, const spev_batch* b, const void* seg, int64_
     if (b->n_ctiles == 0) return SPEV_OK;
     SPEV_REQUIRE(seg && y, SPEV_E_INVALID, "ola: null buffer");
     return launch_pdl(k_ola_pairs, b->n_ctiles * kOlaParts, kOlaWarps * 32, 0, st, view_of(b), static_cast<const float*>(seg),
-                      2 * ld, y, static_cast<const float*>(ctx->d_window));
+                      2 * ld, y, static_cast<const float*>(ctx->d_window), (ctx->gl_variant & 64) ? 1 : 0);
 }
 
 int launch_istft(spev_ctx* ctx, const spev_batch* b, const void* spec, int64_t ld, float* y,

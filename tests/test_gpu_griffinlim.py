@@ -270,7 +270,7 @@ def test_griffinlim_kernel_variants_agree(cuda):
 
 
 def test_griffinlim_fused_iteration_matches_two_kernel_path(cuda):
-    """The fused iteration (default, variant 25 = 9 + rsqrt phase normalisation; 9: the new spectra are inverse-transformed in registers inside the phase
+    """The fused iteration (default, variant 89 = 9 + rsqrt phase normalisation + L2 hints; 9: the new spectra are inverse-transformed in registers inside the phase
     update and leave as pair segments; k_ola_pairs overlap-adds them) against the two-kernel path (variant 1: spectra
     through HBM, k_istft): same arithmetic per frame, only the order of the <= 4 overlap-add terms differs (pairs first),
     so a few iterations agree to rounding; static and dynamic pair scheduling are bit-identical to each other."""
@@ -285,7 +285,7 @@ def test_griffinlim_fused_iteration_matches_two_kernel_path(cuda):
         ph = torch.rand(fb.n_frames, 513, generator=g, device=cuda) * 6.2831853
         outs = {}
         try:
-            for variant in (1, 9, 13, 25, 41):
+            for variant in (1, 9, 13, 25, 41, 89):
                 _lib.check(ctx.lib.spev_set_griffinlim_variant(ctx.handle, variant))
                 outs[variant] = sp.griffinlim_flat(S, fb, ctx, n_iter=n_iter, init_phase=ph).clone()
         finally:
@@ -294,6 +294,7 @@ def test_griffinlim_fused_iteration_matches_two_kernel_path(cuda):
         assert torch.equal(outs[9], outs[13]), frames
         a = outs[1].double()
         # 9 / 13: rolled body, static / dynamic pairs; 25: the default (rsqrt normalisation); 41: straight-line body
+        assert torch.equal(outs[25], outs[89]), frames      # L2 eviction hints change no arithmetic
         for variant in (9, 25, 41):
             b = outs[variant].double()
             off = 0   # per item (a short item must not hide behind a long one)
