@@ -117,14 +117,14 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n) {
 // 31 %); MT = 3 cuts the B traffic to a third.
 template <int BN, int MT>
 struct TcSmem {
-    static constexpr int kStagesA = 2;                 // A ring (per stage: landed tile + its tf32 residual)
+    static constexpr int kStagesA = 3;                 // A ring of LANDING buffers; the tf32 residual tile is one shared buffer
     static constexpr int kSlotsB = 2;                  // B ring (per slot: B_hi + B_lo chunk)
     static constexpr int kCtas = BN > 128 ? 1 : 2;     // two CTAs per SM: one's epilogue overlaps the other's main loop
     static constexpr uint32_t kBBytes = BN * kBK * 4;
-    static constexpr uint32_t kStageA = 2 * kABytes;
+    static constexpr uint32_t kStageA = kABytes;
     static constexpr uint32_t kSlotB = 2 * kBBytes;
     static constexpr uint32_t kBars = 1024;
-    static constexpr uint32_t kTotal = kStagesA * kStageA + kSlotsB * kSlotB + kBars + 1024 /*alignment slack*/;
+    static constexpr uint32_t kTotal = kStagesA * kStageA + kABytes /*A_lo*/ + kSlotsB * kSlotB + kBars + 1024 /*alignment slack*/;
     static constexpr uint32_t kCols = BN * MT;
     static constexpr uint32_t kTmemCols = kCols <= 32 ? 32 : kCols <= 64 ? 64 : kCols <= 128 ? 128 : kCols <= 256 ? 256 : 512;
     static_assert(kCols <= 512 && kTmemCols * kCtas <= 512, "accumulators do not fit TMEM");
@@ -138,12 +138,14 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     constexpr int NSA = L::kStagesA, NSB = L::kSlotsB;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    unsigned char* base_b = base + NSA * L::kStageA;
+    unsigned char* base_lo = base + NSA * L::kStageA;          // the one A_lo tile
+    unsigned char* base_b = base_lo + kABytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(base_b + NSB * L::kSlotB);
     uint64_t* full_a = bars;                        // [NSA] TMA landed an A tile
-    uint64_t* split = full_a + NSA;                 // [NSA] A_hi / A_lo ready
-    uint64_t* empty_a = split + NSA;                // [NSA] MMAs done reading the A stage
-    uint64_t* full_b = empty_a + NSA;               // [NSB] TMA landed a B chunk
+    uint64_t* empty_a = full_a + NSA;               // [NSA] MMAs (and the splitter) done reading the landing buffer
+    uint64_t* lo_full = empty_a + NSA;              // A_lo written (and, with a_exp, the landing buffer rewritten)
+    uint64_t* lo_empty = lo_full + 1;               // the A_lo MMAs of the previous tile are done
+    uint64_t* full_b = lo_empty + 1;                // [NSB] TMA landed a B chunk
     uint64_t* empty_b = full_b + NSB;               // [NSB] MMAs of every tile done reading the B chunk
     uint64_t* tmem_full = empty_b + NSB;
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(tmem_full + 1);
@@ -152,7 +154,8 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     const int m0 = blockIdx.x * (kBM * MT), n0 = blockIdx.y * BN;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NSA; ++s) { mbar_init(full_a + s, 1); mbar_init(split + s, 128); mbar_init(empty_a + s, 1); }
+        for (int s = 0; s < NSA; ++s) { mbar_init(full_a + s, 1); mbar_init(empty_a + s, 1); }
+        mbar_init(lo_full, 128); mbar_init(lo_empty, 1);
         for (int s = 0; s < NSB; ++s) { mbar_init(full_b + s, 1); mbar_init(empty_b + s, 1); }
         mbar_init(tmem_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -194,20 +197,33 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
 #pragma unroll 1
                 for (int mt = 0; mt < MT; ++mt) {
                     const int j = kc * MT + mt, s = j % NSA;
-                    mbar_wait(split + s, (j / NSA) & 1);
-                    tc_fence_after();
-                    const uint32_t a_hi = smem_u32(base + s * L::kStageA), a_lo = a_hi + kABytes;
+                    const uint32_t a_hi = smem_u32(base + s * L::kStageA), a_lo = smem_u32(base_lo);
                     const uint32_t acc = tmem_base + static_cast<uint32_t>(mt * BN);
+                    // kind::tf32 ignores the low 13 mantissa bits of its operands: the tile as it landed IS A_hi, so its
+                    // two products start while the splitter is still computing the residual (with a_exp the splitter
+                    // rewrites the tile first)
+                    auto mma_hi = [&]() {
 #pragma unroll
-                    for (int k = 0; k < kBK / 8; ++k) {   // UMMA_K = 8 for tf32 = 32 bytes along the swizzled row
+                        for (int k = 0; k < kBK / 8; ++k) {   // UMMA_K = 8 for tf32 = 32 bytes along the swizzled row
+                            const uint32_t off = k * 32;
+                            const uint64_t dah = umma_desc_sw128(a_hi + off);
+                            tc_mma_tf32(acc, dah, umma_desc_sw128(b_lo + off), idesc, (kc | k) != 0);   // small term first
+                            tc_mma_tf32(acc, dah, umma_desc_sw128(b_hi + off), idesc, 1);
+                        }
+                    };
+                    mbar_wait(full_a + s, (j / NSA) & 1);
+                    tc_fence_after();
+                    if (!p.a_exp) mma_hi();
+                    mbar_wait(lo_full, j & 1);
+                    tc_fence_after();
+                    if (p.a_exp) mma_hi();
+#pragma unroll
+                    for (int k = 0; k < kBK / 8; ++k) {
                         const uint32_t off = k * 32;
-                        const uint64_t dah = umma_desc_sw128(a_hi + off), dal = umma_desc_sw128(a_lo + off);
-                        const uint64_t dbh = umma_desc_sw128(b_hi + off), dbl = umma_desc_sw128(b_lo + off);
-                        tc_mma_tf32(acc, dal, dbh, idesc, (kc | k) != 0);   // small terms first
-                        tc_mma_tf32(acc, dah, dbl, idesc, 1);
-                        tc_mma_tf32(acc, dah, dbh, idesc, 1);
+                        tc_mma_tf32(acc, umma_desc_sw128(a_lo + off), umma_desc_sw128(b_hi + off), idesc, 1);
                     }
                     tc_commit(empty_a + s);   // implies tcgen05.fence::before_thread_sync
+                    tc_commit(lo_empty);
                 }
                 tc_commit(empty_b + sb);
             }
@@ -219,8 +235,9 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         for (int j = 0; j < n_it; ++j) {
             const int s = j % NSA;
             mbar_wait(full_a + s, (j / NSA) & 1);
+            mbar_wait(lo_empty, (j & 1) ^ 1);          // the previous tile's A_lo products are done with the buffer
             float4* a = reinterpret_cast<float4*>(base + s * L::kStageA);
-            float4* l = reinterpret_cast<float4*>(base + s * L::kStageA + kABytes);
+            float4* l = reinterpret_cast<float4*>(base_lo);
 #pragma unroll
             for (int i = 0; i < static_cast<int>(kABytes / 16 / 128); ++i) {
                 float4 v = a[t + 128 * i];
@@ -230,11 +247,11 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                 h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
                 h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
                 h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-                a[t + 128 * i] = h;
+                if (p.a_exp) a[t + 128 * i] = h;       // only exp() changes what the tensor core must see
                 l[t + 128 * i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
             }
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic writes -> async proxy (UMMA)
-            mbar_arrive(split + s);
+            mbar_arrive(lo_full);
         }
         // ---------------- epilogue: TMEM -> registers -> global ----------------
         mbar_wait(tmem_full, 0);
