@@ -30,8 +30,15 @@
 
 namespace spev {
 
+#ifndef SPEV_TC_NSA
+#define SPEV_TC_NSA 3
+#endif
+#ifndef SPEV_TC_CTAS
+#define SPEV_TC_CTAS 2
+#endif
 constexpr int kBM = 128, kBK = 32;
-constexpr int kTcThreads = 192;
+constexpr int kTcSplit = 256;                  // splitter / epilogue threads (8 warps)
+constexpr int kTcThreads = 64 + kTcSplit;
 constexpr uint32_t kABytes = kBM * kBK * 4;   // 16 KB
 
 enum { EPI_MEL = 0, EPI_MAG = 1 };
@@ -117,9 +124,9 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n) {
 // 31 %); MT = 3 cuts the B traffic to a third.
 template <int BN, int MT>
 struct TcSmem {
-    static constexpr int kStagesA = 3;                 // A ring of LANDING buffers; the tf32 residual tile is one shared buffer
+    static constexpr int kStagesA = BN > 128 ? 3 : SPEV_TC_NSA;                 // A ring of LANDING buffers; the tf32 residual tile is one shared buffer
     static constexpr int kSlotsB = 2;                  // B ring (per slot: B_hi + B_lo chunk)
-    static constexpr int kCtas = BN > 128 ? 1 : 2;     // two CTAs per SM: one's epilogue overlaps the other's main loop
+    static constexpr int kCtas = BN > 128 ? 1 : SPEV_TC_CTAS;     // two CTAs per SM: one's epilogue overlaps the other's main loop
     static constexpr uint32_t kBBytes = BN * kBK * 4;
     static constexpr uint32_t kStageA = kABytes;
     static constexpr uint32_t kSlotB = 2 * kBBytes;
@@ -155,7 +162,7 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSA; ++s) { mbar_init(full_a + s, 1); mbar_init(empty_a + s, 1); }
-        mbar_init(lo_full, 128); mbar_init(lo_empty, 1);
+        mbar_init(lo_full, kTcSplit); mbar_init(lo_empty, 1);
         for (int s = 0; s < NSB; ++s) { mbar_init(full_b + s, 1); mbar_init(empty_b + s, 1); }
         mbar_init(tmem_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -230,7 +237,7 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             tc_commit(tmem_full);
         }
     } else {
-        const int t = threadIdx.x - 64;   // 0..127
+        const int t = threadIdx.x - 64;   // 0..kTcSplit-1
         const int n_it = p.k_chunks * MT;
         for (int j = 0; j < n_it; ++j) {
             const int s = j % NSA;
@@ -239,16 +246,16 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             float4* a = reinterpret_cast<float4*>(base + s * L::kStageA);
             float4* l = reinterpret_cast<float4*>(base_lo);
 #pragma unroll
-            for (int i = 0; i < static_cast<int>(kABytes / 16 / 128); ++i) {
-                float4 v = a[t + 128 * i];
+            for (int i = 0; i < static_cast<int>(kABytes / 16 / kTcSplit); ++i) {
+                float4 v = a[t + kTcSplit * i];
                 if (p.a_exp) { v.x = expf(v.x); v.y = expf(v.y); v.z = expf(v.z); v.w = expf(v.w); }
                 float4 h;
                 h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
                 h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
                 h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
                 h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-                if (p.a_exp) a[t + 128 * i] = h;       // only exp() changes what the tensor core must see
-                l[t + 128 * i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                if (p.a_exp) a[t + kTcSplit * i] = h;       // only exp() changes what the tensor core must see
+                l[t + kTcSplit * i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
             }
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic writes -> async proxy (UMMA)
             mbar_arrive(lo_full);
@@ -263,7 +270,7 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             const bool row_ok = row < p.m_total;
             float* orow = out + static_cast<int64_t>(row) * p.ld_out + n0;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 16) {
+            for (int c0 = ((warp - 2) >> 2) * 16; c0 < BN; c0 += 16 * (kTcSplit / 128)) {   // warps 2..5 / 6..9: alternate 16-column groups
                 uint32_t r[16];
                 tc_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(mt * BN + c0), r);
                 float v[16];
