@@ -7,19 +7,21 @@
 //   K3' mel_to_mag (TC)  : exp(logmel)[F, 80] . pinv[513, 80]^T -> clip, sqrt -> S[F, 513(520)]
 //       replaces librosa.feature.inverse.mel_to_stft under :730
 //
-// One CTA = one 128 x BN output tile, 6 warps, warp-specialised:
+// One CTA = MT 128 x BN output tiles, 10 warps, warp-specialised:
 //   warp 0      TMA producer: cp.async.bulk.tensor (SWIZZLE_128B, K-major, 32-float K chunks) of
-//               the A tile and the pre-split B_hi / B_lo tiles into a 3-stage ring (mbarrier
-//               complete_tx).
-//   warps 2..5  splitter: 3xTF32 needs A = A_hi + A_lo with A_hi exactly representable in TF32.
-//               They rewrite the landed A tile in place (A_hi = bits & 0xFFFFE000, optionally
-//               after exp()) and write A_lo = A - A_hi to a second tile -- elementwise, so the
-//               swizzled placement is preserved without knowing it -- then fence.proxy.async and
-//               arrive on the stage's "split" barrier.  Later the same warps run the epilogue.
+//               the A tiles into a ring of three LANDING buffers and of the pre-split B_hi / B_lo
+//               chunks into a 2-slot ring (mbarrier complete_tx).
+//   warps 2..9  splitter: 3xTF32 needs A = A_hi + A_lo with A_hi exactly representable in TF32.
+//               kind::tf32 ignores the low 13 mantissa bits of its operands, so the tile as it
+//               landed IS A_hi and is left alone (with a fused exp() it is rewritten); the splitter
+//               writes A_lo = A - (bits & 0xFFFFE000) into ONE shared residual tile -- elementwise,
+//               so the swizzled placement is preserved without knowing it -- then fence.proxy.async
+//               and arrive on "lo_full".  Later the same warps run the epilogue.
 //   warp 1      TMEM allocator + MMA issuer: one elected thread issues, per 8-wide K step,
-//               tcgen05.mma.kind::tf32  D += A_hi.B_hi ; D += A_lo.B_hi ; D += A_hi.B_lo
-//               with the accumulator in TMEM (fp32, 128 lanes x BN columns), then
-//               tcgen05.commit -> the stage's "empty" barrier (and finally "tmem_full").
+//               tcgen05.mma.kind::tf32  D += A.B_lo ; D += A.B_hi  as soon as the tile has landed, and
+//               D += A_lo.B_hi once the residual is ready, with the accumulators in TMEM (fp32,
+//               128 lanes x MT*BN columns); tcgen05.commit -> "empty_a" (landing buffer) and
+//               "lo_empty" (residual tile), finally "tmem_full".
 //   epilogue    tcgen05.ld 32x32b.x16 (warp w owns TMEM lanes 32*(w%4)..), log/clamp or
 //               clip/sqrt in registers, 16-byte row stores.
 // Every mbarrier wait is bounded: a protocol bug traps instead of hanging the GPU.
