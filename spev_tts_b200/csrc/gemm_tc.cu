@@ -146,7 +146,9 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     using L = TcSmem<BN, MT>;
     constexpr int NSA = L::kStagesA, NSB = L::kSlotsB;
     extern __shared__ unsigned char smem_raw[];
-    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment by POINTER arithmetic on the shared-memory symbol: the address space stays known to the compiler
+    // (LDS / STS in the splitter; the integer round trip made them generic LD / ST with long-scoreboard latency)
+    unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char* base_lo = base + NSA * L::kStageA;          // the one A_lo tile
     unsigned char* base_b = base_lo + kABytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(base_b + NSB * L::kSlotB);
@@ -244,11 +246,14 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         for (int j = 0; j < n_it; ++j) {
             const int s = j % NSA;
             mbar_wait(full_a + s, (j / NSA) & 1);
-            mbar_wait(lo_empty, (j & 1) ^ 1);          // the previous tile's A_lo products are done with the buffer
             float4* a = reinterpret_cast<float4*>(base + s * L::kStageA);
             float4* l = reinterpret_cast<float4*>(base_lo);
+            constexpr int kPer = static_cast<int>(kABytes / 16 / kTcSplit);
+            float4 lo[kPer];
+            // the residuals are computed in registers BEFORE waiting for the residual tile: the loads and the arithmetic
+            // overlap the previous tile's A_lo products
 #pragma unroll
-            for (int i = 0; i < static_cast<int>(kABytes / 16 / kTcSplit); ++i) {
+            for (int i = 0; i < kPer; ++i) {
                 float4 v = a[t + kTcSplit * i];
                 if (p.a_exp) { v.x = expf(v.x); v.y = expf(v.y); v.z = expf(v.z); v.w = expf(v.w); }
                 float4 h;
@@ -257,8 +262,11 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                 h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
                 h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
                 if (p.a_exp) a[t + kTcSplit * i] = h;       // only exp() changes what the tensor core must see
-                l[t + kTcSplit * i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                lo[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
             }
+            mbar_wait(lo_empty, (j & 1) ^ 1);          // the previous tile's A_lo products are done with the buffer
+#pragma unroll
+            for (int i = 0; i < kPer; ++i) l[t + kTcSplit * i] = lo[i];
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic writes -> async proxy (UMMA)
             mbar_arrive(lo_full);
         }
