@@ -35,6 +35,9 @@ namespace spev {
 #ifndef SPEV_TC_NSA
 #define SPEV_TC_NSA 3
 #endif
+#ifndef SPEV_TC_NLO
+#define SPEV_TC_NLO 1
+#endif
 #ifndef SPEV_TC_CTAS
 #define SPEV_TC_CTAS 2
 #endif
@@ -127,13 +130,14 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n) {
 template <int BN, int MT>
 struct TcSmem {
     static constexpr int kStagesA = BN > 128 ? 3 : SPEV_TC_NSA;                 // A ring of LANDING buffers; the tf32 residual tile is one shared buffer
+    static constexpr int kLo = SPEV_TC_NLO;            // residual (A_lo) tiles
     static constexpr int kSlotsB = 2;                  // B ring (per slot: B_hi + B_lo chunk)
     static constexpr int kCtas = BN > 128 ? 1 : SPEV_TC_CTAS;     // two CTAs per SM: one's epilogue overlaps the other's main loop
     static constexpr uint32_t kBBytes = BN * kBK * 4;
     static constexpr uint32_t kStageA = kABytes;
     static constexpr uint32_t kSlotB = 2 * kBBytes;
     static constexpr uint32_t kBars = 1024;
-    static constexpr uint32_t kTotal = kStagesA * kStageA + kABytes /*A_lo*/ + kSlotsB * kSlotB + kBars + 1024 /*alignment slack*/;
+    static constexpr uint32_t kTotal = kStagesA * kStageA + kLo * kABytes /*A_lo*/ + kSlotsB * kSlotB + kBars + 1024 /*alignment slack*/;
     static constexpr uint32_t kCols = BN * MT;
     static constexpr uint32_t kTmemCols = kCols <= 32 ? 32 : kCols <= 64 ? 64 : kCols <= 128 ? 128 : kCols <= 256 ? 256 : 512;
     static_assert(kCols <= 512 && kTmemCols * kCtas <= 512, "accumulators do not fit TMEM");
@@ -150,13 +154,14 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     // (LDS / STS in the splitter; the integer round trip made them generic LD / ST with long-scoreboard latency)
     unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char* base_lo = base + NSA * L::kStageA;          // the one A_lo tile
-    unsigned char* base_b = base_lo + kABytes;
+    constexpr int NLO = L::kLo;
+    unsigned char* base_b = base_lo + NLO * kABytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(base_b + NSB * L::kSlotB);
     uint64_t* full_a = bars;                        // [NSA] TMA landed an A tile
     uint64_t* empty_a = full_a + NSA;               // [NSA] MMAs (and the splitter) done reading the landing buffer
-    uint64_t* lo_full = empty_a + NSA;              // A_lo written (and, with a_exp, the landing buffer rewritten)
-    uint64_t* lo_empty = lo_full + 1;               // the A_lo MMAs of the previous tile are done
-    uint64_t* full_b = lo_empty + 1;                // [NSB] TMA landed a B chunk
+    uint64_t* lo_full = empty_a + NSA;              // [NLO] A_lo written (and, with a_exp, the landing buffer rewritten)
+    uint64_t* lo_empty = lo_full + NLO;             // [NLO] the A_lo MMAs of an earlier tile are done with the residual tile
+    uint64_t* full_b = lo_empty + NLO;              // [NSB] TMA landed a B chunk
     uint64_t* empty_b = full_b + NSB;               // [NSB] MMAs of every tile done reading the B chunk
     uint64_t* tmem_full = empty_b + NSB;
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(tmem_full + 1);
@@ -165,8 +170,9 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     const int m0 = blockIdx.x * (kBM * MT), n0 = blockIdx.y * BN;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NSA; ++s) { mbar_init(full_a + s, 1); mbar_init(empty_a + s, 1); }
-        mbar_init(lo_full, kTcSplit); mbar_init(lo_empty, 1);
+        // a landing buffer is free once its hi products are done (commit: 1) AND every splitter thread has read it
+        for (int s = 0; s < NSA; ++s) { mbar_init(full_a + s, 1); mbar_init(empty_a + s, 1 + kTcSplit); }
+        for (int q = 0; q < NLO; ++q) { mbar_init(lo_full + q, kTcSplit); mbar_init(lo_empty + q, 1); }
         for (int s = 0; s < NSB; ++s) { mbar_init(full_b + s, 1); mbar_init(empty_b + s, 1); }
         mbar_init(tmem_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -208,7 +214,8 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
 #pragma unroll 1
                 for (int mt = 0; mt < MT; ++mt) {
                     const int j = kc * MT + mt, s = j % NSA;
-                    const uint32_t a_hi = smem_u32(base + s * L::kStageA), a_lo = smem_u32(base_lo);
+                    const int ql = j % NLO;
+                    const uint32_t a_hi = smem_u32(base + s * L::kStageA), a_lo = smem_u32(base_lo + ql * kABytes);
                     const uint32_t acc = tmem_base + static_cast<uint32_t>(mt * BN);
                     // kind::tf32 ignores the low 13 mantissa bits of its operands: the tile as it landed IS A_hi, so its
                     // two products start while the splitter is still computing the residual (with a_exp the splitter
@@ -224,17 +231,16 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                     };
                     mbar_wait(full_a + s, (j / NSA) & 1);
                     tc_fence_after();
-                    if (!p.a_exp) mma_hi();
-                    mbar_wait(lo_full, j & 1);
+                    if (!p.a_exp) { mma_hi(); tc_commit(empty_a + s); }   // (commit implies tcgen05.fence::before_thread_sync)
+                    mbar_wait(lo_full + ql, (j / NLO) & 1);
                     tc_fence_after();
-                    if (p.a_exp) mma_hi();
+                    if (p.a_exp) { mma_hi(); tc_commit(empty_a + s); }
 #pragma unroll
                     for (int k = 0; k < kBK / 8; ++k) {
                         const uint32_t off = k * 32;
                         tc_mma_tf32(acc, umma_desc_sw128(a_lo + off), umma_desc_sw128(b_hi + off), idesc, 1);
                     }
-                    tc_commit(empty_a + s);   // implies tcgen05.fence::before_thread_sync
-                    tc_commit(lo_empty);
+                    tc_commit(lo_empty + ql);
                 }
                 tc_commit(empty_b + sb);
             }
@@ -247,7 +253,8 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             const int s = j % NSA;
             mbar_wait(full_a + s, (j / NSA) & 1);
             float4* a = reinterpret_cast<float4*>(base + s * L::kStageA);
-            float4* l = reinterpret_cast<float4*>(base_lo);
+            const int ql = j % NLO;
+            float4* l = reinterpret_cast<float4*>(base_lo + ql * kABytes);
             constexpr int kPer = static_cast<int>(kABytes / 16 / kTcSplit);
             float4 lo[kPer];
             // the residuals are computed in registers BEFORE waiting for the residual tile: the loads and the arithmetic
@@ -264,11 +271,13 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                 if (p.a_exp) a[t + kTcSplit * i] = h;       // only exp() changes what the tensor core must see
                 lo[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
             }
-            mbar_wait(lo_empty, (j & 1) ^ 1);          // the previous tile's A_lo products are done with the buffer
+            if (!p.a_exp) mbar_arrive(empty_a + s);    // this thread is done with the landing buffer
+            mbar_wait(lo_empty + ql, ((j / NLO) & 1) ^ 1);   // an earlier tile's A_lo products are done with the residual tile
 #pragma unroll
             for (int i = 0; i < kPer; ++i) l[t + kTcSplit * i] = lo[i];
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic writes -> async proxy (UMMA)
-            mbar_arrive(lo_full);
+            if (p.a_exp) mbar_arrive(empty_a + s);     // (rewritten tile: counted once its writes are fenced)
+            mbar_arrive(lo_full + ql);
         }
         // ---------------- epilogue: TMEM -> registers -> global ----------------
         mbar_wait(tmem_full, 0);
