@@ -29,7 +29,9 @@ independent implementations that *are* available in the container
 (``tests/test_oracle.py``): ``torchaudio.functional.melscale_fbanks`` (Slaney
 basis), ``torch.stft`` / ``torch.istft`` in float64 (framing, padding, window,
 overlap-add, window-sum-square normalisation), ``scipy.optimize.fmin_l_bfgs_b``
-(the very routine librosa's NNLS calls) and ``torch.bucketize``.
+(the very routine librosa's NNLS calls), ``torchaudio.functional.griffinlim`` (the
+Griffin-Lim loop: momentum rule, phase normalisation, trailing ISTFT -- compared with
+the re-analysis padded by reflection, as torchaudio does it) and ``torch.bucketize``.
 The LengthRegulator restatement *is* pinned: ``tests/golden/lr_*.npz`` were
 produced by the reference's own class (``oracle/make_golden.py`` imports
 ``/root/reference/spev_real_metrics.py:122-146``).

@@ -121,6 +121,31 @@ def test_griffinlim_golden_and_convergence(golden):
     assert abs(sc8 - float(g["sc8"])) < 1e-4 and sc8 < sc0
 
 
+def test_griffinlim_loop_against_torchaudio(monkeypatch):
+    """The restated Griffin-Lim LOOP (fast Griffin-Lim: momentum / (1 + momentum) on the previous rebuilt spectrum,
+    phase normalisation, rebuilt spectrum kept as tprev, trailing ISTFT) against torchaudio's independent implementation of
+    the same algorithm.  torchaudio pads the re-analysis by reflection where librosa pads with zeros, so the restatement's
+    ``stft`` is swapped for a reflect-padded one for this comparison only: everything else -- which is what this test
+    pins -- is the code the parity tests use."""
+    import torchaudio
+    T, n_iter = 60, 8
+    y0 = synth.speechy(seed=77, n=(T - 1) * 256)
+    S = np.abs(lr.stft(y0, n_fft=1024, hop_length=256)).astype(np.float32)           # [513, T]
+    plain_stft = lr.stft
+
+    def stft_reflect(y, *, n_fft=2048, hop_length=None, **kw):
+        pad = [(0, 0)] * (np.ndim(y) - 1) + [(n_fft // 2, n_fft // 2)]
+        return plain_stft(np.pad(y, pad, mode="reflect"), n_fft=n_fft, hop_length=hop_length, center=False)
+    monkeypatch.setattr(lr, "stft", stft_reflect)
+    got = lr.griffinlim(S, n_iter=n_iter, hop_length=256, n_fft=1024, init_phase=np.zeros(S.shape))
+    ref = torchaudio.functional.griffinlim(torch.from_numpy(S).double(), torch.hann_window(1024, periodic=True, dtype=torch.float64),
+                                           n_fft=1024, hop_length=256, win_length=1024, power=1.0, n_iter=n_iter,
+                                           momentum=0.99, length=None, rand_init=False).numpy()
+    assert got.shape == ref.shape == ((T - 1) * 256,)
+    err = np.linalg.norm(got - ref) / np.linalg.norm(ref)
+    assert err <= 1e-4, err        # float32 storage in the restatement (like librosa) vs float64 throughout
+
+
 def test_rms_and_centroid_vs_torch():
     """8(f) row 1 restatements pinned against torch (float64 STFT magnitude, unfold)."""
     y = synth.speechy(seed=9, n=30000)
