@@ -519,6 +519,9 @@ struct VitParams {
     const double2* tab;       // [n_classes][width] (stay, switch) log transition probabilities
 };
 
+#ifndef SPEV_VIT_CTAS
+#define SPEV_VIT_CTAS 2   // 3 (56 registers) was measured: 28.4 ms either way -- the kernel is ALU / FP64-pipe bound, not latency bound
+#endif
 constexpr int kVitThreads = 384;                 // one thread per pitch bin: it owns the voiced AND the unvoiced state of that bin
 struct ArgMax { double v; int i; };
 __device__ __forceinline__ ArgMax warp_argmax(ArgMax a) {
@@ -541,7 +544,7 @@ __device__ __forceinline__ void upd_max(double& m, int& a, double s, int i) {
 // predecessor of row class cls and bin offset d - half.  kron(switch, local) gives the same value for
 // voiced->voiced and unvoiced->unvoiced (and for the two switches), so two numbers serve all four (vp, v) pairs.
 template <bool LT_SMEM>
-__global__ void __launch_bounds__(kVitThreads, 2)
+__global__ void __launch_bounds__(kVitThreads, SPEV_VIT_CTAS)
 k_pyin_viterbi(const float* __restrict__ logobs, const float* __restrict__ log_unvoiced,
                const int64_t* __restrict__ frame_off, int n_items, VitParams p, unsigned short* __restrict__ ptr,
                int* __restrict__ states, unsigned* __restrict__ work_counter) {
@@ -955,7 +958,7 @@ int spev_pyin_decode(spev_pyin* c, const float* logobs, const float* log_unvoice
     auto kern = tab_smem ? k_pyin_viterbi<true> : k_pyin_viterbi<false>;
     SPEV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     SPEV_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned), st));
-    const int grid = std::min(n_items, 148 * 2);
+    const int grid = std::min(n_items, 148 * SPEV_VIT_CTAS);
     kern<<<grid, kVitThreads, smem, st>>>(logobs, log_unvoiced, frame_off, n_items, p, ptr, states, counter);
     SPEV_CUDA(cudaGetLastError());
     if (f0 || voiced_flag) {
