@@ -224,7 +224,7 @@ int spev_create(spev_ctx** out, int device, int sr, int n_fft, int hop, int win,
     spev_ctx* c = new spev_ctx();
     c->device = device; c->sr = sr; c->n_fft = n_fft; c->hop = hop; c->win = kNfft; c->n_mels = n_mels;
     c->fmin = fmin; c->fmax = fmax; c->num_sms = c->num_sms_device = prop.multiProcessorCount; c->tma = nullptr; c->use_tc = 1; c->k1_variant = 0; c->gl_variant = 89;
-    c->d_tw = nullptr; c->d_window = nullptr; c->d_win2048 = nullptr; c->d_tw2048 = nullptr; c->d_basis = c->d_basis_pad = c->d_basis_hi = c->d_basis_lo = nullptr;
+    c->d_tw = nullptr; c->d_window = nullptr; c->d_win2048 = nullptr; c->d_tw2048 = nullptr; c->d_basis = c->d_basis_pad = c->d_basis_hi = c->d_basis_lo = nullptr; c->d_nnls_rng = nullptr;
     c->d_pinv_t = c->d_pinv_hi = c->d_pinv_lo = nullptr;
     c->d_prog_w = nullptr; c->d_prog_h = nullptr;
 
@@ -319,10 +319,26 @@ int spev_create(spev_ctx** out, int device, int sr, int n_fft, int hop, int win,
         for (int q = 0; q < 4; ++q) { const float w = c->h_window[768 - 256 * q + s]; wss = std::fmaf(w, w, wss); }
         win_iw.push_back(1.0f / wss);
     }
+    // banded view of the basis (NNLS screening kernel): per band its run of non-zero bins, per bin the bands that cover it
+    std::vector<int> nnls_rng(2 * static_cast<size_t>(n_mels) + 2 * kBins);
+    for (int m = 0; m < n_mels; ++m) {
+        int lo = kBins, hi = -1;
+        for (int k = 0; k < kBins; ++k)
+            if (c->h_basis[static_cast<size_t>(m) * kBins + k] != 0.f) { lo = std::min(lo, k); hi = std::max(hi, k); }
+        nnls_rng[2 * m] = hi >= lo ? lo : 0;
+        nnls_rng[2 * m + 1] = hi >= lo ? hi - lo + 1 : 0;
+    }
+    for (int k = 0; k < kBins; ++k) {
+        int lo = n_mels, hi = -1;
+        for (int m = 0; m < n_mels; ++m)
+            if (c->h_basis[static_cast<size_t>(m) * kBins + k] != 0.f) { lo = std::min(lo, m); hi = std::max(hi, m); }
+        nnls_rng[2 * n_mels + 2 * k] = hi >= lo ? lo : 0;
+        nnls_rng[2 * n_mels + 2 * k + 1] = hi >= lo ? hi : -1;
+    }
     int rc = SPEV_OK;
     if ((rc = upload(&c->d_tw, tw)) || (rc = upload(&c->d_window, win_iw)) ||
         (rc = upload(&c->d_win2048, win2048)) || (rc = upload(&c->d_tw2048, tw2048)) ||
-        (rc = upload(&c->d_basis, c->h_basis)) || (rc = upload(&c->d_basis_pad, basis_pad)) || (rc = upload(&c->d_basis_hi, b_hi)) ||
+        (rc = upload(&c->d_basis, c->h_basis)) || (rc = upload(&c->d_nnls_rng, nnls_rng)) || (rc = upload(&c->d_basis_pad, basis_pad)) || (rc = upload(&c->d_basis_hi, b_hi)) ||
         (rc = upload(&c->d_basis_lo, b_lo)) || (rc = upload(&c->d_pinv_t, pinv_t)) ||
         (rc = upload(&c->d_prog_w, prog_w)) || (rc = upload(&c->d_prog_h, prog_h)) ||
         (rc = gemm_tc_init(c)) || (rc = spectral_init(c))) {
@@ -337,7 +353,7 @@ void spev_destroy(spev_ctx* c) {
     if (!c) return;
     DeviceGuard guard(c);
     gemm_tc_destroy(c);
-    cudaFree(c->d_tw); cudaFree(c->d_window); cudaFree(c->d_win2048); cudaFree(c->d_tw2048); cudaFree(c->d_basis); cudaFree(c->d_basis_pad); cudaFree(c->d_basis_hi);
+    cudaFree(c->d_tw); cudaFree(c->d_window); cudaFree(c->d_win2048); cudaFree(c->d_tw2048); cudaFree(c->d_basis); cudaFree(c->d_nnls_rng); cudaFree(c->d_basis_pad); cudaFree(c->d_basis_hi);
     cudaFree(c->d_basis_lo); cudaFree(c->d_pinv_t); cudaFree(c->d_pinv_hi); cudaFree(c->d_pinv_lo);
     cudaFree(c->d_prog_w); cudaFree(c->d_prog_h);
     delete c;

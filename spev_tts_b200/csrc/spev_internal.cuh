@@ -63,6 +63,7 @@ struct spev_ctx {
     float2* d_win2048;   // [1024] 0.5 * periodic Hann-2048 as (w[2n], w[2n+1])  (features.cu)
     float2* d_tw2048;    // [512]  exp(-2 pi i k / 2048)
     float* d_basis;      // [n_mels, 513] dense float32 basis (NNLS objective)
+    int* d_nnls_rng;     // banded view of the basis for the NNLS screening kernel: [n_mels] (first bin, count) then [513] (first band, last band)
     float* d_basis_pad;  // [n_mels, 520] zero padded (K-major B operand of the mel GEMM)
     float* d_basis_hi;   // tf32-truncated part, same shape
     float* d_basis_lo;   // residual, same shape
