@@ -229,7 +229,7 @@ def nnls_blocks(b: int, T: int, n_mels: int):
     return n_columns, blocks
 
 
-def nnls_refine(S: torch.Tensor, mel_rows: torch.Tensor, ctx: Context, b: int, T: int, *, is_log: bool) -> int:
+def nnls_refine(S: torch.Tensor, mel_rows: torch.Tensor, ctx: Context, b: int, T: int, *, is_log: bool, overlap=None) -> int:
     """The L-BFGS-B part of ``librosa.util.nnls`` (inside ``mel_to_stft``, ``spev_real_metrics.py:730``), in place on the
     warm start ``S = clip(pinv(A) M, 0) ** 0.5`` (``[b*T, 520]`` magnitude rows; ``mel_rows``: ``[b*T, n_mels]``).
 
@@ -239,7 +239,12 @@ def nnls_refine(S: torch.Tensor, mel_rows: torch.Tensor, ctx: Context, b: int, T
     at once and the warm start IS the answer.  One launch of ``spev_nnls_objective`` evaluates that test for every
     block (float64, as in librosa); only blocks that fail it -- short utterances, short remainder blocks -- are handed
     to ``scipy.optimize.fmin_l_bfgs_b`` (the very routine librosa calls, same arguments), with objective and gradient
-    evaluated on the GPU.  Returns the number of blocks that iterated."""
+    evaluated on the GPU.  Returns the number of blocks that iterated.
+
+    ``overlap``: a callable that enqueues work which only READS ``S`` (``mel_to_audio`` passes the Griffin-Lim call): it runs
+    right after the screening kernels have been launched, and their result is fetched through a side stream, so the host
+    does not sit in a synchronisation while the device is idle.  If blocks do iterate, ``S`` changes afterwards (stream
+    ordered behind that work) and the caller must redo it."""
     n_mels = ctx.n_mels
     n_columns, blocks = nnls_blocks(b, T, n_mels)
     dev = S.device
@@ -256,12 +261,25 @@ def nnls_refine(S: torch.Tensor, mel_rows: torch.Tensor, ctx: Context, b: int, T
     if T - n_full * n_columns > 0:
         launches.append((n_full * n_columns, T - n_full * n_columns, 0, b * n_full * n_columns))
 
-    def screen(mode):
+    def screen(mode, overlap=None):
         for t0, tb, sc, o in launches:
             _lib.check(lib.spev_nnls_objective(ctx.handle, S.data_ptr(), mode, S.shape[1], mel_rows.data_ptr(), 1 if is_log else 0,
                                                b, T, t0, tb, sc, val[o:].data_ptr(), None, pg[o:].data_ptr(), st),
                        "spev_nnls_objective")
-        host = pg.cpu().numpy()                     # (one synchronisation per pass)
+        if overlap is None:
+            host = pg.cpu().numpy()                 # (one synchronisation per pass)
+        else:
+            main = torch.cuda.current_stream(dev)
+            side, pinned = ctx.side_stream(), ctx.pinned_f64(b * T)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            side.wait_event(ev)
+            with torch.cuda.stream(side):
+                pinned.copy_(pg, non_blocking=True)
+            pg.record_stream(side)
+            overlap()                               # e.g. the whole Griffin-Lim call, enqueued behind the screening
+            side.synchronize()                      # waits for the screening + copy only
+            host = pinned.numpy().copy()
         out = {}
         for t0, tb, sc, o in launches:
             cols = host[o: o + b * tb].reshape(b, tb)
@@ -269,7 +287,7 @@ def nnls_refine(S: torch.Tensor, mel_rows: torch.Tensor, ctx: Context, b: int, T
                 out[(t0 + s0, t0 + min(tb, s0 + (sc or tb)))] = float(cols[:, s0: s0 + (sc or tb)].max(initial=0.0))
         return out
     # float32 screening pass; if any block lies within 10 % of the threshold the pass is repeated in float64
-    norm = screen(2)
+    norm = screen(2, overlap)
     if any(0.9 * NNLS_PGTOL <= v <= 1.1 * NNLS_PGTOL for v in norm.values()):
         norm = screen(1)
     todo = [blk for blk in blocks if norm[blk] > NNLS_PGTOL]
@@ -390,9 +408,18 @@ def mel_to_audio(M: ArrayLike, *, sr=22050, n_fft=2048, hop_length=None, win_len
     batch = ctx.uniform_batch(b, T, with_chunks=True)
     tm = items_to_rows(t.reshape(b, n_mels, T)).view(-1)                  # frame-major -> tensor-core GEMM
     S = mel_to_mag_flat(tm, batch, ctx, layout=0, is_log=is_log)
-    if nnls == "librosa" and b * T > 0:
-        nnls_refine(S, tm.view(b * T, n_mels), ctx, b, T, is_log=is_log)
     ph = _phase_to_internal(init_phase, b, T, t.device) if init_phase is not None else None
     seed = int(np.random.SeedSequence(random_state).generate_state(2, dtype=np.uint32).view(np.uint64)[0])
-    y = griffinlim_flat(S, batch, ctx, n_iter=n_iter, momentum=momentum, init_phase=ph, seed=seed)
+    out = {}
+
+    def run_gl():
+        out["y"] = griffinlim_flat(S, batch, ctx, n_iter=n_iter, momentum=momentum, init_phase=ph, seed=seed, out=out.get("y"))
+    if nnls == "librosa" and b * T > 0:
+        # Griffin-Lim is enqueued on the warm start while the host fetches the screening result; in the (rare: short
+        # utterances, short remainder blocks) case that librosa's solver iterates, S is refined and the loop redone
+        if nnls_refine(S, tm.view(b * T, n_mels), ctx, b, T, is_log=is_log, overlap=run_gl) > 0 or "y" not in out:
+            run_gl()
+    else:
+        run_gl()
+    y = out["y"]
     return _ret(y.view(*lead, (T - 1) * HOP), was_numpy)
