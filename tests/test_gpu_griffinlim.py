@@ -326,3 +326,32 @@ def test_griffinlim_fused_silent_bins_and_items(cuda):
         assert abs(lr.spectral_convergence(got[0], S[0]) - lr.spectral_convergence(ref[0], S[0])) <= 1e-3
         if n_iter == 1:
             assert rel_l2(got[:1], ref) <= 1e-5
+
+
+def test_griffinlim_call_is_graph_capturable(cuda):
+    """``spev_griffinlim`` (memset of the ticket counters, init, ISTFT, n_iter x (fused kernel, pair overlap-add), all with
+    programmatic dependent launch) has no host synchronisation: it can be captured into a CUDA graph and replayed, and the
+    replay gives the eager result bit for bit."""
+    import spev_tts_b200 as sp
+    from spev_tts_b200 import _lib
+    ctx = sp.Context.get(cuda, fmin=0.0, fmax=8000.0)
+    fb = sp.make_batch(ctx, n_frames=[120, 33, 64], with_chunks=True)
+    g = torch.Generator(device=cuda).manual_seed(17)
+    S = torch.rand(fb.n_frames, _lib.SPEC_LD, generator=g, device=cuda)
+    ph = torch.rand(fb.n_frames, 513, generator=g, device=cuda) * 6.2831853
+    ws = torch.empty(ctx.lib.spev_griffinlim_workspace_bytes(fb.n_frames), dtype=torch.uint8, device=cuda)
+    eager = sp.griffinlim_flat(S, fb, ctx, n_iter=5, init_phase=ph, workspace=ws).clone()
+    y = torch.zeros(fb.n_out_samples, device=cuda)
+    s = torch.cuda.Stream(cuda)
+    s.wait_stream(torch.cuda.current_stream(cuda))
+    with torch.cuda.stream(s):
+        sp.griffinlim_flat(S, fb, ctx, n_iter=5, init_phase=ph, out=y, workspace=ws)      # warm-up on the capture stream
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=s):
+            sp.griffinlim_flat(S, fb, ctx, n_iter=5, init_phase=ph, out=y, workspace=ws)
+    torch.cuda.current_stream(cuda).wait_stream(s)
+    for _ in range(2):
+        y.zero_()
+        graph.replay()
+        torch.cuda.synchronize(cuda)
+        assert torch.equal(y, eager)
