@@ -133,13 +133,6 @@ class Context:
             st = self.__dict__["_side"] = torch.cuda.Stream(torch.device("cuda", self.device))
         return st
 
-    def pinned_f64(self, n: int) -> torch.Tensor:
-        """A cached pinned float64 host buffer of at least ``n`` elements (view of the first ``n``)."""
-        buf = self.__dict__.get("_pin64")
-        if buf is None or buf.numel() < n:
-            buf = self.__dict__["_pin64"] = torch.empty(max(int(n), 1024), dtype=torch.float64, pin_memory=True)
-        return buf[:n]
-
     def set_tensor_core(self, enable: bool) -> None:
         """A/B switch: False forces the FFMA kernel for the mel->magnitude projection."""
         _lib.check(self.lib.spev_set_tensor_core(self.handle, 1 if enable else 0), "spev_set_tensor_core")

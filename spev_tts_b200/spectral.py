@@ -270,7 +270,8 @@ def nnls_refine(S: torch.Tensor, mel_rows: torch.Tensor, ctx: Context, b: int, T
             host = pg.cpu().numpy()                 # (one synchronisation per pass)
         else:
             main = torch.cuda.current_stream(dev)
-            side, pinned = ctx.side_stream(), ctx.pinned_f64(b * T)
+            side = ctx.side_stream()
+            pinned = torch.empty(b * T, dtype=torch.float64, pin_memory=True)   # (torch's caching host allocator: per call, thread-safe)
             ev = torch.cuda.Event()
             ev.record(main)
             side.wait_event(ev)
@@ -279,7 +280,7 @@ def nnls_refine(S: torch.Tensor, mel_rows: torch.Tensor, ctx: Context, b: int, T
             pg.record_stream(side)
             overlap()                               # e.g. the whole Griffin-Lim call, enqueued behind the screening
             side.synchronize()                      # waits for the screening + copy only
-            host = pinned.numpy().copy()
+            host = pinned.numpy()
         out = {}
         for t0, tb, sc, o in launches:
             cols = host[o: o + b * tb].reshape(b, tb)
