@@ -12,7 +12,7 @@ host = torch.empty(total, dtype=torch.float32, pin_memory=True)
 host.normal_(0, 0.05)
 F = int((1 + lens // 256).sum())
 out_host = torch.empty((F, 80), dtype=torch.float32, pin_memory=True)
-for cs, nb in ((1 << 26, 2), (1 << 25, 2), (1 << 24, 2), (1 << 24, 3), (1 << 23, 3)):
+for cs, nb in ((1 << 26, 2), (1 << 26, 3), (1 << 25, 3), (1 << 25, 4), (1 << 24, 4), (1 << 26, 2)):
     b = cache.LogMelCacheBuilder(dev, chunk_samples=cs, n_buffers=nb)
     plan = cache.plan_chunks(lens, cs, starts)
     b.build(host, lens, out_host=out_host, plan=plan); torch.cuda.synchronize()
