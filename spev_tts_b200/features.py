@@ -2,7 +2,7 @@
 
 Drop-ins for the two librosa calls of the reference's cache loop that share the STFT framing
 (``spev_real_metrics.py:370-371``) and for the per-phone pooling lines (``:400-417``).  pYIN (f0,
-voiced probability, ``:369``) is the following "next" row and is not built yet.
+voiced probability, ``:369``), the following "next" row, lives in ``pitch.py`` / ``csrc/pyin.cu``.
 """
 from __future__ import annotations
 
