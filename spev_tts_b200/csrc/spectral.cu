@@ -11,6 +11,9 @@
 // K5 k_stft_phase : STFT of the rebuilt signal fused with Griffin-Lim's momentum / phase
 //                   normalisation update.     Replaces librosa.stft + the angle update lines of
 //                   librosa.griffinlim under :730-733.
+// K5f k_gl_fused  : the Griffin-Lim ITERATION as the driver runs it (round 2): STFT + phase update + inverse transform of
+//                   the new spectra in registers; leaves one overlap-add segment per frame pair.  K4p k_ola_pairs sums the
+//                   segments into y.  (K4 / K5 above stay the stand-alone spev_istft / spev_stft / spev_gl_phase_update.)
 // K3 k_mel_to_mag : S = sqrt(max(pinv . exp(logmel), 0)) (FFMA version; the tcgen05 version
 //                   lives in gemm_tc.cu).     Replaces librosa mel_to_stft under :730.
 //
